@@ -1,0 +1,462 @@
+// Implicit-GEMM convolution (fprop and dgrad) on tcgen05 tensor cores.
+//
+//   Y[m, n] = sum_{tap, c} X[pixel(m) + shift(tap), c] * Wk[n, tap, c]        m = linear NHWC pixel, n = out channel
+//
+// * Operands are bf16, accumulation is fp32 in TMEM (double-buffered: 2 x BLOCK_N columns).
+// * A tiles (128 pixels x 64 channels) arrive by 4-D TMA boxes over the NHWC tensor; the conv halo/padding is the
+//   TMA out-of-bounds zero fill, so there is no im2col buffer and no boundary code.
+// * B tiles (BLOCK_N out-channels x 64 k) arrive by 2-D TMA boxes over the packed [Cout][tap][Cin] weight.
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warps 2..9 = epilogue
+//   (TMEM -> registers -> fused math -> swizzled smem staging -> TMA store).
+// * Persistent: grid = #SMs, each CTA walks tiles  tile = blockIdx.x + i * gridDim.x  (n-tile fastest, so the CTAs
+//   running concurrently share A tiles in L2).
+//
+// Epilogue modes
+//   PLAIN : y = acc (+ bias[n])                                       -> bf16           (dgrad, 1x1, generic)
+//   STATS : y = acc -> bf16, plus per-tile per-channel sum / sum-of-squares of the stored values (train-mode BN)
+//   STYLE : z = acc + bias[n] + nw[n]*noise[m];  a = lrelu_0.2(z);  y = a*sp1[b,n] + s1[b,n]
+//           -> a (bf16, kept for backward) and y (bf16, next layer's input)
+//           reference: styleganv1.py:625-628 / 630-633 (conv -> ApplyNoise -> leaky_relu -> ApplyStyle)
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace irfd {
+
+enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_STYLE = 2 };
+
+struct ConvGemmArgs {
+  int M_total, N_total;
+  int num_m_tiles, num_n_tiles;
+  int taps, kw, pad, cin_chunks;
+  int H, W, HW, B;
+  const float* bias;
+  const float* nw;
+  const float* noise;
+  const float* sp1;
+  const float* s1;
+  float* stat_sum;
+  float* stat_sq;
+};
+
+constexpr int kNumThreads = 320;      // 10 warps
+constexpr int kEpiThreads = 256;      // warps 2..9
+constexpr int kMiscBytes = 12 * 1024; // vectors / reduction scratch / barriers
+constexpr int kStgBytes = 16384;      // one 128 x 64 bf16 staging tile
+constexpr int kSmemLimit = 232448;    // 227 KB
+
+template <int BLOCK_N, int MODE>
+struct GemmCfg {
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int NUM_OUT = (MODE == EPI_STYLE) ? 2 : 1;
+  static constexpr int STG_TOTAL = NUM_OUT * 2 * kStgBytes;
+  static constexpr int RAW_STAGES = (kSmemLimit - 1024 - STG_TOTAL - kMiscBytes) / STAGE_BYTES;
+  static constexpr int STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STG_TOTAL + kMiscBytes;
+  static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
+};
+
+template <int BLOCK_N, int MODE>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out2,
+                 const ConvGemmArgs p) {
+  using Cfg = GemmCfg<BLOCK_N, MODE>;
+  constexpr int STAGES = Cfg::STAGES;
+  static_assert(STAGES >= 2, "pipeline too shallow");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stg_base = smem + STAGES * Cfg::STAGE_BYTES;
+  uint8_t* misc = stg_base + Cfg::STG_TOTAL;
+  float* vec = reinterpret_cast<float*>(misc);                       // 6 * 256 floats (STYLE) / red scratch (STATS)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc + 8192);     // [STAGES]
+  uint64_t* empty_bar = full_bar + STAGES;                           // [STAGES]
+  uint64_t* tmem_full = empty_bar + STAGES;                          // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                              // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_kb = p.taps * p.cin_chunks;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);
+    }
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&map_a);
+      tma_prefetch_desc(&map_b);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int m0 = m_tile * 128;
+        const int w0 = m0 % p.W;
+        const int h0 = (m0 / p.W) % p.H;
+        const int n0 = m0 / (p.W * p.H);
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dh = tap / p.kw - p.pad;
+          const int dw = tap % p.kw - p.pad;
+          for (int ch = 0; ch < p.cin_chunks; ++ch) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + Cfg::A_BYTES;
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_4d(sa, &map_a, &full_bar[stage], ch * 64, w0 + dw, h0 + dh, n0);
+            tma_load_2d(sb, &map_b, &full_bar[stage], (tap * p.cin_chunks + ch) * 64, n_tile * BLOCK_N);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        const int as = iter & 1;
+        const uint32_t aphase = (iter >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    const int e = warp - 2;
+    const int q = warp & 3;       // TMEM lane quarter this warp may touch
+    const int half = e >> 2;      // which 32-column half of each 64-column chunk
+    const int etid = threadIdx.x - 64;
+    const int r = q * 32 + lane;  // tile row == TMEM lane
+    float* vb = vec;              // [256] bias
+    float* vnw = vec + 256;       // [256] noise weight
+    float* vsp1 = vec + 512;      // [2][256]
+    float* vs1 = vec + 1024;      // [2][256]
+    int iter = 0;
+    uint32_t chunk_counter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
+      const int m0 = m_tile * 128;
+      const int ng0 = n_tile * BLOCK_N;
+      float noise_r = 0.f;
+      int img_local = 0;
+      if constexpr (MODE == EPI_STYLE) {
+        const int nimg = p.HW < 128 ? 128 / p.HW : 1;
+        const int b0 = m0 / p.HW;
+        for (int i = etid; i < BLOCK_N; i += kEpiThreads) {
+          vb[i] = p.bias[ng0 + i];
+          vnw[i] = p.nw[ng0 + i];
+        }
+        for (int i = etid; i < nimg * BLOCK_N; i += kEpiThreads) {
+          const int img = i / BLOCK_N, c = i - img * BLOCK_N;
+          int bb = b0 + img;
+          if (bb >= p.B) bb = p.B - 1;
+          vsp1[img * 256 + c] = p.sp1[(size_t)bb * p.N_total + ng0 + c];
+          vs1[img * 256 + c] = p.s1[(size_t)bb * p.N_total + ng0 + c];
+        }
+        named_bar_sync(1, kEpiThreads);
+        if (m0 + r < p.M_total) noise_r = p.noise[m0 + r];
+        img_local = p.HW < 128 ? r / p.HW : 0;
+      } else if constexpr (MODE == EPI_PLAIN) {
+        if (p.bias != nullptr) {
+          for (int i = etid; i < BLOCK_N; i += kEpiThreads) vb[i] = p.bias[ng0 + i];
+          named_bar_sync(1, kEpiThreads);
+        }
+      }
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < BLOCK_N / 64; ++chunk, ++chunk_counter) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BLOCK_N + chunk * 64 + half * 32;
+        tmem_ld32(taddr, v);
+        tmem_ld_wait();
+        if (chunk == BLOCK_N / 64 - 1) {
+          // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+        const int buf = chunk_counter & 1;
+        uint8_t* stg0 = stg_base + buf * kStgBytes;
+        uint8_t* stg1 = stg_base + (2 + buf) * kStgBytes;
+        // staging buffer `buf` was last used two chunks ago: make sure its TMA store has drained it
+        if (etid == 0) tma_store_wait_read<1>();
+        named_bar_sync(1, kEpiThreads);
+        const int cbase = chunk * 64 + half * 32;  // column within the BLOCK_N tile
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          float o[8], o2[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int c = cbase + jj * 8 + t;
+            float acc = __uint_as_float(v[jj * 8 + t]);
+            if constexpr (MODE == EPI_STYLE) {
+              float z = acc + vb[c] + vnw[c] * noise_r;
+              float a = z > 0.f ? z : 0.2f * z;
+              o[t] = a;
+              o2[t] = a * vsp1[img_local * 256 + c] + vs1[img_local * 256 + c];
+            } else if constexpr (MODE == EPI_PLAIN) {
+              o[t] = (p.bias != nullptr) ? acc + vb[c] : acc;
+            } else {
+              o[t] = acc;
+            }
+          }
+          const int j = half * 4 + jj;  // 16-byte chunk index inside the 128-byte staging row
+          const int phys = j ^ (r & 7);
+          uint4 pk;
+          pk.x = pack_bf16x2(o[0], o[1]);
+          pk.y = pack_bf16x2(o[2], o[3]);
+          pk.z = pack_bf16x2(o[4], o[5]);
+          pk.w = pack_bf16x2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(stg0 + r * 128 + phys * 16) = pk;
+          if constexpr (MODE == EPI_STYLE) {
+            uint4 pk2;
+            pk2.x = pack_bf16x2(o2[0], o2[1]);
+            pk2.y = pack_bf16x2(o2[2], o2[3]);
+            pk2.z = pack_bf16x2(o2[4], o2[5]);
+            pk2.w = pack_bf16x2(o2[6], o2[7]);
+            *reinterpret_cast<uint4*>(stg1 + r * 128 + phys * 16) = pk2;
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, kEpiThreads);
+        if (etid == 0) {
+          tma_store_2d(&map_out, stg0, ng0 + chunk * 64, m0);
+          if constexpr (MODE == EPI_STYLE) tma_store_2d(&map_out2, stg1, ng0 + chunk * 64, m0);
+          tma_store_commit();
+        }
+        if constexpr (MODE == EPI_STATS) {
+          // per-channel sum / sum of squares over the 128 rows of this staged chunk (values as stored, bf16)
+          const int pr = etid & 31;  // channel pair
+          const int g = etid >> 5;   // 16-row group
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int row = g * 16 + i;
+            const int phys = (pr >> 2) ^ (row & 7);
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(stg0 + row * 128 + phys * 16 + (pr & 3) * 4);
+            const float2 f = unpack_bf16x2(w);
+            s0 += f.x;
+            q0 += f.x * f.x;
+            s1 += f.y;
+            q1 += f.y * f.y;
+          }
+          float* red = vec;  // [8][64][2]
+          red[(g * 64 + 2 * pr) * 2 + 0] = s0;
+          red[(g * 64 + 2 * pr) * 2 + 1] = q0;
+          red[(g * 64 + 2 * pr + 1) * 2 + 0] = s1;
+          red[(g * 64 + 2 * pr + 1) * 2 + 1] = q1;
+          named_bar_sync(1, kEpiThreads);
+          if (etid < 128) {
+            const int ch = etid & 63, which = etid >> 6;
+            float acc = 0.f;
+#pragma unroll
+            for (int gg = 0; gg < 8; ++gg) acc += red[(gg * 64 + ch) * 2 + which];
+            float* dst = which ? p.stat_sq : p.stat_sum;
+            dst[(size_t)m_tile * p.N_total + ng0 + chunk * 64 + ch] = acc;
+          }
+        }
+      }
+    }
+    if (etid == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK_N, int MODE>
+static int launch_conv_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mo2,
+                            const ConvGemmArgs& a, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N, MODE>;
+  static bool configured = false;
+  auto kern = conv_gemm_kernel<BLOCK_N, MODE>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return IRFD_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int total = a.num_m_tiles * a.num_n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  kern<<<grid, kNumThreads, Cfg::SMEM_BYTES, stream>>>(ma, mb, mo, mo2, a);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+template <int MODE>
+static int dispatch_block_n(int block_n, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo,
+                            const CUtensorMap& mo2, const ConvGemmArgs& a, cudaStream_t stream) {
+  switch (block_n) {
+    case 64: return launch_conv_gemm<64, MODE>(ma, mb, mo, mo2, a, stream);
+    case 128: return launch_conv_gemm<128, MODE>(ma, mb, mo, mo2, a, stream);
+    case 256: return launch_conv_gemm<256, MODE>(ma, mb, mo, mo2, a, stream);
+  }
+  set_last_error("bad BLOCK_N %d", block_n);
+  return IRFD_ERR_INVALID_ARGUMENT;
+}
+
+}  // namespace irfd
+
+using namespace irfd;
+
+extern "C" int irfd_conv_gemm_m_tiles(int n, int h, int w) {
+  long long m = (long long)n * h * w;
+  return (int)((m + 127) / 128);
+}
+
+extern "C" int irfd_conv_gemm(const void* x, int n, int h, int w, int cin, const void* wk, int cout, int ksize,
+                              void* out, void* out2, int mode, const float* bias, const float* nw, const float* noise,
+                              const float* sp1, const float* s1, float* stat_sum, float* stat_sq, int force_block_n,
+                              cudaStream_t stream) {
+  IRFD_CHECK_ARG(x && wk && out, "conv_gemm: null pointer");
+  IRFD_CHECK_ARG(ksize == 1 || ksize == 3, "conv_gemm: ksize must be 1 or 3 (got %d)", ksize);
+  IRFD_CHECK_ARG(cin % 64 == 0 && cin > 0, "conv_gemm: Cin must be a multiple of 64 (got %d)", cin);
+  IRFD_CHECK_ARG(cout % 64 == 0 && cout > 0, "conv_gemm: Cout must be a multiple of 64 (got %d)", cout);
+  IRFD_CHECK_ARG(mode >= 0 && mode <= 2, "conv_gemm: bad mode %d", mode);
+  const long long m_total_ll = (long long)n * h * w;
+  IRFD_CHECK_ARG(m_total_ll > 0 && m_total_ll < (1ll << 31) - 256, "conv_gemm: bad pixel count");
+  const int m_total = (int)m_total_ll;
+
+  // pixel-tile geometry: 128 consecutive NHWC pixels == a (tn, th, tw) box
+  int H = h, W = w, NB = n;
+  if (ksize == 1) {  // pointwise conv == plain GEMM over a single long row of pixels
+    H = 1;
+    W = m_total;
+    NB = 1;
+  }
+  int tw, th, tn;
+  if (W >= 128) {
+    IRFD_CHECK_ARG(ksize == 1 || W % 128 == 0, "conv_gemm: W=%d must be a multiple of 128", W);
+    tw = 128; th = 1; tn = 1;
+  } else {
+    IRFD_CHECK_ARG(128 % W == 0, "conv_gemm: W=%d must divide 128", W);
+    tw = W;
+    const int rows = 128 / W;
+    if (H >= rows) {
+      IRFD_CHECK_ARG(H % rows == 0, "conv_gemm: H=%d must be a multiple of %d", H, rows);
+      th = rows; tn = 1;
+    } else {
+      IRFD_CHECK_ARG(rows % H == 0, "conv_gemm: H=%d must divide %d", H, rows);
+      th = H; tn = rows / H;
+    }
+  }
+
+  ConvGemmArgs a;
+  a.M_total = m_total;
+  a.N_total = cout;
+  a.num_m_tiles = (m_total + 127) / 128;
+  a.taps = ksize * ksize;
+  a.kw = ksize;
+  a.pad = ksize / 2;
+  a.cin_chunks = cin / 64;
+  a.H = H; a.W = W; a.HW = h * w; a.B = n;
+  a.bias = bias; a.nw = nw; a.noise = noise; a.sp1 = sp1; a.s1 = s1;
+  a.stat_sum = stat_sum; a.stat_sq = stat_sq;
+  if (mode == EPI_STYLE) {
+    IRFD_CHECK_ARG(bias && nw && noise && sp1 && s1 && out2, "conv_gemm: STYLE mode needs bias/nw/noise/sp1/s1/out2");
+    IRFD_CHECK_ARG(h * w >= 64, "conv_gemm: STYLE mode needs >= 64 pixels per image");
+  }
+  if (mode == EPI_STATS) IRFD_CHECK_ARG(stat_sum && stat_sq, "conv_gemm: STATS mode needs stat buffers");
+
+  int block_n = force_block_n;
+  if (block_n == 0) {
+    block_n = 64;
+    const int cands[3] = {256, 128, 64};
+    for (int i = 0; i < 3; ++i) {
+      if (cout % cands[i] == 0 && (long long)a.num_m_tiles * (cout / cands[i]) >= num_sms()) {
+        block_n = cands[i];
+        break;
+      }
+    }
+  }
+  IRFD_CHECK_ARG((block_n == 64 || block_n == 128 || block_n == 256) && cout % block_n == 0,
+                 "conv_gemm: BLOCK_N %d incompatible with Cout %d", block_n, cout);
+  a.num_n_tiles = cout / block_n;
+
+  CUtensorMap ma, mb, mo, mo2;
+  {
+    const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+    const uint64_t str[3] = {(uint64_t)cin * 2, (uint64_t)W * cin * 2, (uint64_t)H * W * cin * 2};
+    const uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
+    int rc = make_tmap_bf16(&ma, x, 4, dims, str, box, true);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t ktot = (uint64_t)a.taps * cin;
+    const uint64_t dims[2] = {ktot, (uint64_t)cout};
+    const uint64_t str[1] = {ktot * 2};
+    const uint32_t box[2] = {64, (uint32_t)block_n};
+    int rc = make_tmap_bf16(&mb, wk, 2, dims, str, box, true);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)cout, (uint64_t)m_total};
+    const uint64_t str[1] = {(uint64_t)cout * 2};
+    const uint32_t box[2] = {64, 128};
+    int rc = make_tmap_bf16(&mo, out, 2, dims, str, box, true);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&mo2, out2 ? out2 : out, 2, dims, str, box, true);
+    if (rc) return rc;
+  }
+  switch (mode) {
+    case EPI_PLAIN: return dispatch_block_n<EPI_PLAIN>(block_n, ma, mb, mo, mo2, a, stream);
+    case EPI_STATS: return dispatch_block_n<EPI_STATS>(block_n, ma, mb, mo, mo2, a, stream);
+    case EPI_STYLE: return dispatch_block_n<EPI_STYLE>(block_n, ma, mb, mo, mo2, a, stream);
+  }
+  return IRFD_ERR_INVALID_ARGUMENT;
+}

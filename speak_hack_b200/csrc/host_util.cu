@@ -1,0 +1,73 @@
+#include "host_util.h"
+
+#include <stdarg.h>
+#include <string.h>
+
+namespace irfd {
+
+static thread_local char g_last_error[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n) return n;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  return n;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, bool swizzle128) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return IRFD_ERR_CUDA;
+  cuuint64_t gdims[5];
+  cuuint64_t gstr[4];
+  cuuint32_t gbox[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u]",
+                   (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                   (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+                   rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return IRFD_ERR_CUDA;
+  }
+  return IRFD_OK;
+}
+
+}  // namespace irfd
+
+extern "C" const char* irfd_last_error(void) { return irfd::g_last_error; }
+
+extern "C" int irfd_abi_version(void) { return IRFD_ABI_VERSION; }

@@ -1,0 +1,90 @@
+"""-m gpu: tcgen05 implicit-GEMM conv (irfd_conv_gemm) against a torch fp32 conv on the same bf16-rounded operands."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a = a.double()
+    b = b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _mk(n, h, w, cin, cout, k, dev, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(n, h, w, cin, generator=g).to(dev).to(torch.bfloat16)
+    wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(dev).to(torch.bfloat16)
+    wk = wt.permute(0, 2, 3, 1).contiguous().reshape(cout, k * k * cin)  # [Cout][tap][Cin]
+    return x, wt, wk
+
+
+def _ref(x, wt, k):
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), padding=k // 2)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+CASES = [
+    # n, h, w, cin, cout, k
+    (1, 1, 256, 64, 64, 1),      # plain GEMM, single k-block
+    (1, 1, 1000, 128, 64, 1),    # ragged M (not a multiple of 128)
+    (2, 16, 16, 256, 256, 1),
+    (2, 8, 8, 64, 64, 3),        # tile spans two images
+    (3, 8, 8, 64, 128, 3),       # odd image count -> last tile half out of bounds
+    (2, 16, 16, 64, 64, 3),
+    (1, 32, 32, 128, 64, 3),
+    (1, 64, 64, 64, 128, 3),
+    (1, 128, 128, 64, 64, 3),
+    (1, 256, 256, 64, 64, 3),    # W > 128: two tiles per row
+    (2, 32, 32, 512, 512, 3),
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k", CASES)
+@pytest.mark.parametrize("block_n", [0, 64, 128, 256])
+def test_plain(cuda_device, n, h, w, cin, cout, k, block_n):
+    from speak_hack_b200 import ops
+
+    if block_n and cout % block_n:
+        pytest.skip("BLOCK_N does not divide Cout")
+    x, wt, wk = _mk(n, h, w, cin, cout, k, cuda_device)
+    y = ops.conv_gemm(x, wk, k, ops.EPI_PLAIN, force_block_n=block_n)
+    torch.cuda.synchronize()
+    ref = _ref(x, wt, k)
+    assert rel_l2(y.float(), ref) < 4e-3  # bf16 output rounding: 2^-9 per element
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k", [(2, 16, 16, 64, 64, 3), (4, 32, 32, 128, 256, 3), (2, 64, 64, 256, 64, 1)])
+def test_stats(cuda_device, n, h, w, cin, cout, k):
+    from speak_hack_b200 import ops
+
+    x, wt, wk = _mk(n, h, w, cin, cout, k, cuda_device, seed=1)
+    y, ssum, ssq = ops.conv_gemm(x, wk, k, ops.EPI_STATS)
+    torch.cuda.synchronize()
+    ref = _ref(x, wt, k)
+    assert rel_l2(y.float(), ref) < 4e-3
+    yf = y.float().reshape(-1, cout)
+    assert torch.allclose(ssum.sum(0), yf.sum(0), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(ssq.sum(0), (yf * yf).sum(0), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 8, 8, 64, 64), (3, 8, 8, 128, 128), (2, 32, 32, 128, 256), (1, 256, 256, 64, 64)])
+def test_style(cuda_device, n, h, w, cin, cout):
+    from speak_hack_b200 import ops
+
+    dev = cuda_device
+    x, wt, wk = _mk(n, h, w, cin, cout, 3, dev, seed=2)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    bias = torch.randn(cout, generator=g).to(dev)
+    nw = torch.randn(cout, generator=g).to(dev)
+    noise = torch.randn(n * h * w, generator=g).to(dev)
+    sp1 = (torch.randn(n, cout, generator=g) + 1).to(dev)
+    s1 = torch.randn(n, cout, generator=g).to(dev)
+    a, y = ops.conv_gemm(x, wk, 3, ops.EPI_STYLE, bias=bias, nw=nw, noise=noise, sp1=sp1, s1=s1)
+    torch.cuda.synchronize()
+    z = _ref(x, wt, 3) + bias.view(1, 1, 1, -1) + nw.view(1, 1, 1, -1) * noise.view(n, h, w, 1)
+    a_ref = F.leaky_relu(z, 0.2)
+    y_ref = a_ref * sp1.view(n, 1, 1, cout) + s1.view(n, 1, 1, cout)
+    assert rel_l2(a.float(), a_ref) < 4e-3
+    assert rel_l2(y.float(), y_ref) < 4e-3
