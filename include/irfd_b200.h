@@ -58,6 +58,17 @@ int irfd_conv_gemm(const void* x, int n, int h, int w, int cin, const void* wk, 
                    void* out2, int mode, const float* bias, const float* nw, const float* noise, const float* sp1,
                    const float* s1, float* stat_sum, float* stat_sq, int force_block_n, irfd_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Weight gradient of the same convolutions (tcgen05, both operands MN-major, deterministic split-K over pixels).
+ * Replaces: autograd's convolution_backward(weight) for styleganv1.py:615-616 and torchvision resnet.py:133-141.
+ *   x  [n,h,w,cin] bf16 (the conv input)   dy [n,h,w,cout] bf16 (gradient w.r.t. the raw conv output)
+ *   dw [cout][cin][ksize][ksize] fp32 (OIHW, the reference parameter layout):  dw = beta*dw + grad
+ *   workspace: >= irfd_wgrad_workspace_bytes(...) bytes of device scratch (fp32 split-K partials).
+ */
+long long irfd_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout, int ksize);
+int irfd_conv_wgrad(const void* x, const void* dy, int n, int h, int w, int cin, int cout, int ksize, float* dw,
+                    float beta, void* workspace, long long workspace_bytes, irfd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,8 @@ SIGNATURES = {
     "irfd_last_error": (c_char_p, []),
     "irfd_conv_gemm_m_tiles": (c_int, [_I, _I, _I]),
     "irfd_conv_gemm": (c_int, [_P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "irfd_wgrad_workspace_bytes": (_L, [_I, _I, _I, _I, _I, _I]),
+    "irfd_conv_wgrad": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _F, _P, _L, _P]),
 }
 
 _lib = None

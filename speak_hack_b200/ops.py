@@ -73,3 +73,35 @@ def conv_gemm(
     if mode == EPI_STYLE:
         return out, out2
     return out
+
+
+_workspace = {}
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    """Grow-only per-device scratch buffer (split-K partials etc.); stream-ordered use only."""
+    key = (device.type, device.index)
+    buf = _workspace.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspace[key] = buf
+    return buf
+
+
+def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, dw: Optional[torch.Tensor] = None, beta: float = 0.0):
+    """dW (OIHW fp32) of a stride-1 same-padding conv from its NHWC bf16 input and output gradient."""
+    lib = _lib.load()
+    _chk(x, BF16, "x")
+    _chk(dy, BF16, "dy")
+    n, h, w, cin = x.shape
+    cout = dy.shape[-1]
+    if dw is None:
+        dw = torch.empty((cout, cin, ksize, ksize), dtype=F32, device=x.device)
+        beta = 0.0
+    _chk(dw, F32, "dw")
+    need = lib.irfd_wgrad_workspace_bytes(n, h, w, cin, cout, ksize)
+    ws = workspace(need, x.device)
+    rc = lib.irfd_conv_wgrad(x.data_ptr(), dy.data_ptr(), n, h, w, cin, cout, ksize, dw.data_ptr(), beta,
+                             ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "irfd_conv_wgrad")
+    return dw

@@ -88,3 +88,37 @@ def test_style(cuda_device, n, h, w, cin, cout):
     y_ref = a_ref * sp1.view(n, 1, 1, cout) + s1.view(n, 1, 1, cout)
     assert rel_l2(a.float(), a_ref) < 4e-3
     assert rel_l2(y.float(), y_ref) < 4e-3
+
+
+WG_CASES = [
+    (1, 1, 512, 64, 64, 1),
+    (1, 1, 1000, 128, 64, 1),     # ragged pixel count
+    (2, 8, 8, 64, 64, 3),
+    (3, 8, 8, 128, 128, 3),       # odd atom count? 9*2=18 atoms (even); odd image count
+    (2, 16, 16, 64, 256, 3),      # 9 atoms (odd) -> duplicated tail atom
+    (4, 32, 32, 128, 64, 3),
+    (2, 64, 64, 64, 128, 3),
+    (1, 128, 128, 64, 64, 3),
+    (2, 16, 16, 512, 512, 3),
+    (2, 16, 16, 1024, 256, 1),
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k", WG_CASES)
+def test_wgrad(cuda_device, n, h, w, cin, cout, k):
+    from speak_hack_b200 import ops
+
+    dev = cuda_device
+    g = torch.Generator(device="cpu").manual_seed(4)
+    x = torch.randn(n, h, w, cin, generator=g).to(dev).to(torch.bfloat16)
+    dy = torch.randn(n, h, w, cout, generator=g).to(dev).to(torch.bfloat16)
+    dw = ops.conv_wgrad(x, dy, k)
+    torch.cuda.synchronize()
+    wt = torch.zeros(cout, cin, k, k, device=dev, requires_grad=True)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wt, padding=k // 2)
+    (ref,) = torch.autograd.grad(y, wt, dy.float().permute(0, 3, 1, 2))
+    assert rel_l2(dw, ref) < 1e-4  # fp32 accumulation of exact bf16 products; only summation order differs
+    # accumulate form: dw = 1.0*dw + grad
+    dw2 = ops.conv_wgrad(x, dy, k, dw=dw.clone(), beta=1.0)
+    torch.cuda.synchronize()
+    assert rel_l2(dw2, 2 * ref) < 1e-4
