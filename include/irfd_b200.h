@@ -64,10 +64,117 @@ int irfd_conv_gemm(const void* x, int n, int h, int w, int cin, const void* wk, 
  *   x  [n,h,w,cin] bf16 (the conv input)   dy [n,h,w,cout] bf16 (gradient w.r.t. the raw conv output)
  *   dw [cout][cin][ksize][ksize] fp32 (OIHW, the reference parameter layout):  dw = beta*dw + grad
  *   workspace: >= irfd_wgrad_workspace_bytes(...) bytes of device scratch (fp32 split-K partials).
+ *   reduce_cin/reduce_taps (0 = cin/ksize^2): how the GEMM's K index maps onto dw: k -> (tap = k / reduce_cin,
+ *   c = k % reduce_cin), dw[o][c][tap], k >= reduce_cin*reduce_taps dropped.  Lets an explicit-im2col matrix (ksize 1,
+ *   cin = taps*C) produce OIHW gradients for the strided convs (3x3/2: reduce_cin=C, reduce_taps=9; stem: 147, 1).
  */
 long long irfd_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout, int ksize);
 int irfd_conv_wgrad(const void* x, const void* dy, int n, int h, int w, int cin, int cout, int ksize, float* dw,
-                    float beta, void* workspace, long long workspace_bytes, irfd_stream_t stream);
+                    float beta, int reduce_cin, int reduce_taps, void* workspace, long long workspace_bytes,
+                    irfd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * BatchNorm2d around the encoder convs (torch.nn.BatchNorm2d in torchvision Bottleneck, resnet.py:143-164).
+ *   irfd_bn_finalize : per-tile partial sums (conv epilogue, mode 1) -> mean/rstd [c]; momentum update of the running
+ *                      buffers applied `running_updates` times (the reference's reentrant checkpoint re-runs the
+ *                      forward, model.py:84-90); running_mean may be NULL.
+ *   irfd_bn_eval_rstd: eval mode, rstd = 1/sqrt(running_var + eps).
+ *   irfd_bn_apply    : out = [relu]( gamma*(z-mean)*rstd + beta  [+ res]  [or + BN2(res) when mean2 != NULL] )
+ *   irfd_bn_backward : g = (g1 [+ g2]) * (act > 0 if act != NULL);  dz = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat));
+ *                      dgamma/dbeta = grad_beta*old + new;  g_out (optional) receives the masked g (identity shortcut).
+ * All activations [rows, c] bf16 (NHWC flattened), c % 8 == 0, c <= 2048.
+ */
+int irfd_bn_finalize(const float* psum, const float* psq, int tiles, int c, long long count, float eps, float momentum,
+                     float* mean, float* rstd, float* running_mean, float* running_var, int running_updates,
+                     irfd_stream_t stream);
+int irfd_bn_eval_rstd(const float* running_var, float eps, float* rstd, int c, irfd_stream_t stream);
+int irfd_bn_apply(const void* z, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                  const void* res, const float* mean2, const float* rstd2, const float* gamma2, const float* beta2,
+                  void* out, long long rows, int c, int relu, irfd_stream_t stream);
+long long irfd_bn_bwd_workspace_bytes(long long rows, int c);
+int irfd_bn_backward(const void* g1, const void* g2, const void* act, const void* z, const float* mean,
+                     const float* rstd, const float* gamma, void* dz, void* g_out, float* dgamma, float* dbeta,
+                     float grad_beta, long long rows, int c, void* workspace, long long workspace_bytes,
+                     irfd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Layout / gather kernels for the strided ResNet convs and pooling (torchvision resnet.py:197-205, 133-137, 241).
+ *   irfd_pack_conv_weight: fp32 OIHW -> bf16 GEMM operand. mode 0 fprop [o][tap][i]; 1 dgrad [i][flip(tap)][o];
+ *                          2 dcol [(tap,i)][o]; 3 flat [o][kpad] (stem, k = c*49+kh*7+kw, zero padded).
+ *   irfd_im2col_stem     : x NCHW fp32 [n,3,h,w] -> col [n*h/2*w/2][kpad] bf16 (7x7, stride 2, pad 3).
+ *   irfd_im2col_3x3s2 / irfd_col2im_3x3s2: 3x3 stride-2 pad-1 gather [pix][tap*c + ch] and its adjoint.
+ *   irfd_subsample2 / irfd_scatter_add_s2: 1x1 stride-2 gather; adjoint fused with an add (a may be NULL).
+ *   irfd_maxpool_fwd/bwd : MaxPool2d(3,2,1) with uint8 argmax taps (first maximum, like ATen).
+ *   irfd_avgpool_fwd/bwd : AdaptiveAvgPool2d(1): [n,hw,c] bf16 <-> [n,c] fp32.
+ */
+int irfd_pack_conv_weight(const float* w, void* dst, int o, int i, int taps, int mode, int kpad, irfd_stream_t stream);
+int irfd_im2col_stem(const float* x, void* col, int n, int h, int w, int kpad, irfd_stream_t stream);
+int irfd_im2col_3x3s2(const void* a, void* col, int n, int h, int w, int c, irfd_stream_t stream);
+int irfd_col2im_3x3s2(const void* dcol, void* dx, int n, int h, int w, int c, irfd_stream_t stream);
+int irfd_subsample2(const void* a, void* out, int n, int h, int w, int c, irfd_stream_t stream);
+int irfd_scatter_add_s2(const void* a, const void* b, void* out, int n, int h, int w, int c, irfd_stream_t stream);
+int irfd_maxpool_fwd(const void* a, void* out, void* argmax, int n, int h, int w, int c, irfd_stream_t stream);
+int irfd_maxpool_bwd(const void* dout, const void* argmax, void* dx, int n, int h, int w, int c, irfd_stream_t stream);
+int irfd_avgpool_fwd(const void* a, float* out, int n, int hw, int c, irfd_stream_t stream);
+int irfd_avgpool_bwd(const float* dfeat, void* g, int n, int hw, int c, irfd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Synthesis-network pieces that are not conv epilogues (styleganv1.py:593-635).
+ *   irfd_const_input_fwd/bwd: const[1,c,4,4] + bias -> ApplyNoise -> ApplyStyle (styleganv1.py:596-599).
+ *   irfd_upsample2x_fwd/bwd : nn.Upsample(scale 2, bilinear, align_corners=False) (styleganv1.py:621,624) + adjoint.
+ *   irfd_style_bwd          : backward of the fused epilogue of irfd_conv_gemm mode 2: dz (bf16) plus the reductions
+ *                             ds1/dsp1 [b,c], dbias/dnw [c].
+ *   irfd_to_rgb_fwd/bwd     : 1x1 conv c->3 + bias, NCHW fp32 image out (styleganv1.py:588,607).
+ */
+int irfd_const_input_fwd(const float* cst, const float* bias, const float* nw, const float* noise, const float* sp1,
+                         const float* s1, void* a0, void* y0, int b, int c, irfd_stream_t stream);
+int irfd_const_input_bwd(const void* dy, const void* a0, const float* noise, const float* sp1, float* dsp1, float* ds1,
+                         float* dconst, float* dbias, float* dnw, int b, int c, irfd_stream_t stream);
+int irfd_upsample2x_fwd(const void* in, void* out, int b, int h, int w, int c, irfd_stream_t stream);
+int irfd_upsample2x_bwd(const void* dout, void* din, int b, int h, int w, int c, irfd_stream_t stream);
+long long irfd_style_bwd_workspace_bytes(int b, int hw, int c);
+int irfd_style_bwd(const void* dy, const void* a, const float* noise, const float* sp1, void* dz, float* ds1,
+                   float* dsp1, float* dbias, float* dnw, int b, int hw, int c, void* workspace,
+                   long long workspace_bytes, irfd_stream_t stream);
+int irfd_to_rgb_fwd(const void* y, const float* w, const float* bias, float* out, int b, int hw, int c,
+                    irfd_stream_t stream);
+long long irfd_to_rgb_bwd_workspace_bytes(int b, int hw, int c);
+int irfd_to_rgb_bwd(const float* drgb, const void* y, const float* w, void* dy, float* dw, float* dbias, int b, int hw,
+                    int c, void* workspace, long long workspace_bytes, irfd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * fp32 dense layers: `FC` = F.linear(x, W*w_lrmul, b*b_lrmul) + leaky_relu(0.2) (styleganv1.py:471-495) and the
+ * emotion head Linear(2048,8)+softmax (model.py:41,121-122).  Batch <= 64 rows.
+ *   irfd_linear_bwd: dz is the gradient w.r.t. the pre-activation (see irfd_lrelu_bwd);
+ *                    dx = dx_beta*dx + wmul*dz@W (skipped if dx NULL); dw = dw_beta*dw + wmul*dz^T@x; db likewise*bmul.
+ */
+int irfd_linear_fwd(const float* x, const float* w, const float* bias, float* y, int b, int n, int k, float wmul,
+                    float bmul, int lrelu, irfd_stream_t stream);
+int irfd_lrelu_bwd(const float* dy, const float* y, float* dz, long long n, irfd_stream_t stream);
+int irfd_linear_bwd(const float* dz, const float* x, const float* w, float* dx, float dx_beta, float* dw, float* db,
+                    float dw_beta, int b, int n, int k, float wmul, float bmul, irfd_stream_t stream);
+int irfd_softmax_rows(const float* x, float* y, int b, int n, irfd_stream_t stream);
+int irfd_scale_copy(const float* src, float* dst, float scale, long long n, irfd_stream_t stream);
+int irfd_split_style(const float* style, float* sp1, float* s1, int b, int c, irfd_stream_t stream);
+int irfd_merge_style_grad(const float* dsp1, const float* ds1, float* dstyle, int b, int c, irfd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Losses and optimiser: nn.MSELoss means (model.py:356-372), clip_grad_norm_ + Adam (train.py:205-210, 346).
+ *   irfd_mse_fwd : out[0] = out_beta*out[0] + mean((a-b)^2)   (double accumulation, fixed order)
+ *   irfd_mse_bwd : da = gscale[0]*2(a-b)/n, db = -da (either may be NULL)
+ *   irfd_sumsq   : out[0] = out_beta*out[0] + sum(g^2)
+ *   irfd_adam_step: torch.optim.Adam update on a flat buffer; if total_sumsq != NULL the gradient is first scaled by
+ *                  min(1, max_norm/(sqrt(total_sumsq[0])+1e-6)).
+ */
+long long irfd_reduce_workspace_bytes(void);
+int irfd_mse_fwd(const float* a, const float* b, long long n, float* out, float out_beta, void* workspace,
+                 long long workspace_bytes, irfd_stream_t stream);
+int irfd_mse_bwd(const float* a, const float* b, long long n, const float* gscale, float* da, float* db,
+                 irfd_stream_t stream);
+int irfd_sumsq(const float* g, long long n, float* out, float out_beta, void* workspace, long long workspace_bytes,
+               irfd_stream_t stream);
+int irfd_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                   float eps, int step, const float* total_sumsq, float max_norm, irfd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,353 @@
+// Data-movement kernels around the GEMMs: weight packing, explicit im2col for the few strided convs of ResNet-50
+// (7x7/2 stem, 3x3/2, 1x1/2 — torchvision/models/resnet.py:197, 133-137, 241), their adjoints, and max/avg pooling.
+// All activations NHWC bf16, 16-byte vector accesses, one 8-channel vector per thread.
+#include "host_util.h"
+#include "rowvec.cuh"
+
+namespace irfd {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight packing (fp32 OIHW parameter -> bf16 GEMM operand).  dst is always [rows][K] row-major.
+//   mode 0 FPROP: dst[o][tap*I + i]            = w[o][i][tap]
+//   mode 1 DGRAD: dst[i][(T-1-tap)*O + o]      = w[o][i][tap]      (spatially flipped, in/out swapped)
+//   mode 2 DCOL : dst[tap*I + i][o]            = w[o][i][tap]      (for dcol = dz @ W)
+//   mode 3 FLAT : dst[o][k], k < kpad          = w[o][k] (k < I*T) else 0   (stem: K = c*49 + kh*7 + kw, padded)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int O, int I, int T,
+                                   int mode, int kpad) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (mode == 3) {
+    if (idx >= (size_t)O * kpad) return;
+    const int o = idx / kpad, k = idx % kpad;
+    dst[idx] = __float2bfloat16(k < I * T ? w[(size_t)o * I * T + k] : 0.f);
+    return;
+  }
+  if (idx >= (size_t)O * I * T) return;
+  const int tap = idx % T;
+  const int i = (idx / T) % I;
+  const int o = idx / ((size_t)T * I);
+  const __nv_bfloat16 v = __float2bfloat16(w[idx]);
+  size_t d;
+  if (mode == 0) d = ((size_t)o * T + tap) * I + i;
+  else if (mode == 1) d = ((size_t)i * T + (T - 1 - tap)) * O + o;
+  else d = ((size_t)tap * I + i) * O + o;
+  dst[d] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stem im2col: x NCHW fp32 [N,3,H,W] -> col [N*Ho*Wo][kpad] bf16, 7x7 stride 2 pad 3, k = c*49 + kh*7 + kw
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void im2col_stem_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int H, int W,
+                                   int kpad) {
+  const int Ho = H / 2, Wo = W / 2;
+  const int vec_per_row = kpad / 8;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)N * Ho * Wo * vec_per_row;
+  if (idx >= total) return;
+  const int v = idx % vec_per_row;
+  const size_t pix = idx / vec_per_row;
+  const int ow = pix % Wo;
+  const int oh = (pix / Wo) % Ho;
+  const int n = pix / ((size_t)Wo * Ho);
+  float f[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int k = v * 8 + t;
+    float val = 0.f;
+    if (k < 147) {
+      const int c = k / 49, r = k % 49, kh = r / 7, kw = r % 7;
+      const int ih = oh * 2 + kh - 3, iw = ow * 2 + kw - 3;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = x[(((size_t)n * 3 + c) * H + ih) * W + iw];
+    }
+    f[t] = val;
+  }
+  store8(col + pix * kpad + v * 8, f);
+}
+
+// 3x3 stride-2 pad-1 im2col on NHWC bf16: col[pix][tap*C + c]
+__global__ void im2col_3x3s2_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ col, int N, int H,
+                                    int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, vc = C / 8;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)N * Ho * Wo * 9 * vc;
+  if (idx >= total) return;
+  const int v = idx % vc;
+  const int tap = (idx / vc) % 9;
+  const size_t pix = idx / ((size_t)vc * 9);
+  const int ow = pix % Wo, oh = (pix / Wo) % Ho, n = pix / ((size_t)Wo * Ho);
+  const int ih = oh * 2 + tap / 3 - 1, iw = ow * 2 + tap % 3 - 1;
+  uint4 val = make_uint4(0, 0, 0, 0);
+  if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+    val = *reinterpret_cast<const uint4*>(a + (((size_t)n * H + ih) * W + iw) * C + v * 8);
+  *reinterpret_cast<uint4*>(col + (pix * 9 + tap) * C + v * 8) = val;
+}
+
+// adjoint: dx[n,h,w,c] = sum over (oh,ow,tap) hitting (h,w) of dcol[(oh,ow)][tap*C + c]
+__global__ void col2im_3x3s2_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict__ dx, int N,
+                                    int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, vc = C / 8;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)N * H * W * vc;
+  if (idx >= total) return;
+  const int v = idx % vc;
+  const size_t pix = idx / vc;
+  const int w = pix % W, h = (pix / W) % H, n = pix / ((size_t)W * H);
+  float acc[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+  // h = 2*oh + kh - 1
+  for (int kh = 0; kh < 3; ++kh) {
+    const int th = h - kh + 1;
+    if (th < 0 || (th & 1)) continue;
+    const int oh = th >> 1;
+    if (oh >= Ho) continue;
+    for (int kw = 0; kw < 3; ++kw) {
+      const int tw = w - kw + 1;
+      if (tw < 0 || (tw & 1)) continue;
+      const int ow = tw >> 1;
+      if (ow >= Wo) continue;
+      float f[8];
+      load8(dcol + ((((size_t)n * Ho + oh) * Wo + ow) * 9 + kh * 3 + kw) * C + v * 8, f);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[t] += f[t];
+    }
+  }
+  store8(dx + pix * C + v * 8, acc);
+}
+
+// 1x1 stride-2 gather: out[n,oh,ow,:] = a[n,2oh,2ow,:]
+__global__ void subsample2_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ out, int N, int H,
+                                  int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, vc = C / 8;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)N * Ho * Wo * vc) return;
+  const int v = idx % vc;
+  const size_t pix = idx / vc;
+  const int ow = pix % Wo, oh = (pix / Wo) % Ho, n = pix / ((size_t)Wo * Ho);
+  *reinterpret_cast<uint4*>(out + pix * C + v * 8) =
+      *reinterpret_cast<const uint4*>(a + (((size_t)n * H + 2 * oh) * W + 2 * ow) * C + v * 8);
+}
+
+// out[n,h,w,:] = a[n,h,w,:] (or 0 if a == null) + (h,w even ? b[n,h/2,w/2,:] : 0)     (adjoint of subsample2, fused add)
+__global__ void scatter_add_s2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                      __nv_bfloat16* __restrict__ out, int N, int H, int W, int C) {
+  const int vc = C / 8;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)N * H * W * vc) return;
+  const int v = idx % vc;
+  const size_t pix = idx / vc;
+  const int w = pix % W, h = (pix / W) % H, n = pix / ((size_t)W * H);
+  float f[8];
+  if (a != nullptr) load8(a + pix * C + v * 8, f);
+  else {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) f[t] = 0.f;
+  }
+  if (!(h & 1) && !(w & 1)) {
+    float g[8];
+    load8(b + (((size_t)n * (H / 2) + h / 2) * (W / 2) + w / 2) * C + v * 8, g);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) f[t] += g[t];
+  }
+  store8(out + pix * C + v * 8, f);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// MaxPool2d(3, stride 2, pad 1) forward (+ argmax tap, first maximum in scan order like ATen) and backward (gather).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ out,
+                                   uint8_t* __restrict__ arg, int N, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, vc = C / 8;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)N * Ho * Wo * vc) return;
+  const int v = idx % vc;
+  const size_t pix = idx / vc;
+  const int ow = pix % Wo, oh = (pix / Wo) % Ho, n = pix / ((size_t)Wo * Ho);
+  float best[8];
+  int bi[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    best[t] = -INFINITY;
+    bi[t] = 0;
+  }
+  for (int tap = 0; tap < 9; ++tap) {
+    const int ih = oh * 2 + tap / 3 - 1, iw = ow * 2 + tap % 3 - 1;
+    if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+    float f[8];
+    load8(a + (((size_t)n * H + ih) * W + iw) * C + v * 8, f);
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      if (f[t] > best[t]) {
+        best[t] = f[t];
+        bi[t] = tap;
+      }
+  }
+  store8(out + pix * C + v * 8, best);
+  uint2 packed;
+  packed.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+  packed.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+  *reinterpret_cast<uint2*>(arg + pix * C + v * 8) = packed;
+}
+
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ arg,
+                                   __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, vc = C / 8;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)N * H * W * vc) return;
+  const int v = idx % vc;
+  const size_t pix = idx / vc;
+  const int w = pix % W, h = (pix / W) % H, n = pix / ((size_t)W * H);
+  float acc[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+  for (int kh = 0; kh < 3; ++kh) {
+    const int th = h - kh + 1;
+    if (th < 0 || (th & 1)) continue;
+    const int oh = th >> 1;
+    if (oh >= Ho) continue;
+    for (int kw = 0; kw < 3; ++kw) {
+      const int tw = w - kw + 1;
+      if (tw < 0 || (tw & 1)) continue;
+      const int ow = tw >> 1;
+      if (ow >= Wo) continue;
+      const size_t op = (((size_t)n * Ho + oh) * Wo + ow) * C + v * 8;
+      const uint2 packed = *reinterpret_cast<const uint2*>(arg + op);
+      float g[8];
+      load8(dout + op, g);
+      const int tap = kh * 3 + kw;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int a = ((t < 4 ? packed.x : packed.y) >> ((t & 3) * 8)) & 0xff;
+        if (a == tap) acc[t] += g[t];
+      }
+    }
+  }
+  store8(dx + pix * C + v * 8, acc);
+}
+
+// AdaptiveAvgPool2d(1): [N, HW, C] bf16 -> [N, C] fp32 ; backward broadcasts dfeat/HW
+__global__ void __launch_bounds__(kRvThreads)
+avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ a, float* __restrict__ out, int HW, int C) {
+  extern __shared__ float red_smem[];
+  RowVec rv(C);
+  float acc[1][8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) acc[0][t] = 0.f;
+  if (rv.active) {
+    for (int r = rv.row_lane; r < HW; r += rv.rows_par) {
+      float f[8];
+      load8(a + ((size_t)blockIdx.x * HW + r) * C + rv.cv * 8, f);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[0][t] += f[t];
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[0][t] *= 1.f / HW;
+  }
+  block_reduce_rows<1>(rv, C, acc, red_smem, out + (size_t)blockIdx.x * C, 0);
+}
+
+__global__ void avgpool_bwd_kernel(const float* __restrict__ dfeat, __nv_bfloat16* __restrict__ g, int N, int HW,
+                                   int C) {
+  const int vc = C / 8;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)N * HW * vc) return;
+  const int v = idx % vc;
+  const size_t pix = idx / vc;
+  const int n = pix / HW;
+  float f[8];
+  loadf8(dfeat + (size_t)n * C + v * 8, f);
+#pragma unroll
+  for (int t = 0; t < 8; ++t) f[t] *= 1.f / HW;
+  store8(g + pix * C + v * 8, f);
+}
+
+}  // namespace irfd
+
+using namespace irfd;
+
+#define GRID1D(total) (unsigned)(((total) + 255) / 256), 256, 0, stream
+#define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+#define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+
+extern "C" int irfd_pack_conv_weight(const float* w, void* dst, int o, int i, int taps, int mode, int kpad,
+                                     cudaStream_t stream) {
+  IRFD_CHECK_ARG(w && dst && o > 0 && i > 0 && taps > 0 && mode >= 0 && mode <= 3, "pack_conv_weight: bad argument");
+  const size_t total = mode == 3 ? (size_t)o * kpad : (size_t)o * i * taps;
+  pack_weight_kernel<<<GRID1D(total)>>>(w, BF(dst), o, i, taps, mode, kpad);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_im2col_stem(const float* x, void* col, int n, int h, int w, int kpad, cudaStream_t stream) {
+  IRFD_CHECK_ARG(x && col && kpad >= 152 && kpad % 8 == 0 && h % 2 == 0 && w % 2 == 0, "im2col_stem: bad argument");
+  const size_t total = (size_t)n * (h / 2) * (w / 2) * (kpad / 8);
+  im2col_stem_kernel<<<GRID1D(total)>>>(x, BF(col), n, h, w, kpad);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_im2col_3x3s2(const void* a, void* col, int n, int h, int w, int c, cudaStream_t stream) {
+  IRFD_CHECK_ARG(a && col && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "im2col_3x3s2: bad argument");
+  const size_t total = (size_t)n * (h / 2) * (w / 2) * 9 * (c / 8);
+  im2col_3x3s2_kernel<<<GRID1D(total)>>>(CBF(a), BF(col), n, h, w, c);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_col2im_3x3s2(const void* dcol, void* dx, int n, int h, int w, int c, cudaStream_t stream) {
+  IRFD_CHECK_ARG(dcol && dx && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "col2im_3x3s2: bad argument");
+  const size_t total = (size_t)n * h * w * (c / 8);
+  col2im_3x3s2_kernel<<<GRID1D(total)>>>(CBF(dcol), BF(dx), n, h, w, c);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_subsample2(const void* a, void* out, int n, int h, int w, int c, cudaStream_t stream) {
+  IRFD_CHECK_ARG(a && out && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "subsample2: bad argument");
+  const size_t total = (size_t)n * (h / 2) * (w / 2) * (c / 8);
+  subsample2_kernel<<<GRID1D(total)>>>(CBF(a), BF(out), n, h, w, c);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_scatter_add_s2(const void* a, const void* b, void* out, int n, int h, int w, int c,
+                                   cudaStream_t stream) {
+  IRFD_CHECK_ARG(b && out && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "scatter_add_s2: bad argument");
+  const size_t total = (size_t)n * h * w * (c / 8);
+  scatter_add_s2_kernel<<<GRID1D(total)>>>(CBF(a), CBF(b), BF(out), n, h, w, c);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_maxpool_fwd(const void* a, void* out, void* argmax, int n, int h, int w, int c,
+                                cudaStream_t stream) {
+  IRFD_CHECK_ARG(a && out && argmax && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "maxpool_fwd: bad argument");
+  const size_t total = (size_t)n * (h / 2) * (w / 2) * (c / 8);
+  maxpool_fwd_kernel<<<GRID1D(total)>>>(CBF(a), BF(out), reinterpret_cast<uint8_t*>(argmax), n, h, w, c);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_maxpool_bwd(const void* dout, const void* argmax, void* dx, int n, int h, int w, int c,
+                                cudaStream_t stream) {
+  IRFD_CHECK_ARG(dout && dx && argmax && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "maxpool_bwd: bad argument");
+  const size_t total = (size_t)n * h * w * (c / 8);
+  maxpool_bwd_kernel<<<GRID1D(total)>>>(CBF(dout), reinterpret_cast<const uint8_t*>(argmax), BF(dx), n, h, w, c);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_avgpool_fwd(const void* a, float* out, int n, int hw, int c, cudaStream_t stream) {
+  IRFD_CHECK_ARG(a && out && c % 8 == 0 && c <= 2048 && hw > 0, "avgpool_fwd: bad argument");
+  avgpool_fwd_kernel<<<n, kRvThreads, 2048 * sizeof(float), stream>>>(CBF(a), out, hw, c);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_avgpool_bwd(const float* dfeat, void* g, int n, int hw, int c, cudaStream_t stream) {
+  IRFD_CHECK_ARG(dfeat && g && c % 8 == 0 && hw > 0, "avgpool_bwd: bad argument");
+  const size_t total = (size_t)n * hw * (c / 8);
+  avgpool_bwd_kernel<<<GRID1D(total)>>>(dfeat, BF(g), n, hw, c);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}

@@ -1,0 +1,206 @@
+// fp32 dense layers of the generator's mapping/style path (styleganv1.py:471-495 `FC`: F.linear with equalised-lr
+// multipliers followed by leaky_relu(0.2)) and the emotion head (model.py:41,121-122).  The batch is tiny (<= 64 rows)
+// and the path is 0.02 GF/sample but numerically sensitive, so these stay in fp32 FFMA with warp-shuffle
+// reductions instead of going to the tensor cores.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace irfd {
+
+constexpr int kMaxRows = 64;
+
+// y[b, n] = act( wmul * sum_k x[b,k] * W[n,k] + bmul * bias[n] ),  one warp per output column n.
+template <int ROWS>
+__global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                  const float* __restrict__ bias, float* __restrict__ y, int B, int N, int K,
+                                  float wmul, float bmul, int lrelu) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const int n = warp;
+  for (int b0 = 0; b0 < B; b0 += ROWS) {
+    float acc[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 wv = *reinterpret_cast<const float4*>(W + (size_t)n * K + k);
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        if (b0 + r < B) {
+          const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)(b0 + r) * K + k);
+          acc[r] += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const float s = warp_sum(acc[r]);
+      if (lane == 0 && b0 + r < B) {
+        float v = s * wmul + (bias != nullptr ? bias[n] * bmul : 0.f);
+        if (lrelu) v = v > 0.f ? v : 0.2f * v;
+        y[(size_t)(b0 + r) * N + n] = v;
+      }
+    }
+  }
+}
+
+// dz = dy * (y > 0 ? 1 : 0.2)   (y is the post-activation output; lrelu preserves sign)
+__global__ void lrelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz,
+                                 size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dz[i] = dy[i] * (y[i] > 0.f ? 1.f : 0.2f);
+}
+
+// dx[b,k] = beta*dx[b,k] + wmul * sum_n dz[b,n] * W[n,k] ; thread per k, all rows in registers, dz staged in smem
+__global__ void linear_dx_kernel(const float* __restrict__ dz, const float* __restrict__ W, float* __restrict__ dx,
+                                 int B, int N, int K, float wmul, float beta) {
+  extern __shared__ float sdz[];  // [32 n][B]
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  float acc[kMaxRows];
+#pragma unroll
+  for (int r = 0; r < kMaxRows; ++r) acc[r] = 0.f;
+  for (int n0 = 0; n0 < N; n0 += 32) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * B; i += blockDim.x) {
+      const int nn = i / B, b = i % B;
+      sdz[i] = (n0 + nn < N) ? dz[(size_t)b * N + n0 + nn] : 0.f;
+    }
+    __syncthreads();
+    if (k < K) {
+      for (int nn = 0; nn < 32 && n0 + nn < N; ++nn) {
+        const float wv = W[(size_t)(n0 + nn) * K + k];
+#pragma unroll
+        for (int r = 0; r < kMaxRows; ++r)
+          if (r < B) acc[r] += sdz[nn * B + r] * wv;
+      }
+    }
+  }
+  if (k < K) {
+#pragma unroll
+    for (int r = 0; r < kMaxRows; ++r)
+      if (r < B) {
+        float* d = dx + (size_t)r * K + k;
+        *d = (beta != 0.f ? beta * (*d) : 0.f) + wmul * acc[r];
+      }
+  }
+}
+
+// dW[n,k] = beta*dW + wmul * sum_b dz[b,n]*x[b,k] ;  db[n] = beta*db + bmul * sum_b dz[b,n]
+__global__ void linear_dw_kernel(const float* __restrict__ dz, const float* __restrict__ x, float* __restrict__ dW,
+                                 float* __restrict__ db, int B, int N, int K, float wmul, float bmul, float beta) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (k < K) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dz[(size_t)b * N + n] * x[(size_t)b * K + k];
+    float* d = dW + (size_t)n * K + k;
+    *d = (beta != 0.f ? beta * (*d) : 0.f) + wmul * s;
+  }
+  if (db != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dz[(size_t)b * N + n];
+    db[n] = (beta != 0.f ? beta * db[n] : 0.f) + bmul * s;
+  }
+}
+
+// row-wise softmax for the emotion head (N = 8)
+__global__ void softmax_rows_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int N) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float m = -INFINITY;
+  for (int i = 0; i < N; ++i) m = fmaxf(m, x[(size_t)b * N + i]);
+  float s = 0.f;
+  for (int i = 0; i < N; ++i) s += expf(x[(size_t)b * N + i] - m);
+  for (int i = 0; i < N; ++i) y[(size_t)b * N + i] = expf(x[(size_t)b * N + i] - m) / s;
+}
+
+// w_rows: out[b][k] = scale * (use_second ? w2[b][k] : w[b][k])  — helper for style mixing rows (styleganv1.py:536-553)
+__global__ void scale_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, float scale, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = scale * src[i];
+}
+
+// sp1 = style[:, :C] + 1 ; s1 = style[:, C:]   (ApplyStyle view(-1, 2, C), styleganv1.py:464-467)
+__global__ void split_style_kernel(const float* __restrict__ style, float* __restrict__ sp1, float* __restrict__ s1,
+                                   int B, int C) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * C) return;
+  const int b = i / C, c = i % C;
+  sp1[i] = style[(size_t)b * 2 * C + c] + 1.f;
+  s1[i] = style[(size_t)b * 2 * C + C + c];
+}
+__global__ void merge_style_grad_kernel(const float* __restrict__ dsp1, const float* __restrict__ ds1,
+                                        float* __restrict__ dstyle, int B, int C) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * C) return;
+  const int b = i / C, c = i % C;
+  dstyle[(size_t)b * 2 * C + c] = dsp1[i];
+  dstyle[(size_t)b * 2 * C + C + c] = ds1[i];
+}
+
+}  // namespace irfd
+
+using namespace irfd;
+
+extern "C" int irfd_linear_fwd(const float* x, const float* w, const float* bias, float* y, int b, int n, int k,
+                               float wmul, float bmul, int lrelu, cudaStream_t stream) {
+  IRFD_CHECK_ARG(x && w && y && b > 0 && n > 0 && k > 0 && k % 4 == 0, "linear_fwd: bad argument (K %% 4 == 0)");
+  const int warps_per_block = 4;
+  linear_fwd_kernel<8><<<(n + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(
+      x, w, bias, y, b, n, k, wmul, bmul, lrelu);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_lrelu_bwd(const float* dy, const float* y, float* dz, long long n, cudaStream_t stream) {
+  IRFD_CHECK_ARG(dy && y && dz && n > 0, "lrelu_bwd: bad argument");
+  lrelu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dy, y, dz, (size_t)n);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_linear_bwd(const float* dz, const float* x, const float* w, float* dx, float dx_beta, float* dw,
+                               float* db, float dw_beta, int b, int n, int k, float wmul, float bmul,
+                               cudaStream_t stream) {
+  IRFD_CHECK_ARG(dz && b > 0 && b <= kMaxRows && n > 0 && k > 0, "linear_bwd: bad argument (batch <= 64)");
+  if (dx != nullptr) {
+    IRFD_CHECK_ARG(w != nullptr, "linear_bwd: dx needs w");
+    linear_dx_kernel<<<(k + 127) / 128, 128, 32 * b * sizeof(float), stream>>>(dz, w, dx, b, n, k, wmul, dx_beta);
+    IRFD_CHECK_LAUNCH();
+  }
+  if (dw != nullptr) {
+    IRFD_CHECK_ARG(x != nullptr, "linear_bwd: dw needs x");
+    linear_dw_kernel<<<dim3((k + 127) / 128, n), 128, 0, stream>>>(dz, x, dw, db, b, n, k, wmul, bmul, dw_beta);
+    IRFD_CHECK_LAUNCH();
+  }
+  return IRFD_OK;
+}
+
+extern "C" int irfd_softmax_rows(const float* x, float* y, int b, int n, cudaStream_t stream) {
+  IRFD_CHECK_ARG(x && y && b > 0 && n > 0, "softmax_rows: bad argument");
+  softmax_rows_kernel<<<(b + 63) / 64, 64, 0, stream>>>(x, y, b, n);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_scale_copy(const float* src, float* dst, float scale, long long n, cudaStream_t stream) {
+  IRFD_CHECK_ARG(src && dst && n > 0, "scale_copy: bad argument");
+  scale_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, dst, scale, (size_t)n);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_split_style(const float* style, float* sp1, float* s1, int b, int c, cudaStream_t stream) {
+  IRFD_CHECK_ARG(style && sp1 && s1, "split_style: null pointer");
+  split_style_kernel<<<(unsigned)(((size_t)b * c + 255) / 256), 256, 0, stream>>>(style, sp1, s1, b, c);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_merge_style_grad(const float* dsp1, const float* ds1, float* dstyle, int b, int c,
+                                     cudaStream_t stream) {
+  IRFD_CHECK_ARG(dsp1 && ds1 && dstyle, "merge_style_grad: null pointer");
+  merge_style_grad_kernel<<<(unsigned)(((size_t)b * c + 255) / 256), 256, 0, stream>>>(dsp1, ds1, dstyle, b, c);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}

@@ -1,0 +1,402 @@
+// Memory-bound pieces of the StyleGAN-v1-style synthesis network (styleganv1.py:569-635) that are not conv epilogues:
+// constant-input stage, bilinear x2 upsample (+adjoint), backward of the fused noise/lrelu/style epilogue with its
+// warp/block reductions, and the 1x1 to_rgb (+backward).  NHWC bf16 activations, fp32 parameters and reductions.
+#include "host_util.h"
+#include "rowvec.cuh"
+
+namespace irfd {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Constant input: a0 = const[c,h,w] + bias[c] + nw[c]*noise[b,h,w];  y0 = a0*sp1[b,c] + s1[b,c]
+// (styleganv1.py:596-599 — no leaky_relu on this stage)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void const_input_fwd_kernel(const float* __restrict__ cst, const float* __restrict__ bias,
+                                       const float* __restrict__ nw, const float* __restrict__ noise,
+                                       const float* __restrict__ sp1, const float* __restrict__ s1,
+                                       __nv_bfloat16* __restrict__ a0, __nv_bfloat16* __restrict__ y0, int B, int C) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over [B][16][C]
+  if (idx >= (size_t)B * 16 * C) return;
+  const int c = idx % C;
+  const int hw = (idx / C) % 16;
+  const int b = idx / ((size_t)C * 16);
+  const float a = cst[c * 16 + hw] + bias[c] + nw[c] * noise[b * 16 + hw];
+  a0[idx] = __float2bfloat16(a);
+  y0[idx] = __float2bfloat16(a * sp1[(size_t)b * C + c] + s1[(size_t)b * C + c]);
+}
+
+// one thread per channel; loops over B*16 positions (tiny)
+__global__ void const_input_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ a0,
+                                       const float* __restrict__ noise, const float* __restrict__ sp1,
+                                       float* __restrict__ dsp1, float* __restrict__ ds1, float* __restrict__ dconst,
+                                       float* __restrict__ dbias, float* __restrict__ dnw, int B, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float dc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) dc[i] = 0.f;
+  float db = 0.f, dn = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float t0 = 0.f, t1 = 0.f;
+    const float sp = sp1[(size_t)b * C + c];
+#pragma unroll
+    for (int hw = 0; hw < 16; ++hw) {
+      const size_t i = ((size_t)b * 16 + hw) * C + c;
+      const float g = __bfloat162float(dy[i]);
+      t0 += g * __bfloat162float(a0[i]);
+      t1 += g;
+      const float dz = g * sp;
+      dc[hw] += dz;
+      db += dz;
+      dn += dz * noise[b * 16 + hw];
+    }
+    dsp1[(size_t)b * C + c] = t0;
+    ds1[(size_t)b * C + c] = t1;
+  }
+#pragma unroll
+  for (int hw = 0; hw < 16; ++hw) dconst[c * 16 + hw] = dc[hw];
+  dbias[c] = db;
+  dnw[c] = dn;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bilinear x2, align_corners=False (nn.Upsample, styleganv1.py:621,624), ATen index arithmetic restated.
+// ---------------------------------------------------------------------------------------------------------------
+struct Lerp {
+  int i0, i1;
+  float l0, l1;
+};
+__device__ __forceinline__ Lerp lerp_src(int o, int in_size) {
+  float src = 0.5f * (o + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  Lerp r;
+  r.i0 = (int)src;
+  r.i1 = r.i0 + (r.i0 < in_size - 1 ? 1 : 0);
+  r.l1 = src - r.i0;
+  r.l0 = 1.f - r.l1;
+  return r;
+}
+
+__global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B,
+                                      int H, int W, int C) {
+  const int vc = C / 8, Ho = 2 * H, Wo = 2 * W;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * Ho * Wo * vc) return;
+  const int v = idx % vc;
+  const size_t pix = idx / vc;
+  const int ow = pix % Wo, oh = (pix / Wo) % Ho, b = pix / ((size_t)Wo * Ho);
+  const Lerp ly = lerp_src(oh, H), lx = lerp_src(ow, W);
+  const __nv_bfloat16* base = in + (size_t)b * H * W * C + v * 8;
+  float f00[8], f01[8], f10[8], f11[8], o[8];
+  load8(base + ((size_t)ly.i0 * W + lx.i0) * C, f00);
+  load8(base + ((size_t)ly.i0 * W + lx.i1) * C, f01);
+  load8(base + ((size_t)ly.i1 * W + lx.i0) * C, f10);
+  load8(base + ((size_t)ly.i1 * W + lx.i1) * C, f11);
+#pragma unroll
+  for (int t = 0; t < 8; ++t)
+    o[t] = ly.l0 * (lx.l0 * f00[t] + lx.l1 * f01[t]) + ly.l1 * (lx.l0 * f10[t] + lx.l1 * f11[t]);
+  store8(out + pix * C + v * 8, o);
+}
+
+// weight of input index i in output index o (1-D), or 0
+__device__ __forceinline__ float lerp_weight(int o, int i, int in_size) {
+  const Lerp l = lerp_src(o, in_size);
+  float w = 0.f;
+  if (l.i0 == i) w += l.l0;
+  if (l.i1 == i) w += l.l1;
+  return w;
+}
+
+__global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ din, int B,
+                                      int H, int W, int C) {
+  const int vc = C / 8, Ho = 2 * H, Wo = 2 * W;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * H * W * vc) return;
+  const int v = idx % vc;
+  const size_t pix = idx / vc;
+  const int w = pix % W, h = (pix / W) % H, b = pix / ((size_t)W * H);
+  float acc[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+  for (int dy = -1; dy <= 2; ++dy) {
+    const int oh = 2 * h + dy;
+    if (oh < 0 || oh >= Ho) continue;
+    const float wy = lerp_weight(oh, h, H);
+    if (wy == 0.f) continue;
+    for (int dx = -1; dx <= 2; ++dx) {
+      const int ow = 2 * w + dx;
+      if (ow < 0 || ow >= Wo) continue;
+      const float wx = lerp_weight(ow, w, W);
+      if (wx == 0.f) continue;
+      float g[8];
+      load8(dout + (((size_t)b * Ho + oh) * Wo + ow) * C + v * 8, g);
+      const float ww = wy * wx;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[t] += ww * g[t];
+    }
+  }
+  store8(din + pix * C + v * 8, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward of the fused conv epilogue  y = lrelu(z)*sp1 + s1,  z = conv + bias + nw*noise,  a = lrelu(z) saved.
+//   dz = dy * sp1[b,c] * (a > 0 ? 1 : 0.2)
+//   per (b,c): ds1 = sum_hw dy, dsp1 = sum_hw dy*a ;  per c: dbias = sum dz, dnw = sum dz*noise[b,hw]
+// grid = (chunks, B); partial[b][chunk][4][C]
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRvThreads)
+style_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ a,
+                 const float* __restrict__ noise, const float* __restrict__ sp1, __nv_bfloat16* __restrict__ dz,
+                 float* __restrict__ partial, int HW, int C, int rows_per_blk) {
+  extern __shared__ float red_smem[];
+  RowVec rv(C);
+  const int b = blockIdx.y;
+  float acc[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[k][t] = 0.f;
+  if (rv.active) {
+    float sp[8];
+    loadf8(sp1 + (size_t)b * C + rv.cv * 8, sp);
+    const int r0 = blockIdx.x * rows_per_blk;
+    int r1 = r0 + rows_per_blk;
+    if (r1 > HW) r1 = HW;
+    for (int r = r0 + rv.row_lane; r < r1; r += rv.rows_par) {
+      const size_t off = ((size_t)b * HW + r) * C + rv.cv * 8;
+      float g[8], av[8], o[8];
+      load8(dy + off, g);
+      load8(a + off, av);
+      const float nz = noise[(size_t)b * HW + r];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float d = g[t] * sp[t] * (av[t] > 0.f ? 1.f : 0.2f);
+        o[t] = d;
+        acc[0][t] += g[t];
+        acc[1][t] += g[t] * av[t];
+        acc[2][t] += d;
+        acc[3][t] += d * nz;
+      }
+      store8(dz + off, o);
+    }
+  }
+  block_reduce_rows<4>(rv, C, acc, red_smem, partial + ((size_t)b * gridDim.x + blockIdx.x) * 4 * C, (size_t)C);
+}
+
+__global__ void style_bwd_finalize_kernel(const float* __restrict__ partial, int B, int chunks, int C,
+                                          float* __restrict__ ds1, float* __restrict__ dsp1, float* __restrict__ dbias,
+                                          float* __restrict__ dnw) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float tb = 0.f, tn = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    for (int k = 0; k < chunks; ++k) {
+      const float* p = partial + ((size_t)b * chunks + k) * 4 * C + c;
+      t0 += p[0];
+      t1 += p[C];
+      t2 += p[2 * C];
+      t3 += p[3 * C];
+    }
+    ds1[(size_t)b * C + c] = t0;
+    dsp1[(size_t)b * C + c] = t1;
+    tb += t2;
+    tn += t3;
+  }
+  dbias[c] = tb;
+  dnw[c] = tn;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// to_rgb: 1x1 conv C -> 3 with bias, output NCHW fp32 (the reference's output layout) — styleganv1.py:588,607
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void to_rgb_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ w,
+                                  const float* __restrict__ bias, float* __restrict__ out, int B, int HW, int C) {
+  extern __shared__ float sw[];  // [3][C]
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (size_t)B * HW) return;
+  const int b = pix / HW, p = pix % HW;
+  float r0 = bias[0], r1 = bias[1], r2 = bias[2];
+  for (int v = 0; v < C / 8; ++v) {
+    float f[8];
+    load8(y + pix * C + v * 8, f);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      r0 += f[t] * sw[v * 8 + t];
+      r1 += f[t] * sw[C + v * 8 + t];
+      r2 += f[t] * sw[2 * C + v * 8 + t];
+    }
+  }
+  float* o = out + (size_t)b * 3 * HW + p;
+  o[0] = r0;
+  o[HW] = r1;
+  o[2 * HW] = r2;
+}
+
+// dy[pix][c] = sum_k drgb[k][pix]*w[k][c];  partial[blk][4][C]: k<3 -> sum_pix drgb[k]*y[c]; row 3 (ch 0..2) -> dbias
+__global__ void __launch_bounds__(kRvThreads)
+to_rgb_bwd_kernel(const float* __restrict__ drgb, const __nv_bfloat16* __restrict__ y, const float* __restrict__ w,
+                  __nv_bfloat16* __restrict__ dy, float* __restrict__ partial, int B, int HW, int C,
+                  int rows_per_blk) {
+  extern __shared__ float red_smem[];
+  RowVec rv(C);
+  float acc[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[k][t] = 0.f;
+  if (rv.active) {
+    float w0[8], w1[8], w2[8];
+    loadf8(w + rv.cv * 8, w0);
+    loadf8(w + C + rv.cv * 8, w1);
+    loadf8(w + 2 * C + rv.cv * 8, w2);
+    const long long rows = (long long)B * HW;
+    const long long r0 = (long long)blockIdx.x * rows_per_blk;
+    long long r1 = r0 + rows_per_blk;
+    if (r1 > rows) r1 = rows;
+    for (long long r = r0 + rv.row_lane; r < r1; r += rv.rows_par) {
+      const int b = r / HW, p = r % HW;
+      const float* g = drgb + (size_t)b * 3 * HW + p;
+      const float g0 = g[0], g1 = g[HW], g2 = g[2 * HW];
+      float f[8], o[8];
+      load8(y + (size_t)r * C + rv.cv * 8, f);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        o[t] = g0 * w0[t] + g1 * w1[t] + g2 * w2[t];
+        acc[0][t] += g0 * f[t];
+        acc[1][t] += g1 * f[t];
+        acc[2][t] += g2 * f[t];
+      }
+      if (rv.cv == 0) {
+        acc[3][0] += g0;
+        acc[3][1] += g1;
+        acc[3][2] += g2;
+      }
+      store8(dy + (size_t)r * C + rv.cv * 8, o);
+    }
+  }
+  block_reduce_rows<4>(rv, C, acc, red_smem, partial + (size_t)blockIdx.x * 4 * C, (size_t)C);
+}
+
+__global__ void to_rgb_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dw,
+                                           float* __restrict__ dbias) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over 3*C (+3)
+  if (i < 3 * C) {
+    const int k = i / C, c = i % C;
+    float s = 0.f;
+    for (int b = 0; b < nblk; ++b) s += partial[((size_t)b * 4 + k) * C + c];
+    dw[i] = s;
+  } else if (i < 3 * C + 3) {
+    const int k = i - 3 * C;
+    float s = 0.f;
+    for (int b = 0; b < nblk; ++b) s += partial[((size_t)b * 4 + 3) * C + k];
+    dbias[k] = s;
+  }
+}
+
+}  // namespace irfd
+
+using namespace irfd;
+
+#define GRID1D(total) (unsigned)(((total) + 255) / 256), 256, 0, stream
+#define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+#define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+
+extern "C" int irfd_const_input_fwd(const float* cst, const float* bias, const float* nw, const float* noise,
+                                    const float* sp1, const float* s1, void* a0, void* y0, int b, int c,
+                                    cudaStream_t stream) {
+  IRFD_CHECK_ARG(cst && bias && nw && noise && sp1 && s1 && a0 && y0, "const_input_fwd: null pointer");
+  const_input_fwd_kernel<<<GRID1D((size_t)b * 16 * c)>>>(cst, bias, nw, noise, sp1, s1, BF(a0), BF(y0), b, c);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_const_input_bwd(const void* dy, const void* a0, const float* noise, const float* sp1, float* dsp1,
+                                    float* ds1, float* dconst, float* dbias, float* dnw, int b, int c,
+                                    cudaStream_t stream) {
+  IRFD_CHECK_ARG(dy && a0 && noise && sp1 && dsp1 && ds1 && dconst && dbias && dnw, "const_input_bwd: null pointer");
+  const_input_bwd_kernel<<<(c + 63) / 64, 64, 0, stream>>>(CBF(dy), CBF(a0), noise, sp1, dsp1, ds1, dconst, dbias, dnw,
+                                                           b, c);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_upsample2x_fwd(const void* in, void* out, int b, int h, int w, int c, cudaStream_t stream) {
+  IRFD_CHECK_ARG(in && out && c % 8 == 0, "upsample2x_fwd: bad argument");
+  upsample2x_fwd_kernel<<<GRID1D((size_t)b * 4 * h * w * (c / 8))>>>(CBF(in), BF(out), b, h, w, c);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_upsample2x_bwd(const void* dout, void* din, int b, int h, int w, int c, cudaStream_t stream) {
+  IRFD_CHECK_ARG(dout && din && c % 8 == 0, "upsample2x_bwd: bad argument");
+  upsample2x_bwd_kernel<<<GRID1D((size_t)b * h * w * (c / 8))>>>(CBF(dout), BF(din), b, h, w, c);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+static void style_plan(int hw, int c, int b, int* chunks, int* rpb) {
+  int rows_par = kRvThreads / (c / 8);
+  if (rows_par < 1) rows_par = 1;
+  long long want = ((long long)num_sms() * 4 + b - 1) / b;  // chunks per image
+  long long r = (hw + want - 1) / want;
+  r = ((r + rows_par - 1) / rows_par) * rows_par;
+  if (r < rows_par * 4) r = rows_par * 4;
+  *rpb = (int)r;
+  *chunks = (int)((hw + r - 1) / r);
+}
+
+extern "C" long long irfd_style_bwd_workspace_bytes(int b, int hw, int c) {
+  int chunks, rpb;
+  style_plan(hw, c, b, &chunks, &rpb);
+  return (long long)b * chunks * 4 * c * 4;
+}
+
+extern "C" int irfd_style_bwd(const void* dy, const void* a, const float* noise, const float* sp1, void* dz, float* ds1,
+                              float* dsp1, float* dbias, float* dnw, int b, int hw, int c, void* workspace,
+                              long long workspace_bytes, cudaStream_t stream) {
+  IRFD_CHECK_ARG(dy && a && noise && sp1 && dz && ds1 && dsp1 && dbias && dnw && workspace, "style_bwd: null pointer");
+  IRFD_CHECK_ARG(c % 8 == 0 && c <= 2048, "style_bwd: C must be a multiple of 8 and <= 2048");
+  int chunks, rpb;
+  style_plan(hw, c, b, &chunks, &rpb);
+  IRFD_CHECK_ARG(workspace_bytes >= (long long)b * chunks * 4 * c * 4, "style_bwd: workspace too small");
+  float* partial = reinterpret_cast<float*>(workspace);
+  style_bwd_kernel<<<dim3(chunks, b), kRvThreads, 4 * 2048 * sizeof(float), stream>>>(CBF(dy), CBF(a), noise, sp1,
+                                                                                     BF(dz), partial, hw, c, rpb);
+  IRFD_CHECK_LAUNCH();
+  style_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(partial, b, chunks, c, ds1, dsp1, dbias, dnw);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_to_rgb_fwd(const void* y, const float* w, const float* bias, float* out, int b, int hw, int c,
+                               cudaStream_t stream) {
+  IRFD_CHECK_ARG(y && w && bias && out && c % 8 == 0, "to_rgb_fwd: bad argument");
+  const size_t pixels = (size_t)b * hw;
+  to_rgb_fwd_kernel<<<(unsigned)((pixels + 255) / 256), 256, 3 * c * sizeof(float), stream>>>(CBF(y), w, bias, out, b,
+                                                                                             hw, c);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" long long irfd_to_rgb_bwd_workspace_bytes(int b, int hw, int c) {
+  int nblk, rpb;
+  plan_row_blocks((long long)b * hw, c, num_sms(), &nblk, &rpb);
+  return (long long)nblk * 4 * c * 4;
+}
+
+extern "C" int irfd_to_rgb_bwd(const float* drgb, const void* y, const float* w, void* dy, float* dw, float* dbias,
+                               int b, int hw, int c, void* workspace, long long workspace_bytes, cudaStream_t stream) {
+  IRFD_CHECK_ARG(drgb && y && w && dy && dw && dbias && workspace && c % 8 == 0 && c <= 2048, "to_rgb_bwd: bad arg");
+  int nblk, rpb;
+  plan_row_blocks((long long)b * hw, c, num_sms(), &nblk, &rpb);
+  IRFD_CHECK_ARG(workspace_bytes >= (long long)nblk * 4 * c * 4, "to_rgb_bwd: workspace too small");
+  float* partial = reinterpret_cast<float*>(workspace);
+  to_rgb_bwd_kernel<<<nblk, kRvThreads, 4 * 2048 * sizeof(float), stream>>>(drgb, CBF(y), w, BF(dy), partial, b, hw, c,
+                                                                           rpb);
+  IRFD_CHECK_LAUNCH();
+  to_rgb_bwd_finalize_kernel<<<(3 * c + 3 + 127) / 128, 128, 0, stream>>>(partial, nblk, c, dw, dbias);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}

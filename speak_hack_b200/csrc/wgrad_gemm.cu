@@ -181,6 +181,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   if (idx >= (size_t)K_total * N_total) return;
   const int n = idx % N_total;
   const int k = idx / N_total;
+  if (k >= cin * taps) return;  // zero-padded K tail (stem)
   float acc = 0.f;
   const size_t stride = (size_t)K_total * N_total;
   for (int s = 0; s < splits; ++s) acc += partial[s * stride + idx];
@@ -243,8 +244,8 @@ extern "C" long long irfd_wgrad_workspace_bytes(int n, int h, int w, int cin, in
 }
 
 extern "C" int irfd_conv_wgrad(const void* x, const void* dy, int n, int h, int w, int cin, int cout, int ksize,
-                               float* dw, float beta, void* workspace, long long workspace_bytes,
-                               cudaStream_t stream) {
+                               float* dw, float beta, int reduce_cin, int reduce_taps, void* workspace,
+                               long long workspace_bytes, cudaStream_t stream) {
   IRFD_CHECK_ARG(x && dy && dw && workspace, "conv_wgrad: null pointer");
   IRFD_CHECK_ARG(ksize == 1 || ksize == 3, "conv_wgrad: ksize must be 1 or 3");
   IRFD_CHECK_ARG(cin % 64 == 0 && cout % 64 == 0, "conv_wgrad: channels must be multiples of 64");
@@ -300,7 +301,8 @@ extern "C" int irfd_conv_wgrad(const void* x, const void* dy, int n, int h, int 
   if (rc) return rc;
   const size_t total = (size_t)a.K_total * a.N_total;
   wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a.partial, dw, a.splits, a.K_total,
-                                                                          a.N_total, cin, a.taps, beta);
+                                                                          a.N_total, reduce_cin > 0 ? reduce_cin : cin,
+                                                                          reduce_cin > 0 ? reduce_taps : a.taps, beta);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }

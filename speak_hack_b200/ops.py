@@ -1,10 +1,11 @@
-"""Tensor-level wrappers over the C ABI: validate, allocate outputs with torch (device memory plumbing), launch.
+"""Tensor-level wrappers over the C ABI: validate, allocate outputs with torch (device-memory plumbing), launch.
 
-Nothing in here computes with PyTorch; every function either launches a kernel from libirfd_b200.so or raises.
+Nothing in here computes with PyTorch; every function either launches kernels from libirfd_b200.so or raises.
+Activations are NHWC bf16 tensors; parameters and reductions are fp32.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 
@@ -14,6 +15,10 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 
 EPI_PLAIN, EPI_STATS, EPI_STYLE = 0, 1, 2
+PACK_FPROP, PACK_DGRAD, PACK_DCOL, PACK_FLAT = 0, 1, 2, 3
+
+# kernels launched through this module since the last reset (bench.py's gpu_launches claim)
+launch_count = 0
 
 
 def _stream() -> int:
@@ -33,19 +38,32 @@ def _chk(t: torch.Tensor, dtype, name: str) -> None:
         raise _lib.IrfdError(f"{name}: expected a contiguous tensor")
 
 
-def conv_gemm(
-    x: torch.Tensor,            # [N,H,W,Cin] bf16
-    wk: torch.Tensor,           # [Cout, k*k*Cin] bf16 (tap-major)
-    ksize: int,
-    mode: int = EPI_PLAIN,
-    bias: Optional[torch.Tensor] = None,
-    nw: Optional[torch.Tensor] = None,
-    noise: Optional[torch.Tensor] = None,
-    sp1: Optional[torch.Tensor] = None,
-    s1: Optional[torch.Tensor] = None,
-    force_block_n: int = 0,
-):
-    """Stride-1 same-padding conv as implicit GEMM.  Returns out (mode 0), (out, sum, sq) (mode 1), (a, y) (mode 2)."""
+def _call(name: str, *args, launches: int = 1) -> None:
+    global launch_count
+    rc = getattr(_lib.load(), name)(*args)
+    _lib.check(rc, name)
+    launch_count += launches
+
+
+_workspace = {}
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    """Grow-only per-device scratch buffer (split-K partials, reduction partials); stream-ordered use only."""
+    key = (device.type, device.index)
+    buf = _workspace.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 22), dtype=torch.uint8, device=device)
+        _workspace[key] = buf
+    return buf
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# tensor-core GEMMs
+# ----------------------------------------------------------------------------------------------------------------------
+def conv_gemm(x, wk, ksize, mode=EPI_PLAIN, bias=None, nw=None, noise=None, sp1=None, s1=None, force_block_n=0):
+    """Stride-1 same-padding conv as implicit GEMM.  x [N,H,W,Cin] bf16, wk [Cout, k*k*Cin] bf16.
+    Returns out (mode 0), (out, stat_sum, stat_sq) (mode 1), (a, y) (mode 2)."""
     lib = _lib.load()
     _chk(x, BF16, "x")
     _chk(wk, BF16, "wk")
@@ -63,11 +81,8 @@ def conv_gemm(
     for t, nm in ((bias, "bias"), (nw, "nw"), (noise, "noise"), (sp1, "sp1"), (s1, "s1")):
         if t is not None:
             _chk(t, F32, nm)
-    rc = lib.irfd_conv_gemm(
-        x.data_ptr(), n, h, w, cin, wk.data_ptr(), cout, ksize, out.data_ptr(), _ptr(out2), mode, _ptr(bias), _ptr(nw),
-        _ptr(noise), _ptr(sp1), _ptr(s1), _ptr(ssum), _ptr(ssq), force_block_n, _stream(),
-    )
-    _lib.check(rc, "irfd_conv_gemm")
+    _call("irfd_conv_gemm", x.data_ptr(), n, h, w, cin, wk.data_ptr(), cout, ksize, out.data_ptr(), _ptr(out2), mode,
+          _ptr(bias), _ptr(nw), _ptr(noise), _ptr(sp1), _ptr(s1), _ptr(ssum), _ptr(ssq), force_block_n, _stream())
     if mode == EPI_STATS:
         return out, ssum, ssq
     if mode == EPI_STYLE:
@@ -75,33 +90,347 @@ def conv_gemm(
     return out
 
 
-_workspace = {}
+def gemm_rows(a2d, wk, mode=EPI_PLAIN):
+    """Plain GEMM out[M, N] = a2d[M, K] @ wk[N, K]^T through the conv kernel (1x1 conv over a single row of pixels)."""
+    m, k = a2d.shape
+    r = conv_gemm(a2d.view(1, 1, m, k), wk, 1, mode)
+    if mode == EPI_STATS:
+        return r[0].view(m, -1), r[1], r[2]
+    return r.view(m, -1)
 
 
-def workspace(nbytes: int, device) -> torch.Tensor:
-    """Grow-only per-device scratch buffer (split-K partials etc.); stream-ordered use only."""
-    key = (device.type, device.index)
-    buf = _workspace.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _workspace[key] = buf
-    return buf
-
-
-def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, dw: Optional[torch.Tensor] = None, beta: float = 0.0):
-    """dW (OIHW fp32) of a stride-1 same-padding conv from its NHWC bf16 input and output gradient."""
+def conv_wgrad(x, dy, ksize, dw=None, beta=0.0, reduce_cin=0, reduce_taps=0, out_shape=None):
+    """dW (fp32, OIHW) of a stride-1 same-padding conv from its NHWC bf16 input and output gradient."""
     lib = _lib.load()
     _chk(x, BF16, "x")
     _chk(dy, BF16, "dy")
     n, h, w, cin = x.shape
     cout = dy.shape[-1]
     if dw is None:
-        dw = torch.empty((cout, cin, ksize, ksize), dtype=F32, device=x.device)
+        shape = out_shape if out_shape is not None else (cout, cin, ksize, ksize)
+        dw = torch.empty(shape, dtype=F32, device=x.device)
         beta = 0.0
     _chk(dw, F32, "dw")
     need = lib.irfd_wgrad_workspace_bytes(n, h, w, cin, cout, ksize)
     ws = workspace(need, x.device)
-    rc = lib.irfd_conv_wgrad(x.data_ptr(), dy.data_ptr(), n, h, w, cin, cout, ksize, dw.data_ptr(), beta,
-                             ws.data_ptr(), ws.numel(), _stream())
-    _lib.check(rc, "irfd_conv_wgrad")
+    _call("irfd_conv_wgrad", x.data_ptr(), dy.data_ptr(), n, h, w, cin, cout, ksize, dw.data_ptr(), beta, reduce_cin,
+          reduce_taps, ws.data_ptr(), ws.numel(), _stream(), launches=2)
     return dw
+
+
+def pack_conv_weight(w: torch.Tensor, mode: int, kpad: int = 0) -> torch.Tensor:
+    """fp32 OIHW parameter -> bf16 GEMM operand (see irfd_pack_conv_weight)."""
+    _chk(w, F32, "w")
+    o, i, kh, kw = w.shape
+    taps = kh * kw
+    if mode == PACK_FPROP:
+        shape = (o, taps * i)
+    elif mode == PACK_DGRAD:
+        shape = (i, taps * o)
+    elif mode == PACK_DCOL:
+        shape = (taps * i, o)
+    else:
+        shape = (o, kpad)
+    dst = torch.empty(shape, dtype=BF16, device=w.device)
+    _call("irfd_pack_conv_weight", w.data_ptr(), dst.data_ptr(), o, i, taps, mode, kpad, _stream())
+    return dst
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# BatchNorm
+# ----------------------------------------------------------------------------------------------------------------------
+def bn_finalize(ssum, ssq, count, eps, momentum, running_mean=None, running_var=None, running_updates=1):
+    tiles, c = ssum.shape
+    mean = torch.empty(c, dtype=F32, device=ssum.device)
+    rstd = torch.empty(c, dtype=F32, device=ssum.device)
+    _call("irfd_bn_finalize", ssum.data_ptr(), ssq.data_ptr(), tiles, c, int(count), eps, momentum, mean.data_ptr(),
+          rstd.data_ptr(), _ptr(running_mean), _ptr(running_var), running_updates, _stream())
+    return mean, rstd
+
+
+def bn_eval_rstd(running_var, eps):
+    rstd = torch.empty_like(running_var)
+    _call("irfd_bn_eval_rstd", running_var.data_ptr(), eps, rstd.data_ptr(), running_var.numel(), _stream())
+    return rstd
+
+
+def bn_apply(z, mean, rstd, gamma, beta, res=None, bn2=None, relu=True):
+    """out = [relu](BN(z) [+ res | + BN2(res)]); bn2 = (mean2, rstd2, gamma2, beta2)."""
+    _chk(z, BF16, "z")
+    c = z.shape[-1]
+    rows = z.numel() // c
+    out = torch.empty_like(z)
+    m2 = r2 = g2 = b2 = None
+    if bn2 is not None:
+        m2, r2, g2, b2 = bn2
+    _call("irfd_bn_apply", z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+          _ptr(res), _ptr(m2), _ptr(r2), _ptr(g2), _ptr(b2), out.data_ptr(), rows, c, 1 if relu else 0, _stream())
+    return out
+
+
+def bn_backward(g1, g2, act, z, mean, rstd, gamma, want_g_out=False):
+    """Returns dz (bf16), dgamma, dbeta (fp32) [, masked g (bf16)]."""
+    lib = _lib.load()
+    c = z.shape[-1]
+    rows = z.numel() // c
+    dz = torch.empty_like(z)
+    g_out = torch.empty_like(z) if want_g_out else None
+    dgamma = torch.empty(c, dtype=F32, device=z.device)
+    dbeta = torch.empty(c, dtype=F32, device=z.device)
+    ws = workspace(lib.irfd_bn_bwd_workspace_bytes(rows, c), z.device)
+    _call("irfd_bn_backward", g1.data_ptr(), _ptr(g2), _ptr(act), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+          gamma.data_ptr(), dz.data_ptr(), _ptr(g_out), dgamma.data_ptr(), dbeta.data_ptr(), 0.0, rows, c,
+          ws.data_ptr(), ws.numel(), _stream(), launches=3)
+    if want_g_out:
+        return dz, dgamma, dbeta, g_out
+    return dz, dgamma, dbeta
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# layout / pooling
+# ----------------------------------------------------------------------------------------------------------------------
+def im2col_stem(x: torch.Tensor, kpad: int = 192) -> torch.Tensor:
+    _chk(x, F32, "x")
+    n, c, h, w = x.shape
+    if c != 3:
+        raise _lib.IrfdError("im2col_stem expects 3 input channels")
+    col = torch.empty((n * (h // 2) * (w // 2), kpad), dtype=BF16, device=x.device)
+    _call("irfd_im2col_stem", x.data_ptr(), col.data_ptr(), n, h, w, kpad, _stream())
+    return col
+
+
+def im2col_3x3s2(a: torch.Tensor) -> torch.Tensor:
+    n, h, w, c = a.shape
+    col = torch.empty((n * (h // 2) * (w // 2), 9 * c), dtype=BF16, device=a.device)
+    _call("irfd_im2col_3x3s2", a.data_ptr(), col.data_ptr(), n, h, w, c, _stream())
+    return col
+
+
+def col2im_3x3s2(dcol: torch.Tensor, n, h, w, c) -> torch.Tensor:
+    dx = torch.empty((n, h, w, c), dtype=BF16, device=dcol.device)
+    _call("irfd_col2im_3x3s2", dcol.data_ptr(), dx.data_ptr(), n, h, w, c, _stream())
+    return dx
+
+
+def subsample2(a: torch.Tensor) -> torch.Tensor:
+    n, h, w, c = a.shape
+    out = torch.empty((n, h // 2, w // 2, c), dtype=BF16, device=a.device)
+    _call("irfd_subsample2", a.data_ptr(), out.data_ptr(), n, h, w, c, _stream())
+    return out
+
+
+def scatter_add_s2(a: Optional[torch.Tensor], b: torch.Tensor) -> torch.Tensor:
+    n, h2, w2, c = b.shape
+    out = torch.empty((n, h2 * 2, w2 * 2, c), dtype=BF16, device=b.device)
+    _call("irfd_scatter_add_s2", _ptr(a), b.data_ptr(), out.data_ptr(), n, h2 * 2, w2 * 2, c, _stream())
+    return out
+
+
+def maxpool_fwd(a: torch.Tensor):
+    n, h, w, c = a.shape
+    out = torch.empty((n, h // 2, w // 2, c), dtype=BF16, device=a.device)
+    arg = torch.empty((n, h // 2, w // 2, c), dtype=torch.uint8, device=a.device)
+    _call("irfd_maxpool_fwd", a.data_ptr(), out.data_ptr(), arg.data_ptr(), n, h, w, c, _stream())
+    return out, arg
+
+
+def maxpool_bwd(dout: torch.Tensor, arg: torch.Tensor) -> torch.Tensor:
+    n, h2, w2, c = dout.shape
+    dx = torch.empty((n, h2 * 2, w2 * 2, c), dtype=BF16, device=dout.device)
+    _call("irfd_maxpool_bwd", dout.data_ptr(), arg.data_ptr(), dx.data_ptr(), n, h2 * 2, w2 * 2, c, _stream())
+    return dx
+
+
+def avgpool_fwd(a: torch.Tensor) -> torch.Tensor:
+    n, h, w, c = a.shape
+    out = torch.empty((n, c), dtype=F32, device=a.device)
+    _call("irfd_avgpool_fwd", a.data_ptr(), out.data_ptr(), n, h * w, c, _stream())
+    return out
+
+
+def avgpool_bwd(dfeat: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    _chk(dfeat, F32, "dfeat")
+    n, c = dfeat.shape
+    g = torch.empty((n, h, w, c), dtype=BF16, device=dfeat.device)
+    _call("irfd_avgpool_bwd", dfeat.data_ptr(), g.data_ptr(), n, h * w, c, _stream())
+    return g
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# synthesis-network pieces
+# ----------------------------------------------------------------------------------------------------------------------
+def const_input_fwd(cst, bias, nw, noise, sp1, s1):
+    b, c = sp1.shape
+    a0 = torch.empty((b, 4, 4, c), dtype=BF16, device=sp1.device)
+    y0 = torch.empty_like(a0)
+    _call("irfd_const_input_fwd", cst.data_ptr(), bias.data_ptr(), nw.data_ptr(), noise.data_ptr(), sp1.data_ptr(),
+          s1.data_ptr(), a0.data_ptr(), y0.data_ptr(), b, c, _stream())
+    return a0, y0
+
+
+def const_input_bwd(dy, a0, noise, sp1):
+    b, c = sp1.shape
+    dev = sp1.device
+    dsp1 = torch.empty((b, c), dtype=F32, device=dev)
+    ds1 = torch.empty((b, c), dtype=F32, device=dev)
+    dconst = torch.empty((1, c, 4, 4), dtype=F32, device=dev)
+    dbias = torch.empty(c, dtype=F32, device=dev)
+    dnw = torch.empty(c, dtype=F32, device=dev)
+    _call("irfd_const_input_bwd", dy.data_ptr(), a0.data_ptr(), noise.data_ptr(), sp1.data_ptr(), dsp1.data_ptr(),
+          ds1.data_ptr(), dconst.data_ptr(), dbias.data_ptr(), dnw.data_ptr(), b, c, _stream())
+    return dsp1, ds1, dconst, dbias, dnw
+
+
+def upsample2x_fwd(x: torch.Tensor) -> torch.Tensor:
+    _chk(x, BF16, "x")
+    b, h, w, c = x.shape
+    out = torch.empty((b, 2 * h, 2 * w, c), dtype=BF16, device=x.device)
+    _call("irfd_upsample2x_fwd", x.data_ptr(), out.data_ptr(), b, h, w, c, _stream())
+    return out
+
+
+def upsample2x_bwd(dout: torch.Tensor) -> torch.Tensor:
+    _chk(dout, BF16, "dout")
+    b, h2, w2, c = dout.shape
+    din = torch.empty((b, h2 // 2, w2 // 2, c), dtype=BF16, device=dout.device)
+    _call("irfd_upsample2x_bwd", dout.data_ptr(), din.data_ptr(), b, h2 // 2, w2 // 2, c, _stream())
+    return din
+
+
+def style_bwd(dy, a, noise, sp1):
+    """Backward of the fused conv epilogue.  Returns dz (bf16), ds1, dsp1 [B,C], dbias, dnw [C]."""
+    lib = _lib.load()
+    b, h, w, c = dy.shape
+    dev = dy.device
+    dz = torch.empty_like(dy)
+    ds1 = torch.empty((b, c), dtype=F32, device=dev)
+    dsp1 = torch.empty((b, c), dtype=F32, device=dev)
+    dbias = torch.empty(c, dtype=F32, device=dev)
+    dnw = torch.empty(c, dtype=F32, device=dev)
+    ws = workspace(lib.irfd_style_bwd_workspace_bytes(b, h * w, c), dev)
+    _call("irfd_style_bwd", dy.data_ptr(), a.data_ptr(), noise.data_ptr(), sp1.data_ptr(), dz.data_ptr(),
+          ds1.data_ptr(), dsp1.data_ptr(), dbias.data_ptr(), dnw.data_ptr(), b, h * w, c, ws.data_ptr(), ws.numel(),
+          _stream(), launches=2)
+    return dz, ds1, dsp1, dbias, dnw
+
+
+def to_rgb_fwd(y, w, bias):
+    b, h, wd, c = y.shape
+    out = torch.empty((b, 3, h, wd), dtype=F32, device=y.device)
+    _call("irfd_to_rgb_fwd", y.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), b, h * wd, c, _stream())
+    return out
+
+
+def to_rgb_bwd(drgb, y, w):
+    lib = _lib.load()
+    _chk(drgb, F32, "drgb")
+    b, h, wd, c = y.shape
+    dy = torch.empty_like(y)
+    dw = torch.empty((3, c, 1, 1), dtype=F32, device=y.device)
+    dbias = torch.empty(3, dtype=F32, device=y.device)
+    ws = workspace(lib.irfd_to_rgb_bwd_workspace_bytes(b, h * wd, c), y.device)
+    _call("irfd_to_rgb_bwd", drgb.data_ptr(), y.data_ptr(), w.data_ptr(), dy.data_ptr(), dw.data_ptr(),
+          dbias.data_ptr(), b, h * wd, c, ws.data_ptr(), ws.numel(), _stream(), launches=2)
+    return dy, dw, dbias
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# fp32 dense layers
+# ----------------------------------------------------------------------------------------------------------------------
+def linear_fwd(x, w, bias, wmul=1.0, bmul=1.0, lrelu=True):
+    _chk(x, F32, "x")
+    _chk(w, F32, "w")
+    b, k = x.shape
+    n = w.shape[0]
+    y = torch.empty((b, n), dtype=F32, device=x.device)
+    _call("irfd_linear_fwd", x.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), b, n, k, wmul, bmul,
+          1 if lrelu else 0, _stream())
+    return y
+
+
+def lrelu_bwd(dy, y):
+    _chk(dy, F32, "dy")
+    dz = torch.empty_like(dy)
+    _call("irfd_lrelu_bwd", dy.data_ptr(), y.data_ptr(), dz.data_ptr(), dy.numel(), _stream())
+    return dz
+
+
+def linear_bwd(dz, x, w, wmul=1.0, bmul=1.0, need_dx=True, dx=None, dx_beta=0.0, need_dw=True, has_bias=True):
+    """Returns (dx, dw, db); dx may be accumulated into an existing buffer (dx_beta=1)."""
+    b, n = dz.shape
+    k = w.shape[1]
+    dev = dz.device
+    if need_dx and dx is None:
+        dx = torch.empty((b, k), dtype=F32, device=dev)
+        dx_beta = 0.0
+    dw = torch.empty((n, k), dtype=F32, device=dev) if need_dw else None
+    db = torch.empty(n, dtype=F32, device=dev) if (need_dw and has_bias) else None
+    _call("irfd_linear_bwd", dz.data_ptr(), _ptr(x), w.data_ptr(), _ptr(dx) if need_dx else None, dx_beta, _ptr(dw),
+          _ptr(db), 0.0, b, n, k, wmul, bmul, _stream(), launches=int(need_dx) + int(need_dw))
+    return dx, dw, db
+
+
+def softmax_rows(x):
+    y = torch.empty_like(x)
+    _call("irfd_softmax_rows", x.data_ptr(), y.data_ptr(), x.shape[0], x.shape[1], _stream())
+    return y
+
+
+def scale_copy(src, scale):
+    dst = torch.empty_like(src)
+    _call("irfd_scale_copy", src.data_ptr(), dst.data_ptr(), scale, src.numel(), _stream())
+    return dst
+
+
+def split_style(style, c):
+    b = style.shape[0]
+    sp1 = torch.empty((b, c), dtype=F32, device=style.device)
+    s1 = torch.empty((b, c), dtype=F32, device=style.device)
+    _call("irfd_split_style", style.data_ptr(), sp1.data_ptr(), s1.data_ptr(), b, c, _stream())
+    return sp1, s1
+
+
+def merge_style_grad(dsp1, ds1):
+    b, c = dsp1.shape
+    d = torch.empty((b, 2 * c), dtype=F32, device=dsp1.device)
+    _call("irfd_merge_style_grad", dsp1.data_ptr(), ds1.data_ptr(), d.data_ptr(), b, c, _stream())
+    return d
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# losses / optimiser
+# ----------------------------------------------------------------------------------------------------------------------
+def mse_fwd(a, b, out=None, out_beta=0.0):
+    lib = _lib.load()
+    _chk(a, F32, "a")
+    _chk(b, F32, "b")
+    if out is None:
+        out = torch.empty(1, dtype=F32, device=a.device)
+        out_beta = 0.0
+    ws = workspace(lib.irfd_reduce_workspace_bytes(), a.device)
+    _call("irfd_mse_fwd", a.data_ptr(), b.data_ptr(), a.numel(), out.data_ptr(), out_beta, ws.data_ptr(), ws.numel(),
+          _stream(), launches=2)
+    return out
+
+
+def mse_bwd(a, b, gscale, need_da=True, need_db=False):
+    da = torch.empty_like(a) if need_da else None
+    db = torch.empty_like(a) if need_db else None
+    _call("irfd_mse_bwd", a.data_ptr(), b.data_ptr(), a.numel(), gscale.data_ptr(), _ptr(da), _ptr(db), _stream())
+    return da, db
+
+
+def sumsq(g, out=None, out_beta=0.0):
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty(1, dtype=F32, device=g.device)
+        out_beta = 0.0
+    ws = workspace(lib.irfd_reduce_workspace_bytes(), g.device)
+    _call("irfd_sumsq", g.data_ptr(), g.numel(), out.data_ptr(), out_beta, ws.data_ptr(), ws.numel(), _stream(),
+          launches=2)
+    return out
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, total_sumsq=None, max_norm=0.0):
+    _call("irfd_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,
+          step, _ptr(total_sumsq), max_norm, _stream())
