@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py — IRFD train-step throughput on B200 (BASELINE.json metric: IRFD train samples/sec @256^2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--batch B]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A step = one generator training step of the reference (train.py:186-210 restricted to the differentiable losses,
+SURVEY §8(d) config 3): zero_grad -> IRFD.forward (train mode, inputs require grad so the encoders are differentiated)
+-> MSE(x_s,x̂_s)+MSE(x_t,x̂_t)+MSE(fi_s,fi_t) -> backward -> Adam(lr 2e-4) on Gd.  `--batch` pairs per GPU (default
+32: BASELINE config 3 at N=1, weak scaling to config 4's global 256 at N=8).  Synthetic U(-1,1) 256x256 pairs,
+random-init weights (seed 0).  Prints ONE JSON line on rank 0.
+
+--impl reference: the CPU restatement of the reference (oracle/irfd_oracle.py, "port": the reference itself is Python
+and does not travel to the GPU box) running the same step on the host cores, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_TRAIN_PER_PAIR = 529.4e9   # algorithmic, fwd + 2x bwd, recompute not counted
+METRIC = "irfd_train_pairs_per_sec_256"
+UNIT = "pairs/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="pairs per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=2, help="pairs per CPU-baseline step")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.lines:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port)
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_train_steps(pairs: int, steps: int, warmup: int, budget_s: float):
+    """Reference G step on the host cores with the oracle modules.  Returns (pairs/s, steps done, threads, seconds)."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import irfd_oracle as O
+
+    threads = os.cpu_count() or 1
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(threads)
+    torch.manual_seed(O.WEIGHT_SEED)
+    net = O.IRFDRef(use_checkpoint=True).train()
+    opt = torch.optim.Adam(net.Gd.parameters(), lr=2e-4)
+    x_s, x_t = O.synthetic_pair(pairs)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        for p in net.parameters():
+            p.grad = None
+        xs, xt = x_s.clone().requires_grad_(True), x_t.clone().requires_grad_(True)
+        out = net(xs, xt)
+        l_id, l_rec = O.irfd_losses(xs, xt, out)
+        (l_id + l_rec).backward()
+        opt.step()
+        return float(l_id + l_rec)
+
+    torch.manual_seed(O.FORWARD_SEED)
+    t_start = time.time()
+    for _ in range(warmup):
+        step()
+        if time.time() - t_start > budget_s / 3:
+            break
+    done, t0 = 0, time.time()
+    for _ in range(steps):
+        step()
+        done += 1
+        if time.time() - t_start > budget_s:
+            break
+    dt = time.time() - t0
+    return pairs * done / dt, done, threads, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pairs = 1
+    val, done, threads, dt = cpu_train_steps(pairs, args.steps, min(args.warmup, 1), budget_s=240.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / max(done, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "IRFD G train step (3xResNet-50 enc + swap + StyleGAN-v1 gen + MSE + Adam) @256^2 "
+                               "on host CPU, oracle port of the reference", "pairs_per_step": pairs},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{done} train step(s) of {pairs} pair(s) @256^2, fp32, torch CPU"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# native arm
+# ----------------------------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl native needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import speak_hack_b200 as P
+    from speak_hack_b200 import ops
+    from speak_hack_b200.trainer import IRFDTrainer
+
+    B = args.batch
+    torch.manual_seed(0)                        # identical weights on every rank
+    model = P.IRFD().to(dev).train()
+    trainer = IRFDTrainer(model, lr=2e-4)
+    g = torch.Generator().manual_seed(7 + rank)  # each rank its own shard of the global batch
+    host_s = (torch.rand(B, 3, 256, 256, generator=g) * 2 - 1).pin_memory()
+    host_t = (torch.rand(B, 3, 256, 256, generator=g) * 2 - 1).pin_memory()
+    x_s, x_t = host_s.to(dev), host_t.to(dev)
+    torch.manual_seed(11)                       # same CPU draws (swap, style mixing) on every rank
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        trainer.train_step(x_s, x_t)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM ("value")
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    ops.launch_count = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        trainer.train_step(x_s, x_t)
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms_value = max_over_ranks(e0.elapsed_time(e1))
+    launches = ops.launch_count
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    # ---- timed region 2: end to end (pinned host inputs -> H2D every step, loss read back every step)
+    barrier()
+    e0.record()
+    last = None
+    for _ in range(args.steps):
+        xs = host_s.to(dev, non_blocking=True)
+        xt = host_t.to(dev, non_blocking=True)
+        loss = trainer.train_step(xs, xt)
+        last = float(loss.item())               # D2H of the step's result
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- roofline pass: per-launch CUDA events around every tensor-core GEMM launch (same stream), few steps
+    ops.gemm_timing_begin()
+    rsteps = min(args.steps, 3)
+    for _ in range(rsteps):
+        trainer.train_step(x_s, x_t)
+    torch.cuda.synchronize()
+    fam = ops.gemm_timing_end()
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained")
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    if not peak_tf:
+        peak_tf, peak_src = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
+    top = max(fam.values(), key=lambda f: f["ms"]) if fam else None
+    roofline = None
+    if top:
+        ach = top["flops"] / (top["ms"] * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": top["name"], "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src,
+                    "launches_per_step": top["launches"] / rsteps, "ms_per_step": top["ms"] / rsteps,
+                    "families": {k: {"ms_per_step": v["ms"] / rsteps, "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12,
+                                     "launches_per_step": v["launches"] / rsteps,
+                                     "gflop_per_step": v["flops"] / rsteps / 1e9} for k, v in fam.items()}}
+
+    n_pairs = B * world * args.steps
+    value = n_pairs / (ms_value * 1e-3)
+    e2e_val = n_pairs / (ms_e2e * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_value / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "IRFD G train step (3xResNet-50 enc x2 images + S<->T swap + StyleGAN-v1 gen x2 + 3xMSE "
+                               "+ backward incl. encoders + Adam on Gd) @256^2, BASELINE config 3",
+                   "pairs_per_gpu": B, "global_batch_pairs": B * world, "parallelism": f"dp{world}",
+                   "l2_policy": "inputs+activations (>10 GB/step) far exceed the 126 MB L2; no explicit flush",
+                   "algorithmic_tflop_per_step_per_gpu": FLOPS_TRAIN_PER_PAIR * B / 1e12},
+        "model_tflops_per_gpu": FLOPS_TRAIN_PER_PAIR * B / (ms_value / args.steps * 1e-3) / 1e12,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 2 * host_s.numel() * 4,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": last},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            val, done, threads, dt = cpu_train_steps(args.cpu_sample, 1, 0, budget_s=120.0)
+            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{done} train step of {args.cpu_sample} pairs @256^2 (oracle port, fp32, "
+                                              f"torch CPU, {dt:.1f} s, no warm-up)"}
+        except Exception as exc:  # the baseline is informative; never lose the GPU line over it
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {exc}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -81,6 +81,7 @@ int irfd_conv_wgrad(const void* x, const void* dy, int n, int h, int w, int cin,
  *   irfd_bn_eval_rstd: eval mode, rstd = 1/sqrt(running_var + eps).
  *   irfd_bn_apply    : out = [relu]( gamma*(z-mean)*rstd + beta  [+ res]  [or + BN2(res) when mean2 != NULL] )
  *   irfd_bn_backward : g = (g1 [+ g2]) * (act > 0 if act != NULL);  dz = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat));
+ *                      (batch_stats = 0, eval mode: dz = gamma*rstd*g);
  *                      dgamma/dbeta = grad_beta*old + new;  g_out (optional) receives the masked g (identity shortcut).
  * All activations [rows, c] bf16 (NHWC flattened), c % 8 == 0, c <= 2048.
  */
@@ -88,14 +89,17 @@ int irfd_bn_finalize(const float* psum, const float* psq, int tiles, int c, long
                      float* mean, float* rstd, float* running_mean, float* running_var, int running_updates,
                      irfd_stream_t stream);
 int irfd_bn_eval_rstd(const float* running_var, float eps, float* rstd, int c, irfd_stream_t stream);
+/* second momentum update from saved batch mean/rstd (what the reference's checkpoint recompute does) */
+int irfd_bn_running_update(const float* mean, const float* rstd, float eps, long long count, float momentum,
+                           float* running_mean, float* running_var, int c, irfd_stream_t stream);
 int irfd_bn_apply(const void* z, const float* mean, const float* rstd, const float* gamma, const float* beta,
                   const void* res, const float* mean2, const float* rstd2, const float* gamma2, const float* beta2,
                   void* out, long long rows, int c, int relu, irfd_stream_t stream);
 long long irfd_bn_bwd_workspace_bytes(long long rows, int c);
 int irfd_bn_backward(const void* g1, const void* g2, const void* act, const void* z, const float* mean,
                      const float* rstd, const float* gamma, void* dz, void* g_out, float* dgamma, float* dbeta,
-                     float grad_beta, long long rows, int c, void* workspace, long long workspace_bytes,
-                     irfd_stream_t stream);
+                     float grad_beta, int batch_stats, long long rows, int c, void* workspace,
+                     long long workspace_bytes, irfd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Layout / gather kernels for the strided ResNet convs and pooling (torchvision resnet.py:197-205, 133-137, 241).
@@ -114,7 +118,8 @@ int irfd_col2im_3x3s2(const void* dcol, void* dx, int n, int h, int w, int c, ir
 int irfd_subsample2(const void* a, void* out, int n, int h, int w, int c, irfd_stream_t stream);
 int irfd_scatter_add_s2(const void* a, const void* b, void* out, int n, int h, int w, int c, irfd_stream_t stream);
 int irfd_maxpool_fwd(const void* a, void* out, void* argmax, int n, int h, int w, int c, irfd_stream_t stream);
-int irfd_maxpool_bwd(const void* dout, const void* argmax, void* dx, int n, int h, int w, int c, irfd_stream_t stream);
+int irfd_maxpool_bwd(const void* dout, const void* dout2, const void* argmax, void* dx, int n, int h, int w, int c,
+                     irfd_stream_t stream); /* dout2 (optional) is added to dout before routing */
 int irfd_avgpool_fwd(const void* a, float* out, int n, int hw, int c, irfd_stream_t stream);
 int irfd_avgpool_bwd(const float* dfeat, void* g, int n, int hw, int c, irfd_stream_t stream);
 

@@ -53,6 +53,20 @@ __global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* 
   }
 }
 
+// Re-apply the momentum update from saved batch statistics (second update of the reference's checkpoint recompute).
+__global__ void bn_running_update_kernel(const float* __restrict__ mean, const float* __restrict__ rstd, float eps,
+                                         double count, float momentum, float* __restrict__ running_mean,
+                                         float* __restrict__ running_var, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double r = (double)rstd[c];
+  double var = 1.0 / (r * r) - (double)eps;
+  if (var < 0.0) var = 0.0;
+  const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+  running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean[c];
+  running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+}
+
 // eval mode: rstd from the running variance
 __global__ void bn_eval_rstd_kernel(const float* __restrict__ running_var, float eps, float* __restrict__ rstd, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -173,7 +187,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, double count,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float beta_acc,
-                                       float* __restrict__ c1, float* __restrict__ c2) {
+                                       float* __restrict__ c1, float* __restrict__ c2, int batch_stats) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s0 = 0.0, s1 = 0.0;
@@ -183,8 +197,9 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nb
   }
   dbeta[c] = (beta_acc != 0.f ? beta_acc * dbeta[c] : 0.f) + (float)s0;
   dgamma[c] = (beta_acc != 0.f ? beta_acc * dgamma[c] : 0.f) + (float)s1;
-  c1[c] = (float)(s0 / count);
-  c2[c] = (float)(s1 / count);
+  // eval mode (running statistics are constants): no batch-statistic terms in dz
+  c1[c] = batch_stats ? (float)(s0 / count) : 0.f;
+  c2[c] = batch_stats ? (float)(s1 / count) : 0.f;
 }
 
 __global__ void __launch_bounds__(kRvThreads)
@@ -251,6 +266,15 @@ extern "C" int irfd_bn_finalize(const float* psum, const float* psq, int tiles, 
   return IRFD_OK;
 }
 
+extern "C" int irfd_bn_running_update(const float* mean, const float* rstd, float eps, long long count, float momentum,
+                                      float* running_mean, float* running_var, int c, cudaStream_t stream) {
+  IRFD_CHECK_ARG(mean && rstd && running_mean && running_var && c > 0 && count > 0, "bn_running_update: bad argument");
+  bn_running_update_kernel<<<(c + 255) / 256, 256, 0, stream>>>(mean, rstd, eps, (double)count, momentum, running_mean,
+                                                                 running_var, c);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
 extern "C" int irfd_bn_eval_rstd(const float* running_var, float eps, float* rstd, int c, cudaStream_t stream) {
   IRFD_CHECK_ARG(running_var && rstd && c > 0, "bn_eval_rstd: bad argument");
   bn_eval_rstd_kernel<<<(c + 255) / 256, 256, 0, stream>>>(running_var, eps, rstd, c);
@@ -288,8 +312,8 @@ extern "C" long long irfd_bn_bwd_workspace_bytes(long long rows, int c) {
 // Full BN backward (reduce -> finalize -> apply).  workspace layout: [nblk][2][C] partials, then c1[C], c2[C].
 extern "C" int irfd_bn_backward(const void* g1, const void* g2, const void* act, const void* z, const float* mean,
                                 const float* rstd, const float* gamma, void* dz, void* g_out, float* dgamma,
-                                float* dbeta, float grad_beta, long long rows, int c, void* workspace,
-                                long long workspace_bytes, cudaStream_t stream) {
+                                float* dbeta, float grad_beta, int batch_stats, long long rows, int c,
+                                void* workspace, long long workspace_bytes, cudaStream_t stream) {
   IRFD_CHECK_ARG(g1 && z && mean && rstd && gamma && dz && dgamma && dbeta && workspace, "bn_backward: null pointer");
   IRFD_CHECK_ARG(c % 8 == 0 && c <= 2048 && rows > 0, "bn_backward: C must be a multiple of 8 and <= 2048");
   int nblk, rpb;
@@ -308,7 +332,7 @@ extern "C" int irfd_bn_backward(const void* g1, const void* g2, const void* act,
   bn_bwd_reduce_kernel<<<nblk, kRvThreads, smem, stream>>>(G1, G2, A, Z, mean, rstd, partial, rows, c, rpb);
   IRFD_CHECK_LAUNCH();
   bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(partial, nblk, c, (double)rows, dgamma, dbeta, grad_beta,
-                                                               c1, c2);
+                                                               c1, c2, batch_stats);
   IRFD_CHECK_LAUNCH();
   bn_bwd_apply_kernel<<<nblk, kRvThreads, 0, stream>>>(G1, G2, A, Z, mean, rstd, gamma, c1, c2,
                                                         reinterpret_cast<__nv_bfloat16*>(dz),

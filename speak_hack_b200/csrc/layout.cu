@@ -189,7 +189,8 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfl
   *reinterpret_cast<uint2*>(arg + pix * C + v * 8) = packed;
 }
 
-__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ arg,
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ dout2,
+                                   const uint8_t* __restrict__ arg,
                                    __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C) {
   const int Ho = H / 2, Wo = W / 2, vc = C / 8;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -214,6 +215,12 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const
       const uint2 packed = *reinterpret_cast<const uint2*>(arg + op);
       float g[8];
       load8(dout + op, g);
+      if (dout2 != nullptr) {
+        float g2[8];
+        load8(dout2 + op, g2);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) g[t] += g2[t];
+      }
       const int tap = kh * 3 + kw;
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
@@ -328,11 +335,12 @@ extern "C" int irfd_maxpool_fwd(const void* a, void* out, void* argmax, int n, i
   return IRFD_OK;
 }
 
-extern "C" int irfd_maxpool_bwd(const void* dout, const void* argmax, void* dx, int n, int h, int w, int c,
-                                cudaStream_t stream) {
+extern "C" int irfd_maxpool_bwd(const void* dout, const void* dout2, const void* argmax, void* dx, int n, int h, int w,
+                                int c, cudaStream_t stream) {
   IRFD_CHECK_ARG(dout && dx && argmax && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "maxpool_bwd: bad argument");
   const size_t total = (size_t)n * h * w * (c / 8);
-  maxpool_bwd_kernel<<<GRID1D(total)>>>(CBF(dout), reinterpret_cast<const uint8_t*>(argmax), BF(dx), n, h, w, c);
+  maxpool_bwd_kernel<<<GRID1D(total)>>>(CBF(dout), CBF(dout2), reinterpret_cast<const uint8_t*>(argmax), BF(dx), n, h,
+                                        w, c);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }

@@ -1,0 +1,296 @@
+"""StyleGAN-v1-style generator of the IRFD model on sm_100a kernels.
+
+Drop-in for the live half of the reference's styleganv1.py (lines 448-635): same class names, constructor signatures,
+attribute names and state_dict keys, so `load_state_dict(reference.state_dict())` works in both directions.
+What differs is how forward/backward run: the synthesis network is ONE autograd node whose forward and hand-written
+backward launch the kernels of libirfd_b200.so (tcgen05 implicit-GEMM convs with the noise/leaky-relu/style tail fused
+as the epilogue, bf16 NHWC activations), and the equalised-lr dense layers are fp32 CUDA kernels.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# FC — styleganv1.py:471-495
+# ----------------------------------------------------------------------------------------------------------------------
+class _FCFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, wmul, bmul, lrelu):
+        x = x.contiguous()
+        y = ops.linear_fwd(x, weight, bias, wmul, bmul, lrelu)
+        ctx.save_for_backward(x, weight, y)
+        ctx.cfg = (wmul, bmul, lrelu, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        wmul, bmul, lrelu, has_bias = ctx.cfg
+        dy = dy.contiguous()
+        dz = ops.lrelu_bwd(dy, y) if lrelu else dy
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dx, dw, db = ops.linear_bwd(dz, x, weight, wmul, bmul, need_dx=need_dx, need_dw=need_dw, has_bias=has_bias)
+        return dx, dw, db, None, None, None
+
+
+class FC(nn.Module):
+    """Equalised-learning-rate dense layer; leaky_relu(0.2) is ALWAYS applied (reference quirk, styleganv1.py:494)."""
+
+    def __init__(self, in_channels, out_channels, gain=2 ** (0.5), use_wscale=False, lrmul=1.0, bias=True):
+        super().__init__()
+        he_std = gain * in_channels ** (-0.5)
+        if use_wscale:
+            init_std = 1.0 / lrmul
+            self.w_lrmul = he_std * lrmul
+        else:
+            init_std = he_std / lrmul
+            self.w_lrmul = lrmul
+        self.weight = nn.Parameter(torch.randn(out_channels, in_channels) * init_std)
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(out_channels))
+            self.b_lrmul = lrmul
+        else:
+            self.bias = None
+            self.b_lrmul = 1.0
+
+    def forward(self, x):
+        return _FCFn.apply(x, self.weight, self.bias, float(self.w_lrmul), float(self.b_lrmul), True)
+
+
+class ApplyNoise(nn.Module):
+    """Parameter holder for the per-channel noise weight (styleganv1.py:448-456); applied inside the conv epilogue."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.weight = nn.Parameter(torch.zeros(channels))
+
+    def forward(self, x, noise=None):  # pragma: no cover - fused path is used instead
+        raise RuntimeError("ApplyNoise is fused into SynthesisNetwork's conv epilogue; call SynthesisNetwork/StyleGenerator")
+
+
+class ApplyStyle(nn.Module):
+    """Parameter holder for the style affine FC (styleganv1.py:458-468); applied inside the conv epilogue."""
+
+    def __init__(self, latent_size, channels, use_wscale):
+        super().__init__()
+        self.linear = FC(latent_size, channels * 2, gain=1.0, use_wscale=use_wscale)
+
+    def forward(self, x, latent):  # pragma: no cover
+        raise RuntimeError("ApplyStyle is fused into SynthesisNetwork's conv epilogue; call SynthesisNetwork/StyleGenerator")
+
+
+class SynthesisBlock(nn.Module):
+    """Parameter holder with the reference's layout (styleganv1.py:612-621)."""
+
+    def __init__(self, in_channels, out_channels, resolution):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_channels, out_channels, kernel_size=3, padding=1)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, kernel_size=3, padding=1)
+        self.noise1 = ApplyNoise(out_channels)
+        self.noise2 = ApplyNoise(out_channels)
+        self.style_mod1 = ApplyStyle(512, out_channels, use_wscale=True)
+        self.style_mod2 = ApplyStyle(512, out_channels, use_wscale=True)
+        self.upsample = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=False)
+
+    def forward(self, x, w):  # pragma: no cover
+        raise RuntimeError("SynthesisBlock runs fused inside SynthesisNetwork; call SynthesisNetwork/StyleGenerator")
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Synthesis network as one autograd node
+# ----------------------------------------------------------------------------------------------------------------------
+def _style_params(mod: ApplyStyle):
+    return mod.linear.weight, mod.linear.bias, float(mod.linear.w_lrmul), float(mod.linear.b_lrmul)
+
+
+class _SynthesisFn(torch.autograd.Function):
+    """forward(w_rows [L,B,512] fp32, noises, *params) -> image [B,3,R,R] fp32.
+
+    params order: const_input, bias, style_mod.linear.weight, style_mod.linear.bias, noise_input1.weight,
+    then per block: conv1.w, conv1.b, conv2.w, conv2.b, noise1.w, noise2.w, sm1.w, sm1.b, sm2.w, sm2.b,
+    finally to_rgb.weight, to_rgb.bias.
+    """
+
+    @staticmethod
+    def forward(ctx, rows_t, net, noises, *params):
+        rows_t = rows_t.contiguous()
+        B = rows_t.shape[1]
+        it = iter(params)
+        const_input, bias0, sw0, sb0, nw0 = next(it), next(it), next(it), next(it), next(it)
+        wm, bm = float(net.style_mod.linear.w_lrmul), float(net.style_mod.linear.b_lrmul)
+        saved = {"blocks": []}
+        ni = iter(noises)
+
+        def style(row, sw, sb, c):
+            st = ops.linear_fwd(row, sw, sb, wm, bm, lrelu=True)
+            sp1, s1 = ops.split_style(st, c)
+            return st, sp1, s1
+
+        c0 = const_input.shape[1]
+        noise0 = next(ni)
+        st0, sp1_0, s1_0 = style(rows_t[0], sw0, sb0, c0)
+        a0, y = ops.const_input_fwd(const_input, bias0, nw0, noise0, sp1_0, s1_0)
+        saved["const"] = (a0, noise0, sp1_0, st0)
+        for i, blk in enumerate(net.layers):
+            w1, b1, w2, b2, nw1, nw2, s1w, s1b, s2w, s2b = (next(it) for _ in range(10))
+            cout = w1.shape[0]
+            u = ops.upsample2x_fwd(y)
+            n1 = next(ni)
+            st1, sp1_1, s1_1 = style(rows_t[2 * i + 1], s1w, s1b, cout)
+            a1, y1 = ops.conv_gemm(u, ops.pack_conv_weight(w1, ops.PACK_FPROP), 3, ops.EPI_STYLE, bias=b1, nw=nw1,
+                                   noise=n1, sp1=sp1_1, s1=s1_1)
+            n2 = next(ni)
+            st2, sp1_2, s1_2 = style(rows_t[2 * i + 2], s2w, s2b, cout)
+            a2, y2 = ops.conv_gemm(y1, ops.pack_conv_weight(w2, ops.PACK_FPROP), 3, ops.EPI_STYLE, bias=b2, nw=nw2,
+                                   noise=n2, sp1=sp1_2, s1=s1_2)
+            saved["blocks"].append((u, a1, y1, a2, n1, n2, sp1_1, sp1_2, st1, st2))
+            y = y2
+        rgb_w, rgb_b = next(it), next(it)
+        img = ops.to_rgb_fwd(y, rgb_w, rgb_b)
+        ctx.net = net
+        ctx.saved = saved
+        ctx.y_last = y
+        ctx.rows_t = rows_t
+        ctx.params = params
+        return img
+
+    @staticmethod
+    def backward(ctx, dimg):
+        net, saved, params, rows_t = ctx.net, ctx.saved, ctx.params, ctx.rows_t
+        dimg = dimg.contiguous()
+        wm, bm = float(net.style_mod.linear.w_lrmul), float(net.style_mod.linear.b_lrmul)
+        L, B, _ = rows_t.shape
+        drows = torch.zeros_like(rows_t)
+        nblk = len(net.layers)
+        grads: List[Optional[torch.Tensor]] = [None] * len(params)
+
+        def style_backward(dsp1, ds1, st, row_idx, sw, gw_i, gb_i):
+            dst = ops.merge_style_grad(dsp1, ds1)
+            dz = ops.lrelu_bwd(dst, st)
+            dx, dw, db = ops.linear_bwd(dz, rows_t[row_idx], sw, wm, bm, need_dx=True, dx=drows[row_idx], dx_beta=0.0)
+            grads[gw_i], grads[gb_i] = dw, db
+
+        rgb_w = params[-2]
+        dy, grads[-2], grads[-1] = ops.to_rgb_bwd(dimg, ctx.y_last, rgb_w)
+        for i in range(nblk - 1, -1, -1):
+            base = 5 + 10 * i
+            w1, b1, w2, b2, nw1, nw2, s1w, s1b, s2w, s2b = params[base: base + 10]
+            u, a1, y1, a2, n1, n2, sp1_1, sp1_2, st1, st2 = saved["blocks"][i]
+            dz2, ds1_2, dsp1_2, grads[base + 3], grads[base + 5] = ops.style_bwd(dy, a2, n2, sp1_2)
+            style_backward(dsp1_2, ds1_2, st2, 2 * i + 2, s2w, base + 8, base + 9)
+            grads[base + 2] = ops.conv_wgrad(y1, dz2, 3)
+            dy1 = ops.conv_gemm(dz2, ops.pack_conv_weight(w2, ops.PACK_DGRAD), 3, ops.EPI_PLAIN)
+            dz1, ds1_1, dsp1_1, grads[base + 1], grads[base + 4] = ops.style_bwd(dy1, a1, n1, sp1_1)
+            style_backward(dsp1_1, ds1_1, st1, 2 * i + 1, s1w, base + 6, base + 7)
+            grads[base + 0] = ops.conv_wgrad(u, dz1, 3)
+            du = ops.conv_gemm(dz1, ops.pack_conv_weight(w1, ops.PACK_DGRAD), 3, ops.EPI_PLAIN)
+            dy = ops.upsample2x_bwd(du)
+        a0, noise0, sp1_0, st0 = saved["const"]
+        dsp1_0, ds1_0, grads[0], grads[1], grads[4] = ops.const_input_bwd(dy, a0, noise0, sp1_0)
+        style_backward(dsp1_0, ds1_0, st0, 0, params[2], 2, 3)
+        ctx.saved = None
+        return (drows, None, None) + tuple(grads)
+
+
+NoiseFn = Callable[[int, int, int, torch.device], torch.Tensor]
+
+
+def _randn_noise(b: int, h: int, w: int, device) -> torch.Tensor:
+    # same call as the reference's ApplyNoise (styleganv1.py:455) so the device RNG stream is consumed identically
+    return torch.randn(b, 1, h, w, device=device, dtype=torch.float32)
+
+
+class SynthesisNetwork(nn.Module):
+    """styleganv1.py:569-610."""
+
+    def __init__(self, resolution=256, fmap_base=8192, fmap_max=512):
+        super().__init__()
+        self.resolution_log2 = int(np.log2(resolution))
+        self.num_layers = self.resolution_log2 * 2 - 2
+
+        def nf(stage):
+            return min(int(fmap_base / (2.0 ** stage)), fmap_max)
+
+        self.const_input = nn.Parameter(torch.ones(1, nf(1), 4, 4))
+        self.bias = nn.Parameter(torch.zeros(nf(1)))
+        self.style_mod = ApplyStyle(512, nf(1), use_wscale=True)
+        self.noise_input1 = ApplyNoise(nf(1))
+        self.layers = nn.ModuleList()
+        for res in range(3, self.resolution_log2 + 1):
+            self.layers.append(SynthesisBlock(nf(res - 2), nf(res - 1), res))
+        self.to_rgb = nn.Conv2d(nf(self.resolution_log2 - 1), 3, kernel_size=1)
+        self.noise_fn: NoiseFn = _randn_noise
+
+    def _flat_params(self):
+        p = [self.const_input, self.bias, self.style_mod.linear.weight, self.style_mod.linear.bias,
+             self.noise_input1.weight]
+        for blk in self.layers:
+            p += [blk.conv1.weight, blk.conv1.bias, blk.conv2.weight, blk.conv2.bias, blk.noise1.weight,
+                  blk.noise2.weight, blk.style_mod1.linear.weight, blk.style_mod1.linear.bias,
+                  blk.style_mod2.linear.weight, blk.style_mod2.linear.bias]
+        p += [self.to_rgb.weight, self.to_rgb.bias]
+        return p
+
+    def draw_noises(self, batch: int, device) -> List[torch.Tensor]:
+        """One N(0,1) plane per ApplyNoise in execution order: 4x4, then (conv1, conv2) of every block."""
+        out = [self.noise_fn(batch, 4, 4, device)]
+        res = 4
+        for _ in self.layers:
+            res *= 2
+            out.append(self.noise_fn(batch, res, res, device))
+            out.append(self.noise_fn(batch, res, res, device))
+        return [n.reshape(-1).contiguous() for n in out]
+
+    def forward(self, w):
+        """w: [B, num_layers, 512] per-layer latent rows (row 2i+1 / 2i+2 feed block i; the last row is unused)."""
+        if not w.is_cuda:
+            raise ops._lib.IrfdError("SynthesisNetwork: CUDA tensors only (no CPU fallback on the IRFD hot path)")
+        noises = self.draw_noises(w.size(0), w.device)
+        rows_t = w.to(torch.float32).permute(1, 0, 2).contiguous()
+        return _SynthesisFn.apply(rows_t, self, noises, *self._flat_params())
+
+
+class StyleGenerator(nn.Module):
+    """styleganv1.py:497-567: mapping MLP -> per-layer rows -> truncation -> (train) style mixing -> synthesis."""
+
+    def __init__(self, input_dim=6144, latent_dim=512, mapping_layers=8, style_mixing_prob=0.9, truncation_psi=0.7,
+                 truncation_cutoff=8):
+        super().__init__()
+        self.input_dim = input_dim
+        self.latent_dim = latent_dim
+        self.style_mixing_prob = style_mixing_prob
+        self.truncation_psi = truncation_psi
+        self.truncation_cutoff = truncation_cutoff
+        layers = []
+        for i in range(mapping_layers):
+            layers.append(FC(input_dim if i == 0 else latent_dim, latent_dim, lrmul=0.01, use_wscale=True))
+        self.mapping = nn.Sequential(*layers)
+        self.synthesis = SynthesisNetwork()
+        self.bn = None
+
+    def forward(self, features):
+        if features.dim() > 2:  # test_irfd.py:84-91 concatenates [N,2048,1,1] codes; accept it as a harmless superset
+            features = features.flatten(1)
+        features = features.to(torch.float32)
+        w = self.mapping(features)
+        # row assembly: the reference's own tensor ops on a [B, L, 512] fp32 tensor (tiny; autograd plumbing)
+        w = w.unsqueeze(1).repeat(1, self.synthesis.num_layers, 1)
+        if self.truncation_psi and self.truncation_cutoff:
+            coefs = torch.ones_like(w)
+            coefs[:, : self.truncation_cutoff] *= self.truncation_psi
+            w = coefs * w
+        if self.training and self.style_mixing_prob > 0:
+            if torch.rand(1) < self.style_mixing_prob:
+                with torch.no_grad():
+                    w2 = self.mapping(torch.randn_like(features))
+                    w2 = w2.unsqueeze(1).repeat(1, self.synthesis.num_layers, 1)
+                    mix_layer = torch.randint(1, w.size(1), (1,)).item()
+                    w[:, mix_layer:] = w2[:, mix_layer:]
+        return self.synthesis(w)

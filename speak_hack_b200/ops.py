@@ -45,6 +45,46 @@ def _call(name: str, *args, launches: int = 1) -> None:
     launch_count += launches
 
 
+# Optional per-launch CUDA-event timing of the tensor-core GEMM launches (bench.py's roofline pass).
+_gemm_timing = None
+
+
+def gemm_timing_begin() -> None:
+    global _gemm_timing
+    _gemm_timing = []
+
+
+def gemm_timing_end():
+    """Returns {family: {name, ms, flops, launches}}; call after torch.cuda.synchronize()."""
+    global _gemm_timing
+    rec, _gemm_timing = _gemm_timing or [], None
+    fam = {}
+    for name, flops, e0, e1 in rec:
+        f = fam.setdefault(name, {"name": name, "ms": 0.0, "flops": 0.0, "launches": 0})
+        f["ms"] += e0.elapsed_time(e1)
+        f["flops"] += flops
+        f["launches"] += 1
+    return fam
+
+
+class _timed:
+    def __init__(self, name, flops):
+        self.name, self.flops = name, flops
+
+    def __enter__(self):
+        if _gemm_timing is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _gemm_timing is not None:
+            self.e1.record()
+            _gemm_timing.append((self.name, self.flops, self.e0, self.e1))
+        return False
+
+
 _workspace = {}
 
 
@@ -81,8 +121,10 @@ def conv_gemm(x, wk, ksize, mode=EPI_PLAIN, bias=None, nw=None, noise=None, sp1=
     for t, nm in ((bias, "bias"), (nw, "nw"), (noise, "noise"), (sp1, "sp1"), (s1, "s1")):
         if t is not None:
             _chk(t, F32, nm)
-    _call("irfd_conv_gemm", x.data_ptr(), n, h, w, cin, wk.data_ptr(), cout, ksize, out.data_ptr(), _ptr(out2), mode,
-          _ptr(bias), _ptr(nw), _ptr(noise), _ptr(sp1), _ptr(s1), _ptr(ssum), _ptr(ssq), force_block_n, _stream())
+    with _timed("conv_gemm_kernel (tcgen05 fprop/dgrad)", 2.0 * n * h * w * cout * cin * ksize * ksize):
+        _call("irfd_conv_gemm", x.data_ptr(), n, h, w, cin, wk.data_ptr(), cout, ksize, out.data_ptr(), _ptr(out2),
+              mode, _ptr(bias), _ptr(nw), _ptr(noise), _ptr(sp1), _ptr(s1), _ptr(ssum), _ptr(ssq), force_block_n,
+              _stream())
     if mode == EPI_STATS:
         return out, ssum, ssq
     if mode == EPI_STYLE:
@@ -113,8 +155,9 @@ def conv_wgrad(x, dy, ksize, dw=None, beta=0.0, reduce_cin=0, reduce_taps=0, out
     _chk(dw, F32, "dw")
     need = lib.irfd_wgrad_workspace_bytes(n, h, w, cin, cout, ksize)
     ws = workspace(need, x.device)
-    _call("irfd_conv_wgrad", x.data_ptr(), dy.data_ptr(), n, h, w, cin, cout, ksize, dw.data_ptr(), beta, reduce_cin,
-          reduce_taps, ws.data_ptr(), ws.numel(), _stream(), launches=2)
+    with _timed("wgrad_gemm_kernel (tcgen05 split-K + reduce)", 2.0 * n * h * w * cout * cin * ksize * ksize):
+        _call("irfd_conv_wgrad", x.data_ptr(), dy.data_ptr(), n, h, w, cin, cout, ksize, dw.data_ptr(), beta,
+              reduce_cin, reduce_taps, ws.data_ptr(), ws.numel(), _stream(), launches=2)
     return dw
 
 
@@ -148,6 +191,11 @@ def bn_finalize(ssum, ssq, count, eps, momentum, running_mean=None, running_var=
     return mean, rstd
 
 
+def bn_running_update(mean, rstd, eps, count, momentum, running_mean, running_var):
+    _call("irfd_bn_running_update", mean.data_ptr(), rstd.data_ptr(), eps, int(count), momentum,
+          running_mean.data_ptr(), running_var.data_ptr(), mean.numel(), _stream())
+
+
 def bn_eval_rstd(running_var, eps):
     rstd = torch.empty_like(running_var)
     _call("irfd_bn_eval_rstd", running_var.data_ptr(), eps, rstd.data_ptr(), running_var.numel(), _stream())
@@ -168,7 +216,7 @@ def bn_apply(z, mean, rstd, gamma, beta, res=None, bn2=None, relu=True):
     return out
 
 
-def bn_backward(g1, g2, act, z, mean, rstd, gamma, want_g_out=False):
+def bn_backward(g1, g2, act, z, mean, rstd, gamma, want_g_out=False, batch_stats=True):
     """Returns dz (bf16), dgamma, dbeta (fp32) [, masked g (bf16)]."""
     lib = _lib.load()
     c = z.shape[-1]
@@ -179,7 +227,8 @@ def bn_backward(g1, g2, act, z, mean, rstd, gamma, want_g_out=False):
     dbeta = torch.empty(c, dtype=F32, device=z.device)
     ws = workspace(lib.irfd_bn_bwd_workspace_bytes(rows, c), z.device)
     _call("irfd_bn_backward", g1.data_ptr(), _ptr(g2), _ptr(act), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-          gamma.data_ptr(), dz.data_ptr(), _ptr(g_out), dgamma.data_ptr(), dbeta.data_ptr(), 0.0, rows, c,
+          gamma.data_ptr(), dz.data_ptr(), _ptr(g_out), dgamma.data_ptr(), dbeta.data_ptr(), 0.0,
+          1 if batch_stats else 0, rows, c,
           ws.data_ptr(), ws.numel(), _stream(), launches=3)
     if want_g_out:
         return dz, dgamma, dbeta, g_out
@@ -234,10 +283,11 @@ def maxpool_fwd(a: torch.Tensor):
     return out, arg
 
 
-def maxpool_bwd(dout: torch.Tensor, arg: torch.Tensor) -> torch.Tensor:
+def maxpool_bwd(dout: torch.Tensor, arg: torch.Tensor, dout2: Optional[torch.Tensor] = None) -> torch.Tensor:
     n, h2, w2, c = dout.shape
     dx = torch.empty((n, h2 * 2, w2 * 2, c), dtype=BF16, device=dout.device)
-    _call("irfd_maxpool_bwd", dout.data_ptr(), arg.data_ptr(), dx.data_ptr(), n, h2 * 2, w2 * 2, c, _stream())
+    _call("irfd_maxpool_bwd", dout.data_ptr(), _ptr(dout2), arg.data_ptr(), dx.data_ptr(), n, h2 * 2, w2 * 2, c,
+          _stream())
     return dx
 
 
@@ -365,8 +415,11 @@ def linear_bwd(dz, x, w, wmul=1.0, bmul=1.0, need_dx=True, dx=None, dx_beta=0.0,
         dx_beta = 0.0
     dw = torch.empty((n, k), dtype=F32, device=dev) if need_dw else None
     db = torch.empty(n, dtype=F32, device=dev) if (need_dw and has_bias) else None
-    _call("irfd_linear_bwd", dz.data_ptr(), _ptr(x), w.data_ptr(), _ptr(dx) if need_dx else None, dx_beta, _ptr(dw),
-          _ptr(db), 0.0, b, n, k, wmul, bmul, _stream(), launches=int(need_dx) + int(need_dw))
+    for r0 in range(0, b, 64):  # the kernels keep one accumulator per batch row in registers (<= 64 rows per launch)
+        r1 = min(b, r0 + 64)
+        _call("irfd_linear_bwd", dz[r0:r1].data_ptr(), _ptr(x[r0:r1]) if x is not None else None, w.data_ptr(),
+              dx[r0:r1].data_ptr() if need_dx else None, dx_beta, _ptr(dw), _ptr(db), 0.0 if r0 == 0 else 1.0, r1 - r0,
+              n, k, wmul, bmul, _stream(), launches=int(need_dx) + int(need_dw))
     return dx, dw, db
 
 

@@ -309,7 +309,7 @@ def test_to_rgb(cuda_device, b, h, w, c):
 
 
 # ------------------------------------------------------------------------------------------------------------ dense
-@pytest.mark.parametrize("b,n,k", [(2, 512, 6144), (32, 512, 512), (64, 128, 512), (5, 8, 2048)])
+@pytest.mark.parametrize("b,n,k", [(2, 512, 6144), (32, 512, 512), (64, 128, 512), (5, 8, 2048), (130, 64, 512)])
 def test_linear(cuda_device, b, n, k):
     from speak_hack_b200 import ops
 

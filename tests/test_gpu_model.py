@@ -1,0 +1,335 @@
+"""-m gpu: product modules (speak_hack_b200, CUDA) against the CPU oracle (oracle/irfd_oracle.py) and golden vectors.
+
+Tolerances (north_star): bf16 paths rel-L2 <= 1e-2 where the reference's conditioning allows it; the cross-batch swap
+bit-exact.  SURVEY §7 documents that the random-init TRAIN-mode encoder stack amplifies any bf16 rounding to ~7.5e-2
+on features regardless of kernel quality (PyTorch's own bf16 autocast: 9e-2), so end-to-end train-mode checks use the
+stated looser bounds and every measured value is printed.
+"""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+pytestmark = pytest.mark.gpu
+
+
+def _cpu_noise_bank(seed):
+    """Deterministic noise planes shared by oracle (CPU) and product (GPU): keyed by call order."""
+    g = torch.Generator().manual_seed(seed)
+    bank = []
+
+    def draw(b, h, w):
+        t = torch.randn(b, 1, h, w, generator=g)
+        bank.append(t)
+        return t
+
+    return draw, bank
+
+
+def _install_noise(oracle_gd, product_gd, seed, dev):
+    draw, bank = _cpu_noise_bank(seed)
+    oracle_gd.noise_fn = lambda b, h, w, device, dtype: draw(b, h, w)
+    it = {"i": 0}
+
+    def replay(b, h, w, device):
+        t = bank[it["i"]]
+        it["i"] += 1
+        assert t.shape == (b, 1, h, w)
+        return t.to(device)
+
+    product_gd.synthesis.noise_fn = replay
+    return it
+
+
+@pytest.fixture(scope="module")
+def nets(cuda_device):
+    import irfd_oracle as O
+    import speak_hack_b200 as P
+
+    torch.manual_seed(O.WEIGHT_SEED)
+    ref = O.IRFDRef()
+    O.perturb_noise_weights(ref.Gd)
+    prod = P.IRFD()
+    missing = prod.load_state_dict(ref.state_dict(), strict=True)
+    prod = prod.to(cuda_device)
+    return ref, prod
+
+
+def test_generator_forward_eval(cuda_device, nets):
+    import irfd_oracle as O
+
+    ref, prod = nets
+    ref.eval(), prod.eval()
+    feat = torch.randn(2, 6144, generator=torch.Generator().manual_seed(O.DATA_SEED)).abs() * 0.5
+    it = _install_noise(ref.Gd, prod.Gd, 21, cuda_device)
+    with torch.no_grad():
+        img_ref = ref.Gd(feat)
+        img = prod.Gd(feat.to(cuda_device))
+    torch.cuda.synchronize()
+    assert it["i"] == 13
+    err = O.rel_l2(img, img_ref)
+    print(f"[parity] Gd eval forward rel-L2 = {err:.3e} (|img| max {img_ref.abs().max():.3e})")
+    assert img.shape == (2, 3, 256, 256) and img.dtype == torch.float32
+    # 13 un-normalised layers: an ideal bf16-operand / fp32-storage kernel sits at 6.6e-3..8e-3; bf16
+    # activation storage adds one more rounding per upsample.  Per-kernel parity (test_gpu_conv_gemm) is < 4e-3.
+    assert err < 1.5e-2
+
+
+def test_generator_backward_train(cuda_device, nets):
+    import irfd_oracle as O
+
+    ref, prod = nets
+    ref.train(), prod.train()
+    ref.Gd.style_mixing_prob = 0.0      # isolate numerics (SURVEY §8(c) oracle hygiene)
+    prod.Gd.style_mixing_prob = 0.0
+    feat = torch.randn(2, 6144, generator=torch.Generator().manual_seed(3)).abs() * 0.5
+    target = torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(4)) * 2 - 1
+    _install_noise(ref.Gd, prod.Gd, 22, cuda_device)
+    fr = feat.clone().requires_grad_(True)
+    ref.zero_grad()
+    loss_ref = torch.nn.functional.mse_loss(target, ref.Gd(fr))
+    loss_ref.backward()
+    import speak_hack_b200 as P
+
+    fp = feat.to(cuda_device).requires_grad_(True)
+    prod.zero_grad()
+    loss = P.mse_loss(target.to(cuda_device), prod.Gd(fp))
+    loss.backward()
+    torch.cuda.synchronize()
+    print(f"[parity] Gd train loss ref {loss_ref.item():.6e} got {loss.item():.6e}")
+    assert abs(loss.item() - loss_ref.item()) <= 2e-2 * abs(loss_ref.item())
+    worst = ("", 0.0)
+    pr = dict(prod.Gd.named_parameters())
+    for name, p in ref.Gd.named_parameters():
+        assert pr[name].grad is not None, name
+        e = O.rel_l2(pr[name].grad, p.grad)
+        if e > worst[1]:
+            worst = (name, e)
+        # 13 layers of bf16 dz/dy roundings on the way back; noise-weight grads are sums of products with zero-mean
+        # noise (cancellation), the least well-conditioned reductions on this path
+        assert e < (0.1 if "noise" in name else 5e-2), (name, e)
+    ef = O.rel_l2(fp.grad, fr.grad)
+    print(f"[parity] Gd backward: worst param-grad rel-L2 {worst[1]:.3e} ({worst[0]}); d/dfeatures {ef:.3e}")
+    assert ef < 5e-2
+    ref.Gd.style_mixing_prob = 0.9
+    prod.Gd.style_mixing_prob = 0.9
+
+
+def test_encoder_eval_and_train_forward(cuda_device, nets):
+    import irfd_oracle as O
+
+    ref, prod = nets
+    x, _ = O.synthetic_pair(4)
+    ref.eval(), prod.eval()
+    with torch.no_grad():
+        f_ref = ref.Ei(x)
+        f = prod.Ei(x.to(cuda_device))
+    torch.cuda.synchronize()
+    e_eval = O.rel_l2(f, f_ref)
+    print(f"[parity] encoder eval (fresh BN) features rel-L2 = {e_eval:.3e}")
+    assert f.shape == (4, 2048, 1, 1)
+    assert e_eval < 1e-2
+    ref.train(), prod.train()
+    sd0 = {k: v.clone() for k, v in ref.Ee.state_dict().items()}
+    with torch.no_grad():
+        f_ref = ref.Ee(x)
+        f = prod.Ee(x.to(cuda_device))
+    torch.cuda.synchronize()
+    e_train = O.rel_l2(f, f_ref)
+    print(f"[parity] encoder train-mode features rel-L2 = {e_train:.3e} (ideal bf16 kernel: 7.5e-2, SURVEY §7)")
+    assert e_train < 0.2
+    # BN running buffers after one train-mode forward (first layers are well conditioned)
+    ps, rs = prod.Ee.state_dict(), ref.Ee.state_dict()
+    assert O.rel_l2(ps["1.running_mean"], rs["1.running_mean"]) < 1e-2
+    assert O.rel_l2(ps["1.running_var"], rs["1.running_var"]) < 1e-2
+    assert int(ps["1.num_batches_tracked"]) == int(rs["1.num_batches_tracked"])
+    assert O.rel_l2(ps["4.0.bn1.running_var"], rs["4.0.bn1.running_var"]) < 2e-2
+
+
+def test_encoder_backward_eval_end_to_end(cuda_device, nets):
+    """Well-conditioned regime (eval-mode BN, fresh running stats): every gradient of the encoder against the oracle.
+    This exercises the whole wiring: residual adds, downsample branches, stride-2 paths, maxpool, stem."""
+    import irfd_oracle as O
+    import speak_hack_b200 as P
+
+    ref, prod = nets
+    ref.eval(), prod.eval()
+    x, _ = O.synthetic_pair(2, seed=9)
+    tgt = torch.randn(2, 2048, 1, 1, generator=torch.Generator().manual_seed(10)) * 100
+    ref.Ep.zero_grad()
+    lr = torch.nn.functional.mse_loss(ref.Ep(x.clone().requires_grad_(True)), tgt)
+    lr.backward()
+    prod.Ep.zero_grad()
+    lp = P.mse_loss(prod.Ep(x.to(cuda_device).requires_grad_(True)), tgt.to(cuda_device))
+    lp.backward()
+    torch.cuda.synchronize()
+    pr = dict(prod.Ep.named_parameters())
+    errs = {n: O.rel_l2(pr[n].grad, p.grad) for n, p in ref.Ep.named_parameters()}
+    worst = max(errs, key=errs.get)
+    print(f"[parity] encoder eval-mode backward: loss ref {lr.item():.5e} got {lp.item():.5e}; "
+          f"worst grad rel-L2 {errs[worst]:.3e} ({worst}); median {sorted(errs.values())[len(errs) // 2]:.3e}")
+    assert abs(lp.item() - lr.item()) <= 3e-2 * abs(lr.item())
+    assert errs[worst] < 0.12, (worst, errs[worst])          # stem weight: 53 layers of bf16 backward behind it
+    assert sorted(errs.values())[len(errs) // 2] < 4e-2
+
+
+def test_encoder_backward_train_in_context(cuda_device):
+    """Train-mode backward: a random-init train-mode ResNet amplifies bf16 rounding to O(1) inside layer4,
+    so instead of an end-to-end comparison every GEMM / BN-backward call made by the real backward pass is checked
+    against torch on the SAME inputs, and the last BN's gradients (least compounding) against a torch fp32 run."""
+    import torch.nn.functional as F
+    from torchvision.models import resnet50
+
+    import irfd_oracle as O
+    import speak_hack_b200 as P
+    from speak_hack_b200 import ops
+
+    dev = cuda_device
+    log = []
+    orig = (ops.conv_wgrad, ops.conv_gemm, ops.bn_backward)
+
+    def rel(a, b):
+        return O.rel_l2(a, b)
+
+    def wgrad(x, dy, ksize, dw=None, beta=0.0, reduce_cin=0, reduce_taps=0, out_shape=None):
+        r = orig[0](x, dy, ksize, dw, beta, reduce_cin, reduce_taps, out_shape)
+        cin, cout = x.shape[-1], dy.shape[-1]
+        if ksize == 1:
+            full = dy.float().reshape(-1, cout).t() @ x.float().reshape(-1, cin)
+            if reduce_cin:
+                full = full[:, : reduce_cin * reduce_taps].reshape(cout, reduce_taps, reduce_cin).permute(0, 2, 1)
+                got = r.reshape(cout, reduce_cin, reduce_taps)
+            else:
+                got = r.reshape(full.shape)
+        else:
+            with torch.enable_grad():
+                wt = torch.zeros(cout, cin, 3, 3, device=dev, requires_grad=True)
+                (full,) = torch.autograd.grad(F.conv2d(x.float().permute(0, 3, 1, 2), wt, padding=1), wt,
+                                              dy.float().permute(0, 3, 1, 2))
+            got = r
+        log.append(("wgrad", tuple(x.shape), cout, ksize, rel(got, full)))
+        return r
+
+    def gemm(x, wk, ksize, mode=0, **kw):
+        r = orig[1](x, wk, ksize, mode, **kw)
+        if mode == 0:
+            cin, cout = x.shape[-1], wk.shape[0]
+            wt = wk.float().reshape(cout, ksize, ksize, cin).permute(0, 3, 1, 2)
+            full = F.conv2d(x.float().permute(0, 3, 1, 2), wt, padding=ksize // 2).permute(0, 2, 3, 1)
+            log.append(("dgrad", tuple(x.shape), cout, ksize, rel(r.float(), full)))
+        return r
+
+    def bnb(g1, g2, act, z, mean, rstd, gamma, want_g_out=False, batch_stats=True):
+        r = orig[2](g1, g2, act, z, mean, rstd, gamma, want_g_out, batch_stats)
+        c = z.shape[-1]
+        g = g1.float() + (g2.float() if g2 is not None else 0)
+        if act is not None:
+            g = g * (act.float() > 0)
+        g = g.reshape(-1, c)
+        xh = (z.float().reshape(-1, c) - mean) * rstd
+        full = gamma * rstd * (g - g.mean(0) - xh * (g * xh).mean(0))
+        log.append(("bn_bwd", tuple(z.shape), c, 0, rel(r[0].float().reshape(-1, c), full)))
+        return r
+
+    torch.manual_seed(0)
+    ref = torch.nn.Sequential(*list(resnet50(weights=None).children())[:-1]).to(dev).train()
+    enc = P.ResNet50Encoder()
+    enc.load_state_dict(ref.state_dict())
+    enc = enc.to(dev).train()
+    x, _ = O.synthetic_pair(4, seed=9)
+    tgt = torch.randn(4, 2048, 1, 1, generator=torch.Generator().manual_seed(10)).to(dev)
+    lr = F.mse_loss(ref(x.to(dev).requires_grad_(True)), tgt)
+    lr.backward()
+    ops.conv_wgrad, ops.conv_gemm, ops.bn_backward = wgrad, gemm, bnb
+    try:
+        lp = P.mse_loss(enc(x.to(dev).requires_grad_(True)), tgt)
+        lp.backward()
+        torch.cuda.synchronize()
+    finally:
+        ops.conv_wgrad, ops.conv_gemm, ops.bn_backward = orig
+    kinds = {k: max(r[4] for r in log if r[0] == k) for k in ("wgrad", "dgrad", "bn_bwd")}
+    counts = {k: sum(1 for r in log if r[0] == k) for k in kinds}
+    print(f"[parity] encoder train backward, in-context kernel checks: {counts} worst rel-L2 {kinds}")
+    assert counts["wgrad"] == 53 and counts["bn_bwd"] == 53 and counts["dgrad"] == 52  # incl. 3 dcol GEMMs; no stem dgrad
+    assert kinds["wgrad"] < 1e-4 and kinds["dgrad"] < 4e-3 and kinds["bn_bwd"] < 6e-3
+    pr, rr = dict(enc.named_parameters()), dict(ref.named_parameters())
+    e_b, e_w = O.rel_l2(pr["7.2.bn3.bias"].grad, rr["7.2.bn3.bias"].grad), O.rel_l2(pr["7.2.bn3.weight"].grad,
+                                                                                     rr["7.2.bn3.weight"].grad)
+    print(f"[parity] last-BN grads vs torch fp32: dbeta {e_b:.3e}, dgamma {e_w:.3e}; loss {lr.item():.5e} / {lp.item():.5e}")
+    assert e_b < 0.15 and e_w < 0.3
+    assert all(torch.isfinite(p.grad).all() for p in enc.parameters())
+
+
+def test_irfd_forward_swap_bit_exact_and_losses(cuda_device, nets):
+    import irfd_oracle as O
+    import speak_hack_b200 as P
+
+    ref, prod = nets
+    ref.eval(), prod.eval()
+    x_s, x_t = O.synthetic_pair(2)
+    xs, xt = x_s.to(cuda_device), x_t.to(cuda_device)
+    from speak_hack_b200.generator import _randn_noise
+
+    prod.Gd.synthesis.noise_fn = _randn_noise
+    for seed in (11, 12, 13, 14):  # different swap draws
+        torch.manual_seed(seed)
+        expect_swap = torch.randint(0, 3, (1,)).item()
+        torch.manual_seed(seed)
+        with torch.no_grad():
+            out = prod(xs, xt)
+            direct = {"i": (prod.Ei(xs), prod.Ei(xt)), "e": (prod.Ee(xs), prod.Ee(xt)), "p": (prod.Ep(xs), prod.Ep(xt))}
+        torch.cuda.synchronize()
+        fi_s, fe_s, fp_s, fi_t, fe_t, fp_t = out[2:8]
+        got = {"i": (fi_s, fi_t), "e": (fe_s, fe_t), "p": (fp_s, fp_t)}
+        for idx, key in enumerate("iep"):
+            a, b = direct[key]
+            if idx == expect_swap:
+                a, b = b, a
+            assert torch.equal(got[key][0], a) and torch.equal(got[key][1], b), f"swap not bit-exact ({key})"
+    # numeric parity of the whole forward (eval, fresh BN: SURVEY Q6 magnitudes ~1e18, compare in float64);
+    # earlier train-mode tests moved the BN running buffers of both nets slightly differently: re-sync them
+    prod.load_state_dict(ref.state_dict())
+    torch.manual_seed(O.FORWARD_SEED)
+    _install_noise(ref.Gd, prod.Gd, 24, cuda_device)
+    with torch.no_grad():
+        o_ref = ref(x_s, x_t)
+    torch.manual_seed(O.FORWARD_SEED)
+    with torch.no_grad():
+        o = prod(xs, xt)
+    torch.cuda.synchronize()
+    e_feat = max(O.rel_l2(a, b) for a, b in zip(o[2:8], o_ref[2:8]))
+    e_img = max(O.rel_l2(o[0], o_ref[0]), O.rel_l2(o[1], o_ref[1]))
+    print(f"[parity] IRFD eval forward: features {e_feat:.3e}, images {e_img:.3e}")
+    # features: 53 conv+BN layers with bf16 storage of both the raw conv output and the normalised activation.
+    # images: the un-normalised generator multiplies 13 (style+1) factors, so a relative feature error d shows up as
+    # ~10 d in the image (conditioning of the reference model; the generator alone on exact features is ~1e-2).
+    assert e_feat < 2e-2
+    assert e_img < 0.25
+    assert torch.allclose(o[8].cpu(), o_ref[8], atol=2e-2) and torch.allclose(o[9].cpu(), o_ref[9], atol=2e-2)
+    l_id = P.mse_loss(o[2], o[5])
+    l_id_ref, _ = O.irfd_losses(x_s, x_t, o_ref)
+    assert abs(l_id.item() - l_id_ref.item()) <= 2e-2 * abs(l_id_ref.item()) + 1e-12
+
+
+def test_golden_eval_features(cuda_device):
+    """Product, constructed from the reference's seed, against vectors produced by the UNMODIFIED reference."""
+    import irfd_oracle as O
+    import speak_hack_b200 as P
+
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "irfd_eval_b2.pt"), weights_only=False)
+    torch.manual_seed(O.WEIGHT_SEED)
+    net = P.IRFD().to(cuda_device).eval()
+    x_s, x_t = O.synthetic_pair(2)
+    torch.manual_seed(O.FORWARD_SEED)
+    with torch.no_grad():
+        out = net(x_s.to(cuda_device), x_t.to(cuda_device))
+    torch.cuda.synchronize()
+    errs = [O.rel_l2(a, b) for a, b in zip(out[2:8], gold["feat"])]
+    e_img = O.rel_l2(out[0][..., ::8, ::8], gold["img"][0]["sub"])
+    print(f"[parity] golden (reference) eval: features max {max(errs):.3e}, image {e_img:.3e}")
+    assert max(errs) < 2e-2
+    assert e_img < 0.25
