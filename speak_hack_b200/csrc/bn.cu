@@ -11,18 +11,28 @@ namespace irfd {
 // Statistics finalize: per-tile partial sums (from the conv epilogue) -> mean / rstd, running-buffer update.
 // One block per 32 channels, 8 tile-lanes; accumulation in double.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int tiles, int C,
-                                   double count, float eps, float momentum, float* __restrict__ mean,
-                                   float* __restrict__ rstd, float* running_mean, float* running_var,
-                                   int running_updates) {
-  __shared__ double s_sum[8][32];
-  __shared__ double s_sq[8][32];
+__global__ void __launch_bounds__(1024)
+bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int tiles, int C, double count,
+                   float eps, float momentum, float* __restrict__ mean, float* __restrict__ rstd, float* running_mean,
+                   float* running_var, int running_updates) {
+  // block = 32 channels (lanes, coalesced 128-byte reads) x 32 warps striding over the tiles
+  __shared__ double s_sum[32][33];
+  __shared__ double s_sq[32][33];
   const int cl = threadIdx.x & 31;
   const int tl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   double a = 0.0, b = 0.0;
   if (c < C) {
-    for (int t = tl; t < tiles; t += 8) {
+    int t = tl;
+    for (; t + 96 < tiles; t += 128) {  // 4 independent loads in flight per stream
+      const float a0 = psum[(size_t)t * C + c], a1 = psum[(size_t)(t + 32) * C + c];
+      const float a2 = psum[(size_t)(t + 64) * C + c], a3 = psum[(size_t)(t + 96) * C + c];
+      const float b0 = psq[(size_t)t * C + c], b1 = psq[(size_t)(t + 32) * C + c];
+      const float b2 = psq[(size_t)(t + 64) * C + c], b3 = psq[(size_t)(t + 96) * C + c];
+      a += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+      b += ((double)b0 + (double)b1) + ((double)b2 + (double)b3);
+    }
+    for (; t < tiles; t += 32) {
       a += (double)psum[(size_t)t * C + c];
       b += (double)psq[(size_t)t * C + c];
     }
@@ -31,7 +41,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* 
   s_sq[tl][cl] = b;
   __syncthreads();
   if (tl == 0 && c < C) {
-    for (int i = 1; i < 8; ++i) {
+    for (int i = 1; i < 32; ++i) {
       a += s_sum[i][cl];
       b += s_sq[i][cl];
     }
@@ -185,15 +195,29 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
   block_reduce_rows<2>(rv, C, acc, red_smem, partial + (size_t)blockIdx.x * 2 * C, (size_t)C);
 }
 
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, double count,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float beta_acc,
-                                       float* __restrict__ c1, float* __restrict__ c2, int batch_stats) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(1024)
+bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, double count, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta, float beta_acc, float* __restrict__ c1, float* __restrict__ c2,
+                       int batch_stats) {
+  __shared__ double s0s[32][33];
+  __shared__ double s1s[32][33];
+  const int cl = threadIdx.x & 31;
+  const int tl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double s0 = 0.0, s1 = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    s0 += (double)partial[((size_t)b * 2 + 0) * C + c];
-    s1 += (double)partial[((size_t)b * 2 + 1) * C + c];
+  if (c < C) {
+    for (int b = tl; b < nblk; b += 32) {
+      s0 += (double)partial[((size_t)b * 2 + 0) * C + c];
+      s1 += (double)partial[((size_t)b * 2 + 1) * C + c];
+    }
+  }
+  s0s[tl][cl] = s0;
+  s1s[tl][cl] = s1;
+  __syncthreads();
+  if (tl != 0 || c >= C) return;
+  for (int i = 1; i < 32; ++i) {
+    s0 += s0s[i][cl];
+    s1 += s1s[i][cl];
   }
   dbeta[c] = (beta_acc != 0.f ? beta_acc * dbeta[c] : 0.f) + (float)s0;
   dgamma[c] = (beta_acc != 0.f ? beta_acc * dgamma[c] : 0.f) + (float)s1;
@@ -260,7 +284,7 @@ extern "C" int irfd_bn_finalize(const float* psum, const float* psq, int tiles, 
                                 float momentum, float* mean, float* rstd, float* running_mean, float* running_var,
                                 int running_updates, cudaStream_t stream) {
   IRFD_CHECK_ARG(psum && psq && mean && rstd && tiles > 0 && c > 0 && count > 0, "bn_finalize: bad argument");
-  bn_finalize_kernel<<<(c + 31) / 32, 256, 0, stream>>>(psum, psq, tiles, c, (double)count, eps, momentum, mean, rstd,
+  bn_finalize_kernel<<<(c + 31) / 32, 1024, 0, stream>>>(psum, psq, tiles, c, (double)count, eps, momentum, mean, rstd,
                                                          running_mean, running_var, running_updates);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
@@ -331,7 +355,7 @@ extern "C" int irfd_bn_backward(const void* g1, const void* g2, const void* act,
   auto Z = reinterpret_cast<const __nv_bfloat16*>(z);
   bn_bwd_reduce_kernel<<<nblk, kRvThreads, smem, stream>>>(G1, G2, A, Z, mean, rstd, partial, rows, c, rpb);
   IRFD_CHECK_LAUNCH();
-  bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(partial, nblk, c, (double)rows, dgamma, dbeta, grad_beta,
+  bn_bwd_finalize_kernel<<<(c + 31) / 32, 1024, 0, stream>>>(partial, nblk, c, (double)rows, dgamma, dbeta, grad_beta,
                                                                c1, c2, batch_stats);
   IRFD_CHECK_LAUNCH();
   bn_bwd_apply_kernel<<<nblk, kRvThreads, 0, stream>>>(G1, G2, A, Z, mean, rstd, gamma, c1, c2,

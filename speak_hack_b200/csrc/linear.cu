@@ -51,35 +51,39 @@ __global__ void lrelu_bwd_kernel(const float* __restrict__ dy, const float* __re
   if (i < n) dz[i] = dy[i] * (y[i] > 0.f ? 1.f : 0.2f);
 }
 
-// dx[b,k] = beta*dx[b,k] + wmul * sum_n dz[b,n] * W[n,k] ; thread per k, all rows in registers, dz staged in smem
-__global__ void linear_dx_kernel(const float* __restrict__ dz, const float* __restrict__ W, float* __restrict__ dx,
-                                 int B, int N, int K, float wmul, float beta) {
-  extern __shared__ float sdz[];  // [32 n][B]
+// dx[b,k] = beta*dx[b,k] + wmul * sum_n dz[b,n] * W[n,k]
+// grid (K/128, B/8): thread per k, 8 batch rows in registers, dz staged through smem 32 n at a time.
+constexpr int kDxRows = 8;
+__global__ void __launch_bounds__(128)
+linear_dx_kernel(const float* __restrict__ dz, const float* __restrict__ W, float* __restrict__ dx, int B, int N,
+                 int K, float wmul, float beta) {
+  __shared__ float sdz[32 * kDxRows];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  float acc[kMaxRows];
+  const int b0 = blockIdx.y * kDxRows;
+  float acc[kDxRows];
 #pragma unroll
-  for (int r = 0; r < kMaxRows; ++r) acc[r] = 0.f;
+  for (int r = 0; r < kDxRows; ++r) acc[r] = 0.f;
   for (int n0 = 0; n0 < N; n0 += 32) {
     __syncthreads();
-    for (int i = threadIdx.x; i < 32 * B; i += blockDim.x) {
-      const int nn = i / B, b = i % B;
-      sdz[i] = (n0 + nn < N) ? dz[(size_t)b * N + n0 + nn] : 0.f;
+    for (int i = threadIdx.x; i < 32 * kDxRows; i += blockDim.x) {
+      const int nn = i / kDxRows, r = i % kDxRows;
+      sdz[i] = (n0 + nn < N && b0 + r < B) ? dz[(size_t)(b0 + r) * N + n0 + nn] : 0.f;
     }
     __syncthreads();
     if (k < K) {
-      for (int nn = 0; nn < 32 && n0 + nn < N; ++nn) {
-        const float wv = W[(size_t)(n0 + nn) * K + k];
+#pragma unroll 8
+      for (int nn = 0; nn < 32; ++nn) {
+        const float wv = (n0 + nn < N) ? W[(size_t)(n0 + nn) * K + k] : 0.f;
 #pragma unroll
-        for (int r = 0; r < kMaxRows; ++r)
-          if (r < B) acc[r] += sdz[nn * B + r] * wv;
+        for (int r = 0; r < kDxRows; ++r) acc[r] += sdz[nn * kDxRows + r] * wv;
       }
     }
   }
   if (k < K) {
 #pragma unroll
-    for (int r = 0; r < kMaxRows; ++r)
-      if (r < B) {
-        float* d = dx + (size_t)r * K + k;
+    for (int r = 0; r < kDxRows; ++r)
+      if (b0 + r < B) {
+        float* d = dx + (size_t)(b0 + r) * K + k;
         *d = (beta != 0.f ? beta * (*d) : 0.f) + wmul * acc[r];
       }
   }
@@ -165,7 +169,8 @@ extern "C" int irfd_linear_bwd(const float* dz, const float* x, const float* w, 
   IRFD_CHECK_ARG(dz && b > 0 && b <= kMaxRows && n > 0 && k > 0, "linear_bwd: bad argument (batch <= 64)");
   if (dx != nullptr) {
     IRFD_CHECK_ARG(w != nullptr, "linear_bwd: dx needs w");
-    linear_dx_kernel<<<(k + 127) / 128, 128, 32 * b * sizeof(float), stream>>>(dz, w, dx, b, n, k, wmul, dx_beta);
+    linear_dx_kernel<<<dim3((k + 127) / 128, (b + kDxRows - 1) / kDxRows), 128, 0, stream>>>(dz, w, dx, b, n, k, wmul,
+                                                                                              dx_beta);
     IRFD_CHECK_LAUNCH();
   }
   if (dw != nullptr) {

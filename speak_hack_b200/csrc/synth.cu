@@ -182,28 +182,44 @@ style_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __re
   block_reduce_rows<4>(rv, C, acc, red_smem, partial + ((size_t)b * gridDim.x + blockIdx.x) * 4 * C, (size_t)C);
 }
 
-__global__ void style_bwd_finalize_kernel(const float* __restrict__ partial, int B, int chunks, int C,
-                                          float* __restrict__ ds1, float* __restrict__ dsp1, float* __restrict__ dbias,
-                                          float* __restrict__ dnw) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(1024)
+style_bwd_finalize_kernel(const float* __restrict__ partial, int B, int chunks, int C, float* __restrict__ ds1,
+                          float* __restrict__ dsp1, float* __restrict__ dbias, float* __restrict__ dnw) {
+  // block = 32 channels (lanes) x 32 warps striding over images; per-image sums are final, per-channel ones are
+  // combined across warps through shared memory in a fixed order.
+  __shared__ float sb[32][33];
+  __shared__ float sn[32][33];
+  const int cl = threadIdx.x & 31;
+  const int wl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float tb = 0.f, tn = 0.f;
-  for (int b = 0; b < B; ++b) {
-    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-    for (int k = 0; k < chunks; ++k) {
-      const float* p = partial + ((size_t)b * chunks + k) * 4 * C + c;
-      t0 += p[0];
-      t1 += p[C];
-      t2 += p[2 * C];
-      t3 += p[3 * C];
+  if (c < C) {
+    for (int b = wl; b < B; b += 32) {
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+      for (int k = 0; k < chunks; ++k) {
+        const float* p = partial + ((size_t)b * chunks + k) * 4 * C + c;
+        t0 += p[0];
+        t1 += p[C];
+        t2 += p[2 * C];
+        t3 += p[3 * C];
+      }
+      ds1[(size_t)b * C + c] = t0;
+      dsp1[(size_t)b * C + c] = t1;
+      tb += t2;
+      tn += t3;
     }
-    ds1[(size_t)b * C + c] = t0;
-    dsp1[(size_t)b * C + c] = t1;
-    tb += t2;
-    tn += t3;
   }
-  dbias[c] = tb;
-  dnw[c] = tn;
+  sb[wl][cl] = tb;
+  sn[wl][cl] = tn;
+  __syncthreads();
+  if (wl == 0 && c < C) {
+    for (int i = 1; i < 32; ++i) {
+      tb += sb[i][cl];
+      tn += sn[i][cl];
+    }
+    dbias[c] = tb;
+    dnw[c] = tn;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -365,7 +381,7 @@ extern "C" int irfd_style_bwd(const void* dy, const void* a, const float* noise,
   style_bwd_kernel<<<dim3(chunks, b), kRvThreads, 4 * 2048 * sizeof(float), stream>>>(CBF(dy), CBF(a), noise, sp1,
                                                                                      BF(dz), partial, hw, c, rpb);
   IRFD_CHECK_LAUNCH();
-  style_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(partial, b, chunks, c, ds1, dsp1, dbias, dnw);
+  style_bwd_finalize_kernel<<<(c + 31) / 32, 1024, 0, stream>>>(partial, b, chunks, c, ds1, dsp1, dbias, dnw);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }

@@ -144,11 +144,11 @@ class _SynthesisFn(torch.autograd.Function):
             u = ops.upsample2x_fwd(y)
             n1 = next(ni)
             st1, sp1_1, s1_1 = style(rows_t[2 * i + 1], s1w, s1b, cout)
-            a1, y1 = ops.conv_gemm(u, ops.pack_conv_weight(w1, ops.PACK_FPROP), 3, ops.EPI_STYLE, bias=b1, nw=nw1,
+            a1, y1 = ops.conv_gemm(u, ops.pack_conv_weight(blk.conv1.weight, ops.PACK_FPROP), 3, ops.EPI_STYLE, bias=b1, nw=nw1,
                                    noise=n1, sp1=sp1_1, s1=s1_1)
             n2 = next(ni)
             st2, sp1_2, s1_2 = style(rows_t[2 * i + 2], s2w, s2b, cout)
-            a2, y2 = ops.conv_gemm(y1, ops.pack_conv_weight(w2, ops.PACK_FPROP), 3, ops.EPI_STYLE, bias=b2, nw=nw2,
+            a2, y2 = ops.conv_gemm(y1, ops.pack_conv_weight(blk.conv2.weight, ops.PACK_FPROP), 3, ops.EPI_STYLE, bias=b2, nw=nw2,
                                    noise=n2, sp1=sp1_2, s1=s1_2)
             saved["blocks"].append((u, a1, y1, a2, n1, n2, sp1_1, sp1_2, st1, st2))
             y = y2
@@ -186,11 +186,11 @@ class _SynthesisFn(torch.autograd.Function):
             dz2, ds1_2, dsp1_2, grads[base + 3], grads[base + 5] = ops.style_bwd(dy, a2, n2, sp1_2)
             style_backward(dsp1_2, ds1_2, st2, 2 * i + 2, s2w, base + 8, base + 9)
             grads[base + 2] = ops.conv_wgrad(y1, dz2, 3)
-            dy1 = ops.conv_gemm(dz2, ops.pack_conv_weight(w2, ops.PACK_DGRAD), 3, ops.EPI_PLAIN)
+            dy1 = ops.conv_gemm(dz2, ops.pack_conv_weight(net.layers[i].conv2.weight, ops.PACK_DGRAD), 3, ops.EPI_PLAIN)
             dz1, ds1_1, dsp1_1, grads[base + 1], grads[base + 4] = ops.style_bwd(dy1, a1, n1, sp1_1)
             style_backward(dsp1_1, ds1_1, st1, 2 * i + 1, s1w, base + 6, base + 7)
             grads[base + 0] = ops.conv_wgrad(u, dz1, 3)
-            du = ops.conv_gemm(dz1, ops.pack_conv_weight(w1, ops.PACK_DGRAD), 3, ops.EPI_PLAIN)
+            du = ops.conv_gemm(dz1, ops.pack_conv_weight(net.layers[i].conv1.weight, ops.PACK_DGRAD), 3, ops.EPI_PLAIN)
             dy = ops.upsample2x_bwd(du)
         a0, noise0, sp1_0, st0 = saved["const"]
         dsp1_0, ds1_0, grads[0], grads[1], grads[4] = ops.const_input_bwd(dy, a0, noise0, sp1_0)

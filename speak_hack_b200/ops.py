@@ -5,6 +5,7 @@ Activations are NHWC bf16 tensors; parameters and reductions are fp32.
 """
 from __future__ import annotations
 
+import weakref
 from typing import Optional
 
 import torch
@@ -161,8 +162,32 @@ def conv_wgrad(x, dy, ksize, dw=None, beta=0.0, reduce_cin=0, reduce_taps=0, out
     return dw
 
 
+_pack_cache = {}
+
+
+def invalidate_packed(params) -> None:
+    """Drop cached bf16 repacks of `params` (call after updating them through a raw pointer, e.g. irfd_adam_step)."""
+    ptrs = {p.data_ptr() for p in params}
+    for key in [k for k in _pack_cache if k[0] in ptrs]:
+        del _pack_cache[key]
+
+
 def pack_conv_weight(w: torch.Tensor, mode: int, kpad: int = 0) -> torch.Tensor:
-    """fp32 OIHW parameter -> bf16 GEMM operand (see irfd_pack_conv_weight)."""
+    """fp32 OIHW parameter -> bf16 GEMM operand, cached until the parameter changes (private repack).
+
+    The cache key is (storage pointer, mode); an entry is valid while the tensor's autograd version counter is
+    unchanged, which covers every torch-side in-place update (optimizers, load_state_dict, init)."""
+    key = (w.data_ptr(), mode, kpad, tuple(w.shape))
+    hit = _pack_cache.get(key)
+    # the weakref guards against address reuse: a NEW tensor allocated where a freed one lived must not hit
+    if hit is not None and hit[0] == w._version and hit[2]() is w:
+        return hit[1]
+    packed = _pack_conv_weight(w, mode, kpad)
+    _pack_cache[key] = (w._version, packed, weakref.ref(w))
+    return packed
+
+
+def _pack_conv_weight(w: torch.Tensor, mode: int, kpad: int = 0) -> torch.Tensor:
     _chk(w, F32, "w")
     o, i, kh, kw = w.shape
     taps = kh * kw

@@ -41,6 +41,7 @@ class IRFDTrainer:
         self.encoder_grads = encoder_grads
         self.gd_params = list(model.Gd.parameters())
         self.flat, self.gflat = flatten_parameters(self.gd_params)
+        self._gd_conv_weights = [p for p in self.gd_params if p.dim() == 4 and p.shape[-1] == 3]
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
         self.step_count = 0
@@ -91,5 +92,6 @@ class IRFDTrainer:
                         ops.sumsq(p.grad.reshape(-1), out=total_sumsq, out_beta=1.0)
         ops.adam_step(self.flat, self.gflat, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps,
                       self.step_count, total_sumsq=total_sumsq, max_norm=self.grad_clip or 0.0)
+        ops.invalidate_packed(self._gd_conv_weights)  # Adam wrote through the flat buffer: bf16 repacks are stale
         self.last_losses = (l_identity.detach(), l_recon.detach())
         return loss.detach()
