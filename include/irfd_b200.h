@@ -84,21 +84,24 @@ int irfd_conv_wgrad(const void* x, const void* dy, int n, int h, int w, int cin,
  *                      (batch_stats = 0, eval mode: dz = gamma*rstd*g);
  *                      dgamma/dbeta = grad_beta*old + new;  g_out (optional) receives the masked g (identity shortcut).
  * All activations [rows, c] bf16 (NHWC flattened), c % 8 == 0, c <= 2048.
+ * groups >= 1: statistic groups stacked along the row axis (e.g. the source and the target half of a paired encoder
+ * pass, which the reference normalises in two separate BatchNorm2d calls): tiles/count are per group, rows is the
+ * total, mean/rstd are [groups][c], gamma/beta/dgamma/dbeta are shared, running buffers are updated group by group.
  */
 int irfd_bn_finalize(const float* psum, const float* psq, int tiles, int c, long long count, float eps, float momentum,
                      float* mean, float* rstd, float* running_mean, float* running_var, int running_updates,
-                     irfd_stream_t stream);
+                     int groups, irfd_stream_t stream);
 int irfd_bn_eval_rstd(const float* running_var, float eps, float* rstd, int c, irfd_stream_t stream);
 /* second momentum update from saved batch mean/rstd (what the reference's checkpoint recompute does) */
 int irfd_bn_running_update(const float* mean, const float* rstd, float eps, long long count, float momentum,
                            float* running_mean, float* running_var, int c, irfd_stream_t stream);
 int irfd_bn_apply(const void* z, const float* mean, const float* rstd, const float* gamma, const float* beta,
                   const void* res, const float* mean2, const float* rstd2, const float* gamma2, const float* beta2,
-                  void* out, long long rows, int c, int relu, irfd_stream_t stream);
-long long irfd_bn_bwd_workspace_bytes(long long rows, int c);
+                  void* out, long long rows, int c, int relu, int groups, irfd_stream_t stream);
+long long irfd_bn_bwd_workspace_bytes(long long rows, int c, int groups);
 int irfd_bn_backward(const void* g1, const void* g2, const void* act, const void* z, const float* mean,
                      const float* rstd, const float* gamma, void* dz, void* g_out, float* dgamma, float* dbeta,
-                     float grad_beta, int batch_stats, long long rows, int c, void* workspace,
+                     float grad_beta, int batch_stats, long long rows, int c, int groups, void* workspace,
                      long long workspace_bytes, irfd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
@@ -164,6 +167,26 @@ int irfd_split_style(const float* style, float* sp1, float* s1, int b, int c, ir
 int irfd_merge_style_grad(const float* dsp1, const float* ds1, float* dstyle, int b, int c, irfd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Device-side routing (lets a whole training step be one static CUDA graph).  The random decisions are still drawn
+ * from the CPU generator in the reference's order and uploaded as ctrl (int32): ctrl[0] = swap_type (model.py:98),
+ * ctrl[1+g] = first style-mixed row of generator call g, or L when that call does not mix (styleganv1.py:548-552).
+ *   irfd_style_rows_fwd: rows_t[l][b][k] = coef(l) * (l >= ctrl[ctrl_idx] ? w2 : w)[b][k], coef = psi for l < cutoff
+ *                        (styleganv1.py:536-553);  _bwd: dw = sum_l coef(l)*drows_t[l] (all rows, as in the reference,
+ *                        whose no_grad overwrite keeps routing the mixed rows' gradient into the mapping output).
+ *   irfd_swap_cat_fwd  : S<->T swap of code type ctrl[0] + concat [identity|emotion|pose] -> [b, 3c] (model.py:97-108),
+ *                        pure copies (bit-exact);  _bwd scatters the two gradients back to the six codes.
+ */
+int irfd_style_rows_fwd(const float* w, const float* w2, const int* ctrl, int ctrl_idx, float psi, int cutoff,
+                        float* rows_t, int l, int b, int k, irfd_stream_t stream);
+int irfd_style_rows_bwd(const float* drows_t, float psi, int cutoff, float* dw, int l, int b, int k,
+                        irfd_stream_t stream);
+int irfd_swap_cat_fwd(const float* fi_s, const float* fe_s, const float* fp_s, const float* fi_t, const float* fe_t,
+                      const float* fp_t, const int* ctrl, float* gen_s, float* gen_t, int b, int c,
+                      irfd_stream_t stream);
+int irfd_swap_cat_bwd(const float* dgen_s, const float* dgen_t, const int* ctrl, float* dfi_s, float* dfe_s,
+                      float* dfp_s, float* dfi_t, float* dfe_t, float* dfp_t, int b, int c, irfd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Losses and optimiser: nn.MSELoss means (model.py:356-372), clip_grad_norm_ + Adam (train.py:205-210, 346).
  *   irfd_mse_fwd : out[0] = out_beta*out[0] + mean((a-b)^2)   (double accumulation, fixed order)
  *   irfd_mse_bwd : da = gscale[0]*2(a-b)/n, db = -da (either may be NULL)
@@ -179,7 +202,9 @@ int irfd_mse_bwd(const float* a, const float* b, long long n, const float* gscal
 int irfd_sumsq(const float* g, long long n, float* out, float out_beta, void* workspace, long long workspace_bytes,
                irfd_stream_t stream);
 int irfd_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                   float eps, int step, const float* total_sumsq, float max_norm, irfd_stream_t stream);
+                   float eps, int step, int* step_dev, const float* total_sumsq, float max_norm, irfd_stream_t stream);
+/* step_dev (optional, device int32): when given it is incremented on the device and used instead of `step`, so a
+ * captured CUDA graph replays with the right bias correction. */
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,11 @@ bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq
   const int cl = threadIdx.x & 31;
   const int tl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
+  // statistic group (e.g. the source and the target half of a paired encoder pass): its own tiles, its own mean/rstd
+  psum += (size_t)blockIdx.y * tiles * C;
+  psq += (size_t)blockIdx.y * tiles * C;
+  mean += (size_t)blockIdx.y * C;
+  rstd += (size_t)blockIdx.y * C;
   double a = 0.0, b = 0.0;
   if (c < C) {
     int t = tl;
@@ -99,6 +104,18 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z, BnAffine p1, const __nv_bfl
                 __nv_bfloat16* __restrict__ out, long long rows, int C, int rows_per_blk, int relu) {
   RowVec rv(C);
   if (!rv.active) return;
+  {  // statistic group = blockIdx.y: `rows` rows each, own mean/rstd (gamma/beta shared)
+    const size_t goff = (size_t)blockIdx.y * rows * C;
+    z += goff;
+    out += goff;
+    if (RES_MODE != 0) res += goff;
+    p1.mean += (size_t)blockIdx.y * C;
+    p1.rstd += (size_t)blockIdx.y * C;
+    if (RES_MODE == 2) {
+      p2.mean += (size_t)blockIdx.y * C;
+      p2.rstd += (size_t)blockIdx.y * C;
+    }
+  }
   float sc[8], sh[8], sc2[8], sh2[8];
   {
     float m[8], r[8], g[8], b[8];
@@ -159,6 +176,16 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
                      long long rows, int C, int rows_per_blk) {
   extern __shared__ float red_smem[];
   RowVec rv(C);
+  {
+    const size_t goff = (size_t)blockIdx.y * rows * C;
+    g1 += goff;
+    if (g2 != nullptr) g2 += goff;
+    if (act != nullptr) act += goff;
+    z += goff;
+    mean += (size_t)blockIdx.y * C;
+    rstd += (size_t)blockIdx.y * C;
+    partial += (size_t)blockIdx.y * gridDim.x * 2 * C;
+  }
   float acc[2][8];
 #pragma unroll
   for (int t = 0; t < 8; ++t) acc[0][t] = acc[1][t] = 0.f;
@@ -198,32 +225,42 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
 __global__ void __launch_bounds__(1024)
 bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, double count, float* __restrict__ dgamma,
                        float* __restrict__ dbeta, float beta_acc, float* __restrict__ c1, float* __restrict__ c2,
-                       int batch_stats) {
+                       int batch_stats, int groups) {
   __shared__ double s0s[32][33];
   __shared__ double s1s[32][33];
   const int cl = threadIdx.x & 31;
   const int tl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
-  double s0 = 0.0, s1 = 0.0;
-  if (c < C) {
-    for (int b = tl; b < nblk; b += 32) {
-      s0 += (double)partial[((size_t)b * 2 + 0) * C + c];
-      s1 += (double)partial[((size_t)b * 2 + 1) * C + c];
+  double tot0 = 0.0, tot1 = 0.0;
+  for (int g = 0; g < groups; ++g) {
+    const float* pg = partial + (size_t)g * nblk * 2 * C;
+    double s0 = 0.0, s1 = 0.0;
+    if (c < C) {
+      for (int b = tl; b < nblk; b += 32) {
+        s0 += (double)pg[((size_t)b * 2 + 0) * C + c];
+        s1 += (double)pg[((size_t)b * 2 + 1) * C + c];
+      }
+    }
+    __syncthreads();
+    s0s[tl][cl] = s0;
+    s1s[tl][cl] = s1;
+    __syncthreads();
+    if (tl == 0 && c < C) {
+      for (int i = 1; i < 32; ++i) {
+        s0 += s0s[i][cl];
+        s1 += s1s[i][cl];
+      }
+      // each group normalised with its own statistics; eval mode (constants) has no batch-statistic terms in dz
+      c1[(size_t)g * C + c] = batch_stats ? (float)(s0 / count) : 0.f;
+      c2[(size_t)g * C + c] = batch_stats ? (float)(s1 / count) : 0.f;
+      tot0 += s0;
+      tot1 += s1;
     }
   }
-  s0s[tl][cl] = s0;
-  s1s[tl][cl] = s1;
-  __syncthreads();
-  if (tl != 0 || c >= C) return;
-  for (int i = 1; i < 32; ++i) {
-    s0 += s0s[i][cl];
-    s1 += s1s[i][cl];
+  if (tl == 0 && c < C) {
+    dbeta[c] = (beta_acc != 0.f ? beta_acc * dbeta[c] : 0.f) + (float)tot0;
+    dgamma[c] = (beta_acc != 0.f ? beta_acc * dgamma[c] : 0.f) + (float)tot1;
   }
-  dbeta[c] = (beta_acc != 0.f ? beta_acc * dbeta[c] : 0.f) + (float)s0;
-  dgamma[c] = (beta_acc != 0.f ? beta_acc * dgamma[c] : 0.f) + (float)s1;
-  // eval mode (running statistics are constants): no batch-statistic terms in dz
-  c1[c] = batch_stats ? (float)(s0 / count) : 0.f;
-  c2[c] = batch_stats ? (float)(s1 / count) : 0.f;
 }
 
 __global__ void __launch_bounds__(kRvThreads)
@@ -234,6 +271,19 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* _
                     __nv_bfloat16* __restrict__ g_out, long long rows, int C, int rows_per_blk) {
   RowVec rv(C);
   if (!rv.active) return;
+  {
+    const size_t goff = (size_t)blockIdx.y * rows * C;
+    g1 += goff;
+    if (g2 != nullptr) g2 += goff;
+    if (act != nullptr) act += goff;
+    z += goff;
+    dz += goff;
+    if (g_out != nullptr) g_out += goff;
+    mean += (size_t)blockIdx.y * C;
+    rstd += (size_t)blockIdx.y * C;
+    c1 += (size_t)blockIdx.y * C;
+    c2 += (size_t)blockIdx.y * C;
+  }
   float m[8], rs[8], k0[8], k1[8], k2[8];
   {
     float ga[8], a1[8], a2[8];
@@ -280,13 +330,27 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* _
 
 using namespace irfd;
 
+// tiles / count are PER GROUP; mean/rstd are [groups][c].  With groups > 1 the running buffers are updated group by
+// group in order (pass 0 first), exactly like consecutive nn.BatchNorm2d calls.
 extern "C" int irfd_bn_finalize(const float* psum, const float* psq, int tiles, int c, long long count, float eps,
                                 float momentum, float* mean, float* rstd, float* running_mean, float* running_var,
-                                int running_updates, cudaStream_t stream) {
-  IRFD_CHECK_ARG(psum && psq && mean && rstd && tiles > 0 && c > 0 && count > 0, "bn_finalize: bad argument");
-  bn_finalize_kernel<<<(c + 31) / 32, 1024, 0, stream>>>(psum, psq, tiles, c, (double)count, eps, momentum, mean, rstd,
-                                                         running_mean, running_var, running_updates);
+                                int running_updates, int groups, cudaStream_t stream) {
+  IRFD_CHECK_ARG(psum && psq && mean && rstd && tiles > 0 && c > 0 && count > 0 && groups >= 1,
+                 "bn_finalize: bad argument");
+  const bool inline_update = groups == 1;
+  bn_finalize_kernel<<<dim3((c + 31) / 32, groups), 1024, 0, stream>>>(
+      psum, psq, tiles, c, (double)count, eps, momentum, mean, rstd, inline_update ? running_mean : nullptr,
+      inline_update ? running_var : nullptr, running_updates);
   IRFD_CHECK_LAUNCH();
+  if (!inline_update && running_mean != nullptr) {
+    for (int u = 0; u < running_updates; ++u)
+      for (int g = 0; g < groups; ++g) {
+        bn_running_update_kernel<<<(c + 255) / 256, 256, 0, stream>>>(mean + (size_t)g * c, rstd + (size_t)g * c, eps,
+                                                                       (double)count, momentum, running_mean,
+                                                                       running_var, c);
+        IRFD_CHECK_LAUNCH();
+      }
+  }
   return IRFD_OK;
 }
 
@@ -306,46 +370,54 @@ extern "C" int irfd_bn_eval_rstd(const float* running_var, float eps, float* rst
   return IRFD_OK;
 }
 
+// rows = TOTAL rows (all groups, groups stacked along the row axis); mean/rstd (and mean2/rstd2) are [groups][c].
 extern "C" int irfd_bn_apply(const void* z, const float* mean, const float* rstd, const float* gamma, const float* beta,
                              const void* res, const float* mean2, const float* rstd2, const float* gamma2,
-                             const float* beta2, void* out, long long rows, int c, int relu, cudaStream_t stream) {
+                             const float* beta2, void* out, long long rows, int c, int relu, int groups,
+                             cudaStream_t stream) {
   IRFD_CHECK_ARG(z && mean && rstd && gamma && beta && out, "bn_apply: null pointer");
   IRFD_CHECK_ARG(c % 8 == 0 && c <= 2048 && rows > 0, "bn_apply: C must be a multiple of 8 and <= 2048");
+  IRFD_CHECK_ARG(groups >= 1 && rows % groups == 0, "bn_apply: rows must split evenly into groups");
+  const long long grows = rows / groups;
   int nblk, rpb;
-  plan_row_blocks(rows, c, num_sms(), &nblk, &rpb);
+  plan_row_blocks(grows, c, num_sms(), &nblk, &rpb);
   BnAffine p1{mean, rstd, gamma, beta}, p2{mean2, rstd2, gamma2, beta2};
   auto zz = reinterpret_cast<const __nv_bfloat16*>(z);
   auto rr = reinterpret_cast<const __nv_bfloat16*>(res);
   auto oo = reinterpret_cast<__nv_bfloat16*>(out);
+  const dim3 grid(nblk, groups);
   if (res == nullptr)
-    bn_apply_kernel<0><<<nblk, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, rows, c, rpb, relu);
+    bn_apply_kernel<0><<<grid, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, grows, c, rpb, relu);
   else if (mean2 == nullptr)
-    bn_apply_kernel<1><<<nblk, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, rows, c, rpb, relu);
+    bn_apply_kernel<1><<<grid, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, grows, c, rpb, relu);
   else
-    bn_apply_kernel<2><<<nblk, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, rows, c, rpb, relu);
+    bn_apply_kernel<2><<<grid, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, grows, c, rpb, relu);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }
 
-extern "C" long long irfd_bn_bwd_workspace_bytes(long long rows, int c) {
+extern "C" long long irfd_bn_bwd_workspace_bytes(long long rows, int c, int groups) {
+  if (groups < 1) groups = 1;
   int nblk, rpb;
-  plan_row_blocks(rows, c, num_sms(), &nblk, &rpb);
-  return (long long)(nblk * 2 + 2) * c * 4;
+  plan_row_blocks(rows / groups, c, num_sms(), &nblk, &rpb);
+  return (long long)(nblk * 2 + 2) * groups * c * 4;
 }
 
-// Full BN backward (reduce -> finalize -> apply).  workspace layout: [nblk][2][C] partials, then c1[C], c2[C].
+// Full BN backward (reduce -> finalize -> apply).  workspace: [groups][nblk][2][C] partials, c1[groups][C], c2[...].
 extern "C" int irfd_bn_backward(const void* g1, const void* g2, const void* act, const void* z, const float* mean,
                                 const float* rstd, const float* gamma, void* dz, void* g_out, float* dgamma,
-                                float* dbeta, float grad_beta, int batch_stats, long long rows, int c,
+                                float* dbeta, float grad_beta, int batch_stats, long long rows, int c, int groups,
                                 void* workspace, long long workspace_bytes, cudaStream_t stream) {
   IRFD_CHECK_ARG(g1 && z && mean && rstd && gamma && dz && dgamma && dbeta && workspace, "bn_backward: null pointer");
   IRFD_CHECK_ARG(c % 8 == 0 && c <= 2048 && rows > 0, "bn_backward: C must be a multiple of 8 and <= 2048");
+  IRFD_CHECK_ARG(groups >= 1 && rows % groups == 0, "bn_backward: rows must split evenly into groups");
+  const long long grows = rows / groups;
   int nblk, rpb;
-  plan_row_blocks(rows, c, num_sms(), &nblk, &rpb);
-  IRFD_CHECK_ARG(workspace_bytes >= (long long)(nblk * 2 + 2) * c * 4, "bn_backward: workspace too small");
+  plan_row_blocks(grows, c, num_sms(), &nblk, &rpb);
+  IRFD_CHECK_ARG(workspace_bytes >= (long long)(nblk * 2 + 2) * groups * c * 4, "bn_backward: workspace too small");
   float* partial = reinterpret_cast<float*>(workspace);
-  float* c1 = partial + (size_t)nblk * 2 * c;
-  float* c2 = c1 + c;
+  float* c1 = partial + (size_t)groups * nblk * 2 * c;
+  float* c2 = c1 + (size_t)groups * c;
   int rows_par = kRvThreads / (c / 8);
   if (rows_par < 1) rows_par = 1;
   const size_t smem = (size_t)2 * rows_par * c * sizeof(float);
@@ -353,14 +425,15 @@ extern "C" int irfd_bn_backward(const void* g1, const void* g2, const void* act,
   auto G2 = reinterpret_cast<const __nv_bfloat16*>(g2);
   auto A = reinterpret_cast<const __nv_bfloat16*>(act);
   auto Z = reinterpret_cast<const __nv_bfloat16*>(z);
-  bn_bwd_reduce_kernel<<<nblk, kRvThreads, smem, stream>>>(G1, G2, A, Z, mean, rstd, partial, rows, c, rpb);
+  const dim3 grid(nblk, groups);
+  bn_bwd_reduce_kernel<<<grid, kRvThreads, smem, stream>>>(G1, G2, A, Z, mean, rstd, partial, grows, c, rpb);
   IRFD_CHECK_LAUNCH();
-  bn_bwd_finalize_kernel<<<(c + 31) / 32, 1024, 0, stream>>>(partial, nblk, c, (double)rows, dgamma, dbeta, grad_beta,
-                                                               c1, c2, batch_stats);
+  bn_bwd_finalize_kernel<<<(c + 31) / 32, 1024, 0, stream>>>(partial, nblk, c, (double)grows, dgamma, dbeta, grad_beta,
+                                                               c1, c2, batch_stats, groups);
   IRFD_CHECK_LAUNCH();
-  bn_bwd_apply_kernel<<<nblk, kRvThreads, 0, stream>>>(G1, G2, A, Z, mean, rstd, gamma, c1, c2,
+  bn_bwd_apply_kernel<<<grid, kRvThreads, 0, stream>>>(G1, G2, A, Z, mean, rstd, gamma, c1, c2,
                                                         reinterpret_cast<__nv_bfloat16*>(dz),
-                                                        reinterpret_cast<__nv_bfloat16*>(g_out), rows, c, rpb);
+                                                        reinterpret_cast<__nv_bfloat16*>(g_out), grows, c, rpb);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }

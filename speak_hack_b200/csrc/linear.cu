@@ -52,40 +52,49 @@ __global__ void lrelu_bwd_kernel(const float* __restrict__ dy, const float* __re
 }
 
 // dx[b,k] = beta*dx[b,k] + wmul * sum_n dz[b,n] * W[n,k]
-// grid (K/128, B/8): thread per k, 8 batch rows in registers, dz staged through smem 32 n at a time.
+// grid (K/32, B/8), 8 warps per block: the block owns an [8 rows x 32 k] output tile, each warp reduces one eighth of
+// n (lanes over k: coalesced 128-byte reads of W rows; the 8 x N slice of dz is staged in shared memory), then the
+// eight partial tiles are summed through shared memory in a fixed order.
 constexpr int kDxRows = 8;
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 linear_dx_kernel(const float* __restrict__ dz, const float* __restrict__ W, float* __restrict__ dx, int B, int N,
                  int K, float wmul, float beta) {
-  __shared__ float sdz[32 * kDxRows];
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ float sdz[];  // [kDxRows][N]
+  __shared__ float red[8][kDxRows][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + lane;
   const int b0 = blockIdx.y * kDxRows;
+  for (int i = threadIdx.x; i < kDxRows * N; i += 256) {
+    const int r = i / N, n = i - r * N;
+    sdz[i] = (b0 + r < B) ? dz[(size_t)(b0 + r) * N + n] : 0.f;
+  }
+  __syncthreads();
   float acc[kDxRows];
 #pragma unroll
   for (int r = 0; r < kDxRows; ++r) acc[r] = 0.f;
-  for (int n0 = 0; n0 < N; n0 += 32) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 32 * kDxRows; i += blockDim.x) {
-      const int nn = i / kDxRows, r = i % kDxRows;
-      sdz[i] = (n0 + nn < N && b0 + r < B) ? dz[(size_t)(b0 + r) * N + n0 + nn] : 0.f;
-    }
-    __syncthreads();
-    if (k < K) {
-#pragma unroll 8
-      for (int nn = 0; nn < 32; ++nn) {
-        const float wv = (n0 + nn < N) ? W[(size_t)(n0 + nn) * K + k] : 0.f;
+  const int per = (N + 7) / 8;
+  const int n0 = warp * per;
+  const int n1 = n0 + per < N ? n0 + per : N;
+  if (k < K) {
+#pragma unroll 4
+    for (int n = n0; n < n1; ++n) {
+      const float wv = W[(size_t)n * K + k];
 #pragma unroll
-        for (int r = 0; r < kDxRows; ++r) acc[r] += sdz[nn * kDxRows + r] * wv;
-      }
+      for (int r = 0; r < kDxRows; ++r) acc[r] += sdz[r * N + n] * wv;
     }
   }
-  if (k < K) {
 #pragma unroll
-    for (int r = 0; r < kDxRows; ++r)
-      if (b0 + r < B) {
-        float* d = dx + (size_t)(b0 + r) * K + k;
-        *d = (beta != 0.f ? beta * (*d) : 0.f) + wmul * acc[r];
-      }
+  for (int r = 0; r < kDxRows; ++r) red[warp][r][lane] = acc[r];
+  __syncthreads();
+  // 256 threads finish the 8 x 32 tile: thread -> (row, lane)
+  const int r = threadIdx.x >> 5;
+  const int kk = blockIdx.x * 32 + lane;
+  if (kk < K && b0 + r < B) {
+    float s = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) s += red[w8][r][lane];
+    float* d = dx + (size_t)(b0 + r) * K + kk;
+    *d = (beta != 0.f ? beta * (*d) : 0.f) + wmul * s;
   }
 }
 
@@ -169,8 +178,9 @@ extern "C" int irfd_linear_bwd(const float* dz, const float* x, const float* w, 
   IRFD_CHECK_ARG(dz && b > 0 && b <= kMaxRows && n > 0 && k > 0, "linear_bwd: bad argument (batch <= 64)");
   if (dx != nullptr) {
     IRFD_CHECK_ARG(w != nullptr, "linear_bwd: dx needs w");
-    linear_dx_kernel<<<dim3((k + 127) / 128, (b + kDxRows - 1) / kDxRows), 128, 0, stream>>>(dz, w, dx, b, n, k, wmul,
-                                                                                              dx_beta);
+    IRFD_CHECK_ARG((size_t)kDxRows * n * sizeof(float) <= 40 * 1024, "linear_bwd: N too large for the dz tile");
+    linear_dx_kernel<<<dim3((k + 31) / 32, (b + kDxRows - 1) / kDxRows), 256, kDxRows * n * sizeof(float), stream>>>(
+        dz, w, dx, b, n, k, wmul, dx_beta);
     IRFD_CHECK_LAUNCH();
   }
   if (dw != nullptr) {

@@ -82,11 +82,19 @@ __global__ void sumsq_finalize_kernel(const double* __restrict__ partial, int nb
 // torch.optim.Adam semantics (no amsgrad, no weight decay), bias correction from `step` (1-based).
 // clip: if total_sumsq != null, grads are scaled by min(1, max_norm / (sqrt(total_sumsq[0]) + 1e-6)) first
 // (torch.nn.utils.clip_grad_norm_ semantics).
+__global__ void increment_kernel(int* counter) { counter[0] += 1; }
+
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float bc1,
-                            float bc2_sqrt, const float* __restrict__ total_sumsq, float max_norm) {
+                            float bc2_sqrt, const float* __restrict__ total_sumsq, float max_norm,
+                            const int* __restrict__ step_dev) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (step_dev != nullptr) {  // static-graph mode: the step number lives on the device
+    const float t = (float)step_dev[0];
+    bc1 = 1.f - powf(b1, t);
+    bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  }
   float scale = 1.f;
   if (total_sumsq != nullptr) {
     const float nrm = sqrtf(total_sumsq[0]);
@@ -150,13 +158,17 @@ extern "C" int irfd_sumsq(const float* g, long long n, float* out, float out_bet
 }
 
 extern "C" int irfd_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
-                              float beta2, float eps, int step, const float* total_sumsq, float max_norm,
-                              cudaStream_t stream) {
-  IRFD_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "adam_step: bad argument");
+                              float beta2, float eps, int step, int* step_dev, const float* total_sumsq,
+                              float max_norm, cudaStream_t stream) {
+  IRFD_CHECK_ARG(p && g && m && v && n > 0 && (step >= 1 || step_dev), "adam_step: bad argument");
+  if (step_dev != nullptr) {
+    increment_kernel<<<1, 1, 0, stream>>>(step_dev);
+    IRFD_CHECK_LAUNCH();
+  }
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
   adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, g, m, v, (size_t)n, lr, beta1, beta2, eps, bc1,
-                                                                sqrtf(bc2), total_sumsq, max_norm);
+                                                                sqrtf(bc2), total_sumsq, max_norm, step_dev);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }

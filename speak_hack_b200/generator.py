@@ -294,3 +294,39 @@ class StyleGenerator(nn.Module):
                     mix_layer = torch.randint(1, w.size(1), (1,)).item()
                     w[:, mix_layer:] = w2[:, mix_layer:]
         return self.synthesis(w)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Static-graph variant: the style-mixing decision arrives as a device-side control value (see csrc/control.cu)
+# ----------------------------------------------------------------------------------------------------------------------
+class _StyleRowsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w, w2, ctrl, ctrl_idx, psi, cutoff, num_layers):
+        ctx.cfg = (psi, cutoff)
+        return ops.style_rows_fwd(w.contiguous(), w2.contiguous(), ctrl, ctrl_idx, psi, cutoff, num_layers)
+
+    @staticmethod
+    def backward(ctx, drows):
+        psi, cutoff = ctx.cfg
+        return ops.style_rows_bwd(drows.contiguous(), psi, cutoff), None, None, None, None, None, None
+
+
+def _generator_forward_static(self: StyleGenerator, features, ctrl, ctrl_idx):
+    """Same math as StyleGenerator.forward with the mixing cut read on the device: ctrl[ctrl_idx] = first mixed row
+    (== num_layers for "no mixing").  w2 is always computed so the launch sequence is identical every step."""
+    if features.dim() > 2:
+        features = features.flatten(1)
+    features = features.to(torch.float32)
+    L = self.synthesis.num_layers
+    w = self.mapping(features)
+    with torch.no_grad():
+        w2 = self.mapping(torch.randn_like(features))
+    use_trunc = bool(self.truncation_psi and self.truncation_cutoff)
+    psi = float(self.truncation_psi) if use_trunc else 1.0
+    cutoff = int(self.truncation_cutoff) if use_trunc else 0
+    rows_t = _StyleRowsFn.apply(w, w2, ctrl, ctrl_idx, psi, cutoff, L)
+    noises = self.synthesis.draw_noises(features.size(0), features.device)
+    return _SynthesisFn.apply(rows_t, self.synthesis, noises, *self.synthesis._flat_params())
+
+
+StyleGenerator.forward_static = _generator_forward_static

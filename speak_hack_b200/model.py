@@ -85,13 +85,30 @@ class IRFD(nn.Module):
         with torch.no_grad():
             return enc(x)
 
+    def _encode_all(self, x_s, x_t):
+        """The six encoder passes of model.py:84-90.  When shapes allow, source and target go through each encoder as
+        ONE launch sequence with two BatchNorm statistic groups: numerically the same as Ei(x_s) followed by Ei(x_t)
+        (per-call batch statistics, running buffers updated in that order), at half the kernel launches."""
+        same = x_s.shape == x_t.shape and x_s.requires_grad == x_t.requires_grad and x_s.is_cuda
+        if same and x_s.dim() == 4 and (x_s.size(0) * (x_s.size(2) // 32) * (x_s.size(3) // 32)) % 128 == 0:
+            B = x_s.size(0)
+            x = torch.cat([x_s, x_t], dim=0)  # cat keeps requires_grad (SURVEY Q2 semantics)
+            outs = []
+            for enc in (self.Ei, self.Ee, self.Ep):
+                if torch.is_grad_enabled() and x.requires_grad:
+                    enc._recompute_bn_update = enc.training
+                    f = enc.forward_groups(x, 2)
+                else:
+                    with torch.no_grad():
+                        f = enc.forward_groups(x, 2)
+                outs.append((f[:B], f[B:]))
+            (fi_s, fi_t), (fe_s, fe_t), (fp_s, fp_t) = outs
+            return fi_s, fe_s, fp_s, fi_t, fe_t, fp_t
+        return (self._encode(self.Ei, x_s), self._encode(self.Ee, x_s), self._encode(self.Ep, x_s),
+                self._encode(self.Ei, x_t), self._encode(self.Ee, x_t), self._encode(self.Ep, x_t))
+
     def forward(self, x_s, x_t):
-        fi_s = self._encode(self.Ei, x_s)
-        fe_s = self._encode(self.Ee, x_s)
-        fp_s = self._encode(self.Ep, x_s)
-        fi_t = self._encode(self.Ei, x_t)
-        fe_t = self._encode(self.Ee, x_t)
-        fp_t = self._encode(self.Ep, x_t)
+        fi_s, fe_s, fp_s, fi_t, fe_t, fp_t = self._encode_all(x_s, x_t)
 
         # model.py:97-104 — one CPU-generator draw per forward; whole-tensor S<->T swap of one code type
         swap_type = torch.randint(0, 3, (1,)).item()
@@ -156,3 +173,36 @@ class IRFDLoss(nn.Module):
         l_identity = self.identity_loss(fi_s, fi_t)
         l_recon = self.reconstruction_loss(x_s, x_t, x_s_recon, x_t_recon)
         return zero, zero.clone(), l_identity, l_recon
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Static-graph variant of IRFD.forward (used by trainer.IRFDTrainer(use_cuda_graph=True))
+# ----------------------------------------------------------------------------------------------------------------------
+class _SwapCatFn(torch.autograd.Function):
+    """Device-side S<->T swap + concat: ctrl[0] = swap_type.  Pure copies (bit-exact), see csrc/control.cu."""
+
+    @staticmethod
+    def forward(ctx, ctrl, *feats):
+        flat = [f.reshape(f.size(0), -1).contiguous() for f in feats]
+        ctx.ctrl = ctrl
+        ctx.c = flat[0].shape[1]
+        ctx.shapes = [f.shape for f in feats]
+        return ops.swap_cat_fwd(flat, ctrl)
+
+    @staticmethod
+    def backward(ctx, dgen_s, dgen_t):
+        outs = ops.swap_cat_bwd(dgen_s.contiguous(), dgen_t.contiguous(), ctx.ctrl, ctx.c)
+        return (None,) + tuple(o.view(s) for o, s in zip(outs, ctx.shapes))
+
+
+def _irfd_forward_static(self: IRFD, x_s, x_t, ctrl):
+    """IRFD.forward with the swap / style-mixing decisions taken on the device from `ctrl` (int32 [3]).
+    Returns (x_s_recon, x_t_recon, fi_s, fi_t) with fi_* UNswapped (the identity MSE is symmetric in them)."""
+    fi_s, fe_s, fp_s, fi_t, fe_t, fp_t = self._encode_all(x_s, x_t)
+    gen_s, gen_t = _SwapCatFn.apply(ctrl, fi_s, fe_s, fp_s, fi_t, fe_t, fp_t)
+    x_s_recon = self.Gd.forward_static(gen_s, ctrl, 1)
+    x_t_recon = self.Gd.forward_static(gen_t, ctrl, 2)
+    return x_s_recon, x_t_recon, fi_s, fi_t
+
+
+IRFD.forward_static = _irfd_forward_static

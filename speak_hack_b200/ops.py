@@ -207,12 +207,17 @@ def _pack_conv_weight(w: torch.Tensor, mode: int, kpad: int = 0) -> torch.Tensor
 # ----------------------------------------------------------------------------------------------------------------------
 # BatchNorm
 # ----------------------------------------------------------------------------------------------------------------------
-def bn_finalize(ssum, ssq, count, eps, momentum, running_mean=None, running_var=None, running_updates=1):
+def bn_finalize(ssum, ssq, count, eps, momentum, running_mean=None, running_var=None, running_updates=1, groups=1):
+    """count = rows PER GROUP.  Returns mean, rstd of shape [groups, C] ([C] when groups == 1)."""
     tiles, c = ssum.shape
-    mean = torch.empty(c, dtype=F32, device=ssum.device)
-    rstd = torch.empty(c, dtype=F32, device=ssum.device)
-    _call("irfd_bn_finalize", ssum.data_ptr(), ssq.data_ptr(), tiles, c, int(count), eps, momentum, mean.data_ptr(),
-          rstd.data_ptr(), _ptr(running_mean), _ptr(running_var), running_updates, _stream())
+    if tiles % groups:
+        raise _lib.IrfdError(f"bn_finalize: {tiles} tiles do not split into {groups} groups")
+    shape = (c,) if groups == 1 else (groups, c)
+    mean = torch.empty(shape, dtype=F32, device=ssum.device)
+    rstd = torch.empty(shape, dtype=F32, device=ssum.device)
+    _call("irfd_bn_finalize", ssum.data_ptr(), ssq.data_ptr(), tiles // groups, c, int(count), eps, momentum,
+          mean.data_ptr(), rstd.data_ptr(), _ptr(running_mean), _ptr(running_var), running_updates, groups, _stream(),
+          launches=1 if groups == 1 else 1 + groups * running_updates)
     return mean, rstd
 
 
@@ -227,7 +232,7 @@ def bn_eval_rstd(running_var, eps):
     return rstd
 
 
-def bn_apply(z, mean, rstd, gamma, beta, res=None, bn2=None, relu=True):
+def bn_apply(z, mean, rstd, gamma, beta, res=None, bn2=None, relu=True, groups=1):
     """out = [relu](BN(z) [+ res | + BN2(res)]); bn2 = (mean2, rstd2, gamma2, beta2)."""
     _chk(z, BF16, "z")
     c = z.shape[-1]
@@ -237,11 +242,12 @@ def bn_apply(z, mean, rstd, gamma, beta, res=None, bn2=None, relu=True):
     if bn2 is not None:
         m2, r2, g2, b2 = bn2
     _call("irfd_bn_apply", z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-          _ptr(res), _ptr(m2), _ptr(r2), _ptr(g2), _ptr(b2), out.data_ptr(), rows, c, 1 if relu else 0, _stream())
+          _ptr(res), _ptr(m2), _ptr(r2), _ptr(g2), _ptr(b2), out.data_ptr(), rows, c, 1 if relu else 0, groups,
+          _stream())
     return out
 
 
-def bn_backward(g1, g2, act, z, mean, rstd, gamma, want_g_out=False, batch_stats=True):
+def bn_backward(g1, g2, act, z, mean, rstd, gamma, want_g_out=False, batch_stats=True, groups=1):
     """Returns dz (bf16), dgamma, dbeta (fp32) [, masked g (bf16)]."""
     lib = _lib.load()
     c = z.shape[-1]
@@ -250,10 +256,10 @@ def bn_backward(g1, g2, act, z, mean, rstd, gamma, want_g_out=False, batch_stats
     g_out = torch.empty_like(z) if want_g_out else None
     dgamma = torch.empty(c, dtype=F32, device=z.device)
     dbeta = torch.empty(c, dtype=F32, device=z.device)
-    ws = workspace(lib.irfd_bn_bwd_workspace_bytes(rows, c), z.device)
+    ws = workspace(lib.irfd_bn_bwd_workspace_bytes(rows, c, groups), z.device)
     _call("irfd_bn_backward", g1.data_ptr(), _ptr(g2), _ptr(act), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
           gamma.data_ptr(), dz.data_ptr(), _ptr(g_out), dgamma.data_ptr(), dbeta.data_ptr(), 0.0,
-          1 if batch_stats else 0, rows, c,
+          1 if batch_stats else 0, rows, c, groups,
           ws.data_ptr(), ws.numel(), _stream(), launches=3)
     if want_g_out:
         return dz, dgamma, dbeta, g_out
@@ -509,6 +515,42 @@ def sumsq(g, out=None, out_beta=0.0):
     return out
 
 
-def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, total_sumsq=None, max_norm=0.0):
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, total_sumsq=None, max_norm=0.0, step_dev=None):
     _call("irfd_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,
-          step, _ptr(total_sumsq), max_norm, _stream())
+          step, _ptr(step_dev), _ptr(total_sumsq), max_norm, _stream(), launches=1 if step_dev is None else 2)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# device-side routing (static-graph mode)
+# ----------------------------------------------------------------------------------------------------------------------
+def style_rows_fwd(w, w2, ctrl, ctrl_idx, psi, cutoff, num_layers):
+    b, k = w.shape
+    rows_t = torch.empty((num_layers, b, k), dtype=F32, device=w.device)
+    _call("irfd_style_rows_fwd", w.data_ptr(), w2.data_ptr(), ctrl.data_ptr(), ctrl_idx, psi, cutoff,
+          rows_t.data_ptr(), num_layers, b, k, _stream())
+    return rows_t
+
+
+def style_rows_bwd(drows_t, psi, cutoff):
+    l, b, k = drows_t.shape
+    dw = torch.empty((b, k), dtype=F32, device=drows_t.device)
+    _call("irfd_style_rows_bwd", drows_t.data_ptr(), psi, cutoff, dw.data_ptr(), l, b, k, _stream())
+    return dw
+
+
+def swap_cat_fwd(feats, ctrl):
+    """feats = (fi_s, fe_s, fp_s, fi_t, fe_t, fp_t), each [B, C] fp32 contiguous."""
+    b, c = feats[0].shape
+    gen_s = torch.empty((b, 3 * c), dtype=F32, device=feats[0].device)
+    gen_t = torch.empty_like(gen_s)
+    _call("irfd_swap_cat_fwd", *[f.data_ptr() for f in feats], ctrl.data_ptr(), gen_s.data_ptr(), gen_t.data_ptr(), b,
+          c, _stream())
+    return gen_s, gen_t
+
+
+def swap_cat_bwd(dgen_s, dgen_t, ctrl, c):
+    b = dgen_s.shape[0]
+    outs = [torch.empty((b, c), dtype=F32, device=dgen_s.device) for _ in range(6)]
+    _call("irfd_swap_cat_bwd", dgen_s.data_ptr(), dgen_t.data_ptr(), ctrl.data_ptr(), *[o.data_ptr() for o in outs], b,
+          c, _stream())
+    return outs

@@ -4,6 +4,13 @@ One process per GPU.  Each rank runs the IRFD forward/backward on its shard of t
 statistics, like the reference under accelerate/DDP without SyncBN); gradients are averaged by bucketed all-reduce
 overlapped with backward (dp.py); Adam (train.py:346: Gd.parameters() only, lr 2e-4) is one fused kernel over a flat
 parameter buffer, optionally preceded by clip_grad_norm_ over ALL model parameters (train.py:207-208).
+
+`use_cuda_graph=True` captures the WHOLE step (zero_grad, forward, losses, backward, all-reduce, Adam: ~3,700 kernel
+launches) into one CUDA graph.  The reference's CPU-generator decisions (swap type, style-mixing cuts) are still drawn
+on the host in the reference's order every step, but reach the kernels through a 3-int control tensor
+(csrc/control.cu) so the launch sequence is static.  Differences from eager mode: the style-mixing latent w2 is
+computed every step (one extra randn_like draw on the device generator when the reference would not mix), and the
+encoders' bf16 weight repacks are captured as constants (encoders have no optimizer in the reference, train.py:346).
 """
 from __future__ import annotations
 
@@ -34,7 +41,7 @@ def flatten_parameters(params: List[torch.nn.Parameter]):
 
 class IRFDTrainer:
     def __init__(self, model: IRFD, lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8,
-                 grad_clip: Optional[float] = None, encoder_grads: bool = True):
+                 grad_clip: Optional[float] = None, encoder_grads: bool = True, use_cuda_graph: bool = False):
         self.model = model
         self.lr, self.betas, self.eps = lr, betas, eps
         self.grad_clip = grad_clip
@@ -46,31 +53,28 @@ class IRFDTrainer:
         self.v = torch.zeros_like(self.flat)
         self.step_count = 0
         self.encoders = [model.Ei, model.Ee, model.Ep]
-        self.buckets = GradBuckets(self.flat.device)
+        self.device = self.flat.device
+        self.buckets = GradBuckets(self.device)
         self.world = self.buckets.world
         self.schedule = BucketSchedule(self.buckets, self.gflat, self.encoders)
         self.last_losses = None
+        # static-graph state
+        self.use_cuda_graph = use_cuda_graph
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_launches = 0
+        self.ctrl = torch.zeros(3, dtype=torch.int32, device=self.device)
+        self._ctrl_host = torch.zeros(3, dtype=torch.int32).pin_memory() if self.device.type == "cuda" else None
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._static = None
 
+    # ---------------------------------------------------------------------------------------------- shared pieces
     def zero_grad(self):
         self.gflat.zero_()
         for enc in self.encoders:
             for p in enc.parameters():
                 p.grad = None
 
-    def train_step(self, x_s: torch.Tensor, x_t: torch.Tensor):
-        """zero_grad -> forward -> MSE losses -> backward (+ overlapped all-reduce) -> [clip] -> Adam on Gd."""
-        model = self.model
-        self.zero_grad()
-        if self.encoder_grads:
-            # train.py's R1 penalty leaves requires_grad=True on the batch, which is what lets the reference's
-            # reentrant checkpoints differentiate the encoders (SURVEY Q2)
-            x_s = x_s.detach().requires_grad_(True)
-            x_t = x_t.detach().requires_grad_(True)
-        out = model(x_s, x_t)
-        x_s_recon, x_t_recon, fi_s, _, _, fi_t = out[:6]
-        l_identity = mse_loss(fi_s, fi_t)
-        l_recon = mse_loss(x_s.detach(), x_s_recon) + mse_loss(x_t.detach(), x_t_recon)
-        loss = l_identity + l_recon
+    def _backward_and_update(self, loss, static: bool):
         if self.world > 1:
             self.schedule.reset()
             for e in self.encoders:
@@ -91,7 +95,109 @@ class IRFDTrainer:
                     if p.grad is not None:
                         ops.sumsq(p.grad.reshape(-1), out=total_sumsq, out_beta=1.0)
         ops.adam_step(self.flat, self.gflat, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps,
-                      self.step_count, total_sumsq=total_sumsq, max_norm=self.grad_clip or 0.0)
+                      self.step_count, total_sumsq=total_sumsq, max_norm=self.grad_clip or 0.0,
+                      step_dev=self.step_dev if static else None)
         ops.invalidate_packed(self._gd_conv_weights)  # Adam wrote through the flat buffer: bf16 repacks are stale
+
+    def _prep_inputs(self, x_s, x_t):
+        if self.encoder_grads:
+            # train.py's R1 penalty leaves requires_grad=True on the batch, which is what lets the reference's
+            # reentrant checkpoints differentiate the encoders
+            return x_s.detach().requires_grad_(True), x_t.detach().requires_grad_(True)
+        return x_s.detach(), x_t.detach()
+
+    # ---------------------------------------------------------------------------------------------- eager step
+    def train_step_eager(self, x_s: torch.Tensor, x_t: torch.Tensor):
+        """zero_grad -> forward -> MSE losses -> backward (+ overlapped all-reduce) -> [clip] -> Adam on Gd."""
+        self.zero_grad()
+        x_s, x_t = self._prep_inputs(x_s, x_t)
+        out = self.model(x_s, x_t)
+        x_s_recon, x_t_recon, fi_s, _, _, fi_t = out[:6]
+        l_identity = mse_loss(fi_s, fi_t)
+        l_recon = mse_loss(x_s.detach(), x_s_recon) + mse_loss(x_t.detach(), x_t_recon)
+        loss = l_identity + l_recon
+        self._backward_and_update(loss, static=False)
         self.last_losses = (l_identity.detach(), l_recon.detach())
         return loss.detach()
+
+    # ---------------------------------------------------------------------------------------------- static-graph step
+    def _draw_ctrl(self):
+        """The reference's CPU-generator draws, in its order: swap (model.py:98), then per Gd call rand(1) and, when
+        mixing, randint(1, L) (styleganv1.py:548, 552)."""
+        gd = self.model.Gd
+        L = gd.synthesis.num_layers
+        self._ctrl_host[0] = int(torch.randint(0, 3, (1,)).item())
+        for g in range(2):
+            cut = L
+            if gd.training and gd.style_mixing_prob > 0:
+                if torch.rand(1) < gd.style_mixing_prob:
+                    cut = int(torch.randint(1, L, (1,)).item())
+            self._ctrl_host[1 + g] = cut
+        self.ctrl.copy_(self._ctrl_host, non_blocking=True)
+
+    def _static_body(self):
+        xs, xt, loss_out, lid_out, lrec_out = self._static
+        self.zero_grad()
+        x_s, x_t = self._prep_inputs(xs, xt)
+        x_s_recon, x_t_recon, fi_s, fi_t = self.model.forward_static(x_s, x_t, self.ctrl)
+        l_identity = mse_loss(fi_s, fi_t)
+        l_recon = mse_loss(xs, x_s_recon) + mse_loss(xt, x_t_recon)
+        loss = l_identity + l_recon
+        self._backward_and_update(loss, static=True)
+        loss_out.copy_(loss.detach())
+        lid_out.copy_(l_identity.detach())
+        lrec_out.copy_(l_recon.detach())
+
+    def _capture(self, x_s, x_t):
+        dev = self.device
+        self._static = (torch.empty_like(x_s), torch.empty_like(x_t), torch.zeros((), device=dev),
+                        torch.zeros((), device=dev), torch.zeros((), device=dev))
+        self._static[0].copy_(x_s)
+        self._static[1].copy_(x_t)
+        self.step_dev.fill_(self.step_count)
+        # The warm-up passes below are real steps; snapshot everything they mutate (Gd parameters, Adam moments, BN
+        # running buffers, step counters, both RNG streams) and put it back, so capturing is invisible to training.
+        snap = [t.clone() for t in (self.flat, self.m, self.v)]
+        bufs = [b for e in self.encoders for b in e.buffers()]
+        snap_bufs = [b.clone() for b in bufs]
+        snap_step = self.step_count
+        cpu_rng, cuda_rng = torch.get_rng_state(), torch.cuda.get_rng_state(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up on a side stream (allocator, lazy function attributes, pack cache)
+            for _ in range(2):
+                self._draw_ctrl()
+                self._static_body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        before = ops.launch_count
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._static_body()
+        self.graph_launches = ops.launch_count - before
+        # the captured pass was only recorded, not executed; the warm-up passes are rolled back
+        for t, c in zip((self.flat, self.m, self.v), snap):
+            t.copy_(c)
+        for b, c in zip(bufs, snap_bufs):
+            b.copy_(c)
+        self.step_count = snap_step
+        self.step_dev.fill_(snap_step)
+        torch.set_rng_state(cpu_rng)
+        torch.cuda.set_rng_state(cuda_rng, dev)
+
+    def train_step_graph(self, x_s: torch.Tensor, x_t: torch.Tensor):
+        if self.graph is None:
+            self._capture(x_s, x_t)
+        self._static[0].copy_(x_s, non_blocking=True)
+        self._static[1].copy_(x_t, non_blocking=True)
+        self._draw_ctrl()
+        self.graph.replay()
+        self.step_count += 1
+        ops.launch_count += self.graph_launches
+        self.last_losses = (self._static[3], self._static[4])
+        return self._static[2]
+
+    def train_step(self, x_s: torch.Tensor, x_t: torch.Tensor):
+        if self.use_cuda_graph:
+            return self.train_step_graph(x_s, x_t)
+        return self.train_step_eager(x_s, x_t)

@@ -385,3 +385,40 @@ def test_mse_and_adam(cuda_device):
         ops.adam_step(p, gr, m, v, 2e-4, 0.9, 0.999, 1e-8, step, total_sumsq=ss, max_norm=1.0)
     torch.cuda.synchronize()
     assert torch.allclose(p, pr.detach(), atol=1e-6, rtol=1e-5)
+
+
+def test_bn_groups_equal_separate_calls(cuda_device):
+    """Two statistic groups in one launch == two launches (forward outputs, running buffers, dz, dgamma/dbeta)."""
+    from speak_hack_b200 import ops
+
+    dev = cuda_device
+    g = gen(20)
+    n, h, w, c = 4, 8, 8, 256  # 2 groups x 128 rows
+    rows = n * h * w
+    z = (torch.randn(n, h, w, c, generator=g) * 2 + 0.3).to(dev).to(BF)
+    res = torch.randn(n, h, w, c, generator=g).to(dev).to(BF)
+    dout = torch.randn(n, h, w, c, generator=g).to(dev).to(BF)
+    gamma = (torch.rand(c, generator=g) + 0.5).to(dev)
+    beta = torch.randn(c, generator=g).to(dev)
+    zf = z.float().reshape(rows, c)
+    ssum = zf.reshape(-1, 128, c).sum(1).contiguous()
+    ssq = (zf * zf).reshape(-1, 128, c).sum(1).contiguous()
+    rm2, rv2 = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+    mean2, rstd2 = ops.bn_finalize(ssum, ssq, rows // 2, 1e-5, 0.1, rm2, rv2, 1, groups=2)
+    out2 = ops.bn_apply(z, mean2, rstd2, gamma, beta, res=res, relu=True, groups=2)
+    dz2, dg2, db2, go2 = ops.bn_backward(dout, None, out2, z, mean2, rstd2, gamma, want_g_out=True, groups=2)
+    rm1, rv1 = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+    dg1, db1 = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
+    for gi in range(2):
+        sl = slice(gi * 2, gi * 2 + 2)
+        m, r = ops.bn_finalize(ssum[gi:gi + 1].contiguous(), ssq[gi:gi + 1].contiguous(), rows // 2, 1e-5, 0.1, rm1, rv1)
+        assert torch.equal(m, mean2[gi]) and torch.equal(r, rstd2[gi])
+        o = ops.bn_apply(z[sl].contiguous(), m, r, gamma, beta, res=res[sl].contiguous(), relu=True)
+        assert torch.equal(o, out2[sl])
+        dz, dg, db, go = ops.bn_backward(dout[sl].contiguous(), None, o, z[sl].contiguous(), m, r, gamma, want_g_out=True)
+        assert torch.equal(dz, dz2[sl]) and torch.equal(go, go2[sl])
+        dg1 += dg
+        db1 += db
+    torch.cuda.synchronize()
+    assert torch.allclose(rm1, rm2, rtol=1e-6, atol=1e-7) and torch.allclose(rv1, rv2, rtol=1e-6, atol=1e-7)
+    assert torch.allclose(dg1, dg2, rtol=1e-5, atol=1e-5) and torch.allclose(db1, db2, rtol=1e-5, atol=1e-5)

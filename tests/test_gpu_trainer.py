@@ -1,0 +1,100 @@
+"""-m gpu: trainer — static-graph step == eager step (same CPU/GPU seeds), device-side routing kernels, Adam parity."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+pytestmark = pytest.mark.gpu
+
+
+def test_routing_kernels_bit_exact(cuda_device):
+    from speak_hack_b200 import ops
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(0)
+    feats = [torch.randn(3, 2048, generator=g).to(dev) for _ in range(6)]
+    for swap in range(3):
+        ctrl = torch.tensor([swap, 14, 14], dtype=torch.int32, device=dev)
+        gs, gt = ops.swap_cat_fwd(feats, ctrl)
+        s, t = list(feats[:3]), list(feats[3:])
+        s[swap], t[swap] = t[swap], s[swap]
+        assert torch.equal(gs, torch.cat(s, 1)) and torch.equal(gt, torch.cat(t, 1))  # bit-exact code swap
+        outs = ops.swap_cat_bwd(gs, gt, ctrl, 2048)
+        for o, f in zip(outs, feats):
+            assert torch.equal(o, f)  # adjoint of a permutation: scattering the gathered values restores them
+    w, w2 = torch.randn(4, 512, generator=g).to(dev), torch.randn(4, 512, generator=g).to(dev)
+    for cut in (1, 5, 9, 14):
+        ctrl = torch.tensor([0, cut, 14], dtype=torch.int32, device=dev)
+        rows = ops.style_rows_fwd(w, w2, ctrl, 1, 0.7, 8, 14)
+        ref = w.unsqueeze(0).repeat(14, 1, 1)
+        coef = torch.ones(14, 1, 1, device=dev)
+        coef[:8] *= 0.7
+        ref = coef * ref
+        ref[cut:] = w2.unsqueeze(0).repeat(14, 1, 1)[cut:] * coef[cut:]
+        assert torch.allclose(rows, ref, rtol=1e-7, atol=0)
+        d = torch.randn(14, 4, 512, generator=g).to(dev)
+        dw = ops.style_rows_bwd(d, 0.7, 8)
+        assert torch.allclose(dw, (coef * d).sum(0), rtol=1e-5, atol=1e-6)
+
+
+def _make(dev, graph, perturb=False):
+    import irfd_oracle as O
+    import speak_hack_b200 as P
+    from speak_hack_b200.trainer import IRFDTrainer
+
+    torch.manual_seed(O.WEIGHT_SEED)
+    net = P.IRFD()
+    if perturb:
+        O.perturb_noise_weights(net.Gd)
+    net = net.to(dev).train()
+    return net, IRFDTrainer(net, lr=2e-4, use_cuda_graph=graph)
+
+
+def test_graph_step_matches_eager_step(cuda_device):
+    """Same weights, same data, same CPU draws (swap type, mixing cuts).  At initialisation the noise weights are zero
+    (styleganv1.py:451), so the first step's loss does not depend on the device RNG stream, which is the one thing
+    the two modes consume differently: the first losses must agree; later steps must stay finite and count right."""
+    import irfd_oracle as O
+
+    dev = cuda_device
+    x_s, x_t = O.synthetic_pair(2)
+    xs, xt = x_s.to(dev), x_t.to(dev)
+    losses = {}
+    for graph in (False, True):
+        net, tr = _make(dev, graph)
+        net.Gd.style_mixing_prob = 0.0  # mixing replaces rows by a device-RNG latent: stream-dependent
+        torch.manual_seed(123)
+        torch.cuda.manual_seed(456)
+        seq = [float(tr.train_step(xs, xt)) for _ in range(3)]
+        torch.cuda.synchronize()
+        losses[graph] = seq
+        assert tr.step_count == 3
+        assert torch.isfinite(tr.flat).all() and all(l == l for l in seq)
+        if graph:
+            assert tr.graph is not None and tr.graph_launches > 1000
+    print(f"[trainer] eager losses {losses[False]} | graph losses {losses[True]}")
+    assert abs(losses[False][0] - losses[True][0]) <= 1e-3 * abs(losses[False][0])
+
+
+def test_adam_matches_torch_through_trainer(cuda_device):
+    """One eager step: Gd parameter update == torch.optim.Adam applied to the same gradients."""
+    import irfd_oracle as O
+
+    dev = cuda_device
+    net, tr = _make(dev, False, perturb=True)
+    x_s, x_t = O.synthetic_pair(1)
+    before = tr.flat.clone()
+    torch.manual_seed(5)
+    tr.train_step(x_s.to(dev), x_t.to(dev))
+    torch.cuda.synchronize()
+    g = tr.gflat.clone()
+    p = before.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p], lr=2e-4)
+    p.grad = g
+    opt.step()
+    assert torch.allclose(tr.flat, p.detach(), rtol=1e-5, atol=1e-7)
+    assert all(q.grad is not None for q in net.Ei.parameters())  # encoders were differentiated
