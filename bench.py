@@ -166,6 +166,22 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------------
 # native arm
 # ----------------------------------------------------------------------------------------------------------------------
+def _teardown(trainer, dist, world):
+    """Multi-rank exit: a captured CUDA graph that contains NCCL kernels keeps the communicator busy and
+    destroy_process_group() blocks on it, so release the graph, rendezvous once more and leave without destroying."""
+    if world <= 1:
+        return
+    import torch
+
+    trainer.graph = None
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -252,9 +268,7 @@ def run_native(args):
     torch.cuda.synchronize()
     fam = ops.gemm_timing_end()
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        _teardown(trainer, dist, world)
         return
 
     peaks = {}
@@ -307,13 +321,16 @@ def run_native(args):
         except Exception as exc:  # the baseline is informative; never lose the GPU line over it
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {exc}"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    _teardown(trainer, dist, world)
 
 
 def main():
     args = parse_args()
+    wd = float(os.environ.get("IRFD_BENCH_WATCHDOG_S", "0") or 0)
+    if wd > 0:  # debugging aid: dump every thread's stack and exit if the run has not finished after `wd` seconds
+        import faulthandler
+
+        faulthandler.dump_traceback_later(wd, exit=True)
     if args.impl == "reference":
         run_reference(args)
     else:
