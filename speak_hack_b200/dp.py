@@ -31,6 +31,9 @@ class GradBuckets:
         self.device = device
         self.cuda = device.type == "cuda"
         self.comm_stream = torch.cuda.Stream(device) if (self.cuda and self.world > 1) else None
+        # streams (besides the current one) that may have produced the gradients of a bucket: the encoders' backward
+        # passes run on their own streams (model.IRFD.encoder_streams)
+        self.producer_streams = []
         self._pending = []
         self.launched_bytes = 0
 
@@ -47,6 +50,8 @@ class GradBuckets:
         if self.cuda:
             ready = torch.cuda.Event()
             ready.record()
+            for ps in self.producer_streams:
+                self.comm_stream.wait_stream(ps)
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ready)
                 flat.record_stream(self.comm_stream)
@@ -62,7 +67,10 @@ class GradBuckets:
         if self.world == 1:
             return
         if self.cuda:
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(self.comm_stream)
+            for ps in self.producer_streams:  # gradients that were not bucketed are still produced there
+                cur.wait_stream(ps)
         for flat, unflatten in self._pending:
             if unflatten is not None:
                 off, views = 0, []
@@ -98,8 +106,9 @@ class BucketSchedule:
     def pre(self):
         self._launch_ready(final=False)
 
-    def post(self, enc):
-        self.passes[id(enc)] += 1
+    def post(self, enc, passes: int = 1):
+        """`passes` = how many of the reference's per-image encoder calls this backward covered (2 for a paired pass)."""
+        self.passes[id(enc)] += passes
 
     def final(self):
         self._launch_ready(final=True)

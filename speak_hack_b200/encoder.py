@@ -220,7 +220,7 @@ class _EncoderFn(torch.autograd.Function):
         if second_update:
             torch._foreach_add_(enc._bn_counters(), G)
         if enc._bwd_post_cb is not None:
-            enc._bwd_post_cb(enc)
+            enc._bwd_post_cb(enc, ctx.G)
         ctx.S = None
         # dL/dx of the stem is not produced: nothing on the IRFD path consumes the image gradient (train.py only sets
         # requires_grad on the batch as a side effect of the R1 penalty).

@@ -85,6 +85,14 @@ class IRFD(nn.Module):
         with torch.no_grad():
             return enc(x)
 
+    def encoder_streams(self, device):
+        """Three side streams (one per encoder), created on first use."""
+        st = getattr(self, "_enc_streams", None)
+        if st is None or st[0].device != device:
+            st = [torch.cuda.Stream(device) for _ in range(3)]
+            self._enc_streams = st
+        return st
+
     def _encode_all(self, x_s, x_t):
         """The six encoder passes of model.py:84-90.  When shapes allow, source and target go through each encoder as
         ONE launch sequence with two BatchNorm statistic groups: numerically the same as Ei(x_s) followed by Ei(x_t)
@@ -93,16 +101,29 @@ class IRFD(nn.Module):
         if same and x_s.dim() == 4 and (x_s.size(0) * (x_s.size(2) // 32) * (x_s.size(3) // 32)) % 128 == 0:
             B = x_s.size(0)
             x = torch.cat([x_s, x_t], dim=0)  # cat keeps requires_grad (SURVEY Q2 semantics)
-            outs = []
-            for enc in (self.Ei, self.Ee, self.Ep):
-                if torch.is_grad_enabled() and x.requires_grad:
-                    enc._recompute_bn_update = enc.training
-                    f = enc.forward_groups(x, 2)
-                else:
-                    with torch.no_grad():
+            # The three encoders are independent: run them on three streams (fork/join by events, capturable in a
+            # CUDA graph) so the many small, tail-dominated kernels of one encoder overlap with the others'.  Autograd
+            # replays each encoder's backward on the stream its forward ran on.
+            cur = torch.cuda.current_stream(x.device)
+            streams = self.encoder_streams(x.device)
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            feats = []
+            for enc, st in zip((self.Ei, self.Ee, self.Ep), streams):
+                st.wait_event(fork)
+                x.record_stream(st)
+                with torch.cuda.stream(st):
+                    if torch.is_grad_enabled() and x.requires_grad:
+                        enc._recompute_bn_update = enc.training
                         f = enc.forward_groups(x, 2)
-                outs.append((f[:B], f[B:]))
-            (fi_s, fi_t), (fe_s, fe_t), (fp_s, fp_t) = outs
+                    else:
+                        with torch.no_grad():
+                            f = enc.forward_groups(x, 2)
+                f.record_stream(cur)
+                feats.append(f)
+            for st in streams:
+                cur.wait_stream(st)
+            (fi_s, fi_t), (fe_s, fe_t), (fp_s, fp_t) = [(f[:B], f[B:]) for f in feats]
             return fi_s, fe_s, fp_s, fi_t, fe_t, fp_t
         return (self._encode(self.Ei, x_s), self._encode(self.Ee, x_s), self._encode(self.Ep, x_s),
                 self._encode(self.Ei, x_t), self._encode(self.Ee, x_t), self._encode(self.Ep, x_t))

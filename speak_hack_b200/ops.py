@@ -90,8 +90,9 @@ _workspace = {}
 
 
 def workspace(nbytes: int, device) -> torch.Tensor:
-    """Grow-only per-device scratch buffer (split-K partials, reduction partials); stream-ordered use only."""
-    key = (device.type, device.index)
+    """Grow-only scratch buffer (split-K partials, reduction partials), one per (device, stream): every use is
+    stream-ordered, and the three encoders run concurrently on their own streams."""
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0)
     buf = _workspace.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 1 << 22), dtype=torch.uint8, device=device)

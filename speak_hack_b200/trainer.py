@@ -55,6 +55,8 @@ class IRFDTrainer:
         self.encoders = [model.Ei, model.Ee, model.Ep]
         self.device = self.flat.device
         self.buckets = GradBuckets(self.device)
+        if self.device.type == "cuda":
+            self.buckets.producer_streams = list(model.encoder_streams(self.device))
         self.world = self.buckets.world
         self.schedule = BucketSchedule(self.buckets, self.gflat, self.encoders)
         self.last_losses = None
