@@ -11,60 +11,71 @@ namespace irfd {
 // Statistics finalize: per-tile partial sums (from the conv epilogue) -> mean / rstd, running-buffer update.
 // One block per 32 channels, 8 tile-lanes; accumulation in double.
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int kMaxGroups = 4;
+
 __global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int tiles, int C, double count,
                    float eps, float momentum, float* __restrict__ mean, float* __restrict__ rstd, float* running_mean,
-                   float* running_var, int running_updates) {
-  // block = 32 channels (lanes, coalesced 128-byte reads) x 32 warps striding over the tiles
+                   float* running_var, int running_updates, int groups) {
+  // block = 32 channels (lanes, coalesced 128-byte reads) x 32 warps striding over the tiles; statistic groups (e.g.
+  // the source and the target half of a paired encoder pass) are processed one after the other so the running
+  // buffers can be updated in call order by the same thread.
   __shared__ double s_sum[32][33];
   __shared__ double s_sq[32][33];
   const int cl = threadIdx.x & 31;
   const int tl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
-  // statistic group (e.g. the source and the target half of a paired encoder pass): its own tiles, its own mean/rstd
-  psum += (size_t)blockIdx.y * tiles * C;
-  psq += (size_t)blockIdx.y * tiles * C;
-  mean += (size_t)blockIdx.y * C;
-  rstd += (size_t)blockIdx.y * C;
-  double a = 0.0, b = 0.0;
-  if (c < C) {
-    int t = tl;
-    for (; t + 96 < tiles; t += 128) {  // 4 independent loads in flight per stream
-      const float a0 = psum[(size_t)t * C + c], a1 = psum[(size_t)(t + 32) * C + c];
-      const float a2 = psum[(size_t)(t + 64) * C + c], a3 = psum[(size_t)(t + 96) * C + c];
-      const float b0 = psq[(size_t)t * C + c], b1 = psq[(size_t)(t + 32) * C + c];
-      const float b2 = psq[(size_t)(t + 64) * C + c], b3 = psq[(size_t)(t + 96) * C + c];
-      a += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
-      b += ((double)b0 + (double)b1) + ((double)b2 + (double)b3);
+  double gm[kMaxGroups], gv[kMaxGroups];
+  for (int g = 0; g < groups; ++g) {
+    const float* ps = psum + (size_t)g * tiles * C;
+    const float* pq = psq + (size_t)g * tiles * C;
+    double a = 0.0, b = 0.0;
+    if (c < C) {
+      int t = tl;
+      for (; t + 96 < tiles; t += 128) {  // 4 independent loads in flight per stream
+        const float a0 = ps[(size_t)t * C + c], a1 = ps[(size_t)(t + 32) * C + c];
+        const float a2 = ps[(size_t)(t + 64) * C + c], a3 = ps[(size_t)(t + 96) * C + c];
+        const float b0 = pq[(size_t)t * C + c], b1 = pq[(size_t)(t + 32) * C + c];
+        const float b2 = pq[(size_t)(t + 64) * C + c], b3 = pq[(size_t)(t + 96) * C + c];
+        a += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+        b += ((double)b0 + (double)b1) + ((double)b2 + (double)b3);
+      }
+      for (; t < tiles; t += 32) {
+        a += (double)ps[(size_t)t * C + c];
+        b += (double)pq[(size_t)t * C + c];
+      }
     }
-    for (; t < tiles; t += 32) {
-      a += (double)psum[(size_t)t * C + c];
-      b += (double)psq[(size_t)t * C + c];
+    __syncthreads();
+    s_sum[tl][cl] = a;
+    s_sq[tl][cl] = b;
+    __syncthreads();
+    if (tl == 0 && c < C) {
+      for (int i = 1; i < 32; ++i) {
+        a += s_sum[i][cl];
+        b += s_sq[i][cl];
+      }
+      const double m = a / count;
+      double var = b / count - m * m;
+      if (var < 0.0) var = 0.0;
+      mean[(size_t)g * C + c] = (float)m;
+      rstd[(size_t)g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+      gm[g] = m;
+      gv[g] = count > 1.0 ? var * count / (count - 1.0) : var;  // unbiased, for the running buffer
     }
   }
-  s_sum[tl][cl] = a;
-  s_sq[tl][cl] = b;
-  __syncthreads();
-  if (tl == 0 && c < C) {
-    for (int i = 1; i < 32; ++i) {
-      a += s_sum[i][cl];
-      b += s_sq[i][cl];
-    }
-    const double m = a / count;
-    double var = b / count - m * m;
-    if (var < 0.0) var = 0.0;
-    mean[c] = (float)m;
-    rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-    if (running_mean != nullptr) {
-      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-      float rm = running_mean[c], rv = running_var[c];
-      for (int u = 0; u < running_updates; ++u) {  // reentrant checkpoint recompute repeats the update
-        rm = (1.f - momentum) * rm + momentum * (float)m;
-        rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+  if (tl == 0 && c < C && running_mean != nullptr) {
+    // update 1: the forward calls in order (group 0 first).  update 2 (optional): what the reference's reentrant
+    // checkpoint adds when it re-runs each forward during backward, i.e. the same statistics in reverse call order
+    // (model.py:84-90).
+    float rm = running_mean[c], rv = running_var[c];
+    for (int u = 0; u < running_updates; ++u)
+      for (int i = 0; i < groups; ++i) {
+        const int g = (u & 1) ? groups - 1 - i : i;
+        rm = (1.f - momentum) * rm + momentum * (float)gm[g];
+        rv = (1.f - momentum) * rv + momentum * (float)gv[g];
       }
-      running_mean[c] = rm;
-      running_var[c] = rv;
-    }
+    running_mean[c] = rm;
+    running_var[c] = rv;
   }
 }
 
@@ -330,27 +341,16 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* _
 
 using namespace irfd;
 
-// tiles / count are PER GROUP; mean/rstd are [groups][c].  With groups > 1 the running buffers are updated group by
-// group in order (pass 0 first), exactly like consecutive nn.BatchNorm2d calls.
+// tiles / count are PER GROUP; mean/rstd are [groups][c].  The running buffers get `running_updates` rounds of momentum
+// updates: round 1 walks the groups in call order, round 2 (the reference's checkpoint recompute) in reverse order.
 extern "C" int irfd_bn_finalize(const float* psum, const float* psq, int tiles, int c, long long count, float eps,
                                 float momentum, float* mean, float* rstd, float* running_mean, float* running_var,
                                 int running_updates, int groups, cudaStream_t stream) {
-  IRFD_CHECK_ARG(psum && psq && mean && rstd && tiles > 0 && c > 0 && count > 0 && groups >= 1,
-                 "bn_finalize: bad argument");
-  const bool inline_update = groups == 1;
-  bn_finalize_kernel<<<dim3((c + 31) / 32, groups), 1024, 0, stream>>>(
-      psum, psq, tiles, c, (double)count, eps, momentum, mean, rstd, inline_update ? running_mean : nullptr,
-      inline_update ? running_var : nullptr, running_updates);
+  IRFD_CHECK_ARG(psum && psq && mean && rstd && tiles > 0 && c > 0 && count > 0, "bn_finalize: bad argument");
+  IRFD_CHECK_ARG(groups >= 1 && groups <= kMaxGroups, "bn_finalize: 1..4 statistic groups");
+  bn_finalize_kernel<<<(c + 31) / 32, 1024, 0, stream>>>(psum, psq, tiles, c, (double)count, eps, momentum, mean, rstd,
+                                                         running_mean, running_var, running_updates, groups);
   IRFD_CHECK_LAUNCH();
-  if (!inline_update && running_mean != nullptr) {
-    for (int u = 0; u < running_updates; ++u)
-      for (int g = 0; g < groups; ++g) {
-        bn_running_update_kernel<<<(c + 255) / 256, 256, 0, stream>>>(mean + (size_t)g * c, rstd + (size_t)g * c, eps,
-                                                                       (double)count, momentum, running_mean,
-                                                                       running_var, c);
-        IRFD_CHECK_LAUNCH();
-      }
-  }
   return IRFD_OK;
 }
 

@@ -74,7 +74,7 @@ __device__ __forceinline__ void block_reduce_rows(const RowVec& rv, int C, float
 inline void plan_row_blocks(long long rows, int C, int sms, int* nblk, int* rows_per_blk) {
   int rows_par = kRvThreads / (C / 8);
   if (rows_par < 1) rows_par = 1;
-  long long target = (long long)sms * 4;
+  long long target = (long long)sms * 4;  // measured: more blocks only add partials for the finalize pass
   long long rpb = (rows + target - 1) / target;
   rpb = ((rpb + rows_par - 1) / rows_par) * rows_par;
   if (rpb < rows_par * 4) rpb = rows_par * 4;

@@ -59,12 +59,13 @@ class _BNState:
         self.mean, self.rstd, self.count = mean, rstd, count
 
 
-def _bn_stats(bn: nn.BatchNorm2d, ssum, ssq, rows, train: bool, groups: int = 1):
+def _bn_stats(bn: nn.BatchNorm2d, ssum, ssq, rows, train: bool, groups: int = 1, updates: int = 1):
     """Finalize batch statistics (train; one set per statistic group, running buffers updated group by group like
     consecutive nn.BatchNorm2d calls) or fetch the running ones (eval).  `rows` = total rows over all groups."""
     if train:
         count = rows // groups
-        mean, rstd = ops.bn_finalize(ssum, ssq, count, BN_EPS, BN_MOMENTUM, bn.running_mean, bn.running_var, 1, groups)
+        mean, rstd = ops.bn_finalize(ssum, ssq, count, BN_EPS, BN_MOMENTUM, bn.running_mean, bn.running_var, updates,
+                                     groups)
         return _BNState(mean, rstd, count)
     return _BNState(bn.running_mean, ops.bn_eval_rstd(bn.running_var, BN_EPS), rows)
 
@@ -84,15 +85,21 @@ class _EncoderFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, enc, groups, *params):
+    def forward(ctx, x, enc, groups, col0, *params):
         train = enc.training
         G = groups if train else 1  # eval-mode BN uses the shared running statistics: no groups needed
+        # The reference wraps every encoder call in a reentrant checkpoint (model.py:84-90): a differentiated pass
+        # re-runs the forward during backward and so updates the BN running buffers twice.  Both updates are
+        # applied here, in the order the reference would produce them (forward order, then reverse order).
+        recorded = any(ctx.needs_input_grad)  # grad mode is off inside Function.forward; this says a backward can follow
+        U = 2 if (train and getattr(enc, "_recompute_bn_update", False) and recorded) else 1
         x = x.contiguous().to(torch.float32)
         n, _, h, w = x.shape
         S = {}  # saved activations
         # ---- stem: 7x7/2 conv as explicit im2col + GEMM, BN, ReLU, maxpool
         conv0, bn0 = enc[0], enc[1]
-        col0 = ops.im2col_stem(x, 192)
+        if col0 is None:  # the stem's im2col matrix depends only on the images: callers may share it across encoders
+            col0 = ops.im2col_stem(x, 192)
         wk0 = ops.pack_conv_weight(conv0.weight, ops.PACK_FLAT, kpad=192)
         if train:
             z0, s, q = ops.gemm_rows(col0, wk0, ops.EPI_STATS)
@@ -100,7 +107,7 @@ class _EncoderFn(torch.autograd.Function):
             z0, s, q = ops.gemm_rows(col0, wk0, ops.EPI_PLAIN), None, None
         h1, w1 = h // 2, w // 2
         z0 = z0.view(n, h1, w1, 64)
-        st0 = _bn_stats(bn0, s, q, n * h1 * w1, train, G)
+        st0 = _bn_stats(bn0, s, q, n * h1 * w1, train, G, U)
         a0 = ops.bn_apply(z0, st0.mean, st0.rstd, bn0.weight, bn0.bias, relu=True, groups=G)
         p0, arg0 = ops.maxpool_fwd(a0)
         S["stem"] = (col0, z0, st0, a0, arg0)
@@ -111,7 +118,7 @@ class _EncoderFn(torch.autograd.Function):
                 xin = cur
                 nb, hh, ww, cin = xin.shape
                 z1, s, q = _conv_stats(xin, ops.pack_conv_weight(blk.conv1.weight, ops.PACK_FPROP), 1, train)
-                st1 = _bn_stats(blk.bn1, s, q, nb * hh * ww, train, G)
+                st1 = _bn_stats(blk.bn1, s, q, nb * hh * ww, train, G, U)
                 a1 = ops.bn_apply(z1, st1.mean, st1.rstd, blk.bn1.weight, blk.bn1.bias, relu=True, groups=G)
                 planes = a1.shape[-1]
                 wk2 = ops.pack_conv_weight(blk.conv2.weight, ops.PACK_FPROP)
@@ -127,16 +134,16 @@ class _EncoderFn(torch.autograd.Function):
                     else:
                         z2, s, q = ops.gemm_rows(col2, wk2, ops.EPI_PLAIN), None, None
                     z2 = z2.view(nb, ho, wo, planes)
-                st2 = _bn_stats(blk.bn2, s, q, nb * ho * wo, train, G)
+                st2 = _bn_stats(blk.bn2, s, q, nb * ho * wo, train, G, U)
                 a2 = ops.bn_apply(z2, st2.mean, st2.rstd, blk.bn2.weight, blk.bn2.bias, relu=True, groups=G)
                 z3, s, q = _conv_stats(a2, ops.pack_conv_weight(blk.conv3.weight, ops.PACK_FPROP), 1, train)
-                st3 = _bn_stats(blk.bn3, s, q, nb * ho * wo, train, G)
+                st3 = _bn_stats(blk.bn3, s, q, nb * ho * wo, train, G, U)
                 xs = zd = std = None
                 if blk.downsample is not None:
                     dconv, dbn = blk.downsample[0], blk.downsample[1]
                     xs = ops.subsample2(xin) if blk.stride == 2 else xin
                     zd, s, q = _conv_stats(xs, ops.pack_conv_weight(dconv.weight, ops.PACK_FPROP), 1, train)
-                    std = _bn_stats(dbn, s, q, nb * ho * wo, train, G)
+                    std = _bn_stats(dbn, s, q, nb * ho * wo, train, G, U)
                     out = ops.bn_apply(z3, st3.mean, st3.rstd, blk.bn3.weight, blk.bn3.bias, res=zd,
                                        bn2=(std.mean, std.rstd, dbn.weight, dbn.bias), relu=True, groups=G)
                 else:
@@ -145,7 +152,7 @@ class _EncoderFn(torch.autograd.Function):
                 cur = out
         feat = ops.avgpool_fwd(cur)
         if train:  # nn.BatchNorm2d bookkeeping: one fused increment for all 53 counters
-            torch._foreach_add_(enc._bn_counters(), G)
+            torch._foreach_add_(enc._bn_counters(), G * U)
         S["final_hw"] = (cur.shape[1], cur.shape[2])
         ctx.enc = enc
         ctx.S = S
@@ -163,20 +170,11 @@ class _EncoderFn(torch.autograd.Function):
         dfeat = dfeat.contiguous().view(dfeat.shape[0], -1).to(torch.float32)
         fh, fw = S["final_hw"]
         g, g2 = ops.avgpool_bwd(dfeat, fh, fw), None
-        second_update = getattr(enc, "_recompute_bn_update", False) and train
 
         def bn_bwd(bn, st, g1, g2_, act, z, want_g_out=False):
             r = ops.bn_backward(g1, g2_, act, z, st.mean, st.rstd, bn.weight, want_g_out=want_g_out,
                                 batch_stats=train, groups=G)
             grads[bn.weight], grads[bn.bias] = r[1], r[2]
-            if second_update:  # the reference's reentrant checkpoint re-runs the forward in backward
-                if G == 1:
-                    ops.bn_running_update(st.mean, st.rstd, BN_EPS, st.count, BN_MOMENTUM, bn.running_mean,
-                                          bn.running_var)
-                else:  # the recompute runs in backward order: last forward call first
-                    for gi in range(G - 1, -1, -1):
-                        ops.bn_running_update(st.mean[gi], st.rstd[gi], BN_EPS, st.count, BN_MOMENTUM,
-                                              bn.running_mean, bn.running_var)
             return (r[0], r[3]) if want_g_out else r[0]
 
         for rec in reversed(S["blocks"]):
@@ -217,14 +215,12 @@ class _EncoderFn(torch.autograd.Function):
         m0 = dz0.numel() // 64
         grads[enc[0].weight] = ops.conv_wgrad(col0.view(1, 1, m0, 192), dz0.view(1, 1, m0, 64), 1, reduce_cin=147,
                                               reduce_taps=1, out_shape=(64, 3, 7, 7))
-        if second_update:
-            torch._foreach_add_(enc._bn_counters(), G)
         if enc._bwd_post_cb is not None:
             enc._bwd_post_cb(enc, ctx.G)
         ctx.S = None
         # dL/dx of the stem is not produced: nothing on the IRFD path consumes the image gradient (train.py only sets
         # requires_grad on the batch as a side effect of the R1 penalty).
-        return (None, None, None) + tuple(grads.get(p) for p in enc._flat_params())
+        return (None, None, None, None) + tuple(grads.get(p) for p in enc._flat_params())
 
 
 class ResNet50Encoder(nn.Sequential):
@@ -265,7 +261,7 @@ class ResNet50Encoder(nn.Sequential):
             raise ops._lib.IrfdError("ResNet50Encoder: CUDA tensors only (no CPU fallback on the IRFD hot path)")
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] % 32 or x.shape[3] % 32:
             raise ops._lib.IrfdError(f"ResNet50Encoder: expected [N,3,H,W] with H,W multiples of 32, got {tuple(x.shape)}")
-        return _EncoderFn.apply(x, self, 1, *self._flat_params())
+        return _EncoderFn.apply(x, self, 1, None, *self._flat_params())
 
     def can_group(self, x: torch.Tensor, groups: int) -> bool:
         """Grouped statistics need every layer's per-group row count to be a whole number of 128-pixel GEMM tiles."""
@@ -274,10 +270,11 @@ class ResNet50Encoder(nn.Sequential):
         per_group = x.size(0) // groups
         return (per_group * (x.shape[2] // 32) * (x.shape[3] // 32)) % 128 == 0
 
-    def forward_groups(self, x, groups: int):
-        """x = `groups` batches stacked along dim 0; equivalent to `groups` consecutive calls (per-call BN stats)."""
+    def forward_groups(self, x, groups: int, stem_cols=None):
+        """x = `groups` batches stacked along dim 0; equivalent to `groups` consecutive calls (per-call BN stats).
+        stem_cols: optional `ops.im2col_stem(x, 192)` computed by the caller (shared by encoders fed the same x)."""
         if not x.is_cuda:
             raise ops._lib.IrfdError("ResNet50Encoder: CUDA tensors only (no CPU fallback on the IRFD hot path)")
         if not self.can_group(x, groups):
             raise ops._lib.IrfdError(f"ResNet50Encoder.forward_groups: shape {tuple(x.shape)} cannot form {groups} groups")
-        return _EncoderFn.apply(x, self, groups, *self._flat_params())
+        return _EncoderFn.apply(x, self, groups, stem_cols, *self._flat_params())

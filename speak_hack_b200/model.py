@@ -81,7 +81,10 @@ class IRFD(nn.Module):
         second time during backward.  Activations are kept instead of recomputed (180 GB of HBM)."""
         if torch.is_grad_enabled() and x.requires_grad:
             enc._recompute_bn_update = enc.training
-            return enc(x)
+            try:
+                return enc(x)
+            finally:
+                enc._recompute_bn_update = False
         with torch.no_grad():
             return enc(x)
 
@@ -106,19 +109,24 @@ class IRFD(nn.Module):
             # replays each encoder's backward on the stream its forward ran on.
             cur = torch.cuda.current_stream(x.device)
             streams = self.encoder_streams(x.device)
+            cols = ops.im2col_stem(x.detach().contiguous().to(torch.float32), 192)  # shared by the three stems
             fork = torch.cuda.Event()
             fork.record(cur)
             feats = []
             for enc, st in zip((self.Ei, self.Ee, self.Ep), streams):
                 st.wait_event(fork)
                 x.record_stream(st)
+                cols.record_stream(st)
                 with torch.cuda.stream(st):
                     if torch.is_grad_enabled() and x.requires_grad:
                         enc._recompute_bn_update = enc.training
-                        f = enc.forward_groups(x, 2)
+                        try:
+                            f = enc.forward_groups(x, 2, cols)
+                        finally:
+                            enc._recompute_bn_update = False
                     else:
                         with torch.no_grad():
-                            f = enc.forward_groups(x, 2)
+                            f = enc.forward_groups(x, 2, cols)
                 f.record_stream(cur)
                 feats.append(f)
             for st in streams:

@@ -217,8 +217,7 @@ def bn_finalize(ssum, ssq, count, eps, momentum, running_mean=None, running_var=
     mean = torch.empty(shape, dtype=F32, device=ssum.device)
     rstd = torch.empty(shape, dtype=F32, device=ssum.device)
     _call("irfd_bn_finalize", ssum.data_ptr(), ssq.data_ptr(), tiles // groups, c, int(count), eps, momentum,
-          mean.data_ptr(), rstd.data_ptr(), _ptr(running_mean), _ptr(running_var), running_updates, groups, _stream(),
-          launches=1 if groups == 1 else 1 + groups * running_updates)
+          mean.data_ptr(), rstd.data_ptr(), _ptr(running_mean), _ptr(running_var), running_updates, groups, _stream())
     return mean, rstd
 
 
