@@ -261,6 +261,10 @@ def run_native(args):
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
 
     # ---- roofline pass: per-launch CUDA events around every tensor-core GEMM launch (same stream), few steps
+    # serialise the three encoder streams for this pass: an event pair on one stream would otherwise also time the
+    # kernels that happen to run concurrently on the others
+    model._enc_streams = [torch.cuda.current_stream(dev)] * 3
+    trainer.buckets.producer_streams = []
     ops.gemm_timing_begin()
     rsteps = min(args.steps, 3)
     for _ in range(rsteps):

@@ -100,9 +100,11 @@ int irfd_bn_apply(const void* z, const float* mean, const float* rstd, const flo
                   void* out, long long rows, int c, int relu, int groups, irfd_stream_t stream);
 long long irfd_bn_bwd_workspace_bytes(long long rows, int c, int groups);
 int irfd_bn_backward(const void* g1, const void* g2, const void* act, const void* z, const float* mean,
-                     const float* rstd, const float* gamma, void* dz, void* g_out, float* dgamma, float* dbeta,
-                     float grad_beta, int batch_stats, long long rows, int c, int groups, void* workspace,
+                     const float* rstd, const float* gamma, const float* beta, void* dz, void* g_out, float* dgamma,
+                     float* dbeta, float grad_beta, int batch_stats, long long rows, int c, int groups, void* workspace,
                      long long workspace_bytes, irfd_stream_t stream);
+/* mask: act != NULL -> (act > 0);  act == NULL and beta != NULL -> recomputed as gamma*xhat + beta > 0 (a BN+ReLU
+ * without residual, saves reading the activation);  both NULL -> g already masked. */
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Layout / gather kernels for the strided ResNet convs and pooling (torchvision resnet.py:197-205, 133-137, 241).

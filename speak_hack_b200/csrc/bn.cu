@@ -183,8 +183,9 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z, BnAffine p1, const __nv_bfl
 __global__ void __launch_bounds__(kRvThreads)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
                      const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ z,
-                     const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ partial,
-                     long long rows, int C, int rows_per_blk) {
+                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float* __restrict__ partial, long long rows, int C,
+                     int rows_per_blk) {
   extern __shared__ float red_smem[];
   RowVec rv(C);
   {
@@ -201,9 +202,13 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
 #pragma unroll
   for (int t = 0; t < 8; ++t) acc[0][t] = acc[1][t] = 0.f;
   if (rv.active) {
-    float m[8], rs[8];
+    float m[8], rs[8], ga[8], be[8];
     loadf8(mean + rv.cv * 8, m);
     loadf8(rstd + rv.cv * 8, rs);
+    if (beta != nullptr) {  // ReLU mask recomputed from z: relu(gamma*xhat + beta) > 0  (no residual on this BN)
+      loadf8(gamma + rv.cv * 8, ga);
+      loadf8(beta + rv.cv * 8, be);
+    }
     const long long r0 = (long long)blockIdx.x * rows_per_blk;
     long long r1 = r0 + rows_per_blk;
     if (r1 > rows) r1 = rows;
@@ -217,12 +222,15 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
 #pragma unroll
         for (int t = 0; t < 8; ++t) g[t] += h[t];
       }
+      load8(z + off, zz);
       if (act != nullptr) {
         load8(act + off, a);
 #pragma unroll
         for (int t = 0; t < 8; ++t) g[t] = a[t] > 0.f ? g[t] : 0.f;
+      } else if (beta != nullptr) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) g[t] = (ga[t] * ((zz[t] - m[t]) * rs[t]) + be[t]) > 0.f ? g[t] : 0.f;
       }
-      load8(z + off, zz);
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         acc[0][t] += g[t];
@@ -278,8 +286,9 @@ __global__ void __launch_bounds__(kRvThreads)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
                     const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ z,
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-                    const float* __restrict__ c1, const float* __restrict__ c2, __nv_bfloat16* __restrict__ dz,
-                    __nv_bfloat16* __restrict__ g_out, long long rows, int C, int rows_per_blk) {
+                    const float* __restrict__ beta, const float* __restrict__ c1, const float* __restrict__ c2,
+                    __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ g_out, long long rows, int C,
+                    int rows_per_blk) {
   RowVec rv(C);
   if (!rv.active) return;
   {
@@ -295,9 +304,10 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* _
     c1 += (size_t)blockIdx.y * C;
     c2 += (size_t)blockIdx.y * C;
   }
-  float m[8], rs[8], k0[8], k1[8], k2[8];
+  float m[8], rs[8], k0[8], k1[8], k2[8], ga[8], be[8];
+  if (beta != nullptr) loadf8(beta + rv.cv * 8, be);
   {
-    float ga[8], a1[8], a2[8];
+    float a1[8], a2[8];
     loadf8(mean + rv.cv * 8, m);
     loadf8(rstd + rv.cv * 8, rs);
     loadf8(gamma + rv.cv * 8, ga);
@@ -323,13 +333,16 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* _
 #pragma unroll
       for (int t = 0; t < 8; ++t) g[t] += h[t];
     }
+    load8(z + off, zz);
     if (act != nullptr) {
       float a[8];
       load8(act + off, a);
 #pragma unroll
       for (int t = 0; t < 8; ++t) g[t] = a[t] > 0.f ? g[t] : 0.f;
+    } else if (beta != nullptr) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) g[t] = (ga[t] * ((zz[t] - m[t]) * rs[t]) + be[t]) > 0.f ? g[t] : 0.f;
     }
-    load8(z + off, zz);
 #pragma unroll
     for (int t = 0; t < 8; ++t) o[t] = k0[t] * (g[t] - k1[t] - (zz[t] - m[t]) * rs[t] * k2[t]);
     store8(dz + off, o);
@@ -405,9 +418,9 @@ extern "C" long long irfd_bn_bwd_workspace_bytes(long long rows, int c, int grou
 
 // Full BN backward (reduce -> finalize -> apply).  workspace: [groups][nblk][2][C] partials, c1[groups][C], c2[...].
 extern "C" int irfd_bn_backward(const void* g1, const void* g2, const void* act, const void* z, const float* mean,
-                                const float* rstd, const float* gamma, void* dz, void* g_out, float* dgamma,
-                                float* dbeta, float grad_beta, int batch_stats, long long rows, int c, int groups,
-                                void* workspace, long long workspace_bytes, cudaStream_t stream) {
+                                const float* rstd, const float* gamma, const float* beta, void* dz, void* g_out,
+                                float* dgamma, float* dbeta, float grad_beta, int batch_stats, long long rows, int c,
+                                int groups, void* workspace, long long workspace_bytes, cudaStream_t stream) {
   IRFD_CHECK_ARG(g1 && z && mean && rstd && gamma && dz && dgamma && dbeta && workspace, "bn_backward: null pointer");
   IRFD_CHECK_ARG(c % 8 == 0 && c <= 2048 && rows > 0, "bn_backward: C must be a multiple of 8 and <= 2048");
   IRFD_CHECK_ARG(groups >= 1 && rows % groups == 0, "bn_backward: rows must split evenly into groups");
@@ -426,12 +439,13 @@ extern "C" int irfd_bn_backward(const void* g1, const void* g2, const void* act,
   auto A = reinterpret_cast<const __nv_bfloat16*>(act);
   auto Z = reinterpret_cast<const __nv_bfloat16*>(z);
   const dim3 grid(nblk, groups);
-  bn_bwd_reduce_kernel<<<grid, kRvThreads, smem, stream>>>(G1, G2, A, Z, mean, rstd, partial, grows, c, rpb);
+  bn_bwd_reduce_kernel<<<grid, kRvThreads, smem, stream>>>(G1, G2, A, Z, mean, rstd, gamma, beta, partial, grows, c,
+                                                           rpb);
   IRFD_CHECK_LAUNCH();
   bn_bwd_finalize_kernel<<<(c + 31) / 32, 1024, 0, stream>>>(partial, nblk, c, (double)grows, dgamma, dbeta, grad_beta,
                                                                c1, c2, batch_stats, groups);
   IRFD_CHECK_LAUNCH();
-  bn_bwd_apply_kernel<<<grid, kRvThreads, 0, stream>>>(G1, G2, A, Z, mean, rstd, gamma, c1, c2,
+  bn_bwd_apply_kernel<<<grid, kRvThreads, 0, stream>>>(G1, G2, A, Z, mean, rstd, gamma, beta, c1, c2,
                                                         reinterpret_cast<__nv_bfloat16*>(dz),
                                                         reinterpret_cast<__nv_bfloat16*>(g_out), grows, c, rpb);
   IRFD_CHECK_LAUNCH();

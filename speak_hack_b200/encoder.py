@@ -171,9 +171,10 @@ class _EncoderFn(torch.autograd.Function):
         fh, fw = S["final_hw"]
         g, g2 = ops.avgpool_bwd(dfeat, fh, fw), None
 
-        def bn_bwd(bn, st, g1, g2_, act, z, want_g_out=False):
-            r = ops.bn_backward(g1, g2_, act, z, st.mean, st.rstd, bn.weight, want_g_out=want_g_out,
-                                batch_stats=train, groups=G)
+        def bn_bwd(bn, st, g1, g2_, act, z, want_g_out=False, mask_from_z=False):
+            r = ops.bn_backward(g1, g2_, None if mask_from_z else act, z, st.mean, st.rstd, bn.weight,
+                                want_g_out=want_g_out, batch_stats=train, groups=G,
+                                beta=bn.bias if mask_from_z else None)
             grads[bn.weight], grads[bn.bias] = r[1], r[2]
             return (r[0], r[3]) if want_g_out else r[0]
 
@@ -184,7 +185,7 @@ class _EncoderFn(torch.autograd.Function):
             dz3, gmask = bn_bwd(blk.bn3, st3, g, g2, out, z3, want_g_out=True)
             grads[blk.conv3.weight] = ops.conv_wgrad(a2, dz3, 1)
             d_a2 = ops.conv_gemm(dz3, ops.pack_conv_weight(blk.conv3.weight, ops.PACK_DGRAD), 1)
-            dz2 = bn_bwd(blk.bn2, st2, d_a2, None, a2, z2)
+            dz2 = bn_bwd(blk.bn2, st2, d_a2, None, a2, z2, mask_from_z=True)
             if blk.stride == 1:
                 grads[blk.conv2.weight] = ops.conv_wgrad(a1, dz2, 3)
                 d_a1 = ops.conv_gemm(dz2, ops.pack_conv_weight(blk.conv2.weight, ops.PACK_DGRAD), 3)
@@ -195,7 +196,7 @@ class _EncoderFn(torch.autograd.Function):
                                                          out_shape=(planes, planes, 3, 3))
                 dcol = ops.gemm_rows(dz2.view(m2, planes), ops.pack_conv_weight(blk.conv2.weight, ops.PACK_DCOL))
                 d_a1 = ops.col2im_3x3s2(dcol, nb, hh, ww, planes)
-            dz1 = bn_bwd(blk.bn1, st1, d_a1, None, a1, z1)
+            dz1 = bn_bwd(blk.bn1, st1, d_a1, None, a1, z1, mask_from_z=True)
             grads[blk.conv1.weight] = ops.conv_wgrad(xin, dz1, 1)
             d_in = ops.conv_gemm(dz1, ops.pack_conv_weight(blk.conv1.weight, ops.PACK_DGRAD), 1)
             if blk.downsample is not None:
@@ -211,7 +212,7 @@ class _EncoderFn(torch.autograd.Function):
                 g, g2 = d_in, gmask
         col0, z0, st0, a0, arg0 = S["stem"]
         d_a0 = ops.maxpool_bwd(g, arg0, g2)
-        dz0 = bn_bwd(enc[1], st0, d_a0, None, a0, z0)
+        dz0 = bn_bwd(enc[1], st0, d_a0, None, a0, z0, mask_from_z=True)
         m0 = dz0.numel() // 64
         grads[enc[0].weight] = ops.conv_wgrad(col0.view(1, 1, m0, 192), dz0.view(1, 1, m0, 64), 1, reduce_cin=147,
                                               reduce_taps=1, out_shape=(64, 3, 7, 7))

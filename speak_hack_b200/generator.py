@@ -238,6 +238,16 @@ class SynthesisNetwork(nn.Module):
         p += [self.to_rgb.weight, self.to_rgb.bias]
         return p
 
+    def prepack(self, backward: bool = True) -> None:
+        """Build (or refresh) the cached bf16 repacks of every conv weight on the CURRENT stream.  Callers that run
+        several generator calls concurrently on different streams do this before forking, so no stream ever reads a
+        repack another stream is still writing."""
+        for blk in self.layers:
+            for conv in (blk.conv1, blk.conv2):
+                ops.pack_conv_weight(conv.weight, ops.PACK_FPROP)
+                if backward:
+                    ops.pack_conv_weight(conv.weight, ops.PACK_DGRAD)
+
     def draw_noises(self, batch: int, device) -> List[torch.Tensor]:
         """One N(0,1) plane per ApplyNoise in execution order: 4x4, then (conv1, conv2) of every block."""
         out = [self.noise_fn(batch, 4, 4, device)]

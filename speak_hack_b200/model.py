@@ -9,6 +9,7 @@ the reference's order and the [B,6144] concatenation, which is a bit-exact copy)
 from __future__ import annotations
 
 import logging
+import os
 
 import torch
 import torch.nn as nn
@@ -92,7 +93,10 @@ class IRFD(nn.Module):
         """Three side streams (one per encoder), created on first use."""
         st = getattr(self, "_enc_streams", None)
         if st is None or st[0].device != device:
-            st = [torch.cuda.Stream(device) for _ in range(3)]
+            if os.environ.get("IRFD_NO_ENC_STREAMS"):  # profiling aid: serialise everything on the current stream
+                st = [torch.cuda.current_stream(device)] * 3
+            else:
+                st = [torch.cuda.Stream(device) for _ in range(3)]
             self._enc_streams = st
         return st
 
@@ -229,9 +233,25 @@ def _irfd_forward_static(self: IRFD, x_s, x_t, ctrl):
     Returns (x_s_recon, x_t_recon, fi_s, fi_t) with fi_* UNswapped (the identity MSE is symmetric in them)."""
     fi_s, fe_s, fp_s, fi_t, fe_t, fp_t = self._encode_all(x_s, x_t)
     gen_s, gen_t = _SwapCatFn.apply(ctrl, fi_s, fe_s, fp_s, fi_t, fe_t, fp_t)
-    x_s_recon = self.Gd.forward_static(gen_s, ctrl, 1)
-    x_t_recon = self.Gd.forward_static(gen_t, ctrl, 2)
-    return x_s_recon, x_t_recon, fi_s, fi_t
+    # the two generator calls are independent: run them on two streams (autograd replays each backward on the same
+    # stream); the weight repacks they share are built before the fork
+    dev = gen_s.device
+    cur = torch.cuda.current_stream(dev)
+    st_a, st_b = self.encoder_streams(dev)[:2]
+    self.Gd.synthesis.prepack(backward=torch.is_grad_enabled())
+    fork = torch.cuda.Event()
+    fork.record(cur)
+    outs = []
+    for g, st, idx in ((gen_s, st_a, 1), (gen_t, st_b, 2)):
+        st.wait_event(fork)
+        g.record_stream(st)
+        with torch.cuda.stream(st):
+            img = self.Gd.forward_static(g, ctrl, idx)
+        img.record_stream(cur)
+        outs.append(img)
+    cur.wait_stream(st_a)
+    cur.wait_stream(st_b)
+    return outs[0], outs[1], fi_s, fi_t
 
 
 IRFD.forward_static = _irfd_forward_static

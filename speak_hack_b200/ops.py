@@ -247,7 +247,7 @@ def bn_apply(z, mean, rstd, gamma, beta, res=None, bn2=None, relu=True, groups=1
     return out
 
 
-def bn_backward(g1, g2, act, z, mean, rstd, gamma, want_g_out=False, batch_stats=True, groups=1):
+def bn_backward(g1, g2, act, z, mean, rstd, gamma, want_g_out=False, batch_stats=True, groups=1, beta=None):
     """Returns dz (bf16), dgamma, dbeta (fp32) [, masked g (bf16)]."""
     lib = _lib.load()
     c = z.shape[-1]
@@ -258,7 +258,7 @@ def bn_backward(g1, g2, act, z, mean, rstd, gamma, want_g_out=False, batch_stats
     dbeta = torch.empty(c, dtype=F32, device=z.device)
     ws = workspace(lib.irfd_bn_bwd_workspace_bytes(rows, c, groups), z.device)
     _call("irfd_bn_backward", g1.data_ptr(), _ptr(g2), _ptr(act), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-          gamma.data_ptr(), dz.data_ptr(), _ptr(g_out), dgamma.data_ptr(), dbeta.data_ptr(), 0.0,
+          gamma.data_ptr(), _ptr(beta), dz.data_ptr(), _ptr(g_out), dgamma.data_ptr(), dbeta.data_ptr(), 0.0,
           1 if batch_stats else 0, rows, c, groups,
           ws.data_ptr(), ws.numel(), _stream(), launches=3)
     if want_g_out:

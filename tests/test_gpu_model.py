@@ -223,13 +223,15 @@ def test_encoder_backward_train_in_context(cuda_device):
             log.append(("dgrad", tuple(x.shape), cout, ksize, rel(r.float(), full)))
         return r
 
-    def bnb(g1, g2, act, z, mean, rstd, gamma, want_g_out=False, batch_stats=True, groups=1):
+    def bnb(g1, g2, act, z, mean, rstd, gamma, want_g_out=False, batch_stats=True, groups=1, beta=None):
         assert groups == 1
-        r = orig[2](g1, g2, act, z, mean, rstd, gamma, want_g_out, batch_stats, groups)
+        r = orig[2](g1, g2, act, z, mean, rstd, gamma, want_g_out, batch_stats, groups, beta)
         c = z.shape[-1]
         g = g1.float() + (g2.float() if g2 is not None else 0)
         if act is not None:
             g = g * (act.float() > 0)
+        elif beta is not None:  # mask recomputed from z: relu(BN(z)) > 0
+            g = g * ((gamma * ((z.float() - mean) * rstd) + beta) > 0)
         g = g.reshape(-1, c)
         xh = (z.float().reshape(-1, c) - mean) * rstd
         full = gamma * rstd * (g - g.mean(0) - xh * (g * xh).mean(0))
@@ -370,3 +372,38 @@ def test_paired_encoder_pass_equals_two_calls(cuda_device):
         worst = max(worst, O.rel_l2(p2.grad, p1.grad))
     print(f"[parity] paired vs separate encoder passes: worst param-grad rel-L2 {worst:.3e}")
     assert worst < 1e-4
+
+
+def test_golden_train_step_bn_buffers_and_losses(cuda_device):
+    """The reference's G-step side effects (golden vectors from the unmodified reference, train mode, inputs requiring
+    grad): reentrant checkpoints update every BN running buffer twice per call -> num_batches_tracked 4
+    after one step, running statistics after 4 momentum updates; encoders receive gradients."""
+    import irfd_oracle as O
+    import speak_hack_b200 as P
+
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "irfd_train_b2.pt"), weights_only=False)
+    torch.manual_seed(O.WEIGHT_SEED)
+    net = P.IRFD()
+    O.perturb_noise_weights(net.Gd)
+    net = net.to(cuda_device).train()
+    x_s, x_t = O.synthetic_pair(2)
+    xs = x_s.to(cuda_device).requires_grad_(True)
+    xt = x_t.to(cuda_device).requires_grad_(True)
+    torch.manual_seed(O.FORWARD_SEED)
+    out = net(xs, xt)
+    l_id = P.mse_loss(out[2], out[5])
+    l_rec = P.mse_loss(xs.detach(), out[0]) + P.mse_loss(xt.detach(), out[1])
+    (l_id + l_rec).backward()
+    torch.cuda.synchronize()
+    sd = net.state_dict()
+    assert int(sd["Ei.1.num_batches_tracked"]) == int(gold["bn_buffers"]["Ei.1.num_batches_tracked"]) == 4
+    e_m = O.rel_l2(sd["Ei.1.running_mean"], gold["bn_buffers"]["Ei.1.running_mean"])
+    e_v = O.rel_l2(sd["Ei.1.running_var"], gold["bn_buffers"]["Ei.1.running_var"])
+    e_f = max(O.rel_l2(a, b) for a, b in zip(out[2:8], gold["feat"]))
+    print(f"[parity] golden train step: stem BN running mean {e_m:.3e} var {e_v:.3e}; features {e_f:.3e}; "
+          f"l_identity {l_id.item():.4e} (ref {gold['l_identity']:.4e})")
+    assert e_m < 1e-2 and e_v < 1e-2
+    assert e_f < 0.25  # train-mode conditioning (SURVEY §7)
+    assert abs(l_id.item() - gold["l_identity"]) <= 0.3 * abs(gold["l_identity"])
+    got = {n for n, p in net.named_parameters() if p.grad is not None}
+    assert set(gold["grad_norms"]) == got, (set(gold["grad_norms"]) ^ got)  # same 560 tensors receive gradients
