@@ -58,6 +58,13 @@ int irfd_conv_gemm(const void* x, int n, int h, int w, int cin, const void* wk, 
                    void* out2, int mode, const float* bias, const float* nw, const float* noise, const float* sp1,
                    const float* s1, float* stat_sum, float* stat_sq, int force_block_n, irfd_stream_t stream);
 
+/* Inference variant (mode 3): y = [relu](acc*scale[c] + shift[c] [+ res[pixel,c]]) -> bf16.  Folds an eval-mode
+ * BatchNorm2d (scale/shift from irfd_bn_eval_affine), the ReLU and the Bottleneck residual add into the conv
+ * (torchvision/models/resnet.py:143-164 in eval mode); res is NHWC bf16 of the output shape or NULL. */
+int irfd_conv_gemm_affine(const void* x, int n, int h, int w, int cin, const void* wk, int cout, int ksize, void* out,
+                          const float* scale, const float* shift, const void* res, int relu, int force_block_n,
+                          irfd_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Weight gradient of the same convolutions (tcgen05, both operands MN-major, deterministic split-K over pixels).
  * Replaces: autograd's convolution_backward(weight) for styleganv1.py:615-616 and torchvision resnet.py:133-141.
@@ -92,6 +99,8 @@ int irfd_bn_finalize(const float* psum, const float* psq, int tiles, int c, long
                      float* mean, float* rstd, float* running_mean, float* running_var, int running_updates,
                      int groups, irfd_stream_t stream);
 int irfd_bn_eval_rstd(const float* running_var, float eps, float* rstd, int c, irfd_stream_t stream);
+int irfd_bn_eval_affine(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
+                        float eps, float* scale, float* shift, int c, irfd_stream_t stream);
 /* second momentum update from saved batch mean/rstd (what the reference's checkpoint recompute does) */
 int irfd_bn_running_update(const float* mean, const float* rstd, float eps, long long count, float momentum,
                            float* running_mean, float* running_var, int c, irfd_stream_t stream);

@@ -93,6 +93,17 @@ __global__ void bn_running_update_kernel(const float* __restrict__ mean, const f
   running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
 }
 
+// eval mode folded into a conv epilogue: scale = gamma/sqrt(var+eps), shift = beta - mean*scale
+__global__ void bn_eval_affine_kernel(const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                      float* __restrict__ scale, float* __restrict__ shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] * rsqrtf(running_var[c] + eps);
+  scale[c] = sc;
+  shift[c] = beta[c] - running_mean[c] * sc;
+}
+
 // eval mode: rstd from the running variance
 __global__ void bn_eval_rstd_kernel(const float* __restrict__ running_var, float eps, float* __restrict__ rstd, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -372,6 +383,15 @@ extern "C" int irfd_bn_running_update(const float* mean, const float* rstd, floa
   IRFD_CHECK_ARG(mean && rstd && running_mean && running_var && c > 0 && count > 0, "bn_running_update: bad argument");
   bn_running_update_kernel<<<(c + 255) / 256, 256, 0, stream>>>(mean, rstd, eps, (double)count, momentum, running_mean,
                                                                  running_var, c);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_bn_eval_affine(const float* running_mean, const float* running_var, const float* gamma,
+                                   const float* beta, float eps, float* scale, float* shift, int c,
+                                   cudaStream_t stream) {
+  IRFD_CHECK_ARG(running_mean && running_var && gamma && beta && scale && shift && c > 0, "bn_eval_affine: bad argument");
+  bn_eval_affine_kernel<<<(c + 255) / 256, 256, 0, stream>>>(running_mean, running_var, gamma, beta, eps, scale, shift, c);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }

@@ -14,6 +14,8 @@
 // Epilogue modes
 //   PLAIN : y = acc (+ bias[n])                                       -> bf16           (dgrad, 1x1, generic)
 //   STATS : y = acc -> bf16, plus per-tile per-channel sum / sum-of-squares of the stored values (train-mode BN)
+//   AFFINE: y = [relu]( acc*scale[n] + shift[n] [+ res[m,n]] ) -> bf16   (inference: eval-mode BatchNorm, ReLU and the
+//           residual add of a Bottleneck folded into the conv, torchvision/models/resnet.py:143-164)
 //   STYLE : z = acc + bias[n] + nw[n]*noise[m];  a = lrelu_0.2(z);  y = a*sp1[b,n] + s1[b,n]
 //           -> a (bf16, kept for backward) and y (bf16, next layer's input)
 //           reference: styleganv1.py:625-628 / 630-633 (conv -> ApplyNoise -> leaky_relu -> ApplyStyle)
@@ -22,7 +24,7 @@
 
 namespace irfd {
 
-enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_STYLE = 2 };
+enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_STYLE = 2, EPI_AFFINE = 3 };
 
 struct ConvGemmArgs {
   int M_total, N_total;
@@ -36,6 +38,8 @@ struct ConvGemmArgs {
   const float* s1;
   float* stat_sum;
   float* stat_sq;
+  const __nv_bfloat16* res;  // AFFINE: optional residual [M_total][N_total]
+  int relu;                  // AFFINE: apply ReLU
 };
 
 constexpr int kNumThreads = 320;      // 10 warps
@@ -209,6 +213,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int i = etid; i < BLOCK_N; i += kEpiThreads) vb[i] = p.bias[ng0 + i];
           named_bar_sync(1, kEpiThreads);
         }
+      } else if constexpr (MODE == EPI_AFFINE) {
+        for (int i = etid; i < BLOCK_N; i += kEpiThreads) {
+          vb[i] = p.bias[ng0 + i];   // shift
+          vnw[i] = p.nw[ng0 + i];    // scale
+        }
+        named_bar_sync(1, kEpiThreads);
       }
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
@@ -234,6 +244,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           float o[8], o2[8];
+          float rres[8];
+          if constexpr (MODE == EPI_AFFINE) {
+            if (p.res != nullptr && m0 + r < p.M_total) {
+              const uint4 u = *reinterpret_cast<const uint4*>(p.res + (size_t)(m0 + r) * p.N_total + ng0 + cbase + jj * 8);
+              const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+              rres[0] = a0.x; rres[1] = a0.y; rres[2] = a1.x; rres[3] = a1.y;
+              rres[4] = a2.x; rres[5] = a2.y; rres[6] = a3.x; rres[7] = a3.y;
+            } else {
+#pragma unroll
+              for (int t = 0; t < 8; ++t) rres[t] = 0.f;
+            }
+          }
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             const int c = cbase + jj * 8 + t;
@@ -245,6 +267,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               o2[t] = a * vsp1[img_local * 256 + c] + vs1[img_local * 256 + c];
             } else if constexpr (MODE == EPI_PLAIN) {
               o[t] = (p.bias != nullptr) ? acc + vb[c] : acc;
+            } else if constexpr (MODE == EPI_AFFINE) {
+              const float y = acc * vnw[c] + vb[c] + rres[t];
+              o[t] = p.relu ? fmaxf(y, 0.f) : y;
             } else {
               o[t] = acc;
             }
@@ -359,15 +384,15 @@ extern "C" int irfd_conv_gemm_m_tiles(int n, int h, int w) {
   return (int)((m + 127) / 128);
 }
 
-extern "C" int irfd_conv_gemm(const void* x, int n, int h, int w, int cin, const void* wk, int cout, int ksize,
-                              void* out, void* out2, int mode, const float* bias, const float* nw, const float* noise,
-                              const float* sp1, const float* s1, float* stat_sum, float* stat_sq, int force_block_n,
-                              cudaStream_t stream) {
+static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const void* wk, int cout, int ksize, void* out,
+                          void* out2, int mode, const float* bias, const float* nw, const float* noise,
+                          const float* sp1, const float* s1, float* stat_sum, float* stat_sq, const void* res, int relu,
+                          int force_block_n, cudaStream_t stream) {
   IRFD_CHECK_ARG(x && wk && out, "conv_gemm: null pointer");
   IRFD_CHECK_ARG(ksize == 1 || ksize == 3, "conv_gemm: ksize must be 1 or 3 (got %d)", ksize);
   IRFD_CHECK_ARG(cin % 64 == 0 && cin > 0, "conv_gemm: Cin must be a multiple of 64 (got %d)", cin);
   IRFD_CHECK_ARG(cout % 64 == 0 && cout > 0, "conv_gemm: Cout must be a multiple of 64 (got %d)", cout);
-  IRFD_CHECK_ARG(mode >= 0 && mode <= 2, "conv_gemm: bad mode %d", mode);
+  IRFD_CHECK_ARG(mode >= 0 && mode <= 3, "conv_gemm: bad mode %d", mode);
   const long long m_total_ll = (long long)n * h * w;
   IRFD_CHECK_ARG(m_total_ll > 0 && m_total_ll < (1ll << 31) - 256, "conv_gemm: bad pixel count");
   const int m_total = (int)m_total_ll;
@@ -407,6 +432,9 @@ extern "C" int irfd_conv_gemm(const void* x, int n, int h, int w, int cin, const
   a.H = H; a.W = W; a.HW = h * w; a.B = n;
   a.bias = bias; a.nw = nw; a.noise = noise; a.sp1 = sp1; a.s1 = s1;
   a.stat_sum = stat_sum; a.stat_sq = stat_sq;
+  a.res = reinterpret_cast<const __nv_bfloat16*>(res);
+  a.relu = relu;
+  if (mode == EPI_AFFINE) IRFD_CHECK_ARG(bias && nw, "conv_gemm: AFFINE mode needs scale and shift");
   if (mode == EPI_STYLE) {
     IRFD_CHECK_ARG(bias && nw && noise && sp1 && s1 && out2, "conv_gemm: STYLE mode needs bias/nw/noise/sp1/s1/out2");
     IRFD_CHECK_ARG(h * w >= 64, "conv_gemm: STYLE mode needs >= 64 pixels per image");
@@ -457,6 +485,23 @@ extern "C" int irfd_conv_gemm(const void* x, int n, int h, int w, int cin, const
     case EPI_PLAIN: return dispatch_block_n<EPI_PLAIN>(block_n, ma, mb, mo, mo2, a, stream);
     case EPI_STATS: return dispatch_block_n<EPI_STATS>(block_n, ma, mb, mo, mo2, a, stream);
     case EPI_STYLE: return dispatch_block_n<EPI_STYLE>(block_n, ma, mb, mo, mo2, a, stream);
+    case EPI_AFFINE: return dispatch_block_n<EPI_AFFINE>(block_n, ma, mb, mo, mo2, a, stream);
   }
   return IRFD_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" int irfd_conv_gemm(const void* x, int n, int h, int w, int cin, const void* wk, int cout, int ksize,
+                              void* out, void* out2, int mode, const float* bias, const float* nw, const float* noise,
+                              const float* sp1, const float* s1, float* stat_sum, float* stat_sq, int force_block_n,
+                              cudaStream_t stream) {
+  IRFD_CHECK_ARG(mode >= 0 && mode <= 2, "conv_gemm: bad mode %d", mode);
+  return conv_gemm_impl(x, n, h, w, cin, wk, cout, ksize, out, out2, mode, bias, nw, noise, sp1, s1, stat_sum, stat_sq,
+                        nullptr, 0, force_block_n, stream);
+}
+
+extern "C" int irfd_conv_gemm_affine(const void* x, int n, int h, int w, int cin, const void* wk, int cout, int ksize,
+                                     void* out, const float* scale, const float* shift, const void* res, int relu,
+                                     int force_block_n, cudaStream_t stream) {
+  return conv_gemm_impl(x, n, h, w, cin, wk, cout, ksize, out, nullptr, EPI_AFFINE, shift, scale, nullptr, nullptr,
+                        nullptr, nullptr, nullptr, res, relu, force_block_n, stream);
 }

@@ -76,6 +76,46 @@ def _conv_stats(x, wk, ksize, train):
     return ops.conv_gemm(x, wk, ksize, ops.EPI_PLAIN), None, None
 
 
+def _encoder_inference(enc, x, col0=None):
+    """Eval-mode, no-autograd forward: every BatchNorm (+ReLU, + the Bottleneck residual add) is folded into the
+    epilogue of the conv that feeds it (irfd_conv_gemm_affine), so a layer is ONE kernel and the pre-BN tensor is never
+    rounded to bf16 or written to HBM.  Same arithmetic as torchvision's Bottleneck in eval mode (resnet.py:143-164)."""
+    x = x.contiguous().to(torch.float32)
+    n, _, h, w = x.shape
+    if col0 is None:
+        col0 = ops.im2col_stem(x, 192)
+    m0 = col0.shape[0]
+    sc, sh = ops.bn_eval_affine(enc[1])
+    a0 = ops.conv_gemm_affine(col0.view(1, 1, m0, 192), ops.pack_conv_weight(enc[0].weight, ops.PACK_FLAT, kpad=192), 1,
+                              sc, sh, relu=True).view(n, h // 2, w // 2, 64)
+    cur, _ = ops.maxpool_fwd(a0)
+    for li in range(4, 8):
+        for blk in enc[li]:
+            nb, hh, ww, _cin = cur.shape
+            sc, sh = ops.bn_eval_affine(blk.bn1)
+            a1 = ops.conv_gemm_affine(cur, ops.pack_conv_weight(blk.conv1.weight, ops.PACK_FPROP), 1, sc, sh, relu=True)
+            planes = a1.shape[-1]
+            sc, sh = ops.bn_eval_affine(blk.bn2)
+            wk2 = ops.pack_conv_weight(blk.conv2.weight, ops.PACK_FPROP)
+            if blk.stride == 1:
+                a2 = ops.conv_gemm_affine(a1, wk2, 3, sc, sh, relu=True)
+            else:
+                col2 = ops.im2col_3x3s2(a1)
+                a2 = ops.conv_gemm_affine(col2.view(1, 1, col2.shape[0], 9 * planes), wk2, 1, sc, sh,
+                                          relu=True).view(nb, hh // 2, ww // 2, planes)
+            if blk.downsample is not None:
+                xs = ops.subsample2(cur) if blk.stride == 2 else cur
+                sc, sh = ops.bn_eval_affine(blk.downsample[1])
+                idn = ops.conv_gemm_affine(xs, ops.pack_conv_weight(blk.downsample[0].weight, ops.PACK_FPROP), 1, sc, sh,
+                                           relu=False)
+            else:
+                idn = cur
+            sc, sh = ops.bn_eval_affine(blk.bn3)
+            cur = ops.conv_gemm_affine(a2, ops.pack_conv_weight(blk.conv3.weight, ops.PACK_FPROP), 1, sc, sh, res=idn,
+                                       relu=True)
+    return ops.avgpool_fwd(cur).view(n, -1, 1, 1)
+
+
 class _EncoderFn(torch.autograd.Function):
     """forward(x [N,3,H,W] fp32, enc, groups, *params) -> features [N,2048,1,1] fp32.  params = enc._flat_params().
 
@@ -85,13 +125,13 @@ class _EncoderFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, enc, groups, col0, *params):
+    def forward(ctx, x, enc, groups, col0, recorded, *params):
         train = enc.training
         G = groups if train else 1  # eval-mode BN uses the shared running statistics: no groups needed
         # The reference wraps every encoder call in a reentrant checkpoint (model.py:84-90): a differentiated pass
         # re-runs the forward during backward and so updates the BN running buffers twice.  Both updates are
         # applied here, in the order the reference would produce them (forward order, then reverse order).
-        recorded = any(ctx.needs_input_grad)  # grad mode is off inside Function.forward; this says a backward can follow
+        # `recorded` (computed by the caller, where grad mode is visible) says a backward pass can follow
         U = 2 if (train and getattr(enc, "_recompute_bn_update", False) and recorded) else 1
         x = x.contiguous().to(torch.float32)
         n, _, h, w = x.shape
@@ -221,7 +261,7 @@ class _EncoderFn(torch.autograd.Function):
         ctx.S = None
         # dL/dx of the stem is not produced: nothing on the IRFD path consumes the image gradient (train.py only sets
         # requires_grad on the batch as a side effect of the R1 penalty).
-        return (None, None, None, None) + tuple(grads.get(p) for p in enc._flat_params())
+        return (None, None, None, None, None) + tuple(grads.get(p) for p in enc._flat_params())
 
 
 class ResNet50Encoder(nn.Sequential):
@@ -262,7 +302,14 @@ class ResNet50Encoder(nn.Sequential):
             raise ops._lib.IrfdError("ResNet50Encoder: CUDA tensors only (no CPU fallback on the IRFD hot path)")
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] % 32 or x.shape[3] % 32:
             raise ops._lib.IrfdError(f"ResNet50Encoder: expected [N,3,H,W] with H,W multiples of 32, got {tuple(x.shape)}")
-        return _EncoderFn.apply(x, self, 1, None, *self._flat_params())
+        return self._run(x, 1, None)
+
+    def _run(self, x, groups, stem_cols):
+        params = self._flat_params()
+        recorded = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        if not self.training and not recorded:
+            return _encoder_inference(self, x, stem_cols)  # inference: BN/ReLU/residual folded into the convs
+        return _EncoderFn.apply(x, self, groups, stem_cols, recorded, *params)
 
     def can_group(self, x: torch.Tensor, groups: int) -> bool:
         """Grouped statistics need every layer's per-group row count to be a whole number of 128-pixel GEMM tiles."""
@@ -278,4 +325,4 @@ class ResNet50Encoder(nn.Sequential):
             raise ops._lib.IrfdError("ResNet50Encoder: CUDA tensors only (no CPU fallback on the IRFD hot path)")
         if not self.can_group(x, groups):
             raise ops._lib.IrfdError(f"ResNet50Encoder.forward_groups: shape {tuple(x.shape)} cannot form {groups} groups")
-        return _EncoderFn.apply(x, self, groups, stem_cols, *self._flat_params())
+        return self._run(x, groups, stem_cols)

@@ -134,6 +134,32 @@ def conv_gemm(x, wk, ksize, mode=EPI_PLAIN, bias=None, nw=None, noise=None, sp1=
     return out
 
 
+def conv_gemm_affine(x, wk, ksize, scale, shift, res=None, relu=True, force_block_n=0):
+    """Inference conv with eval-mode BN (+ReLU, +residual) folded into the epilogue.  Returns out [N,H,W,Cout] bf16."""
+    _chk(x, BF16, "x")
+    _chk(wk, BF16, "wk")
+    n, h, w, cin = x.shape
+    cout = wk.shape[0]
+    out = torch.empty((n, h, w, cout), dtype=BF16, device=x.device)
+    if res is not None:
+        _chk(res, BF16, "res")
+        if res.numel() != out.numel():
+            raise _lib.IrfdError("conv_gemm_affine: residual shape mismatch")
+    _call("irfd_conv_gemm_affine", x.data_ptr(), n, h, w, cin, wk.data_ptr(), cout, ksize, out.data_ptr(),
+          scale.data_ptr(), shift.data_ptr(), _ptr(res), 1 if relu else 0, force_block_n, _stream())
+    return out
+
+
+def bn_eval_affine(bn):
+    """(scale, shift) of an eval-mode nn.BatchNorm2d, cached on nothing: two tiny launches per call."""
+    c = bn.weight.numel()
+    scale = torch.empty(c, dtype=F32, device=bn.weight.device)
+    shift = torch.empty(c, dtype=F32, device=bn.weight.device)
+    _call("irfd_bn_eval_affine", bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.weight.data_ptr(),
+          bn.bias.data_ptr(), float(bn.eps), scale.data_ptr(), shift.data_ptr(), c, _stream())
+    return scale, shift
+
+
 def gemm_rows(a2d, wk, mode=EPI_PLAIN):
     """Plain GEMM out[M, N] = a2d[M, K] @ wk[N, K]^T through the conv kernel (1x1 conv over a single row of pixels)."""
     m, k = a2d.shape

@@ -122,3 +122,25 @@ def test_wgrad(cuda_device, n, h, w, cin, cout, k):
     dw2 = ops.conv_wgrad(x, dy, k, dw=dw.clone(), beta=1.0)
     torch.cuda.synchronize()
     assert rel_l2(dw2, 2 * ref) < 1e-4
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k", [(2, 16, 16, 64, 256, 1), (3, 8, 8, 128, 128, 3), (1, 64, 64, 64, 64, 3)])
+@pytest.mark.parametrize("with_res,relu", [(False, True), (True, True), (True, False)])
+def test_affine_epilogue(cuda_device, n, h, w, cin, cout, k, with_res, relu):
+    """mode 3: eval-mode BN + ReLU + residual folded into the conv epilogue."""
+    from speak_hack_b200 import ops
+
+    dev = cuda_device
+    x, wt, wk = _mk(n, h, w, cin, cout, k, dev, seed=5)
+    g = torch.Generator(device="cpu").manual_seed(6)
+    scale = (torch.rand(cout, generator=g) + 0.5).to(dev)
+    shift = torch.randn(cout, generator=g).to(dev)
+    res = torch.randn(n, h, w, cout, generator=g).to(dev).to(torch.bfloat16) if with_res else None
+    y = ops.conv_gemm_affine(x, wk, k, scale, shift, res=res, relu=relu)
+    torch.cuda.synchronize()
+    ref = _ref(x, wt, k) * scale.view(1, 1, 1, -1) + shift.view(1, 1, 1, -1)
+    if with_res:
+        ref = ref + res.float()
+    if relu:
+        ref = F.relu(ref)
+    assert rel_l2(y.float(), ref) < 4e-3

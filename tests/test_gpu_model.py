@@ -132,7 +132,7 @@ def test_encoder_eval_and_train_forward(cuda_device, nets):
     e_eval = O.rel_l2(f, f_ref)
     print(f"[parity] encoder eval (fresh BN) features rel-L2 = {e_eval:.3e}")
     assert f.shape == (4, 2048, 1, 1)
-    assert e_eval < 1e-2
+    assert e_eval < 6e-3  # inference path: BN folded into the conv epilogue (ideal bf16-operand kernel: 3.7e-3)
     ref.train(), prod.train()
     sd0 = {k: v.clone() for k, v in ref.Ee.state_dict().items()}
     with torch.no_grad():
@@ -337,8 +337,8 @@ def test_golden_eval_features(cuda_device):
     errs = [O.rel_l2(a, b) for a, b in zip(out[2:8], gold["feat"])]
     e_img = O.rel_l2(out[0][..., ::8, ::8], gold["img"][0]["sub"])
     print(f"[parity] golden (reference) eval: features max {max(errs):.3e}, image {e_img:.3e}")
-    assert max(errs) < 2e-2
-    assert e_img < 0.25
+    assert max(errs) < 1e-2   # north_star bound for bf16 paths (measured 3.9e-3 with BN folded into the conv epilogues)
+    assert e_img < 0.1        # 13 multiplicative style layers amplify the feature error ~10x (measured 4.2e-2)
 
 
 def test_paired_encoder_pass_equals_two_calls(cuda_device):
