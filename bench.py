@@ -285,6 +285,8 @@ def run_native(args):
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
     if not peak_tf:
         peak_tf, peak_src = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
+    hbm = {k: v for k, v in fam.items() if k.endswith("HBM)")}      # memory-bound families: "flops" holds bytes
+    fam = {k: v for k, v in fam.items() if k not in hbm}
     top = max(fam.values(), key=lambda f: f["ms"]) if fam else None
     roofline = None
     if top:
@@ -294,7 +296,12 @@ def run_native(args):
                     "launches_per_step": top["launches"] / rsteps, "ms_per_step": top["ms"] / rsteps,
                     "families": {k: {"ms_per_step": v["ms"] / rsteps, "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12,
                                      "launches_per_step": v["launches"] / rsteps,
-                                     "gflop_per_step": v["flops"] / rsteps / 1e9} for k, v in fam.items()}}
+                                     "gflop_per_step": v["flops"] / rsteps / 1e9} for k, v in fam.items()},
+                    "hbm_families": {k: {"ms_per_step": v["ms"] / rsteps, "gbytes_per_step": v["flops"] / rsteps / 1e9,
+                                         "achieved_gbs": v["flops"] / (v["ms"] * 1e-3) / 1e9,
+                                         "frac_of_measured_hbm": v["flops"] / (v["ms"] * 1e-3) / 1e9 /
+                                         float(peaks.get("hbm_gbs", 6650.0))} for k, v in hbm.items()},
+                    "ncu": "profiles/r1_launches_final_summary.md, profiles/r1_ncu_full_summary.md"}
 
     n_pairs = B * world * args.steps
     value = n_pairs / (ms_value * 1e-3)

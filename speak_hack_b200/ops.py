@@ -283,13 +283,22 @@ def bn_backward(g1, g2, act, z, mean, rstd, gamma, want_g_out=False, batch_stats
     dgamma = torch.empty(c, dtype=F32, device=z.device)
     dbeta = torch.empty(c, dtype=F32, device=z.device)
     ws = workspace(lib.irfd_bn_bwd_workspace_bytes(rows, c, groups), z.device)
+    # algorithmic HBM bytes: both passes read g1 [, g2] [, act], z; the apply pass writes dz [, g_out]
+    n_in = 2 + (g2 is not None) + (act is not None)
+    nbytes = 2.0 * rows * c * (2 * n_in + 1 + (1 if want_g_out else 0))
+    with _timed("bn_backward (reduce+finalize+apply, HBM)", nbytes):
+        _bn_backward_call(g1, g2, act, z, mean, rstd, gamma, beta, dz, g_out, dgamma, dbeta, batch_stats, rows, c, groups,
+                          ws)
+    if want_g_out:
+        return dz, dgamma, dbeta, g_out
+    return dz, dgamma, dbeta
+
+
+def _bn_backward_call(g1, g2, act, z, mean, rstd, gamma, beta, dz, g_out, dgamma, dbeta, batch_stats, rows, c, groups, ws):
     _call("irfd_bn_backward", g1.data_ptr(), _ptr(g2), _ptr(act), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
           gamma.data_ptr(), _ptr(beta), dz.data_ptr(), _ptr(g_out), dgamma.data_ptr(), dbeta.data_ptr(), 0.0,
           1 if batch_stats else 0, rows, c, groups,
           ws.data_ptr(), ws.numel(), _stream(), launches=3)
-    if want_g_out:
-        return dz, dgamma, dbeta, g_out
-    return dz, dgamma, dbeta
 
 
 # ----------------------------------------------------------------------------------------------------------------------
