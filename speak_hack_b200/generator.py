@@ -106,8 +106,27 @@ class SynthesisBlock(nn.Module):
 # ----------------------------------------------------------------------------------------------------------------------
 # Synthesis network as one autograd node
 # ----------------------------------------------------------------------------------------------------------------------
-def _style_params(mod: ApplyStyle):
-    return mod.linear.weight, mod.linear.bias, float(mod.linear.w_lrmul), float(mod.linear.b_lrmul)
+def _cpad(c: int) -> int:
+    """The GEMM tiles are 64 channels wide; narrower layers (the 32-channel last block of a 512^2 network) run zero
+    padded: padded output channels have zero weights, bias, noise weight and style, so they stay exactly zero."""
+    return (c + 63) // 64 * 64
+
+
+def _pad_to(t: torch.Tensor, dim: int, n: int) -> torch.Tensor:
+    if t.shape[dim] == n:
+        return t
+    shape = list(t.shape)
+    shape[dim] = n
+    out = t.new_zeros(shape)
+    out.narrow(dim, 0, t.shape[dim]).copy_(t)
+    return out
+
+
+def _packed(conv_param: torch.Tensor, w: torch.Tensor, mode: int, co_p: int, ci_p: int) -> torch.Tensor:
+    """bf16 GEMM operand of a conv weight: cached repack when no padding is needed, padded temporary otherwise."""
+    if w.shape[0] == co_p and w.shape[1] == ci_p:
+        return ops.pack_conv_weight(conv_param, mode)
+    return ops._pack_conv_weight(_pad_to(_pad_to(w, 0, co_p), 1, ci_p).contiguous(), mode)
 
 
 class _SynthesisFn(torch.autograd.Function):
@@ -121,39 +140,39 @@ class _SynthesisFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rows_t, net, noises, *params):
         rows_t = rows_t.contiguous()
-        B = rows_t.shape[1]
         it = iter(params)
         const_input, bias0, sw0, sb0, nw0 = next(it), next(it), next(it), next(it), next(it)
         wm, bm = float(net.style_mod.linear.w_lrmul), float(net.style_mod.linear.b_lrmul)
         saved = {"blocks": []}
         ni = iter(noises)
 
-        def style(row, sw, sb, c):
+        def style(row, sw, sb, c, cp):
             st = ops.linear_fwd(row, sw, sb, wm, bm, lrelu=True)
             sp1, s1 = ops.split_style(st, c)
-            return st, sp1, s1
+            return st, _pad_to(sp1, 1, cp), _pad_to(s1, 1, cp)
 
         c0 = const_input.shape[1]
         noise0 = next(ni)
-        st0, sp1_0, s1_0 = style(rows_t[0], sw0, sb0, c0)
+        st0, sp1_0, s1_0 = style(rows_t[0], sw0, sb0, c0, c0)
         a0, y = ops.const_input_fwd(const_input, bias0, nw0, noise0, sp1_0, s1_0)
         saved["const"] = (a0, noise0, sp1_0, st0)
         for i, blk in enumerate(net.layers):
             w1, b1, w2, b2, nw1, nw2, s1w, s1b, s2w, s2b = (next(it) for _ in range(10))
             cout = w1.shape[0]
+            cp = _cpad(cout)
             u = ops.upsample2x_fwd(y)
             n1 = next(ni)
-            st1, sp1_1, s1_1 = style(rows_t[2 * i + 1], s1w, s1b, cout)
-            a1, y1 = ops.conv_gemm(u, ops.pack_conv_weight(blk.conv1.weight, ops.PACK_FPROP), 3, ops.EPI_STYLE, bias=b1, nw=nw1,
-                                   noise=n1, sp1=sp1_1, s1=s1_1)
+            st1, sp1_1, s1_1 = style(rows_t[2 * i + 1], s1w, s1b, cout, cp)
+            a1, y1 = ops.conv_gemm(u, _packed(blk.conv1.weight, w1, ops.PACK_FPROP, cp, u.shape[-1]), 3, ops.EPI_STYLE,
+                                   bias=_pad_to(b1, 0, cp), nw=_pad_to(nw1, 0, cp), noise=n1, sp1=sp1_1, s1=s1_1)
             n2 = next(ni)
-            st2, sp1_2, s1_2 = style(rows_t[2 * i + 2], s2w, s2b, cout)
-            a2, y2 = ops.conv_gemm(y1, ops.pack_conv_weight(blk.conv2.weight, ops.PACK_FPROP), 3, ops.EPI_STYLE, bias=b2, nw=nw2,
-                                   noise=n2, sp1=sp1_2, s1=s1_2)
+            st2, sp1_2, s1_2 = style(rows_t[2 * i + 2], s2w, s2b, cout, cp)
+            a2, y2 = ops.conv_gemm(y1, _packed(blk.conv2.weight, w2, ops.PACK_FPROP, cp, cp), 3, ops.EPI_STYLE,
+                                   bias=_pad_to(b2, 0, cp), nw=_pad_to(nw2, 0, cp), noise=n2, sp1=sp1_2, s1=s1_2)
             saved["blocks"].append((u, a1, y1, a2, n1, n2, sp1_1, sp1_2, st1, st2))
             y = y2
         rgb_w, rgb_b = next(it), next(it)
-        img = ops.to_rgb_fwd(y, rgb_w, rgb_b)
+        img = ops.to_rgb_fwd(y, _pad_to(rgb_w, 1, y.shape[-1]).contiguous(), rgb_b)
         ctx.net = net
         ctx.saved = saved
         ctx.y_last = y
@@ -166,35 +185,49 @@ class _SynthesisFn(torch.autograd.Function):
         net, saved, params, rows_t = ctx.net, ctx.saved, ctx.params, ctx.rows_t
         dimg = dimg.contiguous()
         wm, bm = float(net.style_mod.linear.w_lrmul), float(net.style_mod.linear.b_lrmul)
-        L, B, _ = rows_t.shape
         drows = torch.zeros_like(rows_t)
         nblk = len(net.layers)
         grads: List[Optional[torch.Tensor]] = [None] * len(params)
 
-        def style_backward(dsp1, ds1, st, row_idx, sw, gw_i, gb_i):
+        def style_backward(dsp1, ds1, st, row_idx, sw, gw_i, gb_i, c):
+            if dsp1.shape[1] != c:  # drop the zero-padded channels
+                dsp1, ds1 = dsp1[:, :c].contiguous(), ds1[:, :c].contiguous()
             dst = ops.merge_style_grad(dsp1, ds1)
             dz = ops.lrelu_bwd(dst, st)
             dx, dw, db = ops.linear_bwd(dz, rows_t[row_idx], sw, wm, bm, need_dx=True, dx=drows[row_idx], dx_beta=0.0)
             grads[gw_i], grads[gb_i] = dw, db
 
+        def crop(t, *sizes):
+            for d, n in enumerate(sizes):
+                if t.shape[d] != n:
+                    t = t.narrow(d, 0, n)
+            return t.contiguous()
+
         rgb_w = params[-2]
-        dy, grads[-2], grads[-1] = ops.to_rgb_bwd(dimg, ctx.y_last, rgb_w)
+        cl = ctx.y_last.shape[-1]
+        dy, drgb_w, grads[-1] = ops.to_rgb_bwd(dimg, ctx.y_last, _pad_to(rgb_w, 1, cl).contiguous())
+        grads[-2] = crop(drgb_w, 3, rgb_w.shape[1])
         for i in range(nblk - 1, -1, -1):
             base = 5 + 10 * i
             w1, b1, w2, b2, nw1, nw2, s1w, s1b, s2w, s2b = params[base: base + 10]
             u, a1, y1, a2, n1, n2, sp1_1, sp1_2, st1, st2 = saved["blocks"][i]
-            dz2, ds1_2, dsp1_2, grads[base + 3], grads[base + 5] = ops.style_bwd(dy, a2, n2, sp1_2)
-            style_backward(dsp1_2, ds1_2, st2, 2 * i + 2, s2w, base + 8, base + 9)
-            grads[base + 2] = ops.conv_wgrad(y1, dz2, 3)
-            dy1 = ops.conv_gemm(dz2, ops.pack_conv_weight(net.layers[i].conv2.weight, ops.PACK_DGRAD), 3, ops.EPI_PLAIN)
-            dz1, ds1_1, dsp1_1, grads[base + 1], grads[base + 4] = ops.style_bwd(dy1, a1, n1, sp1_1)
-            style_backward(dsp1_1, ds1_1, st1, 2 * i + 1, s1w, base + 6, base + 7)
-            grads[base + 0] = ops.conv_wgrad(u, dz1, 3)
-            du = ops.conv_gemm(dz1, ops.pack_conv_weight(net.layers[i].conv1.weight, ops.PACK_DGRAD), 3, ops.EPI_PLAIN)
+            blk = net.layers[i]
+            cout, cin = w1.shape[0], w1.shape[1]
+            cp = a1.shape[-1]
+            dz2, ds1_2, dsp1_2, db2, dnw2 = ops.style_bwd(dy, a2, n2, sp1_2)
+            grads[base + 3], grads[base + 5] = crop(db2, cout), crop(dnw2, cout)
+            style_backward(dsp1_2, ds1_2, st2, 2 * i + 2, s2w, base + 8, base + 9, cout)
+            grads[base + 2] = crop(ops.conv_wgrad(y1, dz2, 3), cout, cout)
+            dy1 = ops.conv_gemm(dz2, _packed(blk.conv2.weight, w2, ops.PACK_DGRAD, cp, cp), 3, ops.EPI_PLAIN)
+            dz1, ds1_1, dsp1_1, db1, dnw1 = ops.style_bwd(dy1, a1, n1, sp1_1)
+            grads[base + 1], grads[base + 4] = crop(db1, cout), crop(dnw1, cout)
+            style_backward(dsp1_1, ds1_1, st1, 2 * i + 1, s1w, base + 6, base + 7, cout)
+            grads[base + 0] = crop(ops.conv_wgrad(u, dz1, 3), cout, cin)
+            du = ops.conv_gemm(dz1, _packed(blk.conv1.weight, w1, ops.PACK_DGRAD, cp, u.shape[-1]), 3, ops.EPI_PLAIN)
             dy = ops.upsample2x_bwd(du)
         a0, noise0, sp1_0, st0 = saved["const"]
         dsp1_0, ds1_0, grads[0], grads[1], grads[4] = ops.const_input_bwd(dy, a0, noise0, sp1_0)
-        style_backward(dsp1_0, ds1_0, st0, 0, params[2], 2, 3)
+        style_backward(dsp1_0, ds1_0, st0, 0, params[2], 2, 3, params[0].shape[1])
         ctx.saved = None
         return (drows, None, None) + tuple(grads)
 
@@ -244,6 +277,8 @@ class SynthesisNetwork(nn.Module):
         repack another stream is still writing."""
         for blk in self.layers:
             for conv in (blk.conv1, blk.conv2):
+                if conv.weight.shape[0] % 64 or conv.weight.shape[1] % 64:
+                    continue  # zero-padded layers are repacked per call
                 ops.pack_conv_weight(conv.weight, ops.PACK_FPROP)
                 if backward:
                     ops.pack_conv_weight(conv.weight, ops.PACK_DGRAD)

@@ -407,3 +407,59 @@ def test_golden_train_step_bn_buffers_and_losses(cuda_device):
     assert abs(l_id.item() - gold["l_identity"]) <= 0.3 * abs(gold["l_identity"])
     got = {n for n, p in net.named_parameters() if p.grad is not None}
     assert set(gold["grad_norms"]) == got, (set(gold["grad_norms"]) ^ got)  # same 560 tensors receive gradients
+
+
+def test_synthesis_512_and_encoder_512(cuda_device):
+    """BASELINE config 5 shapes: SynthesisNetwork(resolution=512) (7 blocks, 32-channel last block run zero-padded to the
+    64-channel GEMM tile) forward + backward, and an encoder on 512^2 images."""
+    import irfd_oracle as O
+    import speak_hack_b200 as P
+
+    dev = cuda_device
+    torch.manual_seed(4)
+    ref = O.SynthesisNetworkRef(resolution=512)
+    O.perturb_noise_weights(ref)
+    net = P.SynthesisNetwork(resolution=512)
+    net.load_state_dict(ref.state_dict())
+    net = net.to(dev)
+    w = torch.randn(1, 16, 512, generator=torch.Generator().manual_seed(5)) * 0.3
+    draw, bank = _cpu_noise_bank(31)
+    wr = w.clone().requires_grad_(True)
+    img_ref = ref(wr, lambda b, h, ww, device, dtype: draw(b, h, ww))
+    it = {"i": 0}
+
+    def replay(b, h, ww, device):
+        t = bank[it["i"]]
+        it["i"] += 1
+        return t.to(device)
+
+    net.noise_fn = replay
+    wp = w.to(dev).requires_grad_(True)
+    img = net(wp)
+    torch.cuda.synchronize()
+    assert img.shape == (1, 3, 512, 512) and it["i"] == 15
+    e = O.rel_l2(img, img_ref)
+    tgt = torch.rand(1, 3, 512, 512, generator=torch.Generator().manual_seed(6))
+    torch.nn.functional.mse_loss(img_ref, tgt).backward()
+    P.mse_loss(img, tgt.to(dev)).backward()
+    torch.cuda.synchronize()
+    pr = dict(net.named_parameters())
+    worst = max((O.rel_l2(pr[n].grad, p.grad), n) for n, p in ref.named_parameters() if "noise" not in n)
+    e_w = O.rel_l2(wp.grad, wr.grad)
+    print(f"[parity] synthesis 512^2: image rel-L2 {e:.3e}; worst non-noise param grad {worst[0]:.3e} ({worst[1]}); d/dw {e_w:.3e}")
+    assert e < 1.5e-2 and worst[0] < 6e-2 and e_w < 5e-2
+    for n in ("layers.6.conv1.weight", "layers.6.conv2.weight", "to_rgb.weight"):
+        assert pr[n].grad.shape == pr[n].shape
+    # encoder at 512^2 (eval, inference path)
+    torch.manual_seed(7)
+    enc_ref = O.make_encoder_ref().eval()
+    enc = P.ResNet50Encoder()
+    enc.load_state_dict(enc_ref.state_dict())
+    enc = enc.to(dev).eval()
+    x = torch.rand(2, 3, 512, 512, generator=torch.Generator().manual_seed(8)) * 2 - 1
+    with torch.no_grad():
+        f_ref, f = enc_ref(x), enc(x.to(dev))
+    torch.cuda.synchronize()
+    e_f = O.rel_l2(f, f_ref)
+    print(f"[parity] encoder @512^2 eval features rel-L2 {e_f:.3e}")
+    assert f.shape == (2, 2048, 1, 1) and e_f < 6e-3
