@@ -24,6 +24,7 @@ struct WgradArgs {
 
 constexpr int kWgThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 constexpr int kWgWaves = 1;      // split-K target: CTAs per SM over the launch (1 measured faster than 2: fewer partials)
+constexpr int kWgMinKb = 16;    // shorter splits only multiply prologues and fp32 partial traffic
 
 template <int BLOCK_N>
 struct WgCfg {
@@ -226,7 +227,7 @@ static void wgrad_plan(int n, int h, int w, int cin, int cout, int ksize, WgradA
   a->num_kb = (int)((m_total + 63) / 64);
   const int base = a->num_pairs * a->num_n_tiles;
   int splits = (kWgWaves * num_sms() + base - 1) / base;
-  const int max_splits = (a->num_kb + 3) / 4;  // at least 4 k-blocks per split
+  const int max_splits = (a->num_kb + kWgMinKb - 1) / kWgMinKb;  // at least kWgMinKb k-blocks (64 pixels each) per split
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   a->kb_per_split = (a->num_kb + splits - 1) / splits;
