@@ -159,8 +159,14 @@ extern "C" int irfd_linear_fwd(const float* x, const float* w, const float* bias
                                float wmul, float bmul, int lrelu, cudaStream_t stream) {
   IRFD_CHECK_ARG(x && w && y && b > 0 && n > 0 && k > 0 && k % 4 == 0, "linear_fwd: bad argument (K %% 4 == 0)");
   const int warps_per_block = 4;
-  linear_fwd_kernel<8><<<(n + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(
-      x, w, bias, y, b, n, k, wmul, bmul, lrelu);
+  const dim3 grid((n + warps_per_block - 1) / warps_per_block), block(warps_per_block * 32);
+  // rows per pass: each pass streams the weight row once, so cover the whole batch in as few passes as possible
+  if (b > 16)
+    linear_fwd_kernel<32><<<grid, block, 0, stream>>>(x, w, bias, y, b, n, k, wmul, bmul, lrelu);
+  else if (b > 8)
+    linear_fwd_kernel<16><<<grid, block, 0, stream>>>(x, w, bias, y, b, n, k, wmul, bmul, lrelu);
+  else
+    linear_fwd_kernel<8><<<grid, block, 0, stream>>>(x, w, bias, y, b, n, k, wmul, bmul, lrelu);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }
