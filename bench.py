@@ -248,13 +248,34 @@ def run_native(args):
 
     # ---- timed region 2: end to end (pinned host inputs -> H2D every step, loss read back every step)
     barrier()
+    copy_stream = torch.cuda.Stream(dev)
+    main_stream = torch.cuda.current_stream(dev)
+
+    stage = [(torch.empty_like(x_s), torch.empty_like(x_t)) for _ in range(2)]   # double-buffered device staging
+    consumed = [None, None]                                                       # main-stream event: buffer read
+
+    def h2d(slot):
+        """One step's inputs, pinned host -> device staging buffer `slot`, on the copy stream."""
+        with torch.cuda.stream(copy_stream):
+            if consumed[slot] is not None:
+                copy_stream.wait_event(consumed[slot])
+            stage[slot][0].copy_(host_s, non_blocking=True)
+            stage[slot][1].copy_(host_t, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
+
     e0.record()
     last = None
-    for _ in range(args.steps):
-        if trainer.use_cuda_graph:              # H2D straight into the graph's static input buffers
-            loss = trainer.train_step(host_s, host_t)
-        else:
-            loss = trainer.train_step(host_s.to(dev, non_blocking=True), host_t.to(dev, non_blocking=True))
+    ready = h2d(0)
+    for i in range(args.steps):
+        slot = i & 1
+        main_stream.wait_event(ready)
+        loss = trainer.train_step(*stage[slot])  # graph mode: D2D into the static inputs + one graph replay
+        consumed[slot] = torch.cuda.Event()
+        consumed[slot].record(main_stream)
+        if i + 1 < args.steps:
+            ready = h2d(slot ^ 1)               # the next step's H2D overlaps this step's compute
         last = float(loss.item())               # D2H of the step's result
     e1.record()
     barrier()
