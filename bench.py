@@ -126,7 +126,7 @@ def cpu_train_steps(pairs: int, steps: int, warmup: int, budget_s: float):
         l_id, l_rec = O.irfd_losses(xs, xt, out)
         (l_id + l_rec).backward()
         opt.step()
-        return float(l_id + l_rec)
+        return float((l_id + l_rec).detach())
 
     torch.manual_seed(O.FORWARD_SEED)
     t_start = time.time()
