@@ -9,70 +9,110 @@ namespace irfd {
 
 // ---------------------------------------------------------------------------------------------------------------
 // Statistics finalize: per-tile partial sums (from the conv epilogue) -> mean / rstd, running-buffer update.
-// One block per 32 channels, 8 tile-lanes; accumulation in double.
+// One block per 8 channels (one 32-byte sector per tile row) x 128 tile lanes, 8 independent loads per stream in
+// flight per thread; accumulation in double, fixed summation order (bit-deterministic).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kMaxGroups = 4;
+constexpr int kFinCh = 8;       // channels per block
+constexpr int kFinLanes = 128;  // partial-row lanes per block (1024 threads)
+constexpr int kFinBatch = 8;    // loads in flight per thread per stream
+
+// Sum `n` partial rows of two [n][C] fp32 arrays for channel c, this thread taking rows lane, lane+128, ...
+__device__ __forceinline__ void fin_partial_sums(const float* __restrict__ p0, const float* __restrict__ p1, size_t stride0,
+                                                 size_t stride1, int n, int lane, double& a, double& b) {
+  a = 0.0;
+  b = 0.0;
+  for (int t = lane; t < n; t += kFinLanes * kFinBatch) {
+    float x[kFinBatch], y[kFinBatch];
+#pragma unroll
+    for (int u = 0; u < kFinBatch; ++u) {
+      const int tt = t + u * kFinLanes;
+      x[u] = tt < n ? __ldg(p0 + (size_t)tt * stride0) : 0.f;
+      y[u] = tt < n ? __ldg(p1 + (size_t)tt * stride1) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kFinBatch; ++u) {
+      a += (double)x[u];
+      b += (double)y[u];
+    }
+  }
+}
+
+// Block-wide sum over the 128 lanes of one channel: lanes of a warp by shuffle, the 32 warps through shared memory.
+// Valid in the threads with lane == 0 (threadIdx.x < kFinCh).
+__device__ __forceinline__ void fin_block_sums(double& a, double& b, double (*sa)[kFinCh], double (*sb)[kFinCh]) {
+#pragma unroll
+  for (int o = kFinCh; o < 32; o <<= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();  // previous use of sa/sb has been consumed
+  if (l < kFinCh) {
+    sa[w][l] = a;
+    sb[w][l] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x < kFinCh) {
+    a = 0.0;
+    b = 0.0;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+      a += sa[i][threadIdx.x];
+      b += sb[i][threadIdx.x];
+    }
+  }
+}
 
 __global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int tiles, int C, double count,
                    float eps, float momentum, float* __restrict__ mean, float* __restrict__ rstd, float* running_mean,
                    float* running_var, int running_updates, int groups) {
-  // block = 32 channels (lanes, coalesced 128-byte reads) x 32 warps striding over the tiles; statistic groups (e.g.
-  // the source and the target half of a paired encoder pass) are processed one after the other so the running
-  // buffers can be updated in call order by the same thread.
-  __shared__ double s_sum[32][33];
-  __shared__ double s_sq[32][33];
-  const int cl = threadIdx.x & 31;
-  const int tl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
+  // statistic groups (e.g. the source and the target half of a paired encoder pass) are processed one after the
+  // other so the running buffers can be updated in call order by the same thread.
+  __shared__ double s_sum[32][kFinCh];
+  __shared__ double s_sq[32][kFinCh];
+  const int cl = threadIdx.x & (kFinCh - 1);
+  const int lane = threadIdx.x / kFinCh;
+  const int c = blockIdx.x * kFinCh + cl;  // C % 8 == 0 on this path
   double gm[kMaxGroups], gv[kMaxGroups];
-  for (int g = 0; g < groups; ++g) {
-    const float* ps = psum + (size_t)g * tiles * C;
-    const float* pq = psq + (size_t)g * tiles * C;
-    double a = 0.0, b = 0.0;
-    if (c < C) {
-      int t = tl;
-      for (; t + 96 < tiles; t += 128) {  // 4 independent loads in flight per stream
-        const float a0 = ps[(size_t)t * C + c], a1 = ps[(size_t)(t + 32) * C + c];
-        const float a2 = ps[(size_t)(t + 64) * C + c], a3 = ps[(size_t)(t + 96) * C + c];
-        const float b0 = pq[(size_t)t * C + c], b1 = pq[(size_t)(t + 32) * C + c];
-        const float b2 = pq[(size_t)(t + 64) * C + c], b3 = pq[(size_t)(t + 96) * C + c];
-        a += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
-        b += ((double)b0 + (double)b1) + ((double)b2 + (double)b3);
+#pragma unroll
+  for (int g = 0; g < kMaxGroups; ++g) {
+    if (g < groups) {
+      double a, b;
+      fin_partial_sums(psum + (size_t)g * tiles * C + c, psq + (size_t)g * tiles * C + c, C, C, tiles, lane, a, b);
+      fin_block_sums(a, b, s_sum, s_sq);
+      if (threadIdx.x < kFinCh) {
+        const double m = a / count;
+        double var = b / count - m * m;
+        if (var < 0.0) var = 0.0;
+        mean[(size_t)g * C + c] = (float)m;
+        rstd[(size_t)g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+        gm[g] = m;
+        gv[g] = count > 1.0 ? var * count / (count - 1.0) : var;  // unbiased, for the running buffer
       }
-      for (; t < tiles; t += 32) {
-        a += (double)ps[(size_t)t * C + c];
-        b += (double)pq[(size_t)t * C + c];
-      }
-    }
-    __syncthreads();
-    s_sum[tl][cl] = a;
-    s_sq[tl][cl] = b;
-    __syncthreads();
-    if (tl == 0 && c < C) {
-      for (int i = 1; i < 32; ++i) {
-        a += s_sum[i][cl];
-        b += s_sq[i][cl];
-      }
-      const double m = a / count;
-      double var = b / count - m * m;
-      if (var < 0.0) var = 0.0;
-      mean[(size_t)g * C + c] = (float)m;
-      rstd[(size_t)g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
-      gm[g] = m;
-      gv[g] = count > 1.0 ? var * count / (count - 1.0) : var;  // unbiased, for the running buffer
     }
   }
-  if (tl == 0 && c < C && running_mean != nullptr) {
+  if (threadIdx.x < kFinCh && running_mean != nullptr) {
     // update 1: the forward calls in order (group 0 first).  update 2 (optional): what the reference's reentrant
     // checkpoint adds when it re-runs each forward during backward, i.e. the same statistics in reverse call order
     // (model.py:84-90).
     float rm = running_mean[c], rv = running_var[c];
     for (int u = 0; u < running_updates; ++u)
-      for (int i = 0; i < groups; ++i) {
-        const int g = (u & 1) ? groups - 1 - i : i;
-        rm = (1.f - momentum) * rm + momentum * (float)gm[g];
-        rv = (1.f - momentum) * rv + momentum * (float)gv[g];
+#pragma unroll
+      for (int i = 0; i < kMaxGroups; ++i) {
+        if (i < groups) {
+          const int g = (u & 1) ? groups - 1 - i : i;
+          double mg = gm[0], vg = gv[0];
+#pragma unroll
+          for (int k = 1; k < kMaxGroups; ++k)
+            if (k == g) {
+              mg = gm[k];
+              vg = gv[k];
+            }
+          rm = (1.f - momentum) * rm + momentum * (float)mg;
+          rv = (1.f - momentum) * rv + momentum * (float)vg;
+        }
       }
     running_mean[c] = rm;
     running_var[c] = rv;
@@ -165,23 +205,40 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z, BnAffine p1, const __nv_bfl
   const long long r0 = (long long)blockIdx.x * rows_per_blk;
   long long r1 = r0 + rows_per_blk;
   if (r1 > rows) r1 = rows;
-  for (long long r = r0 + rv.row_lane; r < r1; r += rv.rows_par) {
-    const size_t off = (size_t)r * C + rv.cv * 8;
-    float v[8], o[8];
-    load8(z + off, v);
+  // kRowBatch rows per thread per iteration, all loads issued before the first use (memory-level parallelism)
+  for (long long r = r0 + rv.row_lane; r < r1; r += (long long)rv.rows_par * kRowBatch) {
+    uint4 qz[kRowBatch], qr[kRowBatch];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) o[t] = v[t] * sc[t] + sh[t];
-    if (RES_MODE != 0) {
-      float w[8];
-      load8(res + off, w);
-#pragma unroll
-      for (int t = 0; t < 8; ++t) o[t] += (RES_MODE == 2) ? (w[t] * sc2[t] + sh2[t]) : w[t];
+    for (int u = 0; u < kRowBatch; ++u) {
+      const long long rr = r + (long long)u * rv.rows_par;
+      if (rr < r1) {
+        const size_t off = (size_t)rr * C + rv.cv * 8;
+        qz[u] = ldg16(z + off);
+        if (RES_MODE != 0) qr[u] = ldg16(res + off);
+      }
     }
-    if (relu) {
 #pragma unroll
-      for (int t = 0; t < 8; ++t) o[t] = fmaxf(o[t], 0.f);
+    for (int u = 0; u < kRowBatch; ++u) {
+      const long long rr = r + (long long)u * rv.rows_par;
+      if (rr < r1) {
+        const size_t off = (size_t)rr * C + rv.cv * 8;
+        float v[8], o[8];
+        unpack8(qz[u], v);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) o[t] = v[t] * sc[t] + sh[t];
+        if (RES_MODE != 0) {
+          float w[8];
+          unpack8(qr[u], w);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) o[t] += (RES_MODE == 2) ? (w[t] * sc2[t] + sh2[t]) : w[t];
+        }
+        if (relu) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) o[t] = fmaxf(o[t], 0.f);
+        }
+        store8(out + off, o);
+      }
     }
-    store8(out + off, o);
   }
 }
 
@@ -191,7 +248,31 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z, BnAffine p1, const __nv_bfl
 //   finalize: dgamma = sum(g*xhat), dbeta = sum(g); c1 = dbeta/n, c2 = dgamma/n
 //   apply   : dz = gamma*rstd * (g - c1 - xhat*c2)     (+ optional copy of the masked g for the identity shortcut)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRvThreads)
+// MASK: 0 = no ReLU on this BN output, 1 = mask from the saved post-ReLU tensor `act`, 2 = mask recomputed from z.
+template <bool HAS_G2, int MASK>
+__device__ __forceinline__ void bn_bwd_masked_grad(const uint4& qg, const uint4& qh, const uint4& qa, const float (&zz)[8],
+                                                   const float (&m)[8], const float (&rs)[8], const float (&ga)[8],
+                                                   const float (&be)[8], float (&g)[8]) {
+  unpack8(qg, g);
+  if (HAS_G2) {
+    float h[8];
+    unpack8(qh, h);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) g[t] += h[t];
+  }
+  if (MASK == 1) {
+    float a[8];
+    unpack8(qa, a);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) g[t] = a[t] > 0.f ? g[t] : 0.f;
+  } else if (MASK == 2) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) g[t] = (ga[t] * ((zz[t] - m[t]) * rs[t]) + be[t]) > 0.f ? g[t] : 0.f;
+  }
+}
+
+template <bool HAS_G2, int MASK>
+__global__ void __launch_bounds__(kRvThreads, 2)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
                      const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ z,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
@@ -202,8 +283,8 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
   {
     const size_t goff = (size_t)blockIdx.y * rows * C;
     g1 += goff;
-    if (g2 != nullptr) g2 += goff;
-    if (act != nullptr) act += goff;
+    if (HAS_G2) g2 += goff;
+    if (MASK == 1) act += goff;
     z += goff;
     mean += (size_t)blockIdx.y * C;
     rstd += (size_t)blockIdx.y * C;
@@ -216,36 +297,39 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
     float m[8], rs[8], ga[8], be[8];
     loadf8(mean + rv.cv * 8, m);
     loadf8(rstd + rv.cv * 8, rs);
-    if (beta != nullptr) {  // ReLU mask recomputed from z: relu(gamma*xhat + beta) > 0  (no residual on this BN)
+    if (MASK == 2) {  // ReLU mask recomputed from z: relu(gamma*xhat + beta) > 0  (no residual on this BN)
       loadf8(gamma + rv.cv * 8, ga);
       loadf8(beta + rv.cv * 8, be);
     }
     const long long r0 = (long long)blockIdx.x * rows_per_blk;
     long long r1 = r0 + rows_per_blk;
     if (r1 > rows) r1 = rows;
-    for (long long r = r0 + rv.row_lane; r < r1; r += rv.rows_par) {
-      const size_t off = (size_t)r * C + rv.cv * 8;
-      float g[8], a[8], zz[8];
-      load8(g1 + off, g);
-      if (g2 != nullptr) {
-        float h[8];
-        load8(g2 + off, h);
+    for (long long r = r0 + rv.row_lane; r < r1; r += (long long)rv.rows_par * kRowBatch) {
+      uint4 qg[kRowBatch], qh[kRowBatch], qa[kRowBatch], qz[kRowBatch];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) g[t] += h[t];
-      }
-      load8(z + off, zz);
-      if (act != nullptr) {
-        load8(act + off, a);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) g[t] = a[t] > 0.f ? g[t] : 0.f;
-      } else if (beta != nullptr) {
-#pragma unroll
-        for (int t = 0; t < 8; ++t) g[t] = (ga[t] * ((zz[t] - m[t]) * rs[t]) + be[t]) > 0.f ? g[t] : 0.f;
+      for (int u = 0; u < kRowBatch; ++u) {
+        const long long rr = r + (long long)u * rv.rows_par;
+        if (rr < r1) {
+          const size_t off = (size_t)rr * C + rv.cv * 8;
+          qg[u] = ldg16(g1 + off);
+          if (HAS_G2) qh[u] = ldg16(g2 + off);
+          qz[u] = ldg16(z + off);
+          if (MASK == 1) qa[u] = ldg16(act + off);
+        }
       }
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        acc[0][t] += g[t];
-        acc[1][t] += g[t] * ((zz[t] - m[t]) * rs[t]);
+      for (int u = 0; u < kRowBatch; ++u) {
+        const long long rr = r + (long long)u * rv.rows_par;
+        if (rr < r1) {
+          float g[8], zz[8];
+          unpack8(qz[u], zz);
+          bn_bwd_masked_grad<HAS_G2, MASK>(qg[u], qh[u], qa[u], zz, m, rs, ga, be, g);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            acc[0][t] += g[t];
+            acc[1][t] += g[t] * ((zz[t] - m[t]) * rs[t]);
+          }
+        }
       }
     }
   }
@@ -256,30 +340,18 @@ __global__ void __launch_bounds__(1024)
 bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, double count, float* __restrict__ dgamma,
                        float* __restrict__ dbeta, float beta_acc, float* __restrict__ c1, float* __restrict__ c2,
                        int batch_stats, int groups) {
-  __shared__ double s0s[32][33];
-  __shared__ double s1s[32][33];
-  const int cl = threadIdx.x & 31;
-  const int tl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
+  __shared__ double s0s[32][kFinCh];
+  __shared__ double s1s[32][kFinCh];
+  const int cl = threadIdx.x & (kFinCh - 1);
+  const int lane = threadIdx.x / kFinCh;
+  const int c = blockIdx.x * kFinCh + cl;
   double tot0 = 0.0, tot1 = 0.0;
   for (int g = 0; g < groups; ++g) {
-    const float* pg = partial + (size_t)g * nblk * 2 * C;
-    double s0 = 0.0, s1 = 0.0;
-    if (c < C) {
-      for (int b = tl; b < nblk; b += 32) {
-        s0 += (double)pg[((size_t)b * 2 + 0) * C + c];
-        s1 += (double)pg[((size_t)b * 2 + 1) * C + c];
-      }
-    }
-    __syncthreads();
-    s0s[tl][cl] = s0;
-    s1s[tl][cl] = s1;
-    __syncthreads();
-    if (tl == 0 && c < C) {
-      for (int i = 1; i < 32; ++i) {
-        s0 += s0s[i][cl];
-        s1 += s1s[i][cl];
-      }
+    const float* pg = partial + (size_t)g * nblk * 2 * C + c;
+    double s0, s1;
+    fin_partial_sums(pg, pg + C, (size_t)2 * C, (size_t)2 * C, nblk, lane, s0, s1);
+    fin_block_sums(s0, s1, s0s, s1s);
+    if (threadIdx.x < kFinCh) {
       // each group normalised with its own statistics; eval mode (constants) has no batch-statistic terms in dz
       c1[(size_t)g * C + c] = batch_stats ? (float)(s0 / count) : 0.f;
       c2[(size_t)g * C + c] = batch_stats ? (float)(s1 / count) : 0.f;
@@ -287,13 +359,14 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, doubl
       tot1 += s1;
     }
   }
-  if (tl == 0 && c < C) {
+  if (threadIdx.x < kFinCh) {
     dbeta[c] = (beta_acc != 0.f ? beta_acc * dbeta[c] : 0.f) + (float)tot0;
     dgamma[c] = (beta_acc != 0.f ? beta_acc * dgamma[c] : 0.f) + (float)tot1;
   }
 }
 
-__global__ void __launch_bounds__(kRvThreads)
+template <bool HAS_G2, int MASK, bool G_OUT>
+__global__ void __launch_bounds__(kRvThreads, 2)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
                     const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ z,
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
@@ -305,60 +378,87 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* _
   {
     const size_t goff = (size_t)blockIdx.y * rows * C;
     g1 += goff;
-    if (g2 != nullptr) g2 += goff;
-    if (act != nullptr) act += goff;
+    if (HAS_G2) g2 += goff;
+    if (MASK == 1) act += goff;
     z += goff;
     dz += goff;
-    if (g_out != nullptr) g_out += goff;
+    if (G_OUT) g_out += goff;
     mean += (size_t)blockIdx.y * C;
     rstd += (size_t)blockIdx.y * C;
     c1 += (size_t)blockIdx.y * C;
     c2 += (size_t)blockIdx.y * C;
   }
   float m[8], rs[8], k0[8], k1[8], k2[8], ga[8], be[8];
-  if (beta != nullptr) loadf8(beta + rv.cv * 8, be);
-  {
-    float a1[8], a2[8];
-    loadf8(mean + rv.cv * 8, m);
-    loadf8(rstd + rv.cv * 8, rs);
-    loadf8(gamma + rv.cv * 8, ga);
-    loadf8(c1 + rv.cv * 8, a1);
-    loadf8(c2 + rv.cv * 8, a2);
+  if (MASK == 2) loadf8(beta + rv.cv * 8, be);
+  loadf8(mean + rv.cv * 8, m);
+  loadf8(rstd + rv.cv * 8, rs);
+  loadf8(gamma + rv.cv * 8, ga);
+  loadf8(c1 + rv.cv * 8, k1);
+  loadf8(c2 + rv.cv * 8, k2);
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      k0[t] = ga[t] * rs[t];
-      k1[t] = a1[t];
-      k2[t] = a2[t];
-    }
-  }
+  for (int t = 0; t < 8; ++t) k0[t] = ga[t] * rs[t];
   const long long r0 = (long long)blockIdx.x * rows_per_blk;
   long long r1 = r0 + rows_per_blk;
   if (r1 > rows) r1 = rows;
-  for (long long r = r0 + rv.row_lane; r < r1; r += rv.rows_par) {
-    const size_t off = (size_t)r * C + rv.cv * 8;
-    float g[8], zz[8], o[8];
-    load8(g1 + off, g);
-    if (g2 != nullptr) {
-      float h[8];
-      load8(g2 + off, h);
+  for (long long r = r0 + rv.row_lane; r < r1; r += (long long)rv.rows_par * kRowBatch) {
+    uint4 qg[kRowBatch], qh[kRowBatch], qa[kRowBatch], qz[kRowBatch];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) g[t] += h[t];
-    }
-    load8(z + off, zz);
-    if (act != nullptr) {
-      float a[8];
-      load8(act + off, a);
-#pragma unroll
-      for (int t = 0; t < 8; ++t) g[t] = a[t] > 0.f ? g[t] : 0.f;
-    } else if (beta != nullptr) {
-#pragma unroll
-      for (int t = 0; t < 8; ++t) g[t] = (ga[t] * ((zz[t] - m[t]) * rs[t]) + be[t]) > 0.f ? g[t] : 0.f;
+    for (int u = 0; u < kRowBatch; ++u) {
+      const long long rr = r + (long long)u * rv.rows_par;
+      if (rr < r1) {
+        const size_t off = (size_t)rr * C + rv.cv * 8;
+        qg[u] = ldg16(g1 + off);
+        if (HAS_G2) qh[u] = ldg16(g2 + off);
+        qz[u] = ldg16(z + off);
+        if (MASK == 1) qa[u] = ldg16(act + off);
+      }
     }
 #pragma unroll
-    for (int t = 0; t < 8; ++t) o[t] = k0[t] * (g[t] - k1[t] - (zz[t] - m[t]) * rs[t] * k2[t]);
-    store8(dz + off, o);
-    if (g_out != nullptr) store8(g_out + off, g);
+    for (int u = 0; u < kRowBatch; ++u) {
+      const long long rr = r + (long long)u * rv.rows_par;
+      if (rr < r1) {
+        const size_t off = (size_t)rr * C + rv.cv * 8;
+        float g[8], zz[8], o[8];
+        unpack8(qz[u], zz);
+        bn_bwd_masked_grad<HAS_G2, MASK>(qg[u], qh[u], qa[u], zz, m, rs, ga, be, g);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) o[t] = k0[t] * (g[t] - k1[t] - (zz[t] - m[t]) * rs[t] * k2[t]);
+        store8(dz + off, o);
+        if (G_OUT) store8(g_out + off, g);
+      }
+    }
   }
+}
+
+// Runtime (g2, mask, g_out) -> template instance: reduce -> finalize -> apply on one stream.
+struct BnBwdLaunch {
+  dim3 grid;
+  size_t smem;
+  cudaStream_t stream;
+  const __nv_bfloat16 *g1, *g2, *act, *z;
+  const float *mean, *rstd, *gamma, *beta;
+  float *partial, *c1, *c2;
+  __nv_bfloat16 *dz, *g_out;
+  float *dgamma, *dbeta;
+  float grad_beta;
+  int batch_stats;
+  long long grows;
+  int c, rpb, nblk, groups;
+};
+
+template <bool HAS_G2, int MASK>
+static void launch_bn_bwd(const BnBwdLaunch& L) {
+  bn_bwd_reduce_kernel<HAS_G2, MASK><<<L.grid, kRvThreads, L.smem, L.stream>>>(
+      L.g1, L.g2, L.act, L.z, L.mean, L.rstd, L.gamma, L.beta, L.partial, L.grows, L.c, L.rpb);
+  bn_bwd_finalize_kernel<<<L.c / kFinCh, 1024, 0, L.stream>>>(L.partial, L.nblk, L.c, (double)L.grows, L.dgamma,
+                                                                   L.dbeta, L.grad_beta, L.c1, L.c2, L.batch_stats,
+                                                                   L.groups);
+  if (L.g_out != nullptr)
+    bn_bwd_apply_kernel<HAS_G2, MASK, true><<<L.grid, kRvThreads, 0, L.stream>>>(
+        L.g1, L.g2, L.act, L.z, L.mean, L.rstd, L.gamma, L.beta, L.c1, L.c2, L.dz, L.g_out, L.grows, L.c, L.rpb);
+  else
+    bn_bwd_apply_kernel<HAS_G2, MASK, false><<<L.grid, kRvThreads, 0, L.stream>>>(
+        L.g1, L.g2, L.act, L.z, L.mean, L.rstd, L.gamma, L.beta, L.c1, L.c2, L.dz, L.g_out, L.grows, L.c, L.rpb);
 }
 
 }  // namespace irfd
@@ -372,7 +472,8 @@ extern "C" int irfd_bn_finalize(const float* psum, const float* psq, int tiles, 
                                 int running_updates, int groups, cudaStream_t stream) {
   IRFD_CHECK_ARG(psum && psq && mean && rstd && tiles > 0 && c > 0 && count > 0, "bn_finalize: bad argument");
   IRFD_CHECK_ARG(groups >= 1 && groups <= kMaxGroups, "bn_finalize: 1..4 statistic groups");
-  bn_finalize_kernel<<<(c + 31) / 32, 1024, 0, stream>>>(psum, psq, tiles, c, (double)count, eps, momentum, mean, rstd,
+  IRFD_CHECK_ARG(c % kFinCh == 0, "bn_finalize: C must be a multiple of 8 (got %d)", c);
+  bn_finalize_kernel<<<c / kFinCh, 1024, 0, stream>>>(psum, psq, tiles, c, (double)count, eps, momentum, mean, rstd,
                                                          running_mean, running_var, running_updates, groups);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
@@ -458,16 +559,27 @@ extern "C" int irfd_bn_backward(const void* g1, const void* g2, const void* act,
   auto G2 = reinterpret_cast<const __nv_bfloat16*>(g2);
   auto A = reinterpret_cast<const __nv_bfloat16*>(act);
   auto Z = reinterpret_cast<const __nv_bfloat16*>(z);
-  const dim3 grid(nblk, groups);
-  bn_bwd_reduce_kernel<<<grid, kRvThreads, smem, stream>>>(G1, G2, A, Z, mean, rstd, gamma, beta, partial, grows, c,
-                                                           rpb);
-  IRFD_CHECK_LAUNCH();
-  bn_bwd_finalize_kernel<<<(c + 31) / 32, 1024, 0, stream>>>(partial, nblk, c, (double)grows, dgamma, dbeta, grad_beta,
-                                                               c1, c2, batch_stats, groups);
-  IRFD_CHECK_LAUNCH();
-  bn_bwd_apply_kernel<<<grid, kRvThreads, 0, stream>>>(G1, G2, A, Z, mean, rstd, gamma, beta, c1, c2,
-                                                        reinterpret_cast<__nv_bfloat16*>(dz),
-                                                        reinterpret_cast<__nv_bfloat16*>(g_out), grows, c, rpb);
+  BnBwdLaunch L;
+  L.grid = dim3(nblk, groups);
+  L.smem = smem;
+  L.stream = stream;
+  L.g1 = G1; L.g2 = G2; L.act = A; L.z = Z;
+  L.mean = mean; L.rstd = rstd; L.gamma = gamma; L.beta = beta;
+  L.partial = partial; L.c1 = c1; L.c2 = c2;
+  L.dz = reinterpret_cast<__nv_bfloat16*>(dz);
+  L.g_out = reinterpret_cast<__nv_bfloat16*>(g_out);
+  L.dgamma = dgamma; L.dbeta = dbeta; L.grad_beta = grad_beta; L.batch_stats = batch_stats;
+  L.grows = grows; L.c = c; L.rpb = rpb; L.nblk = nblk; L.groups = groups;
+  const int mask = A != nullptr ? 1 : (beta != nullptr ? 2 : 0);
+  if (G2 != nullptr) {
+    if (mask == 0) launch_bn_bwd<true, 0>(L);
+    else if (mask == 1) launch_bn_bwd<true, 1>(L);
+    else launch_bn_bwd<true, 2>(L);
+  } else {
+    if (mask == 0) launch_bn_bwd<false, 0>(L);
+    else if (mask == 1) launch_bn_bwd<false, 1>(L);
+    else launch_bn_bwd<false, 2>(L);
+  }
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }

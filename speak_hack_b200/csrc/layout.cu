@@ -39,16 +39,16 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void im2col_stem_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int H, int W,
                                    int kpad) {
-  const int Ho = H / 2, Wo = W / 2;
-  const int vec_per_row = kpad / 8;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned Ho = H / 2, Wo = W / 2;
+  const unsigned vec_per_row = kpad / 8;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;  // host checks total < 2^32
   const size_t total = (size_t)N * Ho * Wo * vec_per_row;
   if (idx >= total) return;
   const int v = idx % vec_per_row;
-  const size_t pix = idx / vec_per_row;
+  const unsigned pix = idx / vec_per_row;
   const int ow = pix % Wo;
   const int oh = (pix / Wo) % Ho;
-  const int n = pix / ((size_t)Wo * Ho);
+  const int n = pix / ((unsigned)Wo * Ho);
   float f[8];
 #pragma unroll
   for (int t = 0; t < 8; ++t) {
@@ -61,37 +61,37 @@ __global__ void im2col_stem_kernel(const float* __restrict__ x, __nv_bfloat16* _
     }
     f[t] = val;
   }
-  store8(col + pix * kpad + v * 8, f);
+  store8(col + (size_t)pix * kpad + v * 8, f);
 }
 
 // 3x3 stride-2 pad-1 im2col on NHWC bf16: col[pix][tap*C + c]
 __global__ void im2col_3x3s2_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ col, int N, int H,
                                     int W, int C) {
-  const int Ho = H / 2, Wo = W / 2, vc = C / 8;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned Ho = H / 2, Wo = W / 2, vc = C / 8;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;  // host checks total < 2^32
   const size_t total = (size_t)N * Ho * Wo * 9 * vc;
   if (idx >= total) return;
   const int v = idx % vc;
   const int tap = (idx / vc) % 9;
-  const size_t pix = idx / ((size_t)vc * 9);
-  const int ow = pix % Wo, oh = (pix / Wo) % Ho, n = pix / ((size_t)Wo * Ho);
+  const unsigned pix = idx / (vc * 9u);
+  const int ow = pix % Wo, oh = (pix / Wo) % Ho, n = pix / ((unsigned)Wo * Ho);
   const int ih = oh * 2 + tap / 3 - 1, iw = ow * 2 + tap % 3 - 1;
   uint4 val = make_uint4(0, 0, 0, 0);
   if (ih >= 0 && ih < H && iw >= 0 && iw < W)
     val = *reinterpret_cast<const uint4*>(a + (((size_t)n * H + ih) * W + iw) * C + v * 8);
-  *reinterpret_cast<uint4*>(col + (pix * 9 + tap) * C + v * 8) = val;
+  *reinterpret_cast<uint4*>(col + ((size_t)pix * 9 + tap) * C + v * 8) = val;
 }
 
 // adjoint: dx[n,h,w,c] = sum over (oh,ow,tap) hitting (h,w) of dcol[(oh,ow)][tap*C + c]
 __global__ void col2im_3x3s2_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict__ dx, int N,
                                     int H, int W, int C) {
-  const int Ho = H / 2, Wo = W / 2, vc = C / 8;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned Ho = H / 2, Wo = W / 2, vc = C / 8;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;  // host checks total < 2^32
   const size_t total = (size_t)N * H * W * vc;
   if (idx >= total) return;
   const int v = idx % vc;
-  const size_t pix = idx / vc;
-  const int w = pix % W, h = (pix / W) % H, n = pix / ((size_t)W * H);
+  const unsigned pix = idx / vc;
+  const int w = pix % W, h = (pix / W) % H, n = pix / ((unsigned)W * H);
   float acc[8];
 #pragma unroll
   for (int t = 0; t < 8; ++t) acc[t] = 0.f;
@@ -112,33 +112,33 @@ __global__ void col2im_3x3s2_kernel(const __nv_bfloat16* __restrict__ dcol, __nv
       for (int t = 0; t < 8; ++t) acc[t] += f[t];
     }
   }
-  store8(dx + pix * C + v * 8, acc);
+  store8(dx + (size_t)pix * C + v * 8, acc);
 }
 
 // 1x1 stride-2 gather: out[n,oh,ow,:] = a[n,2oh,2ow,:]
 __global__ void subsample2_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ out, int N, int H,
                                   int W, int C) {
-  const int Ho = H / 2, Wo = W / 2, vc = C / 8;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned Ho = H / 2, Wo = W / 2, vc = C / 8;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;  // host checks total < 2^32
   if (idx >= (size_t)N * Ho * Wo * vc) return;
   const int v = idx % vc;
-  const size_t pix = idx / vc;
-  const int ow = pix % Wo, oh = (pix / Wo) % Ho, n = pix / ((size_t)Wo * Ho);
-  *reinterpret_cast<uint4*>(out + pix * C + v * 8) =
+  const unsigned pix = idx / vc;
+  const int ow = pix % Wo, oh = (pix / Wo) % Ho, n = pix / ((unsigned)Wo * Ho);
+  *reinterpret_cast<uint4*>(out + (size_t)pix * C + v * 8) =
       *reinterpret_cast<const uint4*>(a + (((size_t)n * H + 2 * oh) * W + 2 * ow) * C + v * 8);
 }
 
 // out[n,h,w,:] = a[n,h,w,:] (or 0 if a == null) + (h,w even ? b[n,h/2,w/2,:] : 0)     (adjoint of subsample2, fused add)
 __global__ void scatter_add_s2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                                       __nv_bfloat16* __restrict__ out, int N, int H, int W, int C) {
-  const int vc = C / 8;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned vc = C / 8;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;  // host checks total < 2^32
   if (idx >= (size_t)N * H * W * vc) return;
   const int v = idx % vc;
-  const size_t pix = idx / vc;
-  const int w = pix % W, h = (pix / W) % H, n = pix / ((size_t)W * H);
+  const unsigned pix = idx / vc;
+  const int w = pix % W, h = (pix / W) % H, n = pix / ((unsigned)W * H);
   float f[8];
-  if (a != nullptr) load8(a + pix * C + v * 8, f);
+  if (a != nullptr) load8(a + (size_t)pix * C + v * 8, f);
   else {
 #pragma unroll
     for (int t = 0; t < 8; ++t) f[t] = 0.f;
@@ -149,7 +149,7 @@ __global__ void scatter_add_s2_kernel(const __nv_bfloat16* __restrict__ a, const
 #pragma unroll
     for (int t = 0; t < 8; ++t) f[t] += g[t];
   }
-  store8(out + pix * C + v * 8, f);
+  store8(out + (size_t)pix * C + v * 8, f);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -157,12 +157,12 @@ __global__ void scatter_add_s2_kernel(const __nv_bfloat16* __restrict__ a, const
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ out,
                                    uint8_t* __restrict__ arg, int N, int H, int W, int C) {
-  const int Ho = H / 2, Wo = W / 2, vc = C / 8;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned Ho = H / 2, Wo = W / 2, vc = C / 8;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;  // host checks total < 2^32
   if (idx >= (size_t)N * Ho * Wo * vc) return;
   const int v = idx % vc;
-  const size_t pix = idx / vc;
-  const int ow = pix % Wo, oh = (pix / Wo) % Ho, n = pix / ((size_t)Wo * Ho);
+  const unsigned pix = idx / vc;
+  const int ow = pix % Wo, oh = (pix / Wo) % Ho, n = pix / ((unsigned)Wo * Ho);
   float best[8];
   int bi[8];
 #pragma unroll
@@ -182,22 +182,22 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfl
         bi[t] = tap;
       }
   }
-  store8(out + pix * C + v * 8, best);
+  store8(out + (size_t)pix * C + v * 8, best);
   uint2 packed;
   packed.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
   packed.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
-  *reinterpret_cast<uint2*>(arg + pix * C + v * 8) = packed;
+  *reinterpret_cast<uint2*>(arg + (size_t)pix * C + v * 8) = packed;
 }
 
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ dout2,
                                    const uint8_t* __restrict__ arg,
                                    __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C) {
-  const int Ho = H / 2, Wo = W / 2, vc = C / 8;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned Ho = H / 2, Wo = W / 2, vc = C / 8;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;  // host checks total < 2^32
   if (idx >= (size_t)N * H * W * vc) return;
   const int v = idx % vc;
-  const size_t pix = idx / vc;
-  const int w = pix % W, h = (pix / W) % H, n = pix / ((size_t)W * H);
+  const unsigned pix = idx / vc;
+  const int w = pix % W, h = (pix / W) % H, n = pix / ((unsigned)W * H);
   float acc[8];
 #pragma unroll
   for (int t = 0; t < 8; ++t) acc[t] = 0.f;
@@ -229,7 +229,7 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const
       }
     }
   }
-  store8(dx + pix * C + v * 8, acc);
+  store8(dx + (size_t)pix * C + v * 8, acc);
 }
 
 // AdaptiveAvgPool2d(1): [N, HW, C] bf16 -> [N, C] fp32 ; backward broadcasts dfeat/HW
@@ -255,17 +255,17 @@ avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ a, float* __restrict__ out,
 
 __global__ void avgpool_bwd_kernel(const float* __restrict__ dfeat, __nv_bfloat16* __restrict__ g, int N, int HW,
                                    int C) {
-  const int vc = C / 8;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned vc = C / 8;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;  // host checks total < 2^32
   if (idx >= (size_t)N * HW * vc) return;
   const int v = idx % vc;
-  const size_t pix = idx / vc;
-  const int n = pix / HW;
+  const unsigned pix = idx / vc;
+  const unsigned n = pix / (unsigned)HW;
   float f[8];
   loadf8(dfeat + (size_t)n * C + v * 8, f);
 #pragma unroll
   for (int t = 0; t < 8; ++t) f[t] *= 1.f / HW;
-  store8(g + pix * C + v * 8, f);
+  store8(g + (size_t)pix * C + v * 8, f);
 }
 
 }  // namespace irfd
@@ -273,6 +273,7 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ dfeat, __nv_bfloat1
 using namespace irfd;
 
 #define GRID1D(total) (unsigned)(((total) + 255) / 256), 256, 0, stream
+#define CHECK_TOTAL32(total) IRFD_CHECK_ARG((total) > 0 && (total) < ((size_t)1 << 32) - 256, "tensor too large for 32-bit indexing")
 #define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
 #define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
 
@@ -288,6 +289,7 @@ extern "C" int irfd_pack_conv_weight(const float* w, void* dst, int o, int i, in
 extern "C" int irfd_im2col_stem(const float* x, void* col, int n, int h, int w, int kpad, cudaStream_t stream) {
   IRFD_CHECK_ARG(x && col && kpad >= 152 && kpad % 8 == 0 && h % 2 == 0 && w % 2 == 0, "im2col_stem: bad argument");
   const size_t total = (size_t)n * (h / 2) * (w / 2) * (kpad / 8);
+  CHECK_TOTAL32(total);
   im2col_stem_kernel<<<GRID1D(total)>>>(x, BF(col), n, h, w, kpad);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
@@ -296,6 +298,7 @@ extern "C" int irfd_im2col_stem(const float* x, void* col, int n, int h, int w, 
 extern "C" int irfd_im2col_3x3s2(const void* a, void* col, int n, int h, int w, int c, cudaStream_t stream) {
   IRFD_CHECK_ARG(a && col && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "im2col_3x3s2: bad argument");
   const size_t total = (size_t)n * (h / 2) * (w / 2) * 9 * (c / 8);
+  CHECK_TOTAL32(total);
   im2col_3x3s2_kernel<<<GRID1D(total)>>>(CBF(a), BF(col), n, h, w, c);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
@@ -304,6 +307,7 @@ extern "C" int irfd_im2col_3x3s2(const void* a, void* col, int n, int h, int w, 
 extern "C" int irfd_col2im_3x3s2(const void* dcol, void* dx, int n, int h, int w, int c, cudaStream_t stream) {
   IRFD_CHECK_ARG(dcol && dx && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "col2im_3x3s2: bad argument");
   const size_t total = (size_t)n * h * w * (c / 8);
+  CHECK_TOTAL32(total);
   col2im_3x3s2_kernel<<<GRID1D(total)>>>(CBF(dcol), BF(dx), n, h, w, c);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
@@ -312,6 +316,7 @@ extern "C" int irfd_col2im_3x3s2(const void* dcol, void* dx, int n, int h, int w
 extern "C" int irfd_subsample2(const void* a, void* out, int n, int h, int w, int c, cudaStream_t stream) {
   IRFD_CHECK_ARG(a && out && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "subsample2: bad argument");
   const size_t total = (size_t)n * (h / 2) * (w / 2) * (c / 8);
+  CHECK_TOTAL32(total);
   subsample2_kernel<<<GRID1D(total)>>>(CBF(a), BF(out), n, h, w, c);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
@@ -321,6 +326,7 @@ extern "C" int irfd_scatter_add_s2(const void* a, const void* b, void* out, int 
                                    cudaStream_t stream) {
   IRFD_CHECK_ARG(b && out && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "scatter_add_s2: bad argument");
   const size_t total = (size_t)n * h * w * (c / 8);
+  CHECK_TOTAL32(total);
   scatter_add_s2_kernel<<<GRID1D(total)>>>(CBF(a), CBF(b), BF(out), n, h, w, c);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
@@ -330,6 +336,7 @@ extern "C" int irfd_maxpool_fwd(const void* a, void* out, void* argmax, int n, i
                                 cudaStream_t stream) {
   IRFD_CHECK_ARG(a && out && argmax && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "maxpool_fwd: bad argument");
   const size_t total = (size_t)n * (h / 2) * (w / 2) * (c / 8);
+  CHECK_TOTAL32(total);
   maxpool_fwd_kernel<<<GRID1D(total)>>>(CBF(a), BF(out), reinterpret_cast<uint8_t*>(argmax), n, h, w, c);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
@@ -339,6 +346,7 @@ extern "C" int irfd_maxpool_bwd(const void* dout, const void* dout2, const void*
                                 int c, cudaStream_t stream) {
   IRFD_CHECK_ARG(dout && dx && argmax && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "maxpool_bwd: bad argument");
   const size_t total = (size_t)n * h * w * (c / 8);
+  CHECK_TOTAL32(total);
   maxpool_bwd_kernel<<<GRID1D(total)>>>(CBF(dout), CBF(dout2), reinterpret_cast<const uint8_t*>(argmax), BF(dx), n, h,
                                         w, c);
   IRFD_CHECK_LAUNCH();
@@ -355,6 +363,7 @@ extern "C" int irfd_avgpool_fwd(const void* a, float* out, int n, int hw, int c,
 extern "C" int irfd_avgpool_bwd(const float* dfeat, void* g, int n, int hw, int c, cudaStream_t stream) {
   IRFD_CHECK_ARG(dfeat && g && c % 8 == 0 && hw > 0, "avgpool_bwd: bad argument");
   const size_t total = (size_t)n * hw * (c / 8);
+  CHECK_TOTAL32(total);
   avgpool_bwd_kernel<<<GRID1D(total)>>>(dfeat, BF(g), n, hw, c);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;

@@ -25,10 +25,19 @@ struct RowVec {
   }
 };
 
-__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
+// Rows a thread keeps in flight per loop iteration in the streaming kernels: with one row per iteration a B200 SM only
+// has ~20 KB of loads outstanding (measured 2.4 TB/s); four rows cover the HBM latency-bandwidth product.
+constexpr int kRowBatch = 4;
+
+// 16-byte read-only load of 8 bf16, kept packed so that a batch of loads costs 4 registers each until it is consumed.
+__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  unpack8(u, f);
 }
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
   uint4 u;

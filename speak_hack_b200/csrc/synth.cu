@@ -61,80 +61,113 @@ __global__ void const_input_bwd_kernel(const __nv_bfloat16* __restrict__ dy, con
 // ---------------------------------------------------------------------------------------------------------------
 // Bilinear x2, align_corners=False (nn.Upsample, styleganv1.py:621,624), ATen index arithmetic restated.
 // ---------------------------------------------------------------------------------------------------------------
+// For scale 2 the source position of output o is o/2 - 0.25 (clamped at 0), so every weight is exactly 0.25, 0.75 or
+// (at the two borders) 1.0 and the neighbour indices follow from the parity of o: no float->int conversions and no
+// integer divisions in the kernels (the first version spent its time on 64-bit div/mod index arithmetic, not on HBM).
 struct Lerp {
   int i0, i1;
   float l0, l1;
 };
 __device__ __forceinline__ Lerp lerp_src(int o, int in_size) {
-  float src = 0.5f * (o + 0.5f) - 0.5f;
-  if (src < 0.f) src = 0.f;
   Lerp r;
-  r.i0 = (int)src;
-  r.i1 = r.i0 + (r.i0 < in_size - 1 ? 1 : 0);
-  r.l1 = src - r.i0;
-  r.l0 = 1.f - r.l1;
+  const int i = o >> 1;
+  if (o & 1) {  // src = i + 0.25
+    r.i0 = i;
+    r.i1 = i + (i < in_size - 1 ? 1 : 0);
+    r.l1 = 0.25f;
+    r.l0 = 0.75f;
+  } else if (o == 0) {  // src clamped to 0
+    r.i0 = 0;
+    r.i1 = in_size > 1 ? 1 : 0;
+    r.l1 = 0.f;
+    r.l0 = 1.f;
+  } else {  // src = (i - 1) + 0.75
+    r.i0 = i - 1;
+    r.i1 = i;
+    r.l1 = 0.75f;
+    r.l0 = 0.25f;
+  }
   return r;
 }
 
-__global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B,
-                                      int H, int W, int C) {
-  const int vc = C / 8, Ho = 2 * H, Wo = 2 * W;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)B * Ho * Wo * vc) return;
-  const int v = idx % vc;
-  const size_t pix = idx / vc;
-  const int ow = pix % Wo, oh = (pix / Wo) % Ho, b = pix / ((size_t)Wo * Ho);
-  const Lerp ly = lerp_src(oh, H), lx = lerp_src(ow, W);
+// grid = (B*Ho output rows, segments of Wo*C/8 vectors): row decode is per block, the column decode is 32-bit.
+__global__ void __launch_bounds__(256)
+upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W,
+                      int C) {
+  const unsigned vc = C >> 3, Ho = 2 * H, Wo = 2 * W;
+  const unsigned i = blockIdx.y * blockDim.x + threadIdx.x;
+  if (i >= Wo * vc) return;
+  const unsigned ow = i / vc, v = i - ow * vc;
+  const unsigned b = blockIdx.x / Ho, oh = blockIdx.x - b * Ho;
+  const Lerp ly = lerp_src((int)oh, H), lx = lerp_src((int)ow, W);
   const __nv_bfloat16* base = in + (size_t)b * H * W * C + v * 8;
+  const uint4 q00 = ldg16(base + ((size_t)ly.i0 * W + lx.i0) * C);
+  const uint4 q01 = ldg16(base + ((size_t)ly.i0 * W + lx.i1) * C);
+  const uint4 q10 = ldg16(base + ((size_t)ly.i1 * W + lx.i0) * C);
+  const uint4 q11 = ldg16(base + ((size_t)ly.i1 * W + lx.i1) * C);
   float f00[8], f01[8], f10[8], f11[8], o[8];
-  load8(base + ((size_t)ly.i0 * W + lx.i0) * C, f00);
-  load8(base + ((size_t)ly.i0 * W + lx.i1) * C, f01);
-  load8(base + ((size_t)ly.i1 * W + lx.i0) * C, f10);
-  load8(base + ((size_t)ly.i1 * W + lx.i1) * C, f11);
+  unpack8(q00, f00);
+  unpack8(q01, f01);
+  unpack8(q10, f10);
+  unpack8(q11, f11);
 #pragma unroll
   for (int t = 0; t < 8; ++t)
     o[t] = ly.l0 * (lx.l0 * f00[t] + lx.l1 * f01[t]) + ly.l1 * (lx.l0 * f10[t] + lx.l1 * f11[t]);
-  store8(out + pix * C + v * 8, o);
+  store8(out + ((size_t)blockIdx.x * Wo + ow) * C + v * 8, o);
 }
 
-// weight of input index i in output index o (1-D), or 0
-__device__ __forceinline__ float lerp_weight(int o, int i, int in_size) {
-  const Lerp l = lerp_src(o, in_size);
-  float w = 0.f;
-  if (l.i0 == i) w += l.l0;
-  if (l.i1 == i) w += l.l1;
-  return w;
+// Adjoint, gather form: input index i receives from outputs 2i-1 .. 2i+2 with weights (0.25, 0.75, 0.75, 0.25); at
+// the borders the clamped neighbour folds onto i (0.75 -> 1.0) and the out-of-range output does not exist (-> 0).
+__device__ __forceinline__ void lerp_adjoint_weights(int i, int in_size, float (&w)[4]) {
+  w[0] = i > 0 ? 0.25f : 0.f;
+  w[1] = i > 0 ? 0.75f : 1.f;
+  w[2] = i < in_size - 1 ? 0.75f : 1.f;
+  w[3] = i < in_size - 1 ? 0.25f : 0.f;
 }
 
-__global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ din, int B,
-                                      int H, int W, int C) {
-  const int vc = C / 8, Ho = 2 * H, Wo = 2 * W;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)B * H * W * vc) return;
-  const int v = idx % vc;
-  const size_t pix = idx / vc;
-  const int w = pix % W, h = (pix / W) % H, b = pix / ((size_t)W * H);
+// grid = (B*H input rows, segments of W*C/8 vectors)
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ din, int B, int H, int W,
+                      int C) {
+  const unsigned vc = C >> 3, Wo = 2 * W;
+  const unsigned i = blockIdx.y * blockDim.x + threadIdx.x;
+  if (i >= (unsigned)W * vc) return;
+  const int w = i / vc, v = i - w * vc;
+  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
+  float wy[4], wx[4];
+  lerp_adjoint_weights(h, H, wy);
+  lerp_adjoint_weights(w, W, wx);
+  // clamp the coordinates of the zero-weight (non-existent) outputs so that every load is in range: all 16 loads are
+  // then unconditional and in flight together
+  const __nv_bfloat16* base = dout + (size_t)b * (2 * H) * Wo * C + v * 8;
+  uint4 q[4][4];
+#pragma unroll
+  for (int dy = 0; dy < 4; ++dy) {
+    int oh = 2 * h - 1 + dy;
+    oh = oh < 0 ? 0 : (oh > 2 * H - 1 ? 2 * H - 1 : oh);
+#pragma unroll
+    for (int dx = 0; dx < 4; ++dx) {
+      int ow = 2 * w - 1 + dx;
+      ow = ow < 0 ? 0 : (ow > (int)Wo - 1 ? (int)Wo - 1 : ow);
+      q[dy][dx] = ldg16(base + ((size_t)oh * Wo + ow) * C);
+    }
+  }
   float acc[8];
 #pragma unroll
   for (int t = 0; t < 8; ++t) acc[t] = 0.f;
-  for (int dy = -1; dy <= 2; ++dy) {
-    const int oh = 2 * h + dy;
-    if (oh < 0 || oh >= Ho) continue;
-    const float wy = lerp_weight(oh, h, H);
-    if (wy == 0.f) continue;
-    for (int dx = -1; dx <= 2; ++dx) {
-      const int ow = 2 * w + dx;
-      if (ow < 0 || ow >= Wo) continue;
-      const float wx = lerp_weight(ow, w, W);
-      if (wx == 0.f) continue;
-      float g[8];
-      load8(dout + (((size_t)b * Ho + oh) * Wo + ow) * C + v * 8, g);
-      const float ww = wy * wx;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) acc[t] += ww * g[t];
+  for (int dy = 0; dy < 4; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 4; ++dx) {
+      float g[8];
+      unpack8(q[dy][dx], g);
+      const float ww = wy[dy] * wx[dx];
+      if (ww != 0.f) {  // a clamped (non-existent) output must not contribute even when it holds inf/nan
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] += ww * g[t];
+      }
     }
-  }
-  store8(din + pix * C + v * 8, acc);
+  store8(din + ((size_t)blockIdx.x * W + w) * C + v * 8, acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -161,22 +194,39 @@ style_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __re
     const int r0 = blockIdx.x * rows_per_blk;
     int r1 = r0 + rows_per_blk;
     if (r1 > HW) r1 = HW;
-    for (int r = r0 + rv.row_lane; r < r1; r += rv.rows_par) {
-      const size_t off = ((size_t)b * HW + r) * C + rv.cv * 8;
-      float g[8], av[8], o[8];
-      load8(dy + off, g);
-      load8(a + off, av);
-      const float nz = noise[(size_t)b * HW + r];
+    for (int r = r0 + rv.row_lane; r < r1; r += rv.rows_par * kRowBatch) {
+      uint4 qg[kRowBatch], qa[kRowBatch];
+      float nz[kRowBatch];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const float d = g[t] * sp[t] * (av[t] > 0.f ? 1.f : 0.2f);
-        o[t] = d;
-        acc[0][t] += g[t];
-        acc[1][t] += g[t] * av[t];
-        acc[2][t] += d;
-        acc[3][t] += d * nz;
+      for (int u = 0; u < kRowBatch; ++u) {
+        const int rr = r + u * rv.rows_par;
+        if (rr < r1) {
+          const size_t off = ((size_t)b * HW + rr) * C + rv.cv * 8;
+          qg[u] = ldg16(dy + off);
+          qa[u] = ldg16(a + off);
+          nz[u] = __ldg(noise + (size_t)b * HW + rr);
+        }
       }
-      store8(dz + off, o);
+#pragma unroll
+      for (int u = 0; u < kRowBatch; ++u) {
+        const int rr = r + u * rv.rows_par;
+        if (rr < r1) {
+          const size_t off = ((size_t)b * HW + rr) * C + rv.cv * 8;
+          float g[8], av[8], o[8];
+          unpack8(qg[u], g);
+          unpack8(qa[u], av);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const float d = g[t] * sp[t] * (av[t] > 0.f ? 1.f : 0.2f);
+            o[t] = d;
+            acc[0][t] += g[t];
+            acc[1][t] += g[t] * av[t];
+            acc[2][t] += d;
+            acc[3][t] += d * nz[u];
+          }
+          store8(dz + off, o);
+        }
+      }
     }
   }
   block_reduce_rows<4>(rv, C, acc, red_smem, partial + ((size_t)b * gridDim.x + blockIdx.x) * 4 * C, (size_t)C);
@@ -271,25 +321,42 @@ to_rgb_bwd_kernel(const float* __restrict__ drgb, const __nv_bfloat16* __restric
     const long long r0 = (long long)blockIdx.x * rows_per_blk;
     long long r1 = r0 + rows_per_blk;
     if (r1 > rows) r1 = rows;
-    for (long long r = r0 + rv.row_lane; r < r1; r += rv.rows_par) {
-      const int b = r / HW, p = r % HW;
-      const float* g = drgb + (size_t)b * 3 * HW + p;
-      const float g0 = g[0], g1 = g[HW], g2 = g[2 * HW];
-      float f[8], o[8];
-      load8(y + (size_t)r * C + rv.cv * 8, f);
+    for (long long r = r0 + rv.row_lane; r < r1; r += (long long)rv.rows_par * kRowBatch) {
+      uint4 qy[kRowBatch];
+      float g0[kRowBatch], g1[kRowBatch], g2[kRowBatch];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        o[t] = g0 * w0[t] + g1 * w1[t] + g2 * w2[t];
-        acc[0][t] += g0 * f[t];
-        acc[1][t] += g1 * f[t];
-        acc[2][t] += g2 * f[t];
+      for (int u = 0; u < kRowBatch; ++u) {
+        const long long rr = r + (long long)u * rv.rows_par;
+        if (rr < r1) {
+          const unsigned b = (unsigned)(rr / HW), p = (unsigned)(rr - (long long)b * HW);
+          const float* g = drgb + (size_t)b * 3 * HW + p;
+          g0[u] = __ldg(g);
+          g1[u] = __ldg(g + HW);
+          g2[u] = __ldg(g + 2 * (size_t)HW);
+          qy[u] = ldg16(y + (size_t)rr * C + rv.cv * 8);
+        }
       }
-      if (rv.cv == 0) {
-        acc[3][0] += g0;
-        acc[3][1] += g1;
-        acc[3][2] += g2;
+#pragma unroll
+      for (int u = 0; u < kRowBatch; ++u) {
+        const long long rr = r + (long long)u * rv.rows_par;
+        if (rr < r1) {
+          float f[8], o[8];
+          unpack8(qy[u], f);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            o[t] = g0[u] * w0[t] + g1[u] * w1[t] + g2[u] * w2[t];
+            acc[0][t] += g0[u] * f[t];
+            acc[1][t] += g1[u] * f[t];
+            acc[2][t] += g2[u] * f[t];
+          }
+          if (rv.cv == 0) {
+            acc[3][0] += g0[u];
+            acc[3][1] += g1[u];
+            acc[3][2] += g2[u];
+          }
+          store8(dy + (size_t)rr * C + rv.cv * 8, o);
+        }
       }
-      store8(dy + (size_t)r * C + rv.cv * 8, o);
     }
   }
   block_reduce_rows<4>(rv, C, acc, red_smem, partial + (size_t)blockIdx.x * 4 * C, (size_t)C);
@@ -340,14 +407,18 @@ extern "C" int irfd_const_input_bwd(const void* dy, const void* a0, const float*
 
 extern "C" int irfd_upsample2x_fwd(const void* in, void* out, int b, int h, int w, int c, cudaStream_t stream) {
   IRFD_CHECK_ARG(in && out && c % 8 == 0, "upsample2x_fwd: bad argument");
-  upsample2x_fwd_kernel<<<GRID1D((size_t)b * 4 * h * w * (c / 8))>>>(CBF(in), BF(out), b, h, w, c);
+  IRFD_CHECK_ARG(b > 0 && h > 0 && w > 0 && (long long)w * c < (1ll << 24), "upsample2x_fwd: bad shape");
+  upsample2x_fwd_kernel<<<dim3((unsigned)(b * 2 * h), (unsigned)((2 * w * (c / 8) + 255) / 256)), 256, 0, stream>>>(
+      CBF(in), BF(out), b, h, w, c);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }
 
 extern "C" int irfd_upsample2x_bwd(const void* dout, void* din, int b, int h, int w, int c, cudaStream_t stream) {
   IRFD_CHECK_ARG(dout && din && c % 8 == 0, "upsample2x_bwd: bad argument");
-  upsample2x_bwd_kernel<<<GRID1D((size_t)b * h * w * (c / 8))>>>(CBF(dout), BF(din), b, h, w, c);
+  IRFD_CHECK_ARG(b > 0 && h > 0 && w > 0 && (long long)w * c < (1ll << 24), "upsample2x_bwd: bad shape");
+  upsample2x_bwd_kernel<<<dim3((unsigned)(b * h), (unsigned)((w * (c / 8) + 255) / 256)), 256, 0, stream>>>(
+      CBF(dout), BF(din), b, h, w, c);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }

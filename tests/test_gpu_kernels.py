@@ -422,3 +422,67 @@ def test_bn_groups_equal_separate_calls(cuda_device):
     torch.cuda.synchronize()
     assert torch.allclose(rm1, rm2, rtol=1e-6, atol=1e-7) and torch.allclose(rv1, rv2, rtol=1e-6, atol=1e-7)
     assert torch.allclose(dg1, dg2, rtol=1e-5, atol=1e-5) and torch.allclose(db1, db2, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("has_g2", [False, True])
+@pytest.mark.parametrize("mask", ["none", "act", "from_z"])
+@pytest.mark.parametrize("rows,c", [(315, 64), (5000, 128), (777, 1024)])
+def test_bn_backward_variants_ragged(cuda_device, has_g2, mask, rows, c):
+    """Every (second gradient, ReLU-mask source) instance of the batched BN backward on row counts that are not a
+    multiple of the 4-row batch or of the rows a block covers; statistics from many (ragged) 128-row tiles."""
+    from speak_hack_b200 import ops
+
+    dev = cuda_device
+    g = gen(31)
+    z = (torch.randn(1, rows, 1, c, generator=g) * 1.5 + 0.2).to(dev).to(BF)
+    gamma = (torch.rand(c, generator=g) + 0.5).to(dev)
+    beta = (torch.randn(c, generator=g) * 0.5).to(dev)
+    zf = z.float().reshape(rows, c)
+    pad = (-rows) % 128
+    zp = torch.cat([zf, torch.zeros(pad, c, device=dev)]) if pad else zf
+    ssum = zp.reshape(-1, 128, c).sum(1).contiguous()
+    ssq = (zp * zp).reshape(-1, 128, c).sum(1).contiguous()
+    mean, rstd = ops.bn_finalize(ssum, ssq, rows, 1e-5, 0.1)
+    assert torch.allclose(mean, zf.mean(0), atol=1e-4, rtol=1e-4)
+    assert torch.allclose(rstd, (zf.var(0, unbiased=False) + 1e-5).rsqrt(), atol=1e-4, rtol=1e-3)
+    out = ops.bn_apply(z, mean, rstd, gamma, beta, relu=(mask != "none"))
+    xhat = (zf - mean) * rstd
+    assert rel_l2(out.float().reshape(rows, c), F.relu(xhat * gamma + beta) if mask != "none" else xhat * gamma + beta) < BF16_TOL
+    d1 = torch.randn(1, rows, 1, c, generator=g).to(dev).to(BF)
+    d2 = torch.randn(1, rows, 1, c, generator=g).to(dev).to(BF) if has_g2 else None
+    dz, dgamma, dbeta, g_out = ops.bn_backward(
+        d1, d2, out if mask == "act" else None, z, mean, rstd, gamma, want_g_out=True,
+        beta=beta if mask == "from_z" else None)
+    torch.cuda.synchronize()
+    gsum = d1.float() + (d2.float() if has_g2 else 0)
+    if mask == "act":
+        gsum = gsum * (out.float() > 0)
+    elif mask == "from_z":
+        gsum = gsum * ((xhat * gamma + beta).reshape(1, rows, 1, c) > 0)
+    gf = gsum.reshape(rows, c)
+    ref_db, ref_dg = gf.sum(0), (gf * xhat).sum(0)
+    ref_dz = gamma * rstd * (gf - ref_db / rows - xhat * ref_dg / rows)
+    if mask != "from_z":  # the recomputed mask may flip where gamma*xhat+beta rounds across 0; compare those loosely
+        assert rel_l2(g_out.float().reshape(rows, c), gf) < BF16_TOL
+    assert rel_l2(dbeta, ref_db) < 2e-2 if mask == "from_z" else rel_l2(dbeta, ref_db) < 1e-4
+    assert rel_l2(dgamma, ref_dg) < 2e-2 if mask == "from_z" else rel_l2(dgamma, ref_dg) < 1e-3
+    assert rel_l2(dz.float().reshape(rows, c), ref_dz) < (3e-2 if mask == "from_z" else 6e-3)
+
+
+@pytest.mark.parametrize("b,h,w,c", [(1, 1, 1, 64), (2, 3, 5, 72), (1, 128, 128, 64)])
+def test_upsample_borders(cuda_device, b, h, w, c):
+    """Bilinear x2 on odd / degenerate sizes (every border case of the closed-form weights) and the 256^2 layer shape."""
+    from speak_hack_b200 import ops
+
+    dev = cuda_device
+    g = gen(33)
+    x = torch.randn(b, h, w, c, generator=g).to(dev).to(BF)
+    up = ops.upsample2x_fwd(x)
+    xr = nchw(x.float()).requires_grad_(True)
+    ref = F.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=False)
+    assert rel_l2(nchw(up.float()), ref) < BF16_TOL
+    dout = torch.randn(b, 2 * h, 2 * w, c, generator=g).to(dev).to(BF)
+    din = ops.upsample2x_bwd(dout)
+    torch.cuda.synchronize()
+    (dr,) = torch.autograd.grad(ref, xr, nchw(dout.float()))
+    assert rel_l2(nchw(din.float()), dr) < BF16_TOL
