@@ -4,6 +4,7 @@
 // (16-byte loads/stores, fully coalesced: a row of C bf16 is contiguous) so per-channel parameters live in registers.
 // Requires C % 8 == 0 and C/8 <= 256 (C <= 2048), true for every tensor on the IRFD path.
 #pragma once
+#include <stdlib.h>
 #include "ptx.cuh"
 
 namespace irfd {
@@ -78,12 +79,22 @@ __device__ __forceinline__ void block_reduce_rows(const RowVec& rv, int C, float
   }
 }
 
+// Blocks per SM the row-streaming kernels are sized for (IRFD_ROW_WAVES overrides it for experiments).
+inline int row_block_waves() {
+  static int waves = [] {
+    const char* e = getenv("IRFD_ROW_WAVES");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : 1;  // measured on B200: 1 block per SM 710 pairs/s, 2: 697, 4: 686, 8: 667 (per-block prologue + reduction dominate)
+  }();
+  return waves;
+}
+
 // How many row blocks to launch for a [rows, C] tensor: enough to fill the machine, not so many that partial
 // buffers explode.  Also returns rows per block (multiple of rows_par).
 inline void plan_row_blocks(long long rows, int C, int sms, int* nblk, int* rows_per_blk) {
   int rows_par = kRvThreads / (C / 8);
   if (rows_par < 1) rows_par = 1;
-  long long target = (long long)sms * 4;  // measured: more blocks only add partials for the finalize pass
+  long long target = (long long)sms * row_block_waves();
   long long rpb = (rows + target - 1) / target;
   rpb = ((rpb + rows_par - 1) / rows_par) * rows_par;
   if (rpb < rows_par * 4) rpb = rows_par * 4;

@@ -426,7 +426,7 @@ extern "C" int irfd_upsample2x_bwd(const void* dout, void* din, int b, int h, in
 static void style_plan(int hw, int c, int b, int* chunks, int* rpb) {
   int rows_par = kRvThreads / (c / 8);
   if (rows_par < 1) rows_par = 1;
-  long long want = ((long long)num_sms() * 4 + b - 1) / b;  // chunks per image
+  long long want = ((long long)num_sms() * row_block_waves() + b - 1) / b;  // chunks per image
   long long r = (hw + want - 1) / want;
   r = ((r + rows_par - 1) / rows_par) * rows_par;
   if (r < rows_par * 4) r = rows_par * 4;

@@ -225,8 +225,10 @@ static void wgrad_plan(int n, int h, int w, int cin, int cout, int ksize, WgradA
   *block_n = cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64);
   a->num_n_tiles = cout / *block_n;
   a->num_kb = (int)((m_total + 63) / 64);
+  // One CTA per SM is resident (200 KB of pipeline stages), so the launch must fit ONE wave: rounding the split count
+  // up left a second wave of a handful of CTAs (e.g. 153 = 148 + 5) that doubled the kernel time.
   const int base = a->num_pairs * a->num_n_tiles;
-  int splits = (kWgWaves * num_sms() + base - 1) / base;
+  int splits = (kWgWaves * num_sms()) / base;
   const int max_splits = (a->num_kb + kWgMinKb - 1) / kWgMinKb;  // at least kWgMinKb k-blocks (64 pixels each) per split
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
