@@ -310,19 +310,39 @@ def run_native(args):
     fam = {k: v for k, v in fam.items() if k not in hbm}
     top = max(fam.values(), key=lambda f: f["ms"]) if fam else None
     roofline = None
+    peak_bw = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:  # per-launch DRAM bytes of the dominant family from the committed ncu capture (scripts/ncu_traffic.sh)
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as fh:
+            traffic = json.load(fh)
+    except Exception:
+        pass
+
+    def fam_entry(v):
+        # per-launch roofline: each launch is bounded by max(flops / tensor peak, algorithmic bytes / HBM peak)
+        bound_ms = sum(max(f / (peak_tf * 1e12), b / (peak_bw * 1e9)) * 1e3 for _, f, b in v["records"])
+        hbm_bound = sum(1 for _, f, b in v["records"] if b / (peak_bw * 1e9) > f / (peak_tf * 1e12))
+        return {"ms_per_step": v["ms"] / rsteps, "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12,
+                "launches_per_step": v["launches"] / rsteps, "gflop_per_step": v["flops"] / rsteps / 1e9,
+                "algorithmic_gbytes_per_step": v["bytes"] / rsteps / 1e9,
+                "per_launch_bound_ms_per_step": bound_ms / rsteps, "frac_of_per_launch_bound": bound_ms / v["ms"],
+                "hbm_bound_launches_per_step": hbm_bound / rsteps}
+
     if top:
         ach = top["flops"] / (top["ms"] * 1e-3) / 1e12
+        tr = (traffic or {}).get(top["name"])
         roofline = {"bound": "tensor", "kernel": top["name"], "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src,
+                    "frac": ach / peak_tf, "traffic": tr["dram_bytes_per_launch"] if tr else None,
+                    "algorithmic_bytes_per_launch": top["bytes"] / max(top["launches"], 1),
+                    "peak_source": peak_src,
                     "launches_per_step": top["launches"] / rsteps, "ms_per_step": top["ms"] / rsteps,
-                    "families": {k: {"ms_per_step": v["ms"] / rsteps, "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12,
-                                     "launches_per_step": v["launches"] / rsteps,
-                                     "gflop_per_step": v["flops"] / rsteps / 1e9} for k, v in fam.items()},
+                    "families": {k: fam_entry(v) for k, v in fam.items()},
                     "hbm_families": {k: {"ms_per_step": v["ms"] / rsteps, "gbytes_per_step": v["flops"] / rsteps / 1e9,
                                          "achieved_gbs": v["flops"] / (v["ms"] * 1e-3) / 1e9,
-                                         "frac_of_measured_hbm": v["flops"] / (v["ms"] * 1e-3) / 1e9 /
-                                         float(peaks.get("hbm_gbs", 6650.0))} for k, v in hbm.items()},
-                    "ncu": "profiles/r1_launches_final_summary.md, profiles/r1_ncu_full_summary.md"}
+                                         "frac_of_measured_hbm": v["flops"] / (v["ms"] * 1e-3) / 1e9 / peak_bw}
+                                     for k, v in hbm.items()},
+                    "ncu": "profiles/r1_launches_v3_summary.md, profiles/r1_ncu_full_summary.md, "
+                           "profiles/r1_conv_shapes.md (per-shape roofline)"}
 
     n_pairs = B * world * args.steps
     value = n_pairs / (ms_value * 1e-3)

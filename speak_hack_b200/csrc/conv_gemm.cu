@@ -19,6 +19,8 @@
 //   STYLE : z = acc + bias[n] + nw[n]*noise[m];  a = lrelu_0.2(z);  y = a*sp1[b,n] + s1[b,n]
 //           -> a (bf16, kept for backward) and y (bf16, next layer's input)
 //           reference: styleganv1.py:625-628 / 630-633 (conv -> ApplyNoise -> leaky_relu -> ApplyStyle)
+#include <stdlib.h>
+
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -60,6 +62,172 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STG_TOTAL + kMiscBytes;
   static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
 };
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue of ONE 128-row accumulator (TMEM columns [acc_col, acc_col + BLOCK_N)) whose first output row is the flat
+// pixel m0: TMEM -> registers -> fused math -> swizzled smem staging -> TMA store (+ STATS partials).
+// Called by the 8 epilogue warps (threads 64..319).  NBUF = staging buffers per output (1 or 2).
+// `release_bar`: arrived on (one lane per warp) as soon as the accumulator has been drained into registers.
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK_N, int MODE, int NBUF>
+__device__ __forceinline__ void epilogue_acc(const ConvGemmArgs& p, const CUtensorMap* map_out,
+                                             const CUtensorMap* map_out2, uint32_t tmem_base, uint32_t acc_col,
+                                             int m0, int n_tile, uint64_t* release_bar, uint8_t* stg_base, float* vec,
+                                             uint32_t& chunk_counter) {
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int e = warp - 2;
+  const int q = warp & 3;       // TMEM lane quarter this warp may touch
+  const int half = e >> 2;      // which 32-column half of each 64-column chunk
+  const int etid = threadIdx.x - 64;
+  const int r = q * 32 + lane;  // tile row == TMEM lane
+  float* vb = vec;              // [256] bias
+  float* vnw = vec + 256;       // [256] noise weight
+  float* vsp1 = vec + 512;      // [2][256]
+  float* vs1 = vec + 1024;      // [2][256]
+  const int m_tile = m0 >> 7;
+  const int ng0 = n_tile * BLOCK_N;
+  float noise_r = 0.f;
+  int img_local = 0;
+  if constexpr (MODE == EPI_STYLE) {
+    const int nimg = p.HW < 128 ? 128 / p.HW : 1;
+    const int b0 = m0 / p.HW;
+    // (the last barrier of the previous accumulator's chunk loop already separates its vector reads from these writes)
+    for (int i = etid; i < BLOCK_N; i += kEpiThreads) {
+      vb[i] = p.bias[ng0 + i];
+      vnw[i] = p.nw[ng0 + i];
+    }
+    for (int i = etid; i < nimg * BLOCK_N; i += kEpiThreads) {
+      const int img = i / BLOCK_N, c = i - img * BLOCK_N;
+      int bb = b0 + img;
+      if (bb >= p.B) bb = p.B - 1;
+      vsp1[img * 256 + c] = p.sp1[(size_t)bb * p.N_total + ng0 + c];
+      vs1[img * 256 + c] = p.s1[(size_t)bb * p.N_total + ng0 + c];
+    }
+    named_bar_sync(1, kEpiThreads);
+    if (m0 + r < p.M_total) noise_r = p.noise[m0 + r];
+    img_local = p.HW < 128 ? r / p.HW : 0;
+  } else if constexpr (MODE == EPI_PLAIN) {
+    if (p.bias != nullptr) {
+      for (int i = etid; i < BLOCK_N; i += kEpiThreads) vb[i] = p.bias[ng0 + i];
+      named_bar_sync(1, kEpiThreads);
+    }
+  } else if constexpr (MODE == EPI_AFFINE) {
+    for (int i = etid; i < BLOCK_N; i += kEpiThreads) {
+      vb[i] = p.bias[ng0 + i];   // shift
+      vnw[i] = p.nw[ng0 + i];    // scale
+    }
+    named_bar_sync(1, kEpiThreads);
+  }
+#pragma unroll 1
+  for (int chunk = 0; chunk < BLOCK_N / 64; ++chunk, ++chunk_counter) {
+    uint32_t v[32];
+    const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc_col + chunk * 64 + half * 32;
+    tmem_ld32(taddr, v);
+    tmem_ld_wait();
+    if (chunk == BLOCK_N / 64 - 1 && release_bar != nullptr) {
+      // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(release_bar);
+    }
+    const int buf = (NBUF == 2) ? (chunk_counter & 1) : 0;
+    uint8_t* stg0 = stg_base + buf * kStgBytes;
+    uint8_t* stg1 = stg_base + (NBUF + buf) * kStgBytes;
+    // staging buffer `buf` was last used NBUF chunks ago: make sure its TMA store has drained it
+    if (etid == 0) tma_store_wait_read<NBUF - 1>();
+    named_bar_sync(1, kEpiThreads);
+    const int cbase = chunk * 64 + half * 32;  // column within the BLOCK_N tile
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      float o[8], o2[8];
+      float rres[8];
+      if constexpr (MODE == EPI_AFFINE) {
+        if (p.res != nullptr && m0 + r < p.M_total) {
+          const uint4 u = *reinterpret_cast<const uint4*>(p.res + (size_t)(m0 + r) * p.N_total + ng0 + cbase + jj * 8);
+          const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+          rres[0] = a0.x; rres[1] = a0.y; rres[2] = a1.x; rres[3] = a1.y;
+          rres[4] = a2.x; rres[5] = a2.y; rres[6] = a3.x; rres[7] = a3.y;
+        } else {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) rres[t] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int c = cbase + jj * 8 + t;
+        float acc = __uint_as_float(v[jj * 8 + t]);
+        if constexpr (MODE == EPI_STYLE) {
+          float z = acc + vb[c] + vnw[c] * noise_r;
+          float a = z > 0.f ? z : 0.2f * z;
+          o[t] = a;
+          o2[t] = a * vsp1[img_local * 256 + c] + vs1[img_local * 256 + c];
+        } else if constexpr (MODE == EPI_PLAIN) {
+          o[t] = (p.bias != nullptr) ? acc + vb[c] : acc;
+        } else if constexpr (MODE == EPI_AFFINE) {
+          const float y = acc * vnw[c] + vb[c] + rres[t];
+          o[t] = p.relu ? fmaxf(y, 0.f) : y;
+        } else {
+          o[t] = acc;
+        }
+      }
+      const int j = half * 4 + jj;  // 16-byte chunk index inside the 128-byte staging row
+      const int phys = j ^ (r & 7);
+      uint4 pk;
+      pk.x = pack_bf16x2(o[0], o[1]);
+      pk.y = pack_bf16x2(o[2], o[3]);
+      pk.z = pack_bf16x2(o[4], o[5]);
+      pk.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(stg0 + r * 128 + phys * 16) = pk;
+      if constexpr (MODE == EPI_STYLE) {
+        uint4 pk2;
+        pk2.x = pack_bf16x2(o2[0], o2[1]);
+        pk2.y = pack_bf16x2(o2[2], o2[3]);
+        pk2.z = pack_bf16x2(o2[4], o2[5]);
+        pk2.w = pack_bf16x2(o2[6], o2[7]);
+        *reinterpret_cast<uint4*>(stg1 + r * 128 + phys * 16) = pk2;
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, kEpiThreads);
+    if (etid == 0) {
+      tma_store_2d(map_out, stg0, ng0 + chunk * 64, m0);
+      if constexpr (MODE == EPI_STYLE) tma_store_2d(map_out2, stg1, ng0 + chunk * 64, m0);
+      tma_store_commit();
+    }
+    if constexpr (MODE == EPI_STATS) {
+      // per-channel sum / sum of squares over the 128 rows of this staged chunk (values as stored, bf16)
+      const int pr = etid & 31;  // channel pair
+      const int g = etid >> 5;   // 16-row group
+      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int row = g * 16 + i;
+        const int phys = (pr >> 2) ^ (row & 7);
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(stg0 + row * 128 + phys * 16 + (pr & 3) * 4);
+        const float2 f = unpack_bf16x2(w);
+        s0 += f.x;
+        q0 += f.x * f.x;
+        s1 += f.y;
+        q1 += f.y * f.y;
+      }
+      float* red = vec;  // [8][64][2]
+      red[(g * 64 + 2 * pr) * 2 + 0] = s0;
+      red[(g * 64 + 2 * pr) * 2 + 1] = q0;
+      red[(g * 64 + 2 * pr + 1) * 2 + 0] = s1;
+      red[(g * 64 + 2 * pr + 1) * 2 + 1] = q1;
+      named_bar_sync(1, kEpiThreads);
+      if (etid < 128) {
+        const int ch = etid & 63, which = etid >> 6;
+        float acc = 0.f;
+#pragma unroll
+        for (int gg = 0; gg < 8; ++gg) acc += red[(gg * 64 + ch) * 2 + which];
+        float* dst = which ? p.stat_sq : p.stat_sum;
+        dst[(size_t)m_tile * p.N_total + ng0 + chunk * 64 + ch] = acc;
+      }
+    }
+  }
+}
 
 template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -171,15 +339,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
-    const int e = warp - 2;
-    const int q = warp & 3;       // TMEM lane quarter this warp may touch
-    const int half = e >> 2;      // which 32-column half of each 64-column chunk
     const int etid = threadIdx.x - 64;
-    const int r = q * 32 + lane;  // tile row == TMEM lane
-    float* vb = vec;              // [256] bias
-    float* vnw = vec + 256;       // [256] noise weight
-    float* vsp1 = vec + 512;      // [2][256]
-    float* vs1 = vec + 1024;      // [2][256]
     int iter = 0;
     uint32_t chunk_counter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
@@ -187,149 +347,223 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t aphase = (iter >> 1) & 1;
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
-      const int m0 = m_tile * 128;
-      const int ng0 = n_tile * BLOCK_N;
-      float noise_r = 0.f;
-      int img_local = 0;
-      if constexpr (MODE == EPI_STYLE) {
-        const int nimg = p.HW < 128 ? 128 / p.HW : 1;
-        const int b0 = m0 / p.HW;
-        for (int i = etid; i < BLOCK_N; i += kEpiThreads) {
-          vb[i] = p.bias[ng0 + i];
-          vnw[i] = p.nw[ng0 + i];
-        }
-        for (int i = etid; i < nimg * BLOCK_N; i += kEpiThreads) {
-          const int img = i / BLOCK_N, c = i - img * BLOCK_N;
-          int bb = b0 + img;
-          if (bb >= p.B) bb = p.B - 1;
-          vsp1[img * 256 + c] = p.sp1[(size_t)bb * p.N_total + ng0 + c];
-          vs1[img * 256 + c] = p.s1[(size_t)bb * p.N_total + ng0 + c];
-        }
-        named_bar_sync(1, kEpiThreads);
-        if (m0 + r < p.M_total) noise_r = p.noise[m0 + r];
-        img_local = p.HW < 128 ? r / p.HW : 0;
-      } else if constexpr (MODE == EPI_PLAIN) {
-        if (p.bias != nullptr) {
-          for (int i = etid; i < BLOCK_N; i += kEpiThreads) vb[i] = p.bias[ng0 + i];
-          named_bar_sync(1, kEpiThreads);
-        }
-      } else if constexpr (MODE == EPI_AFFINE) {
-        for (int i = etid; i < BLOCK_N; i += kEpiThreads) {
-          vb[i] = p.bias[ng0 + i];   // shift
-          vnw[i] = p.nw[ng0 + i];    // scale
-        }
-        named_bar_sync(1, kEpiThreads);
-      }
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-#pragma unroll 1
-      for (int chunk = 0; chunk < BLOCK_N / 64; ++chunk, ++chunk_counter) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BLOCK_N + chunk * 64 + half * 32;
-        tmem_ld32(taddr, v);
-        tmem_ld_wait();
-        if (chunk == BLOCK_N / 64 - 1) {
-          // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[as]);
-        }
-        const int buf = chunk_counter & 1;
-        uint8_t* stg0 = stg_base + buf * kStgBytes;
-        uint8_t* stg1 = stg_base + (2 + buf) * kStgBytes;
-        // staging buffer `buf` was last used two chunks ago: make sure its TMA store has drained it
-        if (etid == 0) tma_store_wait_read<1>();
-        named_bar_sync(1, kEpiThreads);
-        const int cbase = chunk * 64 + half * 32;  // column within the BLOCK_N tile
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          float o[8], o2[8];
-          float rres[8];
-          if constexpr (MODE == EPI_AFFINE) {
-            if (p.res != nullptr && m0 + r < p.M_total) {
-              const uint4 u = *reinterpret_cast<const uint4*>(p.res + (size_t)(m0 + r) * p.N_total + ng0 + cbase + jj * 8);
-              const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-              rres[0] = a0.x; rres[1] = a0.y; rres[2] = a1.x; rres[3] = a1.y;
-              rres[4] = a2.x; rres[5] = a2.y; rres[6] = a3.x; rres[7] = a3.y;
-            } else {
-#pragma unroll
-              for (int t = 0; t < 8; ++t) rres[t] = 0.f;
-            }
-          }
-#pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const int c = cbase + jj * 8 + t;
-            float acc = __uint_as_float(v[jj * 8 + t]);
-            if constexpr (MODE == EPI_STYLE) {
-              float z = acc + vb[c] + vnw[c] * noise_r;
-              float a = z > 0.f ? z : 0.2f * z;
-              o[t] = a;
-              o2[t] = a * vsp1[img_local * 256 + c] + vs1[img_local * 256 + c];
-            } else if constexpr (MODE == EPI_PLAIN) {
-              o[t] = (p.bias != nullptr) ? acc + vb[c] : acc;
-            } else if constexpr (MODE == EPI_AFFINE) {
-              const float y = acc * vnw[c] + vb[c] + rres[t];
-              o[t] = p.relu ? fmaxf(y, 0.f) : y;
-            } else {
-              o[t] = acc;
-            }
-          }
-          const int j = half * 4 + jj;  // 16-byte chunk index inside the 128-byte staging row
-          const int phys = j ^ (r & 7);
-          uint4 pk;
-          pk.x = pack_bf16x2(o[0], o[1]);
-          pk.y = pack_bf16x2(o[2], o[3]);
-          pk.z = pack_bf16x2(o[4], o[5]);
-          pk.w = pack_bf16x2(o[6], o[7]);
-          *reinterpret_cast<uint4*>(stg0 + r * 128 + phys * 16) = pk;
-          if constexpr (MODE == EPI_STYLE) {
-            uint4 pk2;
-            pk2.x = pack_bf16x2(o2[0], o2[1]);
-            pk2.y = pack_bf16x2(o2[2], o2[3]);
-            pk2.z = pack_bf16x2(o2[4], o2[5]);
-            pk2.w = pack_bf16x2(o2[6], o2[7]);
-            *reinterpret_cast<uint4*>(stg1 + r * 128 + phys * 16) = pk2;
-          }
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1, kEpiThreads);
-        if (etid == 0) {
-          tma_store_2d(&map_out, stg0, ng0 + chunk * 64, m0);
-          if constexpr (MODE == EPI_STYLE) tma_store_2d(&map_out2, stg1, ng0 + chunk * 64, m0);
-          tma_store_commit();
-        }
-        if constexpr (MODE == EPI_STATS) {
-          // per-channel sum / sum of squares over the 128 rows of this staged chunk (values as stored, bf16)
-          const int pr = etid & 31;  // channel pair
-          const int g = etid >> 5;   // 16-row group
-          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int row = g * 16 + i;
-            const int phys = (pr >> 2) ^ (row & 7);
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(stg0 + row * 128 + phys * 16 + (pr & 3) * 4);
-            const float2 f = unpack_bf16x2(w);
-            s0 += f.x;
-            q0 += f.x * f.x;
-            s1 += f.y;
-            q1 += f.y * f.y;
-          }
-          float* red = vec;  // [8][64][2]
-          red[(g * 64 + 2 * pr) * 2 + 0] = s0;
-          red[(g * 64 + 2 * pr) * 2 + 1] = q0;
-          red[(g * 64 + 2 * pr + 1) * 2 + 0] = s1;
-          red[(g * 64 + 2 * pr + 1) * 2 + 1] = q1;
-          named_bar_sync(1, kEpiThreads);
-          if (etid < 128) {
-            const int ch = etid & 63, which = etid >> 6;
-            float acc = 0.f;
-#pragma unroll
-            for (int gg = 0; gg < 8; ++gg) acc += red[(gg * 64 + ch) * 2 + which];
-            float* dst = which ? p.stat_sq : p.stat_sum;
-            dst[(size_t)m_tile * p.N_total + ng0 + chunk * 64 + ch] = acc;
+      epilogue_acc<BLOCK_N, MODE, 2>(p, &map_out, &map_out2, tmem_base, as * BLOCK_N, m_tile * 128, n_tile,
+                                     &tmem_empty[as], stg_base, vec, chunk_counter);
+    }
+    if (etid == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Halo-reuse variant for 3x3 convs on wide images (W % 128 == 0, H even) with BLOCK_N <= 128 — the generator's
+// 128^2 / 256^2 layers, which the per-tap kernel above runs L2->SM fabric-bound (every tap re-fetches its A tile:
+// 9 x 16 KB per 128 pixels and 64 input channels).
+//
+// Tile = 256 output pixels = two image rows x 128 columns -> two accumulators.  Per 64-channel chunk ONE 4-D TMA box
+// brings the [4 rows][130 columns][64 ch] halo (65 KB) that serves all nine taps of both rows: the A operand of tap
+// (dy, dx) for output row j is the same smem buffer at line offset (j + dy) * 130 + dx, i.e. only the descriptor start
+// address moves (128-byte lines; the 128-byte swizzle is a function of the absolute smem address, so a shifted start
+// stays consistent with what TMA wrote).  Each [BLOCK_N x 64] weight tile feeds both accumulators.
+// L2->SM bytes per 128 pixels x 64 channels: 33 KB (A) + 36 KB (B, N = 64) instead of 144 KB + 72 KB.
+//
+// Warp roles: warp 0 = halo (A) producer, warp 1 = MMA issuer, warps 2..9 = epilogue, warp 10 = weight (B) producer.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHaloThreads = 352;
+constexpr int kHaloCols = 130;
+constexpr int kHaloRows = 4;
+
+template <int BLOCK_N, int MODE>
+struct HaloCfg {
+  static_assert(BLOCK_N == 64 || BLOCK_N == 128, "two double-buffered accumulators need 4 x BLOCK_N <= 512 TMEM columns");
+  static constexpr int A_BYTES = kHaloRows * kHaloCols * 128;  // 66,560 = 65 x 1024
+  static constexpr int A_STAGES = 2;
+  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int NUM_OUT = (MODE == EPI_STYLE) ? 2 : 1;
+  static constexpr int NBUF = (NUM_OUT == 2) ? 1 : 2;  // staging buffers per output
+  static constexpr int STG_TOTAL = NUM_OUT * NBUF * kStgBytes;
+  static constexpr int RAW_B = (kSmemLimit - 1024 - A_STAGES * A_BYTES - STG_TOTAL - kMiscBytes) / B_BYTES;
+  static constexpr int B_STAGES = RAW_B > 8 ? 8 : RAW_B;
+  static constexpr int SMEM_BYTES = 1024 + A_STAGES * A_BYTES + B_STAGES * B_BYTES + STG_TOTAL + kMiscBytes;
+  static constexpr uint32_t TMEM_COLS = 4 * BLOCK_N <= 256 ? 256 : 512;
+  static_assert(A_BYTES % 1024 == 0 && B_STAGES >= 2, "halo stage must keep 1024-byte alignment");
+};
+
+struct HaloArgs {
+  int wsegs, hpairs;  // W / 128, H / 2
+  int total_tiles;    // 256-pixel tiles x n tiles
+  int base_offset;    // experiment: fill the descriptor's base-offset field from the start address
+};
+
+template <int BLOCK_N, int MODE>
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out2,
+                 const ConvGemmArgs p, const HaloArgs hp) {
+  using Cfg = HaloCfg<BLOCK_N, MODE>;
+  constexpr int BST = Cfg::B_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_b = smem + Cfg::A_STAGES * Cfg::A_BYTES;
+  uint8_t* stg_base = smem_b + BST * Cfg::B_BYTES;
+  uint8_t* misc = stg_base + Cfg::STG_TOTAL;
+  float* vec = reinterpret_cast<float*>(misc);
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(misc + 8192);  // [2]
+  uint64_t* empty_a = full_a + 2;                               // [2]
+  uint64_t* full_b = empty_a + 2;                               // [BST]
+  uint64_t* empty_b = full_b + BST;                             // [BST]
+  uint64_t* tmem_full = empty_b + BST;                          // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                         // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int chunks = p.cin_chunks;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full_a[i], 1);
+      mbar_init(&empty_a[i], 1);
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);
+    }
+    for (int i = 0; i < BST; ++i) {
+      mbar_init(&full_b[i], 1);
+      mbar_init(&empty_b[i], 1);
+    }
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // tile -> (n tile, image, row pair, column segment); n tile fastest like the per-tap kernel
+  auto decode = [&](int tile, int& n_tile, int& n0, int& h0, int& w0) {
+    const int m2 = tile / p.num_n_tiles;
+    n_tile = tile - m2 * p.num_n_tiles;
+    const int wseg = m2 % hp.wsegs;
+    const int t = m2 / hp.wsegs;
+    const int hpair = t % hp.hpairs;
+    n0 = t / hp.hpairs;
+    h0 = hpair * 2;
+    w0 = wseg * 128;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ halo (A) producer
+    if (lane == 0) {
+      tma_prefetch_desc(&map_a);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < hp.total_tiles; tile += gridDim.x) {
+        int n_tile, n0, h0, w0;
+        decode(tile, n_tile, n0, h0, w0);
+        for (int ch = 0; ch < chunks; ++ch) {
+          mbar_wait(&empty_a[stage], phase ^ 1);
+          mbar_expect_tx(&full_a[stage], Cfg::A_BYTES);
+          tma_load_4d(smem + stage * Cfg::A_BYTES, &map_a, &full_a[stage], ch * 64, w0 - 1, h0 - 1, n0);
+          if (++stage == Cfg::A_STAGES) {
+            stage = 0;
+            phase ^= 1;
           }
         }
       }
+    }
+  } else if (warp == 10) {
+    // ------------------------------------------------------------------ weight (B) producer
+    if (lane == 0) {
+      tma_prefetch_desc(&map_b);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < hp.total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.num_n_tiles;
+        for (int ch = 0; ch < chunks; ++ch) {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&empty_b[stage], phase ^ 1);
+            mbar_expect_tx(&full_b[stage], Cfg::B_BYTES);
+            tma_load_2d(smem_b + stage * Cfg::B_BYTES, &map_b, &full_b[stage], (tap * chunks + ch) * 64,
+                        n_tile * BLOCK_N);
+            if (++stage == BST) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int iter = 0;
+      for (int tile = blockIdx.x; tile < hp.total_tiles; tile += gridDim.x, ++iter) {
+        const int as = iter & 1;
+        const uint32_t aphase = (iter >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 2 * BLOCK_N;
+        for (int ch = 0; ch < chunks; ++ch) {
+          mbar_wait(&full_a[sa], pa);
+          const uint32_t a_addr = smem_u32(smem + sa * Cfg::A_BYTES);
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap - dy * 3;
+            mbar_wait(&full_b[sb], pb);
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(smem_b + sb * Cfg::B_BYTES);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint32_t a_tap = a_addr + ((j + dy) * kHaloCols + dx) * 128;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint64_t adesc = make_smem_desc_sw128(a_tap + k * 32, 0, 1024);
+                if (hp.base_offset) adesc |= static_cast<uint64_t>((a_tap >> 7) & 7u) << 49;
+                const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+                umma_bf16(d_tmem + j * BLOCK_N, adesc, bdesc, idesc, (ch | tap | k) != 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(&empty_b[sb]);
+            if (++sb == BST) {
+              sb = 0;
+              pb ^= 1;
+            }
+          }
+          umma_commit(&empty_a[sa]);
+          if (++sa == Cfg::A_STAGES) {
+            sa = 0;
+            pa ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (8 warps): two accumulators per tile
+    const int etid = threadIdx.x - 64;
+    int iter = 0;
+    uint32_t chunk_counter = 0;
+    for (int tile = blockIdx.x; tile < hp.total_tiles; tile += gridDim.x, ++iter) {
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      int n_tile, n0, h0, w0;
+      decode(tile, n_tile, n0, h0, w0);
+      const int m0 = (n0 * p.H + h0) * p.W + w0;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      epilogue_acc<BLOCK_N, MODE, Cfg::NBUF>(p, &map_out, &map_out2, tmem_base, as * 2 * BLOCK_N, m0, n_tile, nullptr,
+                                             stg_base, vec, chunk_counter);
+      epilogue_acc<BLOCK_N, MODE, Cfg::NBUF>(p, &map_out, &map_out2, tmem_base, as * 2 * BLOCK_N + BLOCK_N, m0 + p.W,
+                                             n_tile, &tmem_empty[as], stg_base, vec, chunk_counter);
     }
     if (etid == 0) tma_store_wait_all<0>();
   }
@@ -373,6 +607,40 @@ static int dispatch_block_n(int block_n, const CUtensorMap& ma, const CUtensorMa
   }
   set_last_error("bad BLOCK_N %d", block_n);
   return IRFD_ERR_INVALID_ARGUMENT;
+}
+
+
+template <int BLOCK_N, int MODE>
+static int launch_conv_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mo2,
+                            const ConvGemmArgs& a, const HaloArgs& h, cudaStream_t stream) {
+  using Cfg = HaloCfg<BLOCK_N, MODE>;
+  static bool configured = false;
+  auto kern = conv_halo_kernel<BLOCK_N, MODE>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(halo smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return IRFD_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int grid = h.total_tiles < num_sms() ? h.total_tiles : num_sms();
+  kern<<<grid, kHaloThreads, Cfg::SMEM_BYTES, stream>>>(ma, mb, mo, mo2, a, h);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+template <int MODE>
+static int dispatch_halo(int block_n, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo,
+                         const CUtensorMap& mo2, const ConvGemmArgs& a, const HaloArgs& h, cudaStream_t stream) {
+  if (block_n == 64) return launch_conv_halo<64, MODE>(ma, mb, mo, mo2, a, h, stream);
+  return launch_conv_halo<128, MODE>(ma, mb, mo, mo2, a, h, stream);
+}
+
+// IRFD_CONV_HALO: 0 = never, 1 (default) = wide 3x3 layers with Cout 64/128, read at every call (tests flip it).
+static int halo_mode() {
+  const char* e = getenv("IRFD_CONV_HALO");
+  return e ? atoi(e) : 1;
 }
 
 }  // namespace irfd
@@ -454,13 +722,23 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
   }
   IRFD_CHECK_ARG((block_n == 64 || block_n == 128 || block_n == 256) && cout % block_n == 0,
                  "conv_gemm: BLOCK_N %d incompatible with Cout %d", block_n, cout);
+  // halo-reuse kernel: 3x3, rows of >= 128 pixels, Cout of one 64/128-wide tile (the fabric-bound generator layers)
+  const int hmode = halo_mode();
+  const bool use_halo = hmode != 0 && ksize == 3 && W % 128 == 0 && H % 2 == 0 && (cout == 64 || cout == 128) &&
+                        (force_block_n == 0 || force_block_n == cout);
+  if (use_halo) block_n = cout;
   a.num_n_tiles = cout / block_n;
 
   CUtensorMap ma, mb, mo, mo2;
   {
     const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
     const uint64_t str[3] = {(uint64_t)cin * 2, (uint64_t)W * cin * 2, (uint64_t)H * W * cin * 2};
-    const uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
+    uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
+    if (use_halo) {
+      box[1] = kHaloCols;
+      box[2] = kHaloRows;
+      box[3] = 1;
+    }
     int rc = make_tmap_bf16(&ma, x, 4, dims, str, box, true);
     if (rc) return rc;
   }
@@ -480,6 +758,20 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
     if (rc) return rc;
     rc = make_tmap_bf16(&mo2, out2 ? out2 : out, 2, dims, str, box, true);
     if (rc) return rc;
+  }
+  if (use_halo) {
+    HaloArgs hargs;
+    hargs.wsegs = W / 128;
+    hargs.hpairs = H / 2;
+    hargs.total_tiles = NB * hargs.hpairs * hargs.wsegs * a.num_n_tiles;
+    hargs.base_offset = hmode == 2 ? 1 : 0;
+    switch (mode) {
+      case EPI_PLAIN: return dispatch_halo<EPI_PLAIN>(block_n, ma, mb, mo, mo2, a, hargs, stream);
+      case EPI_STATS: return dispatch_halo<EPI_STATS>(block_n, ma, mb, mo, mo2, a, hargs, stream);
+      case EPI_STYLE: return dispatch_halo<EPI_STYLE>(block_n, ma, mb, mo, mo2, a, hargs, stream);
+      case EPI_AFFINE: return dispatch_halo<EPI_AFFINE>(block_n, ma, mb, mo, mo2, a, hargs, stream);
+    }
+    return IRFD_ERR_INVALID_ARGUMENT;
   }
   switch (mode) {
     case EPI_PLAIN: return dispatch_block_n<EPI_PLAIN>(block_n, ma, mb, mo, mo2, a, stream);

@@ -56,21 +56,28 @@ def gemm_timing_begin() -> None:
 
 
 def gemm_timing_end():
-    """Returns {family: {name, ms, flops, launches}}; call after torch.cuda.synchronize()."""
+    """Returns {family: {name, ms, flops, bytes, launches, records}}; call after torch.cuda.synchronize().
+    `records` keeps (ms, flops, bytes) per launch so the caller can form a per-launch roofline bound."""
     global _gemm_timing
     rec, _gemm_timing = _gemm_timing or [], None
     fam = {}
-    for name, flops, e0, e1 in rec:
-        f = fam.setdefault(name, {"name": name, "ms": 0.0, "flops": 0.0, "launches": 0})
-        f["ms"] += e0.elapsed_time(e1)
+    for name, flops, nbytes, e0, e1 in rec:
+        f = fam.setdefault(name, {"name": name, "ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0, "records": []})
+        ms = e0.elapsed_time(e1)
+        f["ms"] += ms
         f["flops"] += flops
+        f["bytes"] += nbytes
         f["launches"] += 1
+        f["records"].append((ms, flops, nbytes))
     return fam
 
 
 class _timed:
-    def __init__(self, name, flops):
-        self.name, self.flops = name, flops
+    """flops: algorithmic flops of the launch (for memory-bound families the historical convention is bytes here);
+    nbytes: algorithmic HBM bytes of the launch (inputs read once + outputs written once)."""
+
+    def __init__(self, name, flops, nbytes=0.0):
+        self.name, self.flops, self.nbytes = name, flops, nbytes
 
     def __enter__(self):
         if _gemm_timing is not None:
@@ -82,7 +89,7 @@ class _timed:
     def __exit__(self, *exc):
         if _gemm_timing is not None:
             self.e1.record()
-            _gemm_timing.append((self.name, self.flops, self.e0, self.e1))
+            _gemm_timing.append((self.name, self.flops, self.nbytes, self.e0, self.e1))
         return False
 
 
@@ -123,7 +130,9 @@ def conv_gemm(x, wk, ksize, mode=EPI_PLAIN, bias=None, nw=None, noise=None, sp1=
     for t, nm in ((bias, "bias"), (nw, "nw"), (noise, "noise"), (sp1, "sp1"), (s1, "s1")):
         if t is not None:
             _chk(t, F32, nm)
-    with _timed("conv_gemm_kernel (tcgen05 fprop/dgrad)", 2.0 * n * h * w * cout * cin * ksize * ksize):
+    m = n * h * w
+    nbytes = 2.0 * m * cin + 2.0 * m * cout * (2 if mode == EPI_STYLE else 1) + 2.0 * cin * cout * ksize * ksize
+    with _timed("conv_gemm_kernel (tcgen05 fprop/dgrad)", 2.0 * m * cout * cin * ksize * ksize, nbytes):
         _call("irfd_conv_gemm", x.data_ptr(), n, h, w, cin, wk.data_ptr(), cout, ksize, out.data_ptr(), _ptr(out2),
               mode, _ptr(bias), _ptr(nw), _ptr(noise), _ptr(sp1), _ptr(s1), _ptr(ssum), _ptr(ssq), force_block_n,
               _stream())
@@ -183,7 +192,8 @@ def conv_wgrad(x, dy, ksize, dw=None, beta=0.0, reduce_cin=0, reduce_taps=0, out
     _chk(dw, F32, "dw")
     need = lib.irfd_wgrad_workspace_bytes(n, h, w, cin, cout, ksize)
     ws = workspace(need, x.device)
-    with _timed("wgrad_gemm_kernel (tcgen05 split-K + reduce)", 2.0 * n * h * w * cout * cin * ksize * ksize):
+    nbytes = 2.0 * n * h * w * (cin + cout) + 4.0 * cin * cout * ksize * ksize
+    with _timed("wgrad_gemm_kernel (tcgen05 split-K + reduce)", 2.0 * n * h * w * cout * cin * ksize * ksize, nbytes):
         _call("irfd_conv_wgrad", x.data_ptr(), dy.data_ptr(), n, h, w, cin, cout, ksize, dw.data_ptr(), beta,
               reduce_cin, reduce_taps, ws.data_ptr(), ws.numel(), _stream(), launches=2)
     return dw

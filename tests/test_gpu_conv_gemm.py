@@ -144,3 +144,51 @@ def test_affine_epilogue(cuda_device, n, h, w, cin, cout, k, with_res, relu):
     if relu:
         ref = F.relu(ref)
     assert rel_l2(y.float(), ref) < 4e-3
+
+
+HALO_CASES = [
+    # n, h, w, cin, cout — 3x3 convs eligible for the halo-reuse kernel (W % 128 == 0, H even, Cout 64 / 128)
+    (1, 2, 128, 64, 64),       # a single 256-pixel tile: every halo row above/below is out of bounds
+    (3, 4, 128, 128, 64),      # odd image count, two cin chunks
+    (1, 128, 128, 256, 128),   # generator L4.conv1 shape (one image)
+    (2, 6, 256, 64, 128),      # two column segments per row: left/right halo columns come from the neighbour segment
+    (1, 256, 256, 128, 64),    # generator L5.conv1 shape (one image)
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", HALO_CASES)
+def test_halo_kernel_matches_per_tap_kernel(cuda_device, monkeypatch, n, h, w, cin, cout):
+    """The halo-reuse kernel (one [4 x 130] halo per 64-channel chunk serving all nine taps of two output rows) against
+    the per-tap kernel and a torch fp32 conv, all four epilogues' building blocks (PLAIN, STATS, STYLE)."""
+    from speak_hack_b200 import ops
+
+    dev = cuda_device
+    x, wt, wk = _mk(n, h, w, cin, cout, 3, dev, seed=7)
+    ref = _ref(x, wt, 3)
+    monkeypatch.setenv("IRFD_CONV_HALO", "0")
+    y_tap = ops.conv_gemm(x, wk, 3, ops.EPI_PLAIN)
+    monkeypatch.setenv("IRFD_CONV_HALO", "1")
+    y_halo = ops.conv_gemm(x, wk, 3, ops.EPI_PLAIN)
+    ys, ssum, ssq = ops.conv_gemm(x, wk, 3, ops.EPI_STATS)
+    g = torch.Generator(device="cpu").manual_seed(8)
+    bias = torch.randn(cout, generator=g).to(dev)
+    nw = torch.randn(cout, generator=g).to(dev)
+    noise = torch.randn(n * h * w, generator=g).to(dev)
+    sp1 = (torch.randn(n, cout, generator=g) + 1).to(dev)
+    s1 = torch.randn(n, cout, generator=g).to(dev)
+    a, y = ops.conv_gemm(x, wk, 3, ops.EPI_STYLE, bias=bias, nw=nw, noise=noise, sp1=sp1, s1=s1)
+    torch.cuda.synchronize()
+    assert rel_l2(y_tap.float(), ref) < 4e-3
+    assert rel_l2(y_halo.float(), ref) < 4e-3
+    # same bf16 products, fp32 accumulation in a different order: equal up to the last bf16 rounding of a few outputs
+    assert rel_l2(y_halo.float(), y_tap.float()) < 2e-3
+    assert torch.equal(ys, y_halo)
+    yf = ys.float().reshape(-1, cout)
+    assert ssum.shape[0] == (n * h * w) // 128
+    assert torch.allclose(ssum.sum(0), yf.sum(0), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(ssq.sum(0), (yf * yf).sum(0), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(ssum[1], yf[128:256].sum(0), rtol=1e-4, atol=1e-2)  # per-tile rows land in flat tile order
+    z = ref + bias.view(1, 1, 1, -1) + nw.view(1, 1, 1, -1) * noise.view(n, h, w, 1)
+    a_ref = F.leaky_relu(z, 0.2)
+    assert rel_l2(a.float(), a_ref) < 4e-3
+    assert rel_l2(y.float(), a_ref * sp1.view(n, 1, 1, cout) + s1.view(n, 1, 1, cout)) < 4e-3
