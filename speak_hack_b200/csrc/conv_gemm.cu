@@ -305,8 +305,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp converged, one lane issues)
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -321,20 +321,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          const uint64_t adesc0 = make_smem_desc_sw128(a_addr, 0, 1024);
+          const uint64_t bdesc0 = make_smem_desc_sw128(a_addr + Cfg::A_BYTES, 0, 1024);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
-            const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)  // +32 bytes per K=16 step: +2 in the descriptor's 16-byte address field
+              umma_bf16(d_tmem, adesc0 + 2 * k, bdesc0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);
           }
-          umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[as]);
+        if (elect_one_sync()) umma_commit(&tmem_full[as]);
+        __syncwarp();
       }
     }
   } else {
@@ -370,7 +372,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // brings the [4 rows][130 columns][64 ch] halo (65 KB) that serves all nine taps of both rows: the A operand of tap
 // (dy, dx) for output row j is the same smem buffer at line offset (j + dy) * 130 + dx, i.e. only the descriptor start
 // address moves (128-byte lines; the 128-byte swizzle is a function of the absolute smem address, so a shifted start
-// stays consistent with what TMA wrote).  Each [BLOCK_N x 64] weight tile feeds both accumulators.
+// stays consistent with what TMA wrote; measured: filling the descriptor's base-offset field instead gives garbage).  Each [BLOCK_N x 64] weight tile feeds both accumulators.
 // L2->SM bytes per 128 pixels x 64 channels: 33 KB (A) + 36 KB (B, N = 64) instead of 144 KB + 72 KB.
 //
 // Warp roles: warp 0 = halo (A) producer, warp 1 = MMA issuer, warps 2..9 = epilogue, warp 10 = weight (B) producer.
@@ -398,7 +400,6 @@ struct HaloCfg {
 struct HaloArgs {
   int wsegs, hpairs;  // W / 128, H / 2
   int total_tiles;    // 256-pixel tiles x n tiles
-  int base_offset;    // experiment: fill the descriptor's base-offset field from the start address
 };
 
 template <int BLOCK_N, int MODE>
@@ -501,8 +502,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp converged, one lane issues)
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
@@ -515,36 +516,40 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint32_t d_tmem = tmem_base + as * 2 * BLOCK_N;
         for (int ch = 0; ch < chunks; ++ch) {
           mbar_wait(&full_a[sa], pa);
-          const uint32_t a_addr = smem_u32(smem + sa * Cfg::A_BYTES);
+          // descriptor of the halo's first line; a tap / K step only adds to its 16-byte-granular address field
+          const uint64_t adesc0 = make_smem_desc_sw128(smem_u32(smem + sa * Cfg::A_BYTES), 0, 1024);
+#pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3, dx = tap - dy * 3;
+            constexpr int kLine = 128 / 16;  // one halo line (pixel) in descriptor address units
+            const int dy = tap / 3, dx = tap % 3;
             mbar_wait(&full_b[sb], pb);
             tc_fence_after();
-            const uint32_t b_addr = smem_u32(smem_b + sb * Cfg::B_BYTES);
+            const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smem_b + sb * Cfg::B_BYTES), 0, 1024);
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const uint32_t a_tap = a_addr + ((j + dy) * kHaloCols + dx) * 128;
+              for (int j = 0; j < 2; ++j) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                uint64_t adesc = make_smem_desc_sw128(a_tap + k * 32, 0, 1024);
-                if (hp.base_offset) adesc |= static_cast<uint64_t>((a_tap >> 7) & 7u) << 49;
-                const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-                umma_bf16(d_tmem + j * BLOCK_N, adesc, bdesc, idesc, (ch | tap | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(d_tmem + j * BLOCK_N, adesc0 + ((j + dy) * kHaloCols + dx) * kLine + 2 * k, bdesc0 + 2 * k,
+                            idesc, (tap | k) != 0 ? 1u : (ch != 0 ? 1u : 0u));
               }
+              umma_commit(&empty_b[sb]);
             }
-            umma_commit(&empty_b[sb]);
+            __syncwarp();
             if (++sb == BST) {
               sb = 0;
               pb ^= 1;
             }
           }
-          umma_commit(&empty_a[sa]);
+          if (elect_one_sync()) umma_commit(&empty_a[sa]);
+          __syncwarp();
           if (++sa == Cfg::A_STAGES) {
             sa = 0;
             pa ^= 1;
           }
         }
-        umma_commit(&tmem_full[as]);
+        if (elect_one_sync()) umma_commit(&tmem_full[as]);
+        __syncwarp();
       }
     }
   } else {
@@ -764,7 +769,6 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
     hargs.wsegs = W / 128;
     hargs.hpairs = H / 2;
     hargs.total_tiles = NB * hargs.hpairs * hargs.wsegs * a.num_n_tiles;
-    hargs.base_offset = hmode == 2 ? 1 : 0;
     switch (mode) {
       case EPI_PLAIN: return dispatch_halo<EPI_PLAIN>(block_n, ma, mb, mo, mo2, a, hargs, stream);
       case EPI_STATS: return dispatch_halo<EPI_STATS>(block_n, ma, mb, mo, mo2, a, hargs, stream);

@@ -13,6 +13,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// One lane of a fully converged warp (elect.sync).  The MMA / TMA issue loops run with the WHOLE warp converged and only
+// the instruction itself under this predicate: addresses and descriptors then stay warp-uniform (uniform registers),
+// whereas an `if (lane == 0)` region forces a per-instruction ELECT / R2UR.BROADCAST loop in front of every UTCHMMA
+// (~14 SASS instructions, ~100 cycles: more than a whole N <= 128 MMA).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------

@@ -116,29 +116,30 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);  // both operands MN-major
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int i = 0; i < my_kb; ++i) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+    // MMA issuer: whole warp converged, one elected lane issues (keeps descriptors in uniform registers)
+    constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);  // both operands MN-major
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < my_kb; ++i) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+      const uint64_t adesc0 = make_smem_desc_sw128(a_addr, 8192, 1024);
+      const uint64_t bdesc0 = make_smem_desc_sw128(a_addr + Cfg::A_BYTES, 8192, 1024);
+      if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 16 pixels (= 16 rows of 128 B) per MMA
-          const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 2048, 8192, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024);
-          umma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < 4; ++k)  // 16 pixels (= 16 rows of 128 B = 2048 B = 128 address units) per MMA
+          umma_bf16(tmem_base, adesc0 + 128 * k, bdesc0 + 128 * k, idesc, (i | k) != 0 ? 1u : 0u);
         umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
       }
-      umma_commit(done_bar);
+      __syncwarp();
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
     }
+    if (elect_one_sync()) umma_commit(done_bar);
+    __syncwarp();
   } else {
     // epilogue: 4 warps, thread <-> TMEM lane <-> k row
     const int q = warp & 3;
