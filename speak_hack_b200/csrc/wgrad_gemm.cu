@@ -8,6 +8,8 @@
 //   B tile (N = BLOCK_N out channels = BLOCK_N/64 atoms)        <- 2-D TMA boxes [64 pixels x 64 ch] of dY
 // Split-K over pixel ranges: each CTA owns (k-pair, n-tile, pixel-range) and writes an fp32 partial
 // [split][Ktot][Cout]; irfd_wgrad_reduce sums the splits in a fixed order (deterministic) into OIHW fp32.
+#include <stdlib.h>
+
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -178,19 +180,269 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 }
 
 // dW[o][c][tap] (OIHW, fp32) = beta * dW + sum_s partial[s][tap*Cin + c][o]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int K_total,
-                                    int N_total, int cin, int taps, float beta) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over [K_total][N_total], n fastest
-  if (idx >= (size_t)K_total * N_total) return;
-  const int n = idx % N_total;
-  const int k = idx / N_total;
-  if (k >= cin * taps) return;  // zero-padded K tail (stem)
-  float acc = 0.f;
+// Block = (256 / LANES) consecutive outputs (coalesced partial reads) x LANES split lanes: every thread sums the
+// splits s = lane, lane + LANES, ... with four loads in flight, the partial sums are combined in a fixed order
+// (bit-deterministic).  The first version walked all splits (up to 148) serially in one thread per output: ~20 us of
+// pure load latency per launch on the 1x1 layers.
+template <int LANES>  // split lanes per output: 256 threads = (256 / LANES) consecutive outputs x LANES
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int K_total, int N_total,
+                    int cin, int taps, float beta) {
+  constexpr int OUTS = 256 / LANES;
+  __shared__ float part[LANES][OUTS + 1];
+  const int o = threadIdx.x % OUTS, w = threadIdx.x / OUTS;
+  const size_t idx = (size_t)blockIdx.x * OUTS + o;  // over [K_total][N_total], n fastest
   const size_t stride = (size_t)K_total * N_total;
-  for (int s = 0; s < splits; ++s) acc += partial[s * stride + idx];
+  const bool in_range = idx < stride;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (in_range) {
+    const float* p = partial + idx;
+    int s = w;
+    for (; s + 3 * LANES < splits; s += 4 * LANES) {
+      a0 += __ldg(p + (size_t)s * stride);
+      a1 += __ldg(p + (size_t)(s + LANES) * stride);
+      a2 += __ldg(p + (size_t)(s + 2 * LANES) * stride);
+      a3 += __ldg(p + (size_t)(s + 3 * LANES) * stride);
+    }
+    for (; s < splits; s += LANES) a0 += __ldg(p + (size_t)s * stride);
+  }
+  float acc = (a0 + a1) + (a2 + a3);
+  if (LANES > 1) {
+    part[w][o] = acc;
+    __syncthreads();
+    if (w != 0) return;
+    acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < LANES; ++i) acc += part[i][o];
+  }
+  if (!in_range) return;
+  const int n = (int)(idx % N_total);
+  const int k = (int)(idx / N_total);
+  if (k >= cin * taps) return;  // zero-padded K tail (stem)
   const int tap = k / cin, c = k - tap * cin;
   float* d = dw + ((size_t)n * cin + c) * taps + tap;
   *d = (beta != 0.f) ? beta * (*d) + acc : acc;
+}
+
+// few splits: one thread per output; many splits (1x1 layers, halo kernel: up to 148): 8 lanes share the walk
+static void launch_wgrad_reduce(const float* partial, float* dw, int splits, int K_total, int N_total, int cin, int taps,
+                                float beta, cudaStream_t stream) {
+  const size_t total = (size_t)K_total * N_total;
+  if (splits <= 6)
+    wgrad_reduce_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(partial, dw, splits, K_total, N_total,
+                                                                                cin, taps, beta);
+  else if (splits <= 24)
+    wgrad_reduce_kernel<4><<<(unsigned)((total + 63) / 64), 256, 0, stream>>>(partial, dw, splits, K_total, N_total, cin,
+                                                                              taps, beta);
+  else
+    wgrad_reduce_kernel<8><<<(unsigned)((total + 31) / 32), 256, 0, stream>>>(partial, dw, splits, K_total, N_total, cin,
+                                                                              taps, beta);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Halo-reuse weight gradient for 3x3 convs (any W that is a multiple of 16).
+//
+// The per-tap kernel above streams, for every (tap, Cin-chunk) pair, ALL pixels of X again (9x the activation traffic
+// through L2 -> SM; measured fabric-bound at ~9 TB/s on the generator's 256^2 layers).  Here a CTA owns one 64-channel
+// Cin chunk x one 64-wide Cout tile x a pixel range and keeps all nine taps' accumulators in TMEM (five M=128 MMAs of
+// tap pairs = 320 columns): per 128-pixel K block ONE TMA box brings the [TH+2][TW+2] halo of X, and the A operand of
+// tap (dy, dx) for the 16 pixels starting at (row r, column s) is that buffer at line (r + dy) * (TW + 2) + s + dx —
+// only the MN-major descriptor start moves; the second 64-row atom of each M=128 MMA is the next tap, reached through
+// the descriptor's leading-dimension byte offset (128 B for a dx step, (TW + 2 - 2) lines for the dy wrap).
+// ------------------------------------------------------------------------------------------------
+struct WgHaloArgs {
+  int N_total, K_total, cin;
+  int chunks, num_n_tiles, splits;
+  int num_kb, kb_per_split;  // K blocks of 128 pixels
+  int H, W, TH, TW, P;       // image size, pixel block (TH rows x TW columns), halo pitch in lines (TW + 2)
+  int hblocks, wsegs;        // H / TH, W / TW
+  int spr_shift;             // log2(16-pixel segments per block row)
+  int a_tx_bytes;            // (TH + 2) * (TW + 2) * 128
+  float* partial;            // [splits][K_total][N_total]
+};
+
+constexpr int kWhA = 50176;   // halo stage (<= 3 x 130 lines), 1024-aligned
+constexpr int kWhB = 16384;   // 128 pixels x 64 output channels
+constexpr int kWhStages = 3;
+constexpr int kWhSmem = 1024 + kWhStages * (kWhA + kWhB) + 1024;
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
+                  const WgHaloArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kWhStages * (kWhA + kWhB));
+  uint64_t* empty_bar = full_bar + kWhStages;
+  uint64_t* done_bar = empty_bar + kWhStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  int item = blockIdx.x;
+  const int split = item % p.splits;
+  item /= p.splits;
+  const int n_tile = item % p.num_n_tiles;
+  const int chunk = item / p.num_n_tiles;
+  const int kb_begin = split * p.kb_per_split;
+  int kb_end = kb_begin + p.kb_per_split;
+  if (kb_end > p.num_kb) kb_end = p.num_kb;
+  const int my_kb = kb_end > kb_begin ? kb_end - kb_begin : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWhStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&map_x);
+      tma_prefetch_desc(&map_dy);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int wseg = kb % p.wsegs;
+        const int t = kb / p.wsegs;
+        const int hb = t % p.hblocks;
+        const int n0 = t / p.hblocks;
+        const int h0 = hb * p.TH, w0 = wseg * p.TW;
+        const int m0 = (n0 * p.H + h0) * p.W + w0;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * (kWhA + kWhB);
+        mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + kWhB);
+        tma_load_4d(sa, &map_x, &full_bar[stage], chunk * 64, w0 - 1, h0 - 1, n0);
+        tma_load_2d(sa + kWhA, &map_dy, &full_bar[stage], n_tile * 64, m0);
+        if (++stage == kWhStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // MMA issuer: whole warp converged, one elected lane issues
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);  // both operands MN-major
+    // tap pairs (0,1) (2,3) (4,5) (6,7) (8,x): first tap's line offset dy * P + dx, second atom `lbo` lines further
+    const uint32_t P = (uint32_t)p.P;
+    const uint32_t off[5] = {0u, 2u, P + 1u, 2u * P, 2u * P + 2u};
+    const uint32_t lbo[5] = {1u, P - 2u, 1u, 1u, 1u};  // pair 4's second atom is a throw-away duplicate shift
+    const uint32_t spr_mask = (1u << p.spr_shift) - 1u;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < my_kb; ++i) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem + stage * (kWhA + kWhB));
+      const uint64_t bdesc0 = make_smem_desc_sw128(a_addr + kWhA, 8192, 1024);
+      uint64_t adesc[5];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) adesc[q] = make_smem_desc_sw128(a_addr + off[q] * 128u, lbo[q] * 128u, 1024);
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {  // 16 pixels per MMA
+          const uint32_t r = (uint32_t)ks >> p.spr_shift, sg = (uint32_t)ks & spr_mask;
+          const uint64_t a_step = (uint64_t)((r * P + sg * 16u) * 8u);  // lines -> 16-byte address units
+#pragma unroll
+          for (int q = 0; q < 5; ++q)
+            umma_bf16(tmem_base + q * 64, adesc[q] + a_step, bdesc0 + 128 * ks, idesc, (i | ks) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+      }
+      __syncwarp();
+      if (++stage == kWhStages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    if (elect_one_sync()) umma_commit(done_bar);
+    __syncwarp();
+  } else {
+    // epilogue: 4 warps; TMEM lane = (tap parity within the pair) * 64 + input channel
+    const int q4 = warp & 3;
+    const int ci = (q4 & 1) * 32 + lane;
+    if (my_kb > 0) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int pr = 0; pr < 5; ++pr) {
+      const int tap = 2 * pr + (q4 >> 1);
+      const size_t krow = (size_t)tap * p.cin + (size_t)chunk * 64 + ci;
+      float* dst = p.partial + ((size_t)split * p.K_total + krow) * p.N_total + (size_t)n_tile * 64;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        if (my_kb > 0) {
+          tmem_ld32(tmem_base + (uint32_t(q4 * 32) << 16) + pr * 64 + half * 32, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) v[t] = 0u;
+        }
+        if (tap < 9) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            float4 o = make_float4(__uint_as_float(v[4 * t]), __uint_as_float(v[4 * t + 1]),
+                                   __uint_as_float(v[4 * t + 2]), __uint_as_float(v[4 * t + 3]));
+            *reinterpret_cast<float4*>(dst + half * 32 + 4 * t) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+// Geometry of the halo wgrad for a [n, h, w] image batch; false when the shape is not eligible.
+static bool wgrad_halo_plan(int n, int h, int w, int cin, int cout, int ksize, WgHaloArgs* a) {
+  const char* e = getenv("IRFD_WGRAD_HALO");
+  if (e && atoi(e) == 0) return false;
+  if (ksize != 3 || w < 16 || w % 16 != 0 || cin % 64 != 0 || cout % 64 != 0) return false;
+  // Measured on B200 (scripts/exp_wgrad_halo.py): 2.6x faster on the 256^2 layers with Cout 64, 1.4x at 128^2 / Cout
+  // 128 and on the encoder's 64^2 stage; with Cout >= 256 or narrow images the per-tap kernel's 256-wide tile wins.
+  // IRFD_WGRAD_HALO=2 forces the halo kernel on every eligible shape (tests).
+  if (!(e && atoi(e) == 2) && (cout > 128 || w < 64)) return false;
+  int TW, TH;
+  if (w >= 128) {
+    if (w % 128 != 0) return false;
+    TW = 128;
+    TH = 1;
+  } else {
+    if (128 % w != 0 || h % (128 / w) != 0) return false;
+    TW = w;
+    TH = 128 / w;
+  }
+  a->N_total = cout;
+  a->K_total = 9 * cin;
+  a->cin = cin;
+  a->chunks = cin / 64;
+  a->num_n_tiles = cout / 64;
+  a->H = h; a->W = w; a->TH = TH; a->TW = TW; a->P = TW + 2;
+  a->hblocks = h / TH;
+  a->wsegs = w / TW;
+  a->num_kb = n * a->hblocks * a->wsegs;
+  int spr = TW / 16, sh = 0;
+  while ((1 << sh) < spr) ++sh;
+  a->spr_shift = sh;
+  a->a_tx_bytes = (TH + 2) * (TW + 2) * 128;
+  const int base = a->chunks * a->num_n_tiles;
+  int splits = num_sms() / base;  // one CTA per SM is resident: the launch must fit one wave
+  if (splits > a->num_kb) splits = a->num_kb;
+  if (splits < 1) splits = 1;
+  a->kb_per_split = (a->num_kb + splits - 1) / splits;
+  a->splits = (a->num_kb + a->kb_per_split - 1) / a->kb_per_split;
+  return true;
 }
 
 template <int BLOCK_N>
@@ -242,6 +494,8 @@ static void wgrad_plan(int n, int h, int w, int cin, int cout, int ksize, WgradA
 using namespace irfd;
 
 extern "C" long long irfd_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout, int ksize) {
+  WgHaloArgs ha;
+  if (wgrad_halo_plan(n, h, w, cin, cout, ksize, &ha)) return (long long)ha.splits * ha.K_total * ha.N_total * 4;
   WgradArgs a;
   int bn;
   wgrad_plan(n, h, w, cin, cout, ksize, &a, &bn);
@@ -254,6 +508,42 @@ extern "C" int irfd_conv_wgrad(const void* x, const void* dy, int n, int h, int 
   IRFD_CHECK_ARG(x && dy && dw && workspace, "conv_wgrad: null pointer");
   IRFD_CHECK_ARG(ksize == 1 || ksize == 3, "conv_wgrad: ksize must be 1 or 3");
   IRFD_CHECK_ARG(cin % 64 == 0 && cout % 64 == 0, "conv_wgrad: channels must be multiples of 64");
+  WgHaloArgs ha;
+  if (wgrad_halo_plan(n, h, w, cin, cout, ksize, &ha)) {
+    IRFD_CHECK_ARG(workspace_bytes >= (long long)ha.splits * ha.K_total * ha.N_total * 4,
+                   "conv_wgrad: workspace too small");
+    ha.partial = reinterpret_cast<float*>(workspace);
+    CUtensorMap mx, mdy;
+    {
+      const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+      const uint64_t str[3] = {(uint64_t)cin * 2, (uint64_t)w * cin * 2, (uint64_t)h * w * cin * 2};
+      const uint32_t box[4] = {64, (uint32_t)(ha.TW + 2), (uint32_t)(ha.TH + 2), 1};
+      int rc = make_tmap_bf16(&mx, x, 4, dims, str, box, true);
+      if (rc) return rc;
+    }
+    {
+      const uint64_t dims[2] = {(uint64_t)cout, (uint64_t)((long long)n * h * w)};
+      const uint64_t str[1] = {(uint64_t)cout * 2};
+      const uint32_t box[2] = {64, 128};
+      int rc = make_tmap_bf16(&mdy, dy, 2, dims, str, box, true);
+      if (rc) return rc;
+    }
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWhSmem);
+      if (e != cudaSuccess) {
+        set_last_error("cudaFuncSetAttribute(wgrad halo smem=%d): %s", kWhSmem, cudaGetErrorString(e));
+        return IRFD_ERR_CUDA;
+      }
+      configured = true;
+    }
+    wgrad_halo_kernel<<<ha.chunks * ha.num_n_tiles * ha.splits, kWgThreads, kWhSmem, stream>>>(mx, mdy, ha);
+    IRFD_CHECK_LAUNCH();
+    launch_wgrad_reduce(ha.partial, dw, ha.splits, ha.K_total, ha.N_total, reduce_cin > 0 ? reduce_cin : cin,
+                        reduce_cin > 0 ? reduce_taps : 9, beta, stream);
+    IRFD_CHECK_LAUNCH();
+    return IRFD_OK;
+  }
   WgradArgs a;
   int block_n;
   wgrad_plan(n, h, w, cin, cout, ksize, &a, &block_n);
@@ -304,10 +594,8 @@ extern "C" int irfd_conv_wgrad(const void* x, const void* dy, int n, int h, int 
     default: rc = launch_wgrad<256>(mx, mdy, a, stream); break;
   }
   if (rc) return rc;
-  const size_t total = (size_t)a.K_total * a.N_total;
-  wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a.partial, dw, a.splits, a.K_total,
-                                                                          a.N_total, reduce_cin > 0 ? reduce_cin : cin,
-                                                                          reduce_cin > 0 ? reduce_taps : a.taps, beta);
+  launch_wgrad_reduce(a.partial, dw, a.splits, a.K_total, a.N_total, reduce_cin > 0 ? reduce_cin : cin,
+                      reduce_cin > 0 ? reduce_taps : a.taps, beta, stream);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }

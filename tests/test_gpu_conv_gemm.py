@@ -192,3 +192,28 @@ def test_halo_kernel_matches_per_tap_kernel(cuda_device, monkeypatch, n, h, w, c
     a_ref = F.leaky_relu(z, 0.2)
     assert rel_l2(a.float(), a_ref) < 4e-3
     assert rel_l2(y.float(), a_ref * sp1.view(n, 1, 1, cout) + s1.view(n, 1, 1, cout)) < 4e-3
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 64, 64), (3, 8, 32, 128, 64), (1, 4, 64, 64, 192),
+                                             (2, 3, 128, 64, 128), (1, 2, 256, 128, 64)])
+def test_wgrad_halo_matches_per_tap_kernel(cuda_device, monkeypatch, n, h, w, cin, cout):
+    """Halo-reuse wgrad (all nine taps of a Cin chunk accumulated in TMEM from one halo tile per 128 pixels) against
+    the per-tap split-K kernel and torch autograd, for every row-width class (16, 32, 64, 128, 256)."""
+    from speak_hack_b200 import ops
+
+    dev = cuda_device
+    g = torch.Generator(device="cpu").manual_seed(9)
+    x = torch.randn(n, h, w, cin, generator=g).to(dev).to(torch.bfloat16)
+    dy = torch.randn(n, h, w, cout, generator=g).to(dev).to(torch.bfloat16)
+    monkeypatch.setenv("IRFD_WGRAD_HALO", "0")
+    dw_tap = ops.conv_wgrad(x, dy, 3)
+    monkeypatch.setenv("IRFD_WGRAD_HALO", "2")  # force the halo kernel on every eligible shape
+    dw_halo = ops.conv_wgrad(x, dy, 3)
+    torch.cuda.synchronize()
+    wt = torch.zeros(cout, cin, 3, 3, device=dev, requires_grad=True)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wt, padding=1)
+    (ref,) = torch.autograd.grad(y, wt, dy.float().permute(0, 3, 1, 2))
+    assert rel_l2(dw_tap, ref) < 1e-4
+    assert rel_l2(dw_halo, ref) < 1e-4
+    for tap in range(9):  # every tap on its own: a wrong line offset would only corrupt some taps
+        assert rel_l2(dw_halo[:, :, tap // 3, tap % 3], ref[:, :, tap // 3, tap % 3]) < 1e-4
