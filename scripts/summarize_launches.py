@@ -1,5 +1,5 @@
 """Summarise an ncu launch list (scripts/ncu_launches.sh -> gpurun_out/launches.csv) into a markdown table.
-usage: python scripts/summarize_launches.py gpurun_out/launches.csv "title" > profiles/<name>_summary.md"""
+usage: python scripts/summarize_launches.py gpurun_out/launches.csv "title" [traffic.json] > profiles/<name>_summary.md"""
 import collections
 import csv
 import re
@@ -25,21 +25,43 @@ def short(name):
 def family(k):
     if k.startswith("bn_"):
         return "bn_* (BatchNorm fwd+bwd)"
-    if k.startswith("conv_gemm"):
+    if k.startswith("conv_gemm") or k.startswith("conv_halo"):
         return "conv_gemm_kernel (all variants)"
     if k.startswith("wgrad"):
         return "wgrad_gemm_kernel + wgrad_reduce"
     return "other"
 
 
+def to_bytes(value, unit):
+    v = float(value.replace(",", ""))
+    return v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+
+
 def main():
-    rows = load(sys.argv[1])
+    allrows = load(sys.argv[1])
     title = sys.argv[2] if len(sys.argv) > 2 else "ncu launch list"
-    t, n = collections.Counter(), collections.Counter()
+    rows = [d for d in allrows if d["Metric Name"] == "gpu__time_duration.sum"]
+    t, n, dram = collections.Counter(), collections.Counter(), collections.Counter()
     for d in rows:
         k = short(d["Kernel Name"])
         t[k] += int(d["Metric Value"]) / 1e6
         n[k] += 1
+    for d in allrows:
+        if d["Metric Name"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            dram[short(d["Kernel Name"])] += to_bytes(d["Metric Value"], d["Metric Unit"])
+    if len(sys.argv) > 3 and dram:  # per-family DRAM traffic per launch -> json (bench.py's roofline.traffic)
+        import json
+
+        fams = {"conv_gemm_kernel (tcgen05 fprop/dgrad)": ("conv_gemm_kernel", "conv_halo_kernel"),
+                "wgrad_gemm_kernel (tcgen05 split-K + reduce)": ("wgrad_gemm_kernel", "wgrad_halo_kernel", "wgrad_reduce")}
+        out = {}
+        for fam_name, prefixes in fams.items():
+            ks = [k for k in n if k.startswith(prefixes)]
+            launches = sum(n[k] for k in ks if not k.startswith("wgrad_reduce"))
+            out[fam_name] = {"dram_bytes_per_launch": sum(dram[k] for k in ks) / max(launches, 1),
+                             "dram_bytes_in_capture": sum(dram[k] for k in ks), "launches_in_capture": launches,
+                             "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, " + sys.argv[1]}
+        json.dump(out, open(sys.argv[3], "w"), indent=1)
     total = sum(t.values())
     print(f"# {title}\n")
     print(f"{len(rows)} launches captured; cold-cache, serialised times: compare SHARES.\nTotal {total:.2f} ms.\n")
@@ -49,9 +71,11 @@ def main():
     print("## by family\n\n| family | ms | share |\n|---|---|---|")
     for f, ms in fam.most_common():
         print(f"| {f} | {ms:.2f} | {100 * ms / total:.1f}% |")
-    print("\n## by kernel\n\n| kernel | launches | ms | share | avg us |\n|---|---|---|---|---|")
+    print("\n## by kernel\n\n| kernel | launches | ms | share | avg us | DRAM MB/launch | DRAM GB/s |\n|---|---|---|---|---|---|---|")
     for k, ms in t.most_common(45):
-        print(f"| {k} | {n[k]} | {ms:.2f} | {100 * ms / total:.1f}% | {1e3 * ms / n[k]:.1f} |")
+        db = dram.get(k, 0.0)
+        print(f"| {k} | {n[k]} | {ms:.2f} | {100 * ms / total:.1f}% | {1e3 * ms / n[k]:.1f} | "
+              f"{db / n[k] / 1e6:.1f} | {db / (ms * 1e-3) / 1e9 if ms else 0:.0f} |")
 
 
 if __name__ == "__main__":
