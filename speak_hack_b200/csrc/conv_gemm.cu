@@ -273,10 +273,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      tma_prefetch_desc(&map_a);
-      tma_prefetch_desc(&map_b);
+    // ------------------------------------------------------------------ TMA producer (whole warp converged, one lane issues)
+    {
+      if (lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+      }
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -292,10 +295,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int ch = 0; ch < p.cin_chunks; ++ch) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-            uint8_t* sb = sa + Cfg::A_BYTES;
-            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            tma_load_4d(sa, &map_a, &full_bar[stage], ch * 64, w0 + dw, h0 + dh, n0);
-            tma_load_2d(sb, &map_b, &full_bar[stage], (tap * p.cin_chunks + ch) * 64, n_tile * BLOCK_N);
+            if (elect_one_sync()) {
+              mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              tma_load_4d(sa, &map_a, &full_bar[stage], ch * 64, w0 + dw, h0 + dh, n0);
+              tma_load_2d(sa + Cfg::A_BYTES, &map_b, &full_bar[stage], (tap * p.cin_chunks + ch) * 64, n_tile * BLOCK_N);
+            }
+            __syncwarp();
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -461,8 +466,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   if (warp == 0) {
     // ------------------------------------------------------------------ halo (A) producer
-    if (lane == 0) {
-      tma_prefetch_desc(&map_a);
+    {
+      if (lane == 0) tma_prefetch_desc(&map_a);
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < hp.total_tiles; tile += gridDim.x) {
@@ -470,8 +476,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         decode(tile, n_tile, n0, h0, w0);
         for (int ch = 0; ch < chunks; ++ch) {
           mbar_wait(&empty_a[stage], phase ^ 1);
-          mbar_expect_tx(&full_a[stage], Cfg::A_BYTES);
-          tma_load_4d(smem + stage * Cfg::A_BYTES, &map_a, &full_a[stage], ch * 64, w0 - 1, h0 - 1, n0);
+          if (elect_one_sync()) {
+            mbar_expect_tx(&full_a[stage], Cfg::A_BYTES);
+            tma_load_4d(smem + stage * Cfg::A_BYTES, &map_a, &full_a[stage], ch * 64, w0 - 1, h0 - 1, n0);
+          }
+          __syncwarp();
           if (++stage == Cfg::A_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -481,8 +490,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (warp == 10) {
     // ------------------------------------------------------------------ weight (B) producer
-    if (lane == 0) {
-      tma_prefetch_desc(&map_b);
+    {
+      if (lane == 0) tma_prefetch_desc(&map_b);
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < hp.total_tiles; tile += gridDim.x) {
@@ -490,9 +500,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int ch = 0; ch < chunks; ++ch) {
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&empty_b[stage], phase ^ 1);
-            mbar_expect_tx(&full_b[stage], Cfg::B_BYTES);
-            tma_load_2d(smem_b + stage * Cfg::B_BYTES, &map_b, &full_b[stage], (tap * chunks + ch) * 64,
-                        n_tile * BLOCK_N);
+            if (elect_one_sync()) {
+              mbar_expect_tx(&full_b[stage], Cfg::B_BYTES);
+              tma_load_2d(smem_b + stage * Cfg::B_BYTES, &map_b, &full_b[stage], (tap * chunks + ch) * 64,
+                          n_tile * BLOCK_N);
+            }
+            __syncwarp();
             if (++stage == BST) {
               stage = 0;
               phase ^= 1;

@@ -82,39 +82,45 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
+    // TMA producer: whole warp converged, one elected lane issues
     if (lane == 0) {
       tma_prefetch_desc(&map_x);
       tma_prefetch_desc(&map_dy);
-      int atom[2];
-      atom[0] = pair * 2;
-      atom[1] = pair * 2 + 1 < p.num_atoms ? pair * 2 + 1 : p.num_atoms - 1;  // odd tail: duplicate, discarded later
-      int dh[2], dw[2], c0[2];
-      for (int i = 0; i < 2; ++i) {
-        const int tap = atom[i] / p.cin_chunks;
-        c0[i] = (atom[i] - tap * p.cin_chunks) * 64;
-        dh[i] = tap / p.kw - p.pad;
-        dw[i] = tap % p.kw - p.pad;
-      }
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        const int p0 = kb * 64;
-        const int w0 = p0 % p.W;
-        const int h0 = (p0 / p.W) % p.H;
-        const int n0 = p0 / (p.W * p.H);
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-        uint8_t* sb = sa + Cfg::A_BYTES;
+    }
+    __syncwarp();
+    int atom[2];
+    atom[0] = pair * 2;
+    atom[1] = pair * 2 + 1 < p.num_atoms ? pair * 2 + 1 : p.num_atoms - 1;  // odd tail: duplicate, discarded later
+    int dh[2], dw[2], c0[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int tap = atom[i] / p.cin_chunks;
+      c0[i] = (atom[i] - tap * p.cin_chunks) * 64;
+      dh[i] = tap / p.kw - p.pad;
+      dw[i] = tap % p.kw - p.pad;
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      const int p0 = kb * 64;
+      const int w0 = p0 % p.W;
+      const int h0 = (p0 / p.W) % p.H;
+      const int n0 = p0 / (p.W * p.H);
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+      uint8_t* sb = sa + Cfg::A_BYTES;
+      if (elect_one_sync()) {
         mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
         tma_load_4d(sa, &map_x, &full_bar[stage], c0[0], w0 + dw[0], h0 + dh[0], n0);
         tma_load_4d(sa + 8192, &map_x, &full_bar[stage], c0[1], w0 + dw[1], h0 + dh[1], n0);
 #pragma unroll
         for (int j = 0; j < BLOCK_N / 64; ++j)
           tma_load_2d(sb + j * 8192, &map_dy, &full_bar[stage], n_tile * BLOCK_N + j * 64, p0);
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
+      }
+      __syncwarp();
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
       }
     }
   } else if (warp == 1) {
@@ -305,27 +311,32 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
+    // TMA producer: whole warp converged, one elected lane issues
     if (lane == 0) {
       tma_prefetch_desc(&map_x);
       tma_prefetch_desc(&map_dy);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        const int wseg = kb % p.wsegs;
-        const int t = kb / p.wsegs;
-        const int hb = t % p.hblocks;
-        const int n0 = t / p.hblocks;
-        const int h0 = hb * p.TH, w0 = wseg * p.TW;
-        const int m0 = (n0 * p.H + h0) * p.W + w0;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * (kWhA + kWhB);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      const int wseg = kb % p.wsegs;
+      const int t = kb / p.wsegs;
+      const int hb = t % p.hblocks;
+      const int n0 = t / p.hblocks;
+      const int h0 = hb * p.TH, w0 = wseg * p.TW;
+      const int m0 = (n0 * p.H + h0) * p.W + w0;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* sa = smem + stage * (kWhA + kWhB);
+      if (elect_one_sync()) {
         mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + kWhB);
         tma_load_4d(sa, &map_x, &full_bar[stage], chunk * 64, w0 - 1, h0 - 1, n0);
         tma_load_2d(sa + kWhA, &map_dy, &full_bar[stage], n_tile * 64, m0);
-        if (++stage == kWhStages) {
-          stage = 0;
-          phase ^= 1;
-        }
+      }
+      __syncwarp();
+      if (++stage == kWhStages) {
+        stage = 0;
+        phase ^= 1;
       }
     }
   } else if (warp == 1) {
