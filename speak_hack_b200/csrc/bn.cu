@@ -164,6 +164,7 @@ template <int RES_MODE>  // 0 none, 1 identity tensor, 2 second BN branch
 __global__ void __launch_bounds__(kRvThreads)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ z, BnAffine p1, const __nv_bfloat16* __restrict__ res, BnAffine p2,
                 __nv_bfloat16* __restrict__ out, long long rows, int C, int rows_per_blk, int relu) {
+  constexpr int RB = 8;  // rows per thread in flight: 8 (z only) or 16 (z + residual) 16-byte loads
   RowVec rv(C);
   if (!rv.active) return;
   {  // statistic group = blockIdx.y: `rows` rows each, own mean/rstd (gamma/beta shared)
@@ -205,11 +206,11 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z, BnAffine p1, const __nv_bfl
   const long long r0 = (long long)blockIdx.x * rows_per_blk;
   long long r1 = r0 + rows_per_blk;
   if (r1 > rows) r1 = rows;
-  // kRowBatch rows per thread per iteration, all loads issued before the first use (memory-level parallelism)
-  for (long long r = r0 + rv.row_lane; r < r1; r += (long long)rv.rows_par * kRowBatch) {
-    uint4 qz[kRowBatch], qr[kRowBatch];
+  // RB rows per thread per iteration, all loads issued before the first use (memory-level parallelism)
+  for (long long r = r0 + rv.row_lane; r < r1; r += (long long)rv.rows_par * RB) {
+    uint4 qz[RB], qr[RB];
 #pragma unroll
-    for (int u = 0; u < kRowBatch; ++u) {
+    for (int u = 0; u < RB; ++u) {
       const long long rr = r + (long long)u * rv.rows_par;
       if (rr < r1) {
         const size_t off = (size_t)rr * C + rv.cv * 8;
@@ -218,7 +219,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z, BnAffine p1, const __nv_bfl
       }
     }
 #pragma unroll
-    for (int u = 0; u < kRowBatch; ++u) {
+    for (int u = 0; u < RB; ++u) {
       const long long rr = r + (long long)u * rv.rows_par;
       if (rr < r1) {
         const size_t off = (size_t)rr * C + rv.cv * 8;
@@ -278,6 +279,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float* __restrict__ partial, long long rows, int C,
                      int rows_per_blk) {
+  constexpr int RB = kRowBatch;  // measured: 8 rows for the two-tensor instances is slower (register pressure)
   extern __shared__ float red_smem[];
   RowVec rv(C);
   {
@@ -304,10 +306,10 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
     const long long r0 = (long long)blockIdx.x * rows_per_blk;
     long long r1 = r0 + rows_per_blk;
     if (r1 > rows) r1 = rows;
-    for (long long r = r0 + rv.row_lane; r < r1; r += (long long)rv.rows_par * kRowBatch) {
-      uint4 qg[kRowBatch], qh[kRowBatch], qa[kRowBatch], qz[kRowBatch];
+    for (long long r = r0 + rv.row_lane; r < r1; r += (long long)rv.rows_par * RB) {
+      uint4 qg[RB], qh[RB], qa[RB], qz[RB];
 #pragma unroll
-      for (int u = 0; u < kRowBatch; ++u) {
+      for (int u = 0; u < RB; ++u) {
         const long long rr = r + (long long)u * rv.rows_par;
         if (rr < r1) {
           const size_t off = (size_t)rr * C + rv.cv * 8;
@@ -318,7 +320,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
         }
       }
 #pragma unroll
-      for (int u = 0; u < kRowBatch; ++u) {
+      for (int u = 0; u < RB; ++u) {
         const long long rr = r + (long long)u * rv.rows_par;
         if (rr < r1) {
           float g[8], zz[8];
@@ -373,6 +375,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* _
                     const float* __restrict__ beta, const float* __restrict__ c1, const float* __restrict__ c2,
                     __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ g_out, long long rows, int C,
                     int rows_per_blk) {
+  constexpr int RB = kRowBatch;
   RowVec rv(C);
   if (!rv.active) return;
   {
@@ -400,10 +403,10 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* _
   const long long r0 = (long long)blockIdx.x * rows_per_blk;
   long long r1 = r0 + rows_per_blk;
   if (r1 > rows) r1 = rows;
-  for (long long r = r0 + rv.row_lane; r < r1; r += (long long)rv.rows_par * kRowBatch) {
-    uint4 qg[kRowBatch], qh[kRowBatch], qa[kRowBatch], qz[kRowBatch];
+  for (long long r = r0 + rv.row_lane; r < r1; r += (long long)rv.rows_par * RB) {
+    uint4 qg[RB], qh[RB], qa[RB], qz[RB];
 #pragma unroll
-    for (int u = 0; u < kRowBatch; ++u) {
+    for (int u = 0; u < RB; ++u) {
       const long long rr = r + (long long)u * rv.rows_par;
       if (rr < r1) {
         const size_t off = (size_t)rr * C + rv.cv * 8;
@@ -414,7 +417,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* _
       }
     }
 #pragma unroll
-    for (int u = 0; u < kRowBatch; ++u) {
+    for (int u = 0; u < RB; ++u) {
       const long long rr = r + (long long)u * rv.rows_par;
       if (rr < r1) {
         const size_t off = (size_t)rr * C + rv.cv * 8;

@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(kRvThreads)
 style_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ a,
                  const float* __restrict__ noise, const float* __restrict__ sp1, __nv_bfloat16* __restrict__ dz,
                  float* __restrict__ partial, int HW, int C, int rows_per_blk) {
+  constexpr int RB = 8;  // two streamed tensors: 16 loads of 16 bytes in flight per thread
   extern __shared__ float red_smem[];
   RowVec rv(C);
   const int b = blockIdx.y;
@@ -221,11 +222,11 @@ style_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __re
     const int r0 = blockIdx.x * rows_per_blk;
     int r1 = r0 + rows_per_blk;
     if (r1 > HW) r1 = HW;
-    for (int r = r0 + rv.row_lane; r < r1; r += rv.rows_par * kRowBatch) {
-      uint4 qg[kRowBatch], qa[kRowBatch];
-      float nz[kRowBatch];
+    for (int r = r0 + rv.row_lane; r < r1; r += rv.rows_par * RB) {
+      uint4 qg[RB], qa[RB];
+      float nz[RB];
 #pragma unroll
-      for (int u = 0; u < kRowBatch; ++u) {
+      for (int u = 0; u < RB; ++u) {
         const int rr = r + u * rv.rows_par;
         if (rr < r1) {
           const size_t off = ((size_t)b * HW + rr) * C + rv.cv * 8;
@@ -235,7 +236,7 @@ style_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __re
         }
       }
 #pragma unroll
-      for (int u = 0; u < kRowBatch; ++u) {
+      for (int u = 0; u < RB; ++u) {
         const int rr = r + u * rv.rows_par;
         if (rr < r1) {
           const size_t off = ((size_t)b * HW + rr) * C + rv.cv * 8;
@@ -332,6 +333,7 @@ __global__ void __launch_bounds__(kRvThreads)
 to_rgb_bwd_kernel(const float* __restrict__ drgb, const __nv_bfloat16* __restrict__ y, const float* __restrict__ w,
                   __nv_bfloat16* __restrict__ dy, float* __restrict__ partial, int B, int HW, int C,
                   int rows_per_blk) {
+  constexpr int RB = 8;
   extern __shared__ float red_smem[];
   RowVec rv(C);
   float acc[4][8];
@@ -348,11 +350,11 @@ to_rgb_bwd_kernel(const float* __restrict__ drgb, const __nv_bfloat16* __restric
     const long long r0 = (long long)blockIdx.x * rows_per_blk;
     long long r1 = r0 + rows_per_blk;
     if (r1 > rows) r1 = rows;
-    for (long long r = r0 + rv.row_lane; r < r1; r += (long long)rv.rows_par * kRowBatch) {
-      uint4 qy[kRowBatch];
-      float g0[kRowBatch], g1[kRowBatch], g2[kRowBatch];
+    for (long long r = r0 + rv.row_lane; r < r1; r += (long long)rv.rows_par * RB) {
+      uint4 qy[RB];
+      float g0[RB], g1[RB], g2[RB];
 #pragma unroll
-      for (int u = 0; u < kRowBatch; ++u) {
+      for (int u = 0; u < RB; ++u) {
         const long long rr = r + (long long)u * rv.rows_par;
         if (rr < r1) {
           const unsigned b = (unsigned)(rr / HW), p = (unsigned)(rr - (long long)b * HW);
@@ -364,7 +366,7 @@ to_rgb_bwd_kernel(const float* __restrict__ drgb, const __nv_bfloat16* __restric
         }
       }
 #pragma unroll
-      for (int u = 0; u < kRowBatch; ++u) {
+      for (int u = 0; u < RB; ++u) {
         const long long rr = r + (long long)u * rv.rows_par;
         if (rr < r1) {
           float f[8], o[8];
