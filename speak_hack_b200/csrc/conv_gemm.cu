@@ -135,7 +135,10 @@ __device__ __forceinline__ void epilogue_acc(const ConvGemmArgs& p, const CUtens
     uint8_t* stg0 = stg_base + buf * kStgBytes;
     uint8_t* stg1 = stg_base + (NBUF + buf) * kStgBytes;
     // staging buffer `buf` was last used NBUF chunks ago: make sure its TMA store has drained it
-    if (etid == 0) tma_store_wait_read<NBUF - 1>();
+    if (warp == 2) {  // store leader: the elected lane of warp 2 (elect.sync is deterministic for a full mask)
+      __syncwarp();
+      if (elect_one_sync()) tma_store_wait_read<NBUF - 1>();
+    }
     named_bar_sync(1, kEpiThreads);
     const int cbase = chunk * 64 + half * 32;  // column within the BLOCK_N tile
 #pragma unroll
@@ -190,10 +193,13 @@ __device__ __forceinline__ void epilogue_acc(const ConvGemmArgs& p, const CUtens
     }
     fence_proxy_async_smem();
     named_bar_sync(1, kEpiThreads);
-    if (etid == 0) {
-      tma_store_2d(map_out, stg0, ng0 + chunk * 64, m0);
-      if constexpr (MODE == EPI_STYLE) tma_store_2d(map_out2, stg1, ng0 + chunk * 64, m0);
-      tma_store_commit();
+    if (warp == 2) {
+      __syncwarp();
+      if (elect_one_sync()) {
+        tma_store_2d(map_out, stg0, ng0 + chunk * 64, m0);
+        if constexpr (MODE == EPI_STYLE) tma_store_2d(map_out2, stg1, ng0 + chunk * 64, m0);
+        tma_store_commit();
+      }
     }
     if constexpr (MODE == EPI_STATS) {
       // per-channel sum / sum of squares over the 128 rows of this staged chunk (values as stored, bf16)
@@ -359,7 +365,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       epilogue_acc<BLOCK_N, MODE, 2>(p, &map_out, &map_out2, tmem_base, as * BLOCK_N, m_tile * 128, n_tile,
                                      &tmem_empty[as], stg_base, vec, chunk_counter);
     }
-    if (etid == 0) tma_store_wait_all<0>();
+    // the staging buffers only have to outlive the TMA engine's READS; global visibility comes with grid completion
+    if (warp == 2) {
+      __syncwarp();
+      if (elect_one_sync()) tma_store_wait_read<0>();
+    }
   }
 
   tc_fence_before();
@@ -583,7 +593,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       epilogue_acc<BLOCK_N, MODE, Cfg::NBUF>(p, &map_out, &map_out2, tmem_base, as * 2 * BLOCK_N + BLOCK_N, m0 + p.W,
                                              n_tile, &tmem_empty[as], stg_base, vec, chunk_counter);
     }
-    if (etid == 0) tma_store_wait_all<0>();
+    // the staging buffers only have to outlive the TMA engine's READS; global visibility comes with grid completion
+    if (warp == 2) {
+      __syncwarp();
+      if (elect_one_sync()) tma_store_wait_read<0>();
+    }
   }
 
   tc_fence_before();
@@ -737,6 +751,9 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
         break;
       }
     }
+    // small-M layers: 128-wide tiles on >= 2/3 of the SMs beat 64-wide tiles on all of them (measured,
+    // scripts/exp_blockn.py: 512->512 3x3 @8^2 x64 images 41 -> 29 us, 2048->512 1x1 23.5 -> 18.4 us)
+    if (block_n == 64 && cout % 128 == 0 && (long long)a.num_m_tiles * (cout / 128) * 3 >= 2ll * num_sms()) block_n = 128;
   }
   IRFD_CHECK_ARG((block_n == 64 || block_n == 128 || block_n == 256) && cout % block_n == 0,
                  "conv_gemm: BLOCK_N %d incompatible with Cout %d", block_n, cout);
