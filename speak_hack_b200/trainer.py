@@ -203,3 +203,66 @@ class IRFDTrainer:
         if self.use_cuda_graph:
             return self.train_step_graph(x_s, x_t)
         return self.train_step_eager(x_s, x_t)
+
+    # ---------------------------------------------------------------------------------------------- checkpoints
+    # The reference saves {'model_state_dict', 'optimizer_G', 'optimizer_D', 'epoch', 'resolution', 'config'}
+    # (train.py:232-240) and resumes with load_state_dict on each (train.py:362-368).  optimizer_G is
+    # torch.optim.Adam(model.Gd.parameters(), lr=2e-4) (train.py:346); the fused trainer keeps the same state in flat
+    # buffers, exported / imported here in torch.optim.Adam's state_dict layout so checkpoints move both ways.
+    def optimizer_state_dict(self) -> dict:
+        state, off = {}, 0
+        for i, p in enumerate(self.gd_params):
+            n = p.numel()
+            if self.step_count > 0:
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.m[off: off + n].view_as(p).clone(),
+                            "exp_avg_sq": self.v[off: off + n].view_as(p).clone()}
+            off += n
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "params": list(range(len(self.gd_params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd: dict) -> None:
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.gd_params):
+            raise ValueError("optimizer_G state does not match Gd.parameters() (one group, %d tensors expected)"
+                             % len(self.gd_params))
+        g = groups[0]
+        if g.get("weight_decay", 0) or g.get("amsgrad", False) or g.get("maximize", False):
+            raise ValueError("the fused Adam step implements torch.optim.Adam without weight_decay/amsgrad/maximize")
+        self.lr, self.betas, self.eps = float(g["lr"]), tuple(g["betas"]), float(g["eps"])
+        steps, off = set(), 0
+        self.m.zero_()
+        self.v.zero_()
+        for i, p in zip(g["params"], self.gd_params):
+            n = p.numel()
+            st = sd["state"].get(i)
+            if st is not None:
+                if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError(f"optimizer_G state {i}: shape {tuple(st['exp_avg'].shape)} != {tuple(p.shape)}")
+                self.m[off: off + n].copy_(st["exp_avg"].reshape(-1))
+                self.v[off: off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.add(int(float(st["step"])))
+            off += n
+        if len(steps) > 1:
+            raise ValueError("optimizer_G state has different step counts per parameter; the fused step keeps one")
+        self.step_count = steps.pop() if steps else 0
+        self.step_dev.fill_(self.step_count)
+        self.graph = None  # a captured graph is still valid (it reads the buffers), but lr/betas are baked in: recapture
+
+    def save_checkpoint(self, path: str, epoch: int = 0, config=None, optimizer_d: Optional[dict] = None) -> None:
+        """Writes the reference's checkpoint dictionary (train.py:232-240); loadable by the reference's resume code."""
+        torch.save({"model_state_dict": self.model.state_dict(), "optimizer_G": self.optimizer_state_dict(),
+                    "optimizer_D": optimizer_d if optimizer_d is not None else {}, "epoch": epoch,
+                    "resolution": getattr(self.model, "current_resolution", 256), "config": config}, path)
+
+    def load_checkpoint(self, path: str, map_location=None) -> dict:
+        """Resume from a checkpoint written by save_checkpoint OR by the reference's train.py; returns the dictionary
+        (the caller restores optimizer_D / epoch / config, which are outside the hot path)."""
+        ckpt = torch.load(path, map_location=map_location or self.device, weights_only=False)
+        self.model.load_state_dict(ckpt["model_state_dict"])  # copies INTO the flat parameter views
+        ops.invalidate_packed(list(self.model.parameters()))
+        if ckpt.get("optimizer_G"):
+            self.load_optimizer_state_dict(ckpt["optimizer_G"])
+        return ckpt
