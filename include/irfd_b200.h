@@ -58,7 +58,8 @@ int irfd_conv_gemm(const void* x, int n, int h, int w, int cin, const void* wk, 
                    void* out2, int mode, const float* bias, const float* nw, const float* noise, const float* sp1,
                    const float* s1, float* stat_sum, float* stat_sq, int force_block_n, irfd_stream_t stream);
 
-/* Inference variant (mode 3): y = [relu](acc*scale[c] + shift[c] [+ res[pixel,c]]) -> bf16.  Folds an eval-mode
+/* Affine variant (mode 3): y = act(acc*scale[c] + shift[c] [+ res[pixel,c]]) -> bf16; relu: 0 none, 1 ReLU,
+ * 2 leaky ReLU(0.2) (the discriminator's conv + bias + leaky_relu, styleganv1.py:662-669,689-694, with scale = 1).  Folds an eval-mode
  * BatchNorm2d (scale/shift from irfd_bn_eval_affine), the ReLU and the Bottleneck residual add into the conv
  * (torchvision/models/resnet.py:143-164 in eval mode); res is NHWC bf16 of the output shape or NULL. */
 int irfd_conv_gemm_affine(const void* x, int n, int h, int w, int cin, const void* wk, int cout, int ksize, void* out,
@@ -216,6 +217,18 @@ int irfd_adam_step(float* p, const float* g, float* m, float* v, long long n, fl
                    float eps, int step, int* step_dev, const float* total_sumsq, float max_norm, irfd_stream_t stream);
 /* step_dev (optional, device int32): when given it is incremented on the device and used instead of `step`, so a
  * captured CUDA graph replays with the right bias correction. */
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Discriminator pieces that are not conv epilogues (styleganv1.py:637-695).
+ *   irfd_from_rgb_fwd   : spectral-norm 1x1 conv 3 -> c on the NCHW fp32 image + bias + leaky_relu(0.2) -> NHWC bf16
+ *                         (styleganv1.py:643,662); w is [c][3] fp32 (already divided by sigma).
+ *   irfd_bias_lrelu_bwd : backward of y = leaky_relu(conv + bias): dz = g * (y > 0 ? 1 : 0.2) (bf16), dbias = sum dz.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int irfd_from_rgb_fwd(const float* x, const float* w, const float* bias, void* out, int b, int hw, int c,
+                      irfd_stream_t stream);
+long long irfd_bias_lrelu_bwd_workspace_bytes(long long rows, int c);
+int irfd_bias_lrelu_bwd(const void* g, const void* y, void* dz, float* dbias, long long rows, int c, void* workspace,
+                        long long workspace_bytes, irfd_stream_t stream);
 
 #ifdef __cplusplus
 }

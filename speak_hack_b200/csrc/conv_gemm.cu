@@ -41,7 +41,7 @@ struct ConvGemmArgs {
   float* stat_sum;
   float* stat_sq;
   const __nv_bfloat16* res;  // AFFINE: optional residual [M_total][N_total]
-  int relu;                  // AFFINE: apply ReLU
+  int relu;                  // AFFINE: 0 = none, 1 = ReLU, 2 = leaky ReLU (slope 0.2)
 };
 
 constexpr int kNumThreads = 320;      // 10 warps
@@ -169,7 +169,7 @@ __device__ __forceinline__ void epilogue_acc(const ConvGemmArgs& p, const CUtens
           o[t] = (p.bias != nullptr) ? acc + vb[c] : acc;
         } else if constexpr (MODE == EPI_AFFINE) {
           const float y = acc * vnw[c] + vb[c] + rres[t];
-          o[t] = p.relu ? fmaxf(y, 0.f) : y;
+          o[t] = p.relu == 1 ? fmaxf(y, 0.f) : (p.relu == 2 ? (y > 0.f ? y : 0.2f * y) : y);
         } else {
           o[t] = acc;
         }

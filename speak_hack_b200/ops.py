@@ -144,7 +144,9 @@ def conv_gemm(x, wk, ksize, mode=EPI_PLAIN, bias=None, nw=None, noise=None, sp1=
 
 
 def conv_gemm_affine(x, wk, ksize, scale, shift, res=None, relu=True, force_block_n=0):
-    """Inference conv with eval-mode BN (+ReLU, +residual) folded into the epilogue.  Returns out [N,H,W,Cout] bf16."""
+    """Conv with y = act(acc*scale + shift [+ res]) folded into the epilogue (eval-mode BN + ReLU + residual of the
+    encoders; conv + bias + leaky ReLU of the discriminator).  relu: False/0 none, True/1 ReLU, 2 leaky ReLU(0.2).
+    Returns out [N,H,W,Cout] bf16."""
     _chk(x, BF16, "x")
     _chk(wk, BF16, "wk")
     n, h, w, cin = x.shape
@@ -155,7 +157,7 @@ def conv_gemm_affine(x, wk, ksize, scale, shift, res=None, relu=True, force_bloc
         if res.numel() != out.numel():
             raise _lib.IrfdError("conv_gemm_affine: residual shape mismatch")
     _call("irfd_conv_gemm_affine", x.data_ptr(), n, h, w, cin, wk.data_ptr(), cout, ksize, out.data_ptr(),
-          scale.data_ptr(), shift.data_ptr(), _ptr(res), 1 if relu else 0, force_block_n, _stream())
+          scale.data_ptr(), shift.data_ptr(), _ptr(res), int(relu), force_block_n, _stream())
     return out
 
 
@@ -458,6 +460,38 @@ def to_rgb_bwd(drgb, y, w):
     _call("irfd_to_rgb_bwd", drgb.data_ptr(), y.data_ptr(), w.data_ptr(), dy.data_ptr(), dw.data_ptr(),
           dbias.data_ptr(), b, h * wd, c, ws.data_ptr(), ws.numel(), _stream(), launches=2)
     return dy, dw, dbias
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# discriminator pieces
+# ----------------------------------------------------------------------------------------------------------------------
+def from_rgb_fwd(x, w, bias):
+    """x [B,3,H,W] fp32, w [C,3] fp32, bias [C] -> leaky_relu(conv1x1 + bias) as NHWC bf16 [B,H,W,C]."""
+    _chk(x, F32, "x")
+    _chk(w, F32, "w")
+    _chk(bias, F32, "bias")
+    b, ch, h, wd = x.shape
+    if ch != 3 or w.shape[1] != 3:
+        raise _lib.IrfdError("from_rgb_fwd expects 3 input channels")
+    c = w.shape[0]
+    out = torch.empty((b, h, wd, c), dtype=BF16, device=x.device)
+    _call("irfd_from_rgb_fwd", x.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), b, h * wd, c, _stream())
+    return out
+
+
+def bias_lrelu_bwd(g, y):
+    """Backward of y = leaky_relu(conv + bias): returns dz (bf16, shape of y) and dbias [C] fp32."""
+    lib = _lib.load()
+    _chk(g, BF16, "g")
+    _chk(y, BF16, "y")
+    c = y.shape[-1]
+    rows = y.numel() // c
+    dz = torch.empty_like(y)
+    dbias = torch.empty(c, dtype=F32, device=y.device)
+    ws = workspace(lib.irfd_bias_lrelu_bwd_workspace_bytes(rows, c), y.device)
+    _call("irfd_bias_lrelu_bwd", g.data_ptr(), y.data_ptr(), dz.data_ptr(), dbias.data_ptr(), rows, c, ws.data_ptr(),
+          ws.numel(), _stream(), launches=2)
+    return dz, dbias
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -85,8 +85,17 @@ def test_no_cpu_fallback(net):
         net(x, x)
 
 
-def test_discriminator_is_plain_torch_and_runs(net):
-    # D is outside the hot path; it only has to exist with the reference's interface
-    with torch.no_grad():
-        out = net.D(torch.zeros(1, 3, 256, 256))
+def test_discriminator_interface_and_no_silent_fallback(net):
+    # D: native on CUDA; a CPU tensor must raise, like the encoders and the generator ...
+    from speak_hack_b200._lib import IrfdError
+
+    with pytest.raises(IrfdError):
+        net.D(torch.zeros(1, 3, 256, 256))
+    # ... unless the caller explicitly selects the reference's PyTorch composition (R1 double-backward path)
+    net.D.use_native = False
+    try:
+        with torch.no_grad():
+            out = net.D(torch.zeros(1, 3, 256, 256))
+    finally:
+        net.D.use_native = True
     assert out.shape == (1, 1)
