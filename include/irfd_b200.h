@@ -221,10 +221,11 @@ int irfd_adam_step(float* p, const float* g, float* m, float* v, long long n, fl
 /* ------------------------------------------------------------------------------------------------------------------
  * Discriminator pieces that are not conv epilogues (styleganv1.py:637-695).
  *   irfd_from_rgb_fwd   : spectral-norm 1x1 conv 3 -> c on the NCHW fp32 image + bias + leaky_relu(0.2) -> NHWC bf16
- *                         (styleganv1.py:643,662); w is [c][3] fp32 (already divided by sigma).
+ *                         (styleganv1.py:643,662); w is [c][3] fp32 (already divided by sigma); bias may be NULL and
+ *                         lrelu = 0 gives the plain linear map (used by the R1 second-order chain).
  *   irfd_bias_lrelu_bwd : backward of y = leaky_relu(conv + bias): dz = g * (y > 0 ? 1 : 0.2) (bf16), dbias = sum dz.
  * ------------------------------------------------------------------------------------------------------------------ */
-int irfd_from_rgb_fwd(const float* x, const float* w, const float* bias, void* out, int b, int hw, int c,
+int irfd_from_rgb_fwd(const float* x, const float* w, const float* bias, void* out, int b, int hw, int c, int lrelu,
                       irfd_stream_t stream);
 long long irfd_bias_lrelu_bwd_workspace_bytes(long long rows, int c);
 int irfd_bias_lrelu_bwd(const void* g, const void* y, void* dz, float* dbias, long long rows, int c, void* workspace,

@@ -11,10 +11,10 @@ namespace irfd {
 // C/8 threads of a pixel), the write is one coalesced 16-byte store.
 __global__ void __launch_bounds__(256)
 from_rgb_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                    __nv_bfloat16* __restrict__ out, int B, int HW, int C) {
+                    __nv_bfloat16* __restrict__ out, int B, int HW, int C, int lrelu) {
   extern __shared__ float sw[];  // [C][3] weights + [C] bias
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) sw[3 * C + i] = bias[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sw[3 * C + i] = bias != nullptr ? bias[i] : 0.f;
   __syncthreads();
   const unsigned vc = C >> 3;
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;  // host checks B*HW*vc < 2^32
@@ -28,7 +28,7 @@ from_rgb_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, co
   for (int t = 0; t < 8; ++t) {
     const int c = v * 8 + t;
     const float z = sw[c * 3] * r + sw[c * 3 + 1] * g + sw[c * 3 + 2] * bl + sw[3 * C + c];
-    o[t] = z > 0.f ? z : 0.2f * z;
+    o[t] = (lrelu == 0 || z > 0.f) ? z : 0.2f * z;
   }
   store8(out + (size_t)pix * C + v * 8, o);
 }
@@ -98,12 +98,12 @@ __global__ void bias_bwd_finalize_kernel(const float* __restrict__ partial, int 
 using namespace irfd;
 
 extern "C" int irfd_from_rgb_fwd(const float* x, const float* w, const float* bias, void* out, int b, int hw, int c,
-                                 cudaStream_t stream) {
-  IRFD_CHECK_ARG(x && w && bias && out && b > 0 && hw > 0 && c % 8 == 0 && c <= 2048, "from_rgb_fwd: bad argument");
+                                 int lrelu, cudaStream_t stream) {
+  IRFD_CHECK_ARG(x && w && out && b > 0 && hw > 0 && c % 8 == 0 && c <= 2048, "from_rgb_fwd: bad argument");
   const size_t total = (size_t)b * hw * (c / 8);
   IRFD_CHECK_ARG(total < ((size_t)1 << 32) - 256, "from_rgb_fwd: tensor too large for 32-bit indexing");
   from_rgb_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 4 * c * sizeof(float), stream>>>(
-      x, w, bias, reinterpret_cast<__nv_bfloat16*>(out), b, hw, c);
+      x, w, bias, reinterpret_cast<__nv_bfloat16*>(out), b, hw, c, lrelu);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }

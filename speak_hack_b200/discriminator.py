@@ -10,9 +10,11 @@ NHWC im2col the encoders use), NHWC bf16 activations, fp32 dense head.  That is 
 needs from D (train.py:197-201: `D(x_recon)` -> BCE -> backward into Gd) and what the real/fake terms of its D step need
 (train.py:160-175).
 
-Not covered yet: the R1 penalty (train.py:246-255) differentiates THROUGH the image gradient (`create_graph=True`); the
-native node is once-differentiable, so `compute_r1_reg` needs `use_native=False` (plain PyTorch, as before) until the
-second-order chain (masked dgrad -> masked fprop -> wgrad) is written.
+The R1 penalty (train.py:246-255) differentiates THROUGH the image gradient (`create_graph=True`).  The native node is
+once-differentiable, so a generic `torch.autograd.grad(..., create_graph=True)` over it is not available; instead
+`D.r1_penalty(real_img)` / `compute_r1_reg(D, real_img)` below compute the penalty and its parameter gradients directly
+(`_R1Fn`: forward, dgrad chain, masked forward chain, one wgrad per layer).  `use_native = False` selects the
+reference's PyTorch composition for callers that insist on a generic double backward.
 
 Spectral normalisation itself (one power iteration on each [Cout, Cin*k*k] matrix, styleganv1.py:643-654 via
 torch.nn.utils.spectral_norm) stays in its torch hook: it is parameter preparation — a few mat-vecs per layer, like the
@@ -25,6 +27,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+from torch.autograd.function import once_differentiable
 from torch.nn.utils import spectral_norm
 
 from . import ops
@@ -59,99 +62,179 @@ def _ones(c: int, device) -> torch.Tensor:
     return _ones_cache[key]
 
 
+def _pack(w: torch.Tensor, mode: int) -> torch.Tensor:
+    # the normalised weight is a fresh tensor every forward: repack without the (pointer-keyed) cache
+    return ops._pack_conv_weight(w.contiguous(), mode)
+
+
+def _disc_forward(x, nblocks, wb):
+    """Returns (logits [B,1], saved).  Layer order in wb: rgb, (conv1, conv2) x nblocks, final, dense0, dense1; each as
+    (spectrally normalised weight, bias)."""
+    x = x.contiguous().to(torch.float32)
+    dev = x.device
+    w_rgb, b_rgb = wb[0], wb[1]
+    c0 = w_rgb.shape[0]
+    a = ops.from_rgb_fwd(x, w_rgb.reshape(c0, 3).contiguous(), b_rgb.contiguous())
+    acts, cols = [a], []
+    i = 2
+    for _ in range(nblocks):
+        w1, b1, w2, b2 = wb[i], wb[i + 1], wb[i + 2], wb[i + 3]
+        i += 4
+        cin, cout = w1.shape[0], w2.shape[0]
+        y1 = ops.conv_gemm_affine(a, _pack(w1, ops.PACK_FPROP), 3, _ones(cin, dev), b1.contiguous(), relu=2)
+        nb, hh, ww, _ = y1.shape
+        col = ops.im2col_3x3s2(y1)
+        y2 = ops.conv_gemm_affine(col.view(1, 1, col.shape[0], 9 * cin), _pack(w2, ops.PACK_FPROP), 1, _ones(cout, dev),
+                                  b2.contiguous(), relu=2).view(nb, hh // 2, ww // 2, cout)
+        acts += [y1, y2]
+        cols.append(col)
+        a = y2
+    w_f, b_f = wb[i], wb[i + 1]
+    yf = ops.conv_gemm_affine(a, _pack(w_f, ops.PACK_FPROP), 3, _ones(w_f.shape[0], dev), b_f.contiguous(), relu=2)
+    acts.append(yf)
+    pooled = ops.avgpool_fwd(yf)
+    wd0, bd0, wd1, bd1 = wb[i + 2], wb[i + 3], wb[i + 4], wb[i + 5]
+    hdn = ops.linear_fwd(pooled, wd0.contiguous(), bd0.contiguous(), 1.0, 1.0, lrelu=True)
+    out = ops.linear_fwd(hdn, wd1.contiguous(), bd1.contiguous(), 1.0, 1.0, lrelu=False)
+    return out, {"x": x, "acts": acts, "cols": cols, "pooled": pooled, "hdn": hdn}
+
+
+def _disc_backward(S, nblocks, wb, dout, need_dx=True, need_dw=True, keep_u=False):
+    """First-order backward chain.  Returns (dx or None, grads aligned with wb (None where not computed), U) where U
+    holds every layer's masked upstream gradient u_l = lrelu'(z_l) * dL/dy_l (the R1 chain needs them)."""
+    acts, cols, pooled, hdn = S["acts"], S["cols"], S["pooled"], S["hdn"]
+    grads = [None] * len(wb)
+    U = {"blk": [None] * nblocks}
+    i = 2 + 4 * nblocks
+    wd0, wd1 = wb[i + 2], wb[i + 4]
+    dout = dout.contiguous().to(torch.float32)
+    dh, dw1_, db1_ = ops.linear_bwd(dout, hdn, wd1.contiguous(), 1.0, 1.0, need_dw=need_dw)
+    dz0 = ops.lrelu_bwd(dh, hdn)
+    dpool, dw0_, db0_ = ops.linear_bwd(dz0, pooled, wd0.contiguous(), 1.0, 1.0, need_dw=need_dw)
+    grads[i + 2], grads[i + 3], grads[i + 4], grads[i + 5] = dw0_, db0_, dw1_, db1_
+    U["head"] = dz0
+    yf = acts[-1]
+    g = ops.avgpool_bwd(dpool, yf.shape[1], yf.shape[2])
+    dz, grads[i + 1] = ops.bias_lrelu_bwd(g, yf)
+    U["final"] = dz
+    if need_dw:
+        grads[i] = ops.conv_wgrad(acts[-2], dz, 3)
+    g = ops.conv_gemm(dz, _pack(wb[i], ops.PACK_DGRAD), 3)
+    for bi in reversed(range(nblocks)):
+        j = 2 + 4 * bi
+        w1, w2 = wb[j], wb[j + 2]
+        a_in, y1, y2 = acts[2 * bi], acts[2 * bi + 1], acts[2 * bi + 2]
+        cin, cout = w1.shape[0], w2.shape[0]
+        col = cols[bi]
+        m2 = col.shape[0]
+        dz2, grads[j + 3] = ops.bias_lrelu_bwd(g, y2)
+        if need_dw:
+            grads[j + 2] = ops.conv_wgrad(col.view(1, 1, m2, 9 * cin), dz2.view(1, 1, m2, cout), 1, reduce_cin=cin,
+                                          reduce_taps=9, out_shape=(cout, cin, 3, 3))
+        dcol = ops.gemm_rows(dz2.view(m2, cout), _pack(w2, ops.PACK_DCOL))
+        nb, hh, ww, _ = y1.shape
+        g = ops.col2im_3x3s2(dcol, nb, hh, ww, cin)
+        dz1, grads[j + 1] = ops.bias_lrelu_bwd(g, y1)
+        if need_dw:
+            grads[j] = ops.conv_wgrad(a_in, dz1, 3)
+        g = ops.conv_gemm(dz1, _pack(w1, ops.PACK_DGRAD), 3)
+        U["blk"][bi] = (dz1, dz2)
+    # RGB stem: z = W x + b per pixel
+    a0 = acts[0]
+    c0 = a0.shape[-1]
+    dz, grads[1] = ops.bias_lrelu_bwd(g, a0)
+    U["rgb"] = dz
+    w_rgb_t = wb[0].reshape(c0, 3).t().contiguous()
+    if need_dw:
+        # dW[c][k] = sum_pix dz[pix][c] * x[k][pix]: the 1x1 to_rgb backward with the roles of image and activation
+        # swapped (its dy output is a by-product here)
+        _, dwt, _ = ops.to_rgb_bwd(S["x"], dz, w_rgb_t)
+        grads[0] = dwt.view(3, c0).t().contiguous().view_as(wb[0])
+    dx = None
+    if need_dx:  # dx[k][pix] = sum_c W[c][k] dz[pix][c]: the 1x1 to_rgb forward with W^T and no bias
+        dx = ops.to_rgb_fwd(dz, w_rgb_t, torch.zeros(3, dtype=torch.float32, device=dz.device))
+    if not need_dw:
+        grads = [None] * len(wb)
+    return dx, grads, (U if keep_u else None)
+
+
 class _DiscFn(torch.autograd.Function):
     """forward(x [B,3,H,W] fp32, nblocks, w_rgb, b_rgb, (w1, b1, w2, b2) x nblocks, w_final, b_final, wd0, bd0, wd1, bd1)
     -> logits [B,1] fp32.  The weights are the spectrally normalised ones (autograd continues into weight_orig)."""
 
     @staticmethod
     def forward(ctx, x, nblocks, *wb):
-        x = x.contiguous().to(torch.float32)
-        bsz, _, h, w = x.shape
-        dev = x.device
-        w_rgb, b_rgb = wb[0], wb[1]
-        c0 = w_rgb.shape[0]
-        a = ops.from_rgb_fwd(x, w_rgb.reshape(c0, 3).contiguous(), b_rgb.contiguous())
-        acts = [a]
-        cols = []
-        i = 2
-        for _ in range(nblocks):
-            w1, b1, w2, b2 = wb[i], wb[i + 1], wb[i + 2], wb[i + 3]
-            i += 4
-            cin, cout = w1.shape[0], w2.shape[0]
-            y1 = ops.conv_gemm_affine(a, ops._pack_conv_weight(w1.contiguous(), ops.PACK_FPROP), 3, _ones(cin, dev),
-                                      b1.contiguous(), relu=2)
-            nb, hh, ww, _ = y1.shape
-            col = ops.im2col_3x3s2(y1)
-            y2 = ops.conv_gemm_affine(col.view(1, 1, col.shape[0], 9 * cin),
-                                      ops._pack_conv_weight(w2.contiguous(), ops.PACK_FPROP), 1, _ones(cout, dev),
-                                      b2.contiguous(), relu=2).view(nb, hh // 2, ww // 2, cout)
-            acts += [y1, y2]
-            cols.append(col)
-            a = y2
-        w_f, b_f = wb[i], wb[i + 1]
-        yf = ops.conv_gemm_affine(a, ops._pack_conv_weight(w_f.contiguous(), ops.PACK_FPROP), 3,
-                                  _ones(w_f.shape[0], dev), b_f.contiguous(), relu=2)
-        acts.append(yf)
-        pooled = ops.avgpool_fwd(yf)
-        wd0, bd0, wd1, bd1 = wb[i + 2], wb[i + 3], wb[i + 4], wb[i + 5]
-        hdn = ops.linear_fwd(pooled, wd0.contiguous(), bd0.contiguous(), 1.0, 1.0, lrelu=True)
-        out = ops.linear_fwd(hdn, wd1.contiguous(), bd1.contiguous(), 1.0, 1.0, lrelu=False)
-        ctx.nblocks = nblocks
-        ctx.shape = (bsz, h, w)
-        ctx.x, ctx.acts, ctx.cols, ctx.head = x, acts, cols, (pooled, hdn)
-        ctx.wb = wb
+        out, S = _disc_forward(x, nblocks, wb)
+        ctx.nblocks, ctx.S, ctx.wb = nblocks, S, wb
         ctx.need_dx = ctx.needs_input_grad[0]
         return out
 
     @staticmethod
+    @once_differentiable  # a create_graph=True caller gets an error, not a silently constant image gradient
     def backward(ctx, dout):
-        wb, acts, cols, nblocks = ctx.wb, ctx.acts, ctx.cols, ctx.nblocks
-        pooled, hdn = ctx.head
-        bsz, h, w = ctx.shape
+        dx, grads, _ = _disc_backward(ctx.S, ctx.nblocks, ctx.wb, dout, need_dx=ctx.need_dx)
+        ctx.S = None
+        return (dx, None) + tuple(grads)
+
+
+class _R1Fn(torch.autograd.Function):
+    """R1 penalty  mean_b || d D(x).sum() / dx ||^2  (train.py:246-255) with its gradient w.r.t. the (normalised)
+    weights, without a generic double backward: D is piecewise linear in x, so with the leaky-ReLU masks m_l of the
+    forward pass held fixed the image gradient is the chain  g_{l-1} = C_l^T (m_l * g_l)  and
+
+        dR1/dW_l = wgrad(input = p_{l-1}, output gradient = u_l),   u_l = m_l * g_l,   p_l = m_l * (C_l p_{l-1}),   p_x = 2 g_x / B
+
+    i.e. one forward, one dgrad chain (u_l, g_x), one masked forward chain on p, one wgrad per layer — all on the same
+    kernels as the first-order path.  Biases only enter through the masks: their R1 gradient is zero."""
+
+    @staticmethod
+    def forward(ctx, x, nblocks, *wb):
+        bsz = x.shape[0]
+        out, S = _disc_forward(x, nblocks, wb)
+        dev = out.device
+        dout = torch.ones_like(out)
+        gx, _, U = _disc_backward(S, nblocks, wb, dout, need_dx=True, need_dw=False, keep_u=True)
+        pen = ops.sumsq(gx) / bsz
+        acts, hdn = S["acts"], S["hdn"]
         grads = [None] * len(wb)
-        i = 2 + 4 * nblocks
-        wd0, wd1 = wb[i + 2], wb[i + 4]
-        dout = dout.contiguous().to(torch.float32)
-        dh, grads[i + 4], grads[i + 5] = ops.linear_bwd(dout, hdn, wd1.contiguous(), 1.0, 1.0)
-        dz0 = ops.lrelu_bwd(dh, hdn)
-        dpool, grads[i + 2], grads[i + 3] = ops.linear_bwd(dz0, pooled, wd0.contiguous(), 1.0, 1.0)
-        yf = acts[-1]
-        g = ops.avgpool_bwd(dpool, yf.shape[1], yf.shape[2])
-        # final 3x3 conv
-        a_in = acts[-2]
-        dz, grads[i + 1] = ops.bias_lrelu_bwd(g, yf)
-        grads[i] = ops.conv_wgrad(a_in, dz, 3)
-        g = ops.conv_gemm(dz, ops._pack_conv_weight(wb[i].contiguous(), ops.PACK_DGRAD), 3)
-        for bi in reversed(range(nblocks)):
+        px = ops.scale_copy(gx, 2.0 / bsz)
+        c0 = acts[0].shape[-1]
+        w_rgb = wb[0].reshape(c0, 3).contiguous()
+        _, dwt, _ = ops.to_rgb_bwd(px, U["rgb"], w_rgb.t().contiguous())
+        grads[0] = dwt.view(3, c0).t().contiguous().view_as(wb[0])
+        p, _ = ops.bias_lrelu_bwd(ops.from_rgb_fwd(px, w_rgb, None, lrelu=False), acts[0])
+        for bi in range(nblocks):
             j = 2 + 4 * bi
             w1, w2 = wb[j], wb[j + 2]
-            a_in, y1, y2 = acts[2 * bi], acts[2 * bi + 1], acts[2 * bi + 2]
+            y1, y2 = acts[2 * bi + 1], acts[2 * bi + 2]
             cin, cout = w1.shape[0], w2.shape[0]
-            col = cols[bi]
-            m2 = col.shape[0]
-            dz2, grads[j + 3] = ops.bias_lrelu_bwd(g, y2)
-            grads[j + 2] = ops.conv_wgrad(col.view(1, 1, m2, 9 * cin), dz2.view(1, 1, m2, cout), 1, reduce_cin=cin,
+            u1, u2 = U["blk"][bi]
+            grads[j] = ops.conv_wgrad(p, u1, 3)
+            p, _ = ops.bias_lrelu_bwd(ops.conv_gemm(p, _pack(w1, ops.PACK_FPROP), 3), y1)
+            pcol = ops.im2col_3x3s2(p)
+            m2 = pcol.shape[0]
+            grads[j + 2] = ops.conv_wgrad(pcol.view(1, 1, m2, 9 * cin), u2.view(1, 1, m2, cout), 1, reduce_cin=cin,
                                           reduce_taps=9, out_shape=(cout, cin, 3, 3))
-            dcol = ops.gemm_rows(dz2.view(m2, cout), ops._pack_conv_weight(w2.contiguous(), ops.PACK_DCOL))
-            nb, hh, ww, _ = y1.shape
-            g = ops.col2im_3x3s2(dcol, nb, hh, ww, cin)
-            dz1, grads[j + 1] = ops.bias_lrelu_bwd(g, y1)
-            grads[j] = ops.conv_wgrad(a_in, dz1, 3)
-            g = ops.conv_gemm(dz1, ops._pack_conv_weight(w1.contiguous(), ops.PACK_DGRAD), 3)
-        # RGB stem: z = W x + b per pixel
-        a0 = acts[0]
-        c0 = a0.shape[-1]
-        dz, grads[1] = ops.bias_lrelu_bwd(g, a0)
-        w_rgb = wb[0].reshape(c0, 3)
-        # dW[c][k] = sum_pix dz[pix][c] * x[k][pix]: the 1x1 to_rgb backward with the roles of image and activation
-        # swapped (its dy output is a by-product here)
-        _, dwt, _ = ops.to_rgb_bwd(ctx.x, dz, w_rgb.t().contiguous())
-        grads[0] = dwt.view(3, c0).t().contiguous().view_as(wb[0])
-        dx = None
-        if ctx.need_dx:  # dx[k][pix] = sum_c W[c][k] dz[pix][c]: the 1x1 to_rgb forward with W^T and no bias
-            dx = ops.to_rgb_fwd(dz, w_rgb.t().contiguous(), torch.zeros(3, dtype=torch.float32, device=dz.device))
-        ctx.acts = ctx.cols = ctx.head = ctx.x = None
-        return (dx, None) + tuple(grads)
+            q = ops.gemm_rows(pcol, _pack(w2, ops.PACK_FPROP)).view(y2.shape)
+            p, _ = ops.bias_lrelu_bwd(q, y2)
+        i = 2 + 4 * nblocks
+        grads[i] = ops.conv_wgrad(p, U["final"], 3)
+        p, _ = ops.bias_lrelu_bwd(ops.conv_gemm(p, _pack(wb[i], ops.PACK_FPROP), 3), acts[-1])
+        ppool = ops.avgpool_fwd(p)
+        wd0, wd1 = wb[i + 2].contiguous(), wb[i + 4].contiguous()
+        t = ops.linear_fwd(ppool, wd0, None, 1.0, 1.0, lrelu=False)
+        _, grads[i + 2], _ = ops.linear_bwd(U["head"], ppool, wd0, 1.0, 1.0, need_dx=False, has_bias=False)
+        pdh = ops.lrelu_bwd(t, hdn)
+        _, grads[i + 4], _ = ops.linear_bwd(dout, pdh, wd1, 1.0, 1.0, need_dx=False, has_bias=False)
+        ctx.grads = grads
+        del S, U
+        return pen.view(())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dpen):
+        grads, ctx.grads = ctx.grads, None
+        return (None, None) + tuple(None if g is None else g * dpen for g in grads)
 
 
 class StyleDiscriminator(nn.Module):
@@ -180,16 +263,29 @@ class StyleDiscriminator(nn.Module):
             return False
         return all(b.conv1.weight_orig.shape[0] % 64 == 0 and b.conv2.weight_orig.shape[0] % 64 == 0 for b in self.blocks)
 
+    def _weights_and_biases(self):
+        mods = [self.fromrgb]
+        for blk in self.blocks:
+            mods += [blk.conv1, blk.conv2]
+        mods += [self.final_conv, self.dense0, self.dense1]
+        wb = []
+        for m in mods:
+            wb += [_normalized_weight(m), m.bias]
+        return wb
+
+    def r1_penalty(self, real_img):
+        """`compute_r1_reg(D, real_img)` of train.py:246-255 on the sm_100a path: the penalty (scalar) with gradients
+        w.r.t. the parameters.  Like the reference it marks the batch as requiring grad and runs the
+        spectral-norm hooks once (one power iteration in train mode, as `D(real_img)` would)."""
+        real_img.requires_grad_(True)
+        if not self._native_ok(real_img):
+            raise ops._lib.IrfdError(f"StyleDiscriminator.r1_penalty: input {tuple(real_img.shape)} on {real_img.device} "
+                                     "does not fit the sm_100a path")
+        return _R1Fn.apply(real_img.detach(), len(self.blocks), *self._weights_and_biases())
+
     def forward(self, x):
         if self._native_ok(x):
-            mods = [self.fromrgb]
-            for blk in self.blocks:
-                mods += [blk.conv1, blk.conv2]
-            mods += [self.final_conv, self.dense0, self.dense1]
-            wb = []
-            for m in mods:
-                wb += [_normalized_weight(m), m.bias]
-            return _DiscFn.apply(x, len(self.blocks), *wb)
+            return _DiscFn.apply(x, len(self.blocks), *self._weights_and_biases())
         if self.use_native:  # no silent fallback: the native path either runs or the call fails
             raise ops._lib.IrfdError(
                 f"StyleDiscriminator: input {tuple(x.shape)} on {x.device} does not fit the sm_100a path (CUDA, square "
@@ -203,3 +299,13 @@ class StyleDiscriminator(nn.Module):
         x = self.adaptive_pool(x).flatten(1)
         x = F.leaky_relu(self.dense0(x), 0.2)
         return self.dense1(x)
+
+
+def compute_r1_reg(D: StyleDiscriminator, real_img):
+    """train.py:246-255.  Native when D is; otherwise the reference's double backward through the PyTorch composition."""
+    if D.use_native:
+        return D.r1_penalty(real_img)
+    real_img = real_img.requires_grad_(True)
+    real_pred = D(real_img)
+    grad_real = torch.autograd.grad(outputs=real_pred.sum(), inputs=real_img, create_graph=True)[0]
+    return grad_real.pow(2).reshape(grad_real.shape[0], -1).sum(1).mean()

@@ -465,17 +465,19 @@ def to_rgb_bwd(drgb, y, w):
 # ----------------------------------------------------------------------------------------------------------------------
 # discriminator pieces
 # ----------------------------------------------------------------------------------------------------------------------
-def from_rgb_fwd(x, w, bias):
-    """x [B,3,H,W] fp32, w [C,3] fp32, bias [C] -> leaky_relu(conv1x1 + bias) as NHWC bf16 [B,H,W,C]."""
+def from_rgb_fwd(x, w, bias, lrelu=True):
+    """x [B,3,H,W] fp32, w [C,3] fp32, bias [C] or None -> [leaky_relu](conv1x1 + bias) as NHWC bf16 [B,H,W,C]."""
     _chk(x, F32, "x")
     _chk(w, F32, "w")
-    _chk(bias, F32, "bias")
+    if bias is not None:
+        _chk(bias, F32, "bias")
     b, ch, h, wd = x.shape
     if ch != 3 or w.shape[1] != 3:
         raise _lib.IrfdError("from_rgb_fwd expects 3 input channels")
     c = w.shape[0]
     out = torch.empty((b, h, wd, c), dtype=BF16, device=x.device)
-    _call("irfd_from_rgb_fwd", x.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), b, h * wd, c, _stream())
+    _call("irfd_from_rgb_fwd", x.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), b, h * wd, c,
+          1 if lrelu else 0, _stream())
     return out
 
 

@@ -120,3 +120,48 @@ def test_discriminator_matches_oracle_from_state_dict(cuda_device):
     torch.cuda.synchronize()
     scale = float(o_ref.abs().max().clamp_min(1e-6))
     assert float((o.cpu() - o_ref).abs().max()) / scale < 3e-2, (o, o_ref)
+
+
+def test_r1_penalty_native_matches_double_backward(cuda_device):
+    """`compute_r1_reg` (train.py:246-255): the native second-order chain (dgrad chain, masked forward chain, wgrads)
+    against torch's generic double backward through the PyTorch composition: penalty value and every weight gradient
+    (through the spectral normalisation); the biases get no gradient in either (they only move the masks)."""
+    from speak_hack_b200.discriminator import StyleDiscriminator, compute_r1_reg
+
+    dev = cuda_device
+    torch.manual_seed(0)
+    d_nat = StyleDiscriminator().to(dev)
+    d_ref = StyleDiscriminator().to(dev)
+    d_ref.use_native = False
+    g = torch.Generator().manual_seed(1)
+    x = (torch.rand(2, 3, 256, 256, generator=g) * 2 - 1).to(dev)
+    d_ref.train()
+    with torch.no_grad():
+        for _ in range(8):
+            d_ref(x)
+    d_nat.load_state_dict(d_ref.state_dict())
+    d_nat.eval()
+    d_ref.eval()
+    xn, xr = x.clone(), x.clone()
+    rn = compute_r1_reg(d_nat, xn)
+    rr = compute_r1_reg(d_ref, xr)
+    assert xn.requires_grad and xr.requires_grad  # the reference's side effect on the batch (SURVEY Q2)
+    rn.backward()
+    rr.backward()
+    torch.cuda.synchronize()
+    assert abs(float(rn) - float(rr)) / abs(float(rr)) < 5e-3, (float(rn), float(rr))
+    worst = 0.0
+    for (k, pn), (_, pr) in zip(d_nat.named_parameters(), d_ref.named_parameters()):
+        if k.endswith("bias"):
+            assert pn.grad is None or float(pn.grad.abs().max()) == 0.0, k
+            assert pr.grad is None or float(pr.grad.abs().max()) == 0.0, k
+            continue
+        e = rel_l2(pn.grad, pr.grad)
+        worst = max(worst, e)
+        assert e < 8e-2, (k, e)
+    print(f"[disc] R1 native {float(rn):.6e} vs torch {float(rr):.6e}, worst weight-grad rel-L2 {worst:.3e}")
+    # a generic double backward over the native node must fail loudly instead of returning a constant
+    xg = x.clone().requires_grad_(True)
+    gimg = torch.autograd.grad(d_nat(xg).sum(), xg, create_graph=True)[0]
+    with pytest.raises(RuntimeError):
+        gimg.pow(2).sum().backward()
