@@ -8,9 +8,14 @@ hdr, units = rows[0], rows[1]
 W = [("Kernel Name", "kernel"), ("Grid Size", "grid"), ("gpu__time_duration.sum", "time us"),
      ("dram__bytes_read.sum", "DRAM rd"), ("dram__bytes_write.sum", "DRAM wr"),
      ("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor %"),
+     ("sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "TMEM/tensor-mem %"),
      ("l1tex__m_xbar2l1tex_read_bytes.sum", "L2->SM"), ("lts__t_sector_hit_rate.pct", "L2 hit %"),
      ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %"), ("launch__registers_per_thread", "regs")]
-idx = [(hdr.index(k), n) for k, n in W if k in hdr]
+idx = []
+for k, n in W:  # some sections prefix the metric name (e.g. "TPC.TriageCompute."): match by suffix
+    hit = [i for i, h in enumerate(hdr) if h == k or h.endswith("." + k)]
+    if hit and n not in [m for _, m in idx]:
+        idx.append((hit[0], n))
 print("| " + " | ".join(n for _, n in idx) + " |")
 print("|" + "---|" * len(idx))
 for r in rows[2:]:
