@@ -230,10 +230,58 @@ wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, i
   *d = (beta != 0.f) ? beta * (*d) + acc : acc;
 }
 
+// Few splits but large outputs (the 512x512x9 layers: 2.4 M elements): the partials are [k = tap*Cin + c][n] with n
+// fastest while OIHW wants (c, tap) fastest, so a one-thread-per-output kernel writes 4 bytes at an 18 KB stride.  Here
+// a block owns 32 n x 32 c x all taps: coalesced 128-byte reads along n (summing the splits in order), a shared-memory
+// tile transposed on the fly, then each n row is written as 32*taps contiguous floats.
+template <int TAPS>
+__global__ void __launch_bounds__(256)
+wgrad_reduce_transpose_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int K_total,
+                              int N_total, int cin, float beta) {
+  constexpr int ROW = 32 * TAPS;
+  __shared__ float tile[32][ROW + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // tx -> n within the tile, ty -> (tap, c) lane
+  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const size_t stride = (size_t)K_total * N_total;
+  for (int i0 = ty; i0 < ROW; i0 += 32) {  // i = tap * 32 + c_local; four partial rows (x splits) in flight per thread
+    const float* p[4];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + 8 * u, tap = i >> 5, cl = i & 31;
+      p[u] = partial + ((size_t)tap * cin + c0 + cl) * N_total + n0 + tx;
+    }
+    for (int sidx = 0; sidx < splits; ++sidx) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] += __ldg(p[u] + (size_t)sidx * stride);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + 8 * u;
+      tile[tx][(i & 31) * TAPS + (i >> 5)] = acc[u];
+    }
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {  // one n row per warp iteration: 32 * TAPS contiguous floats of OIHW
+    float* d = dw + ((size_t)(n0 + r) * cin + c0) * TAPS;
+    for (int j = tx; j < ROW; j += 32) d[j] = (beta != 0.f) ? beta * d[j] + tile[r][j] : tile[r][j];
+  }
+}
+
 // few splits: one thread per output; many splits (1x1 layers, halo kernel: up to 148): 8 lanes share the walk
 static void launch_wgrad_reduce(const float* partial, float* dw, int splits, int K_total, int N_total, int cin, int taps,
                                 float beta, cudaStream_t stream) {
   const size_t total = (size_t)K_total * N_total;
+  // the transposing kernel needs whole 32 x 32 tiles and the plain k = tap*cin + c layout (no padded K tail)
+  const bool tileable = cin % 32 == 0 && N_total % 32 == 0 && K_total == cin * taps && (taps == 9 || taps == 1);
+  if (splits <= 6 && tileable && total >= (size_t)1 << 18) {
+    const dim3 grid(N_total / 32, cin / 32);
+    if (taps == 9)
+      wgrad_reduce_transpose_kernel<9><<<grid, 256, 0, stream>>>(partial, dw, splits, K_total, N_total, cin, beta);
+    else
+      wgrad_reduce_transpose_kernel<1><<<grid, 256, 0, stream>>>(partial, dw, splits, K_total, N_total, cin, beta);
+    return;
+  }
   if (splits <= 6)
     wgrad_reduce_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(partial, dw, splits, K_total, N_total,
                                                                                 cin, taps, beta);
