@@ -71,11 +71,16 @@ def main():
     print("## by family\n\n| family | ms | share |\n|---|---|---|")
     for f, ms in fam.most_common():
         print(f"| {f} | {ms:.2f} | {100 * ms / total:.1f}% |")
-    print("\n## by kernel\n\n| kernel | launches | ms | share | avg us | DRAM MB/launch | DRAM GB/s |\n|---|---|---|---|---|---|---|")
+    if dram:
+        print("\n## by kernel\n\n| kernel | launches | ms | share | avg us | DRAM MB/launch | DRAM GB/s |\n|---|---|---|---|---|---|---|")
+    else:
+        print("\n## by kernel\n\n| kernel | launches | ms | share | avg us |\n|---|---|---|---|---|")
     for k, ms in t.most_common(45):
         db = dram.get(k, 0.0)
-        print(f"| {k} | {n[k]} | {ms:.2f} | {100 * ms / total:.1f}% | {1e3 * ms / n[k]:.1f} | "
-              f"{db / n[k] / 1e6:.1f} | {db / (ms * 1e-3) / 1e9 if ms else 0:.0f} |")
+        line = f"| {k} | {n[k]} | {ms:.2f} | {100 * ms / total:.1f}% | {1e3 * ms / n[k]:.1f} |"
+        if dram:
+            line += f" {db / n[k] / 1e6:.1f} | {db / (ms * 1e-3) / 1e9 if ms else 0:.0f} |"
+        print(line)
 
 
 if __name__ == "__main__":
