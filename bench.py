@@ -341,7 +341,7 @@ def run_native(args):
                                          "achieved_gbs": v["flops"] / (v["ms"] * 1e-3) / 1e9,
                                          "frac_of_measured_hbm": v["flops"] / (v["ms"] * 1e-3) / 1e9 / peak_bw}
                                      for k, v in hbm.items()},
-                    "ncu": "profiles/r1_launches_v3_summary.md, profiles/r1_ncu_full_summary.md, "
+                    "ncu": "profiles/r1_launches_v3_summary.md, profiles/r1_launches_final2_summary.md, profiles/r1_ncu_shapes_summary.md, "
                            "profiles/r1_conv_shapes.md (per-shape roofline)"}
 
     n_pairs = B * world * args.steps

@@ -352,7 +352,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
-    const int etid = threadIdx.x - 64;
     int iter = 0;
     uint32_t chunk_counter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
@@ -577,7 +576,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps): two accumulators per tile
-    const int etid = threadIdx.x - 64;
     int iter = 0;
     uint32_t chunk_counter = 0;
     for (int tile = blockIdx.x; tile < hp.total_tiles; tile += gridDim.x, ++iter) {
