@@ -165,3 +165,37 @@ def test_r1_penalty_native_matches_double_backward(cuda_device):
     gimg = torch.autograd.grad(d_nat(xg).sum(), xg, create_graph=True)[0]
     with pytest.raises(RuntimeError):
         gimg.pow(2).sum().backward()
+
+
+def test_discriminator_and_r1_against_reference_golden(cuda_device):
+    """Native D and native R1 against golden vectors of the UNMODIFIED reference (tests/golden/disc_b2.pt, protocol in
+    oracle/make_golden_disc.py): the oracle (pinned to the same vectors on CPU) supplies the warmed-up state."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import irfd_oracle as O
+    import make_golden_disc as G
+    from speak_hack_b200.discriminator import StyleDiscriminator, compute_r1_reg
+
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "disc_b2.pt"), weights_only=False)
+    torch.manual_seed(O.WEIGHT_SEED)
+    ref_d = O.IRFDRef().D
+    x_s, _ = O.synthetic_pair(2)
+    G.warm_up(ref_d, x_s)
+    nat = StyleDiscriminator()
+    nat.load_state_dict(ref_d.state_dict())
+    nat = nat.to(cuda_device).eval()
+    rec = G.protocol(nat, x_s.to(cuda_device), compute_r1_reg)
+    torch.cuda.synchronize()
+    scale = float(gold["logits"].abs().max())
+    err = float((rec["logits"].cpu() - gold["logits"]).abs().max()) / scale
+    print(f"[disc-golden] logits {rec['logits'].flatten().tolist()} vs {gold['logits'].flatten().tolist()} (err {err:.2e}), "
+          f"R1 {rec['r1']:.6e} vs {gold['r1']:.6e}")
+    assert err < 0.1
+    assert rec["bce"] == pytest.approx(gold["bce"], rel=1e-4)
+    for k, g in gold["grads"].items():
+        tol = 0.2 if k.startswith("fromrgb.weight") else 0.1
+        assert rec["grads"][k]["norm"] == pytest.approx(g["norm"], rel=tol), k
+    assert rec["dx"]["norm"] == pytest.approx(gold["dx"]["norm"], rel=0.2)
+    assert rec["r1"] == pytest.approx(gold["r1"], rel=2e-2)
+    for k, g in gold["r1_grads"].items():
+        assert rec["r1_grads"][k]["norm"] == pytest.approx(g["norm"], rel=0.1), k
+    assert rec["r1_bias_grads_zero"]

@@ -105,3 +105,38 @@ def test_train_forward_backward(oracle_net):
             assert O.rel_l2(sd[k], v) < TOL, k
         else:
             assert torch.equal(sd[k], v), k
+
+
+def _disc_protocol_on_oracle():
+    """oracle/make_golden_disc.py's protocol executed by the oracle's restatement of D and of compute_r1_reg."""
+    import make_golden_disc as G
+
+    torch.manual_seed(O.WEIGHT_SEED)
+    net = O.IRFDRef()
+    x_s, _ = O.synthetic_pair(2)
+    G.warm_up(net.D, x_s)
+
+    def r1_ref(D, real_img):  # train.py:246-255 restated
+        real_img = real_img.requires_grad_(True)
+        grad_real = torch.autograd.grad(outputs=D(real_img).sum(), inputs=real_img, create_graph=True)[0]
+        return grad_real.pow(2).reshape(grad_real.shape[0], -1).sum(1).mean()
+
+    return G.protocol(net.D, x_s, r1_ref), net.D, x_s
+
+
+def test_discriminator_and_r1_against_reference_golden():
+    """Pins the oracle's StyleDiscriminatorRef and its R1 restatement against the UNMODIFIED reference
+    (tests/golden/disc_b2.pt from oracle/make_golden_disc.py): logits, BCE, image / parameter gradients, R1 penalty."""
+    gold = _load("disc_b2.pt")
+    rec, _, _ = _disc_protocol_on_oracle()
+    assert torch.allclose(rec["logits"], gold["logits"], rtol=1e-4, atol=1e-9)
+    assert rec["bce"] == pytest.approx(gold["bce"], rel=1e-6)
+    assert rec["dx"]["norm"] == pytest.approx(gold["dx"]["norm"], rel=1e-4)
+    assert torch.allclose(rec["dx"]["sample"], gold["dx"]["sample"], rtol=1e-3, atol=1e-4 * gold["dx"]["norm"])
+    for k, g in gold["grads"].items():
+        assert rec["grads"][k]["norm"] == pytest.approx(g["norm"], rel=1e-4), k
+        assert torch.allclose(rec["grads"][k]["sample"], g["sample"], rtol=1e-3, atol=1e-4 * g["norm"]), k
+    assert rec["r1"] == pytest.approx(gold["r1"], rel=1e-4)
+    for k, g in gold["r1_grads"].items():
+        assert rec["r1_grads"][k]["norm"] == pytest.approx(g["norm"], rel=1e-3), k
+    assert rec["r1_bias_grads_zero"] and gold["r1_bias_grads_zero"]
