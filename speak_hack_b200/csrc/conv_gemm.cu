@@ -6,16 +6,20 @@
 // * A tiles (128 pixels x 64 channels) arrive by 4-D TMA boxes over the NHWC tensor; the conv halo/padding is the
 //   TMA out-of-bounds zero fill, so there is no im2col buffer and no boundary code.
 // * B tiles (BLOCK_N out-channels x 64 k) arrive by 2-D TMA boxes over the packed [Cout][tap][Cin] weight.
-// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warps 2..9 = epilogue
-//   (TMEM -> registers -> fused math -> swizzled smem staging -> TMA store).
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue
+//   (TMEM -> registers -> fused math -> swizzled smem staging -> TMA store).  Producer and issuer run their loops
+//   warp-converged and put only the TMA / MMA / commit instruction under elect.sync (see ptx.cuh: elect_one_sync).
 // * Persistent: grid = #SMs, each CTA walks tiles  tile = blockIdx.x + i * gridDim.x  (n-tile fastest, so the CTAs
 //   running concurrently share A tiles in L2).
+// * conv_halo_kernel (further down) is the variant for 3x3 convs on rows of >= 128 pixels: one halo tile per
+//   64-channel chunk serves all nine taps.
 //
 // Epilogue modes
 //   PLAIN : y = acc (+ bias[n])                                       -> bf16           (dgrad, 1x1, generic)
 //   STATS : y = acc -> bf16, plus per-tile per-channel sum / sum-of-squares of the stored values (train-mode BN)
-//   AFFINE: y = [relu]( acc*scale[n] + shift[n] [+ res[m,n]] ) -> bf16   (inference: eval-mode BatchNorm, ReLU and the
-//           residual add of a Bottleneck folded into the conv, torchvision/models/resnet.py:143-164)
+//   AFFINE: y = act( acc*scale[n] + shift[n] [+ res[m,n]] ) -> bf16, act = none / ReLU / leaky ReLU(0.2)
+//           (inference: eval-mode BatchNorm, ReLU and the residual add of a Bottleneck folded into the conv,
+//           torchvision/models/resnet.py:143-164; discriminator: conv + bias + leaky_relu, styleganv1.py:662-694)
 //   STYLE : z = acc + bias[n] + nw[n]*noise[m];  a = lrelu_0.2(z);  y = a*sp1[b,n] + s1[b,n]
 //           -> a (bf16, kept for backward) and y (bf16, next layer's input)
 //           reference: styleganv1.py:625-628 / 630-633 (conv -> ApplyNoise -> leaky_relu -> ApplyStyle)

@@ -7,7 +7,9 @@
 //   A tile (M = 128 = two 64-channel atoms of (tap, c-chunk))  <- two 4-D TMA boxes [64 pixels x 64 ch] of X, shifted
 //   B tile (N = BLOCK_N out channels = BLOCK_N/64 atoms)        <- 2-D TMA boxes [64 pixels x 64 ch] of dY
 // Split-K over pixel ranges: each CTA owns (k-pair, n-tile, pixel-range) and writes an fp32 partial
-// [split][Ktot][Cout]; irfd_wgrad_reduce sums the splits in a fixed order (deterministic) into OIHW fp32.
+// [split][Ktot][Cout]; the wgrad_reduce kernels sum the splits in a fixed order (deterministic) into OIHW fp32.
+// wgrad_halo_kernel (further down) is the 3x3 variant that keeps all nine taps of a Cin chunk in TMEM and streams X
+// once per chunk instead of once per (tap, chunk) pair.
 #include <stdlib.h>
 
 #include "host_util.h"
