@@ -64,3 +64,37 @@ def test_sass_uses_blackwell_tensor_and_tma_instructions():
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG"):
         assert mnemonic in sass, mnemonic
     assert "sm_100a" in subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+
+
+def test_sass_mma_issue_is_back_to_back():
+    """Regression guard for the warp-converged elect.sync issue loops: every tcgen05 GEMM kernel issues
+    its MMAs of one pipeline stage as consecutive UTCHMMA instructions.  With an `if (lane == 0)` issue region nvcc
+    puts an ELECT / R2UR.BROADCAST loop (~14 instructions) in front of each one and no two are adjacent."""
+    import re
+    import shutil
+    import subprocess
+
+    from speak_hack_b200 import _lib
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    longest = {}
+    name, run = None, 0
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name, run = m.group(1), 0
+            continue
+        if name is None or "/*" not in line or re.match(r"\s*/\* 0x", line):
+            continue  # not an instruction line (the second half of each encoding sits on its own line)
+        if "UTCHMMA" in line:
+            run += 1
+            longest[name] = max(longest.get(name, 0), run)
+        else:
+            run = 0
+    gemm = {k: v for k, v in longest.items() if "gemm_kernel" in k or "halo_kernel" in k}
+    assert len(gemm) >= 16, sorted(gemm)  # conv (3 tiles x 4 epilogues), conv halo, wgrad (3 tiles), wgrad halo
+    for k, v in gemm.items():
+        assert v >= 4, (k, v)  # four K=16 steps per 64-wide stage, back to back (eight / forty in the halo kernels)
