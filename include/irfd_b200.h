@@ -58,6 +58,14 @@ int irfd_conv_gemm(const void* x, int n, int h, int w, int cin, const void* wk, 
                    void* out2, int mode, const float* bias, const float* nw, const float* noise, const float* sp1,
                    const float* s1, float* stat_sum, float* stat_sq, int force_block_n, irfd_stream_t stream);
 
+/* STYLE mode with a split-bf16 y: additionally writes out_y_lo = bf16(y - bf16(y)) so that the bilinear upsample that
+ * consumes y (irfd_upsample2x_split_fwd) sees ~16 mantissa bits and the next conv's operand is rounded once, like the
+ * fp32 reference's would be (styleganv1.py:623-635).  Used for the <= 32^2 layers, where the extra bytes are free. */
+int irfd_conv_gemm_style_split(const void* x, int n, int h, int w, int cin, const void* wk, int cout, int ksize,
+                               void* out_a, void* out_y, void* out_y_lo, const float* bias, const float* nw,
+                               const float* noise, const float* sp1, const float* s1, int force_block_n,
+                               irfd_stream_t stream);
+
 /* Affine variant (mode 3): y = act(acc*scale[c] + shift[c] [+ res[pixel,c]]) -> bf16; relu: 0 none, 1 ReLU,
  * 2 leaky ReLU(0.2) (the discriminator's conv + bias + leaky_relu, styleganv1.py:662-669,689-694, with scale = 1).  Folds an eval-mode
  * BatchNorm2d (scale/shift from irfd_bn_eval_affine), the ReLU and the Bottleneck residual add into the conv
@@ -151,6 +159,12 @@ int irfd_const_input_fwd(const float* cst, const float* bias, const float* nw, c
 int irfd_const_input_bwd(const void* dy, const void* a0, const float* noise, const float* sp1, float* dsp1, float* ds1,
                          float* dconst, float* dbias, float* dnw, int b, int c, irfd_stream_t stream);
 int irfd_upsample2x_fwd(const void* in, void* out, int b, int h, int w, int c, irfd_stream_t stream);
+/* split-bf16 variants: the input of the upsample is in + in_lo (in_lo / y0_lo may be NULL = plain variant) */
+int irfd_upsample2x_split_fwd(const void* in, const void* in_lo, void* out, int b, int h, int w, int c,
+                              irfd_stream_t stream);
+int irfd_const_input_split_fwd(const float* cst, const float* bias, const float* nw, const float* noise,
+                               const float* sp1, const float* s1, void* a0, void* y0, void* y0_lo, int b, int c,
+                               irfd_stream_t stream);
 int irfd_upsample2x_bwd(const void* dout, void* din, int b, int h, int w, int c, irfd_stream_t stream);
 long long irfd_style_bwd_workspace_bytes(int b, int hw, int c);
 int irfd_style_bwd(const void* dy, const void* a, const float* noise, const float* sp1, void* dz, float* ds1,

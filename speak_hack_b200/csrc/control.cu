@@ -8,8 +8,9 @@
 
 namespace irfd {
 
-// rows_t[l][b][k] = coef(l) * (l >= cut ? w2 : w)[b][k],  coef(l) = psi for l < cutoff else 1
-// (styleganv1.py:536-553: repeat -> truncation coefficients -> rows >= mix_layer overwritten with w2's rows)
+// rows_t[l][b][k] = l >= cut ? w2[b][k] : coef(l) * w[b][k],  coef(l) = psi for l < cutoff else 1
+// (styleganv1.py:536-553: repeat -> truncation coefficients on w ONLY -> rows >= mix_layer overwritten with the
+// UNtruncated rows of w2)
 __global__ void style_rows_fwd_kernel(const float* __restrict__ w, const float* __restrict__ w2,
                                       const int* __restrict__ ctrl, int ctrl_idx, float psi, int cutoff,
                                       float* __restrict__ rows_t, int L, int BK) {
@@ -19,7 +20,7 @@ __global__ void style_rows_fwd_kernel(const float* __restrict__ w, const float* 
   const int j = i - (size_t)l * BK;
   const int cut = ctrl[ctrl_idx];
   const float coef = l < cutoff ? psi : 1.f;
-  rows_t[i] = coef * (l >= cut ? w2[j] : w[j]);
+  rows_t[i] = l >= cut ? w2[j] : coef * w[j];
 }
 
 // dw[b][k] = sum_l coef(l) * drows_t[l][b][k] over ALL rows: the reference overwrites the mixed rows under no_grad, so

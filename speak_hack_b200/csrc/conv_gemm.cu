@@ -45,6 +45,7 @@ struct ConvGemmArgs {
   float* stat_sum;
   float* stat_sq;
   const __nv_bfloat16* res;  // AFFINE: optional residual [M_total][N_total]
+  __nv_bfloat16* y_lo;       // STYLE: optional second half of a split-bf16 y (y ~= y + y_lo), direct 16-byte stores
   int relu;                  // AFFINE: 0 = none, 1 = ReLU, 2 = leaky ReLU (slope 0.2)
 };
 
@@ -193,6 +194,19 @@ __device__ __forceinline__ void epilogue_acc(const ConvGemmArgs& p, const CUtens
         pk2.z = pack_bf16x2(o2[4], o2[5]);
         pk2.w = pack_bf16x2(o2[6], o2[7]);
         *reinterpret_cast<uint4*>(stg1 + r * 128 + phys * 16) = pk2;
+        if (p.y_lo != nullptr && m0 + r < p.M_total) {
+          // the rounding residual of y, itself rounded to bf16: the bilinear upsample that consumes y reads
+          // y + y_lo (~16 mantissa bits), so the next conv's operand is rounded ONCE like the fp32 reference's
+          // would be.  Only requested for the small layers (<= 32^2), where the extra bytes are free.
+          const float2 h0 = unpack_bf16x2(pk2.x), h1 = unpack_bf16x2(pk2.y), h2 = unpack_bf16x2(pk2.z),
+                       h3 = unpack_bf16x2(pk2.w);
+          uint4 lo;
+          lo.x = pack_bf16x2(o2[0] - h0.x, o2[1] - h0.y);
+          lo.y = pack_bf16x2(o2[2] - h1.x, o2[3] - h1.y);
+          lo.z = pack_bf16x2(o2[4] - h2.x, o2[5] - h2.y);
+          lo.w = pack_bf16x2(o2[6] - h3.x, o2[7] - h3.y);
+          *reinterpret_cast<uint4*>(p.y_lo + (size_t)(m0 + r) * p.N_total + ng0 + cbase + jj * 8) = lo;
+        }
       }
     }
     fence_proxy_async_smem();
@@ -687,7 +701,7 @@ extern "C" int irfd_conv_gemm_m_tiles(int n, int h, int w) {
 }
 
 static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const void* wk, int cout, int ksize, void* out,
-                          void* out2, int mode, const float* bias, const float* nw, const float* noise,
+                          void* out2, void* out_lo, int mode, const float* bias, const float* nw, const float* noise,
                           const float* sp1, const float* s1, float* stat_sum, float* stat_sq, const void* res, int relu,
                           int force_block_n, cudaStream_t stream) {
   IRFD_CHECK_ARG(x && wk && out, "conv_gemm: null pointer");
@@ -735,6 +749,7 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
   a.bias = bias; a.nw = nw; a.noise = noise; a.sp1 = sp1; a.s1 = s1;
   a.stat_sum = stat_sum; a.stat_sq = stat_sq;
   a.res = reinterpret_cast<const __nv_bfloat16*>(res);
+  a.y_lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
   a.relu = relu;
   if (mode == EPI_AFFINE) IRFD_CHECK_ARG(bias && nw, "conv_gemm: AFFINE mode needs scale and shift");
   if (mode == EPI_STYLE) {
@@ -823,13 +838,22 @@ extern "C" int irfd_conv_gemm(const void* x, int n, int h, int w, int cin, const
                               const float* sp1, const float* s1, float* stat_sum, float* stat_sq, int force_block_n,
                               cudaStream_t stream) {
   IRFD_CHECK_ARG(mode >= 0 && mode <= 2, "conv_gemm: bad mode %d", mode);
-  return conv_gemm_impl(x, n, h, w, cin, wk, cout, ksize, out, out2, mode, bias, nw, noise, sp1, s1, stat_sum, stat_sq,
-                        nullptr, 0, force_block_n, stream);
+  return conv_gemm_impl(x, n, h, w, cin, wk, cout, ksize, out, out2, nullptr, mode, bias, nw, noise, sp1, s1, stat_sum,
+                        stat_sq, nullptr, 0, force_block_n, stream);
+}
+
+extern "C" int irfd_conv_gemm_style_split(const void* x, int n, int h, int w, int cin, const void* wk, int cout,
+                                          int ksize, void* out_a, void* out_y, void* out_y_lo, const float* bias,
+                                          const float* nw, const float* noise, const float* sp1, const float* s1,
+                                          int force_block_n, cudaStream_t stream) {
+  IRFD_CHECK_ARG(out_y_lo != nullptr, "conv_gemm_style_split: out_y_lo is required");
+  return conv_gemm_impl(x, n, h, w, cin, wk, cout, ksize, out_a, out_y, out_y_lo, EPI_STYLE, bias, nw, noise, sp1, s1,
+                        nullptr, nullptr, nullptr, 0, force_block_n, stream);
 }
 
 extern "C" int irfd_conv_gemm_affine(const void* x, int n, int h, int w, int cin, const void* wk, int cout, int ksize,
                                      void* out, const float* scale, const float* shift, const void* res, int relu,
                                      int force_block_n, cudaStream_t stream) {
-  return conv_gemm_impl(x, n, h, w, cin, wk, cout, ksize, out, nullptr, EPI_AFFINE, shift, scale, nullptr, nullptr,
+  return conv_gemm_impl(x, n, h, w, cin, wk, cout, ksize, out, nullptr, nullptr, EPI_AFFINE, shift, scale, nullptr, nullptr,
                         nullptr, nullptr, nullptr, res, relu, force_block_n, stream);
 }

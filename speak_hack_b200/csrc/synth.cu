@@ -13,7 +13,8 @@ namespace irfd {
 __global__ void const_input_fwd_kernel(const float* __restrict__ cst, const float* __restrict__ bias,
                                        const float* __restrict__ nw, const float* __restrict__ noise,
                                        const float* __restrict__ sp1, const float* __restrict__ s1,
-                                       __nv_bfloat16* __restrict__ a0, __nv_bfloat16* __restrict__ y0, int B, int C) {
+                                       __nv_bfloat16* __restrict__ a0, __nv_bfloat16* __restrict__ y0,
+                                       __nv_bfloat16* __restrict__ y0_lo, int B, int C) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over [B][16][C]
   if (idx >= (size_t)B * 16 * C) return;
   const int c = idx % C;
@@ -21,7 +22,10 @@ __global__ void const_input_fwd_kernel(const float* __restrict__ cst, const floa
   const int b = idx / ((size_t)C * 16);
   const float a = cst[c * 16 + hw] + bias[c] + nw[c] * noise[b * 16 + hw];
   a0[idx] = __float2bfloat16(a);
-  y0[idx] = __float2bfloat16(a * sp1[(size_t)b * C + c] + s1[(size_t)b * C + c]);
+  const float y = a * sp1[(size_t)b * C + c] + s1[(size_t)b * C + c];
+  const __nv_bfloat16 yh = __float2bfloat16(y);
+  y0[idx] = yh;
+  if (y0_lo != nullptr) y0_lo[idx] = __float2bfloat16(y - __bfloat162float(yh));  // split-bf16 source of the upsample
 }
 
 // one thread per channel; loops over B*16 positions (tiny)
@@ -94,9 +98,11 @@ __device__ __forceinline__ Lerp lerp_src(int o, int in_size) {
 // block (4 x 16 B) — 2.25 loads per store instead of 4, a quarter of the CTAs.  Per output the arithmetic is exactly
 // ATen's:  ly.l0 * (lx.l0 * v00 + lx.l1 * v01) + ly.l1 * (lx.l0 * v10 + lx.l1 * v11).
 // grid = (B*H input rows, segments of W*C/8 vectors): row decode is per block, the column decode is 32-bit.
+// LO: the input is split bf16, value = in + in_lo (the small layers, see conv_gemm STYLE / irfd_conv_gemm_style_split).
+template <bool LO>
 __global__ void __launch_bounds__(256)
-upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W,
-                      int C) {
+upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ in_lo,
+                      __nv_bfloat16* __restrict__ out, int B, int H, int W, int C) {
   const unsigned vc = C >> 3, Wo = 2 * W;
   const unsigned i = blockIdx.y * blockDim.x + threadIdx.x;
   if (i >= (unsigned)W * vc) return;
@@ -105,11 +111,23 @@ upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __res
   const int hs[3] = {h > 0 ? h - 1 : 0, h, h < H - 1 ? h + 1 : h};
   const int ws[3] = {w > 0 ? w - 1 : 0, w, w < W - 1 ? w + 1 : w};
   const __nv_bfloat16* base = in + (size_t)b * H * W * C + v * 8;
-  uint4 q[3][3];
+  uint4 q[3][3], ql[3][3];
 #pragma unroll
   for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) q[r][c] = ldg16(base + ((size_t)hs[r] * W + ws[c]) * C);
+    for (int c = 0; c < 3; ++c) {
+      q[r][c] = ldg16(base + ((size_t)hs[r] * W + ws[c]) * C);
+      if constexpr (LO) ql[r][c] = ldg16(in_lo + (size_t)b * H * W * C + v * 8 + ((size_t)hs[r] * W + ws[c]) * C);
+    }
+  auto fetch = [&](int r, int c, float (&f)[8]) {  // r, c are compile-time after unrolling
+    unpack8(c == 0 ? q[r][0] : (c == 1 ? q[r][1] : q[r][2]), f);
+    if constexpr (LO) {
+      float l[8];
+      unpack8(c == 0 ? ql[r][0] : (c == 1 ? ql[r][1] : ql[r][2]), l);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) f[t] += l[t];
+    }
+  };
   // horizontal pass: hl[r][dx] = lx.l0 * row[lx.i0] + lx.l1 * row[lx.i1] for the two output columns 2w, 2w + 1
   float hl[3][2][8];
 #pragma unroll
@@ -119,8 +137,8 @@ upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __res
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       float f0[8], f1[8];
-      unpack8(c0 == 0 ? q[r][0] : (c0 == 1 ? q[r][1] : q[r][2]), f0);
-      unpack8(c1 == 0 ? q[r][0] : (c1 == 1 ? q[r][1] : q[r][2]), f1);
+      fetch(r, c0, f0);
+      fetch(r, c1, f1);
 #pragma unroll
       for (int t = 0; t < 8; ++t) hl[r][dx][t] = lx.l0 * f0[t] + lx.l1 * f1[t];
     }
@@ -415,13 +433,19 @@ using namespace irfd;
 #define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
 #define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
 
+extern "C" int irfd_const_input_split_fwd(const float* cst, const float* bias, const float* nw, const float* noise,
+                                          const float* sp1, const float* s1, void* a0, void* y0, void* y0_lo, int b,
+                                          int c, cudaStream_t stream) {
+  IRFD_CHECK_ARG(cst && bias && nw && noise && sp1 && s1 && a0 && y0, "const_input_fwd: null pointer");
+  const_input_fwd_kernel<<<GRID1D((size_t)b * 16 * c)>>>(cst, bias, nw, noise, sp1, s1, BF(a0), BF(y0), BF(y0_lo), b, c);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
 extern "C" int irfd_const_input_fwd(const float* cst, const float* bias, const float* nw, const float* noise,
                                     const float* sp1, const float* s1, void* a0, void* y0, int b, int c,
                                     cudaStream_t stream) {
-  IRFD_CHECK_ARG(cst && bias && nw && noise && sp1 && s1 && a0 && y0, "const_input_fwd: null pointer");
-  const_input_fwd_kernel<<<GRID1D((size_t)b * 16 * c)>>>(cst, bias, nw, noise, sp1, s1, BF(a0), BF(y0), b, c);
-  IRFD_CHECK_LAUNCH();
-  return IRFD_OK;
+  return irfd_const_input_split_fwd(cst, bias, nw, noise, sp1, s1, a0, y0, nullptr, b, c, stream);
 }
 
 extern "C" int irfd_const_input_bwd(const void* dy, const void* a0, const float* noise, const float* sp1, float* dsp1,
@@ -434,13 +458,21 @@ extern "C" int irfd_const_input_bwd(const void* dy, const void* a0, const float*
   return IRFD_OK;
 }
 
-extern "C" int irfd_upsample2x_fwd(const void* in, void* out, int b, int h, int w, int c, cudaStream_t stream) {
+extern "C" int irfd_upsample2x_split_fwd(const void* in, const void* in_lo, void* out, int b, int h, int w, int c,
+                                         cudaStream_t stream) {
   IRFD_CHECK_ARG(in && out && c % 8 == 0, "upsample2x_fwd: bad argument");
   IRFD_CHECK_ARG(b > 0 && h > 0 && w > 0 && (long long)w * c < (1ll << 24), "upsample2x_fwd: bad shape");
-  upsample2x_fwd_kernel<<<dim3((unsigned)(b * h), (unsigned)((w * (c / 8) + 255) / 256)), 256, 0, stream>>>(
-      CBF(in), BF(out), b, h, w, c);
+  const dim3 grid((unsigned)(b * h), (unsigned)((w * (c / 8) + 255) / 256));
+  if (in_lo != nullptr)
+    upsample2x_fwd_kernel<true><<<grid, 256, 0, stream>>>(CBF(in), CBF(in_lo), BF(out), b, h, w, c);
+  else
+    upsample2x_fwd_kernel<false><<<grid, 256, 0, stream>>>(CBF(in), nullptr, BF(out), b, h, w, c);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
+}
+
+extern "C" int irfd_upsample2x_fwd(const void* in, void* out, int b, int h, int w, int c, cudaStream_t stream) {
+  return irfd_upsample2x_split_fwd(in, nullptr, out, b, h, w, c, stream);
 }
 
 extern "C" int irfd_upsample2x_bwd(const void* dout, void* din, int b, int h, int w, int c, cudaStream_t stream) {

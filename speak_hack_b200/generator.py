@@ -106,6 +106,9 @@ class SynthesisBlock(nn.Module):
 # ----------------------------------------------------------------------------------------------------------------------
 # Synthesis network as one autograd node
 # ----------------------------------------------------------------------------------------------------------------------
+SPLIT_MAX_RES = 32  # block outputs up to this resolution are stored as split bf16 (see _SynthesisFn.forward)
+
+
 def _cpad(c: int) -> int:
     """The GEMM tiles are 64 channels wide; narrower layers (the 32-channel last block of a 512^2 network) run zero
     padded: padded output channels have zero weights, bias, noise weight and style, so they stay exactly zero."""
@@ -154,23 +157,29 @@ class _SynthesisFn(torch.autograd.Function):
         c0 = const_input.shape[1]
         noise0 = next(ni)
         st0, sp1_0, s1_0 = style(rows_t[0], sw0, sb0, c0, c0)
-        a0, y = ops.const_input_fwd(const_input, bias0, nw0, noise0, sp1_0, s1_0)
+        # The output of a block feeds a bilinear upsample and only then a conv: stored as plain bf16 it would be rounded
+        # twice on the way into that conv (once here, once after the interpolation) where the fp32 reference rounds
+        # never and an ideal bf16-operand kernel once.  Up to SPLIT_MAX_RES the block output is therefore kept as split
+        # bf16 (y + y_lo, ~16 mantissa bits; the tensors are small) and the upsample reads both halves.
+        a0, y, y_lo = ops.const_input_fwd(const_input, bias0, nw0, noise0, sp1_0, s1_0, split_y=True)
         saved["const"] = (a0, noise0, sp1_0, st0)
         for i, blk in enumerate(net.layers):
             w1, b1, w2, b2, nw1, nw2, s1w, s1b, s2w, s2b = (next(it) for _ in range(10))
             cout = w1.shape[0]
             cp = _cpad(cout)
-            u = ops.upsample2x_fwd(y)
+            u = ops.upsample2x_fwd(y, y_lo)
             n1 = next(ni)
             st1, sp1_1, s1_1 = style(rows_t[2 * i + 1], s1w, s1b, cout, cp)
             a1, y1 = ops.conv_gemm(u, _packed(blk.conv1.weight, w1, ops.PACK_FPROP, cp, u.shape[-1]), 3, ops.EPI_STYLE,
                                    bias=_pad_to(b1, 0, cp), nw=_pad_to(nw1, 0, cp), noise=n1, sp1=sp1_1, s1=s1_1)
             n2 = next(ni)
             st2, sp1_2, s1_2 = style(rows_t[2 * i + 2], s2w, s2b, cout, cp)
-            a2, y2 = ops.conv_gemm(y1, _packed(blk.conv2.weight, w2, ops.PACK_FPROP, cp, cp), 3, ops.EPI_STYLE,
-                                   bias=_pad_to(b2, 0, cp), nw=_pad_to(nw2, 0, cp), noise=n2, sp1=sp1_2, s1=s1_2)
+            split = y1.shape[1] <= SPLIT_MAX_RES and i + 1 < len(net.layers)
+            r2 = ops.conv_gemm(y1, _packed(blk.conv2.weight, w2, ops.PACK_FPROP, cp, cp), 3, ops.EPI_STYLE,
+                               bias=_pad_to(b2, 0, cp), nw=_pad_to(nw2, 0, cp), noise=n2, sp1=sp1_2, s1=s1_2,
+                               split_y=split)
+            a2, y, y_lo = r2 if split else (r2[0], r2[1], None)
             saved["blocks"].append((u, a1, y1, a2, n1, n2, sp1_1, sp1_2, st1, st2))
-            y = y2
         rgb_w, rgb_b = next(it), next(it)
         img = ops.to_rgb_fwd(y, _pad_to(rgb_w, 1, y.shape[-1]).contiguous(), rgb_b)
         ctx.net = net
@@ -319,26 +328,35 @@ class StyleGenerator(nn.Module):
         self.mapping = nn.Sequential(*layers)
         self.synthesis = SynthesisNetwork()
         self.bn = None
+        # the style-mixing latent: same call as the reference (styleganv1.py:550), replaceable like synthesis.noise_fn
+        # so a test can feed the oracle and the product the same draws
+        self.latent_fn = torch.randn_like
+
+    def _trunc(self):
+        use = bool(self.truncation_psi and self.truncation_cutoff)
+        return (float(self.truncation_psi), int(self.truncation_cutoff)) if use else (1.0, 0)
 
     def forward(self, features):
         if features.dim() > 2:  # test_irfd.py:84-91 concatenates [N,2048,1,1] codes; accept it as a harmless superset
             features = features.flatten(1)
+        if not features.is_cuda:
+            raise ops._lib.IrfdError("StyleGenerator: CUDA tensors only (no CPU fallback on the IRFD hot path)")
         features = features.to(torch.float32)
+        L = self.synthesis.num_layers
         w = self.mapping(features)
-        # row assembly: the reference's own tensor ops on a [B, L, 512] fp32 tensor (tiny; autograd plumbing)
-        w = w.unsqueeze(1).repeat(1, self.synthesis.num_layers, 1)
-        if self.truncation_psi and self.truncation_cutoff:
-            coefs = torch.ones_like(w)
-            coefs[:, : self.truncation_cutoff] *= self.truncation_psi
-            w = coefs * w
+        # styleganv1.py:546-553: the CPU generator decides whether to mix (rand) and where (randint); the mixed latent
+        # comes from the device generator (randn_like) BETWEEN those two draws.  Same order here.
+        cut, w2 = L, w
         if self.training and self.style_mixing_prob > 0:
             if torch.rand(1) < self.style_mixing_prob:
                 with torch.no_grad():
-                    w2 = self.mapping(torch.randn_like(features))
-                    w2 = w2.unsqueeze(1).repeat(1, self.synthesis.num_layers, 1)
-                    mix_layer = torch.randint(1, w.size(1), (1,)).item()
-                    w[:, mix_layer:] = w2[:, mix_layer:]
-        return self.synthesis(w)
+                    w2 = self.mapping(self.latent_fn(features))
+                cut = int(torch.randint(1, L, (1,)).item())
+        psi, cutoff = self._trunc()
+        ctrl = torch.tensor([cut], dtype=torch.int32, device=features.device)
+        rows_t = _StyleRowsFn.apply(w, w2.detach(), ctrl, 0, psi, cutoff, L)   # repeat + truncation + mixing: one kernel
+        noises = self.synthesis.draw_noises(features.size(0), features.device)
+        return _SynthesisFn.apply(rows_t, self.synthesis, noises, *self.synthesis._flat_params())
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -364,11 +382,12 @@ def _generator_forward_static(self: StyleGenerator, features, ctrl, ctrl_idx):
     features = features.to(torch.float32)
     L = self.synthesis.num_layers
     w = self.mapping(features)
-    with torch.no_grad():
-        w2 = self.mapping(torch.randn_like(features))
-    use_trunc = bool(self.truncation_psi and self.truncation_cutoff)
-    psi = float(self.truncation_psi) if use_trunc else 1.0
-    cutoff = int(self.truncation_cutoff) if use_trunc else 0
+    if self.training and self.style_mixing_prob > 0:
+        with torch.no_grad():
+            w2 = self.mapping(self.latent_fn(features))
+    else:
+        w2 = w.detach()  # eval / mixing disabled: the cut is always L, w2 is never read
+    psi, cutoff = self._trunc()
     rows_t = _StyleRowsFn.apply(w, w2, ctrl, ctrl_idx, psi, cutoff, L)
     noises = self.synthesis.draw_noises(features.size(0), features.device)
     return _SynthesisFn.apply(rows_t, self.synthesis, noises, *self.synthesis._flat_params())

@@ -94,6 +94,7 @@ class _timed:
 
 
 _workspace = {}
+_workspace_retired = []  # outgrown buffers stay alive: a captured CUDA graph may still hold their addresses
 
 
 def workspace(nbytes: int, device) -> torch.Tensor:
@@ -102,6 +103,8 @@ def workspace(nbytes: int, device) -> torch.Tensor:
     key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0)
     buf = _workspace.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _workspace_retired.append(buf)
         buf = torch.empty(max(int(nbytes), 1 << 22), dtype=torch.uint8, device=device)
         _workspace[key] = buf
     return buf
@@ -110,9 +113,10 @@ def workspace(nbytes: int, device) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------------------------------
 # tensor-core GEMMs
 # ----------------------------------------------------------------------------------------------------------------------
-def conv_gemm(x, wk, ksize, mode=EPI_PLAIN, bias=None, nw=None, noise=None, sp1=None, s1=None, force_block_n=0):
+def conv_gemm(x, wk, ksize, mode=EPI_PLAIN, bias=None, nw=None, noise=None, sp1=None, s1=None, force_block_n=0,
+              split_y=False):
     """Stride-1 same-padding conv as implicit GEMM.  x [N,H,W,Cin] bf16, wk [Cout, k*k*Cin] bf16.
-    Returns out (mode 0), (out, stat_sum, stat_sq) (mode 1), (a, y) (mode 2)."""
+    Returns out (mode 0), (out, stat_sum, stat_sq) (mode 1), (a, y) (mode 2), (a, y, y_lo) (mode 2, split_y)."""
     lib = _lib.load()
     _chk(x, BF16, "x")
     _chk(wk, BF16, "wk")
@@ -132,14 +136,20 @@ def conv_gemm(x, wk, ksize, mode=EPI_PLAIN, bias=None, nw=None, noise=None, sp1=
             _chk(t, F32, nm)
     m = n * h * w
     nbytes = 2.0 * m * cin + 2.0 * m * cout * (2 if mode == EPI_STYLE else 1) + 2.0 * cin * cout * ksize * ksize
+    out_lo = torch.empty_like(out) if (mode == EPI_STYLE and split_y) else None
     with _timed("conv_gemm_kernel (tcgen05 fprop/dgrad)", 2.0 * m * cout * cin * ksize * ksize, nbytes):
-        _call("irfd_conv_gemm", x.data_ptr(), n, h, w, cin, wk.data_ptr(), cout, ksize, out.data_ptr(), _ptr(out2),
-              mode, _ptr(bias), _ptr(nw), _ptr(noise), _ptr(sp1), _ptr(s1), _ptr(ssum), _ptr(ssq), force_block_n,
-              _stream())
+        if out_lo is not None:
+            _call("irfd_conv_gemm_style_split", x.data_ptr(), n, h, w, cin, wk.data_ptr(), cout, ksize, out.data_ptr(),
+                  out2.data_ptr(), out_lo.data_ptr(), _ptr(bias), _ptr(nw), _ptr(noise), _ptr(sp1), _ptr(s1),
+                  force_block_n, _stream())
+        else:
+            _call("irfd_conv_gemm", x.data_ptr(), n, h, w, cin, wk.data_ptr(), cout, ksize, out.data_ptr(), _ptr(out2),
+                  mode, _ptr(bias), _ptr(nw), _ptr(noise), _ptr(sp1), _ptr(s1), _ptr(ssum), _ptr(ssq), force_block_n,
+                  _stream())
     if mode == EPI_STATS:
         return out, ssum, ssq
     if mode == EPI_STYLE:
-        return out, out2
+        return (out, out2, out_lo) if split_y else (out, out2)
     return out
 
 
@@ -156,8 +166,11 @@ def conv_gemm_affine(x, wk, ksize, scale, shift, res=None, relu=True, force_bloc
         _chk(res, BF16, "res")
         if res.numel() != out.numel():
             raise _lib.IrfdError("conv_gemm_affine: residual shape mismatch")
-    _call("irfd_conv_gemm_affine", x.data_ptr(), n, h, w, cin, wk.data_ptr(), cout, ksize, out.data_ptr(),
-          scale.data_ptr(), shift.data_ptr(), _ptr(res), int(relu), force_block_n, _stream())
+    m = n * h * w
+    nbytes = 2.0 * m * cin + 2.0 * m * cout * (2 if res is not None else 1) + 2.0 * cin * cout * ksize * ksize
+    with _timed("conv_gemm_kernel (tcgen05 fprop/dgrad)", 2.0 * m * cout * cin * ksize * ksize, nbytes):
+        _call("irfd_conv_gemm_affine", x.data_ptr(), n, h, w, cin, wk.data_ptr(), cout, ksize, out.data_ptr(),
+              scale.data_ptr(), shift.data_ptr(), _ptr(res), int(relu), force_block_n, _stream())
     return out
 
 
@@ -387,13 +400,15 @@ def avgpool_bwd(dfeat: torch.Tensor, h: int, w: int) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------------------------------
 # synthesis-network pieces
 # ----------------------------------------------------------------------------------------------------------------------
-def const_input_fwd(cst, bias, nw, noise, sp1, s1):
+def const_input_fwd(cst, bias, nw, noise, sp1, s1, split_y=False):
+    """Returns (a0, y0) or, with split_y, (a0, y0, y0_lo): y0 + y0_lo is the split-bf16 source of the first upsample."""
     b, c = sp1.shape
     a0 = torch.empty((b, 4, 4, c), dtype=BF16, device=sp1.device)
     y0 = torch.empty_like(a0)
-    _call("irfd_const_input_fwd", cst.data_ptr(), bias.data_ptr(), nw.data_ptr(), noise.data_ptr(), sp1.data_ptr(),
-          s1.data_ptr(), a0.data_ptr(), y0.data_ptr(), b, c, _stream())
-    return a0, y0
+    y0_lo = torch.empty_like(a0) if split_y else None
+    _call("irfd_const_input_split_fwd", cst.data_ptr(), bias.data_ptr(), nw.data_ptr(), noise.data_ptr(),
+          sp1.data_ptr(), s1.data_ptr(), a0.data_ptr(), y0.data_ptr(), _ptr(y0_lo), b, c, _stream())
+    return (a0, y0, y0_lo) if split_y else (a0, y0)
 
 
 def const_input_bwd(dy, a0, noise, sp1):
@@ -409,11 +424,16 @@ def const_input_bwd(dy, a0, noise, sp1):
     return dsp1, ds1, dconst, dbias, dnw
 
 
-def upsample2x_fwd(x: torch.Tensor) -> torch.Tensor:
+def upsample2x_fwd(x: torch.Tensor, x_lo: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Bilinear x2 of x (+ x_lo when the source is split bf16)."""
     _chk(x, BF16, "x")
+    if x_lo is not None:
+        _chk(x_lo, BF16, "x_lo")
+        if x_lo.shape != x.shape:
+            raise _lib.IrfdError("upsample2x_fwd: x_lo shape mismatch")
     b, h, w, c = x.shape
     out = torch.empty((b, 2 * h, 2 * w, c), dtype=BF16, device=x.device)
-    _call("irfd_upsample2x_fwd", x.data_ptr(), out.data_ptr(), b, h, w, c, _stream())
+    _call("irfd_upsample2x_split_fwd", x.data_ptr(), _ptr(x_lo), out.data_ptr(), b, h, w, c, _stream())
     return out
 
 

@@ -65,7 +65,12 @@ class IRFDTrainer:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_launches = 0
         self.ctrl = torch.zeros(3, dtype=torch.int32, device=self.device)
-        self._ctrl_host = torch.zeros(3, dtype=torch.int32).pin_memory() if self.device.type == "cuda" else None
+        # ring of pinned control buffers: an async H2D copy reads its pinned source when the STREAM reaches it, and the
+        # CPU runs several graph replays ahead, so a slot is rewritten only after the copy that read it has completed
+        self._ctrl_ring = ([(torch.zeros(3, dtype=torch.int32).pin_memory(), torch.cuda.Event()) for _ in range(8)]
+                           if self.device.type == "cuda" else [])
+        self._ctrl_slot = 0
+        self._graph_key = None
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._static = None
 
@@ -128,14 +133,23 @@ class IRFDTrainer:
         mixing, randint(1, L) (styleganv1.py:548, 552)."""
         gd = self.model.Gd
         L = gd.synthesis.num_layers
-        self._ctrl_host[0] = int(torch.randint(0, 3, (1,)).item())
+        vals = [int(torch.randint(0, 3, (1,)).item())]
         for g in range(2):
             cut = L
             if gd.training and gd.style_mixing_prob > 0:
                 if torch.rand(1) < gd.style_mixing_prob:
                     cut = int(torch.randint(1, L, (1,)).item())
-            self._ctrl_host[1 + g] = cut
-        self.ctrl.copy_(self._ctrl_host, non_blocking=True)
+            vals.append(cut)
+        self._upload_ctrl(vals)
+
+    def _upload_ctrl(self, vals):
+        host, ev = self._ctrl_ring[self._ctrl_slot]
+        self._ctrl_slot = (self._ctrl_slot + 1) % len(self._ctrl_ring)
+        ev.synchronize()  # no-op unless the CPU is a whole ring ahead of the device
+        host[0], host[1], host[2] = vals
+        self.ctrl.copy_(host, non_blocking=True)
+        ev.record()
+        self.last_ctrl = tuple(vals)
 
     def _static_body(self):
         xs, xt, loss_out, lid_out, lrec_out = self._static
@@ -187,9 +201,22 @@ class IRFDTrainer:
         torch.set_rng_state(cpu_rng)
         torch.cuda.set_rng_state(cuda_rng, dev)
 
+    def _graph_state(self, x_s):
+        """What a captured graph bakes in besides the buffers it owns: the train/eval mode of every sub-network, the
+        input shape, and the encoders' bf16 weight repacks (constants in the graph; keyed by the weights' version
+        counters so load_state_dict / an external optimizer on the encoders forces a recapture)."""
+        m = self.model
+        enc_ver = tuple(e[0].weight._version for e in self.encoders)
+        return (m.training, m.Gd.training, tuple(e.training for e in self.encoders), tuple(x_s.shape), enc_ver,
+                float(m.Gd.style_mixing_prob))
+
     def train_step_graph(self, x_s: torch.Tensor, x_t: torch.Tensor):
+        key = self._graph_state(x_s)
+        if self.graph is not None and key != self._graph_key:
+            self.graph = None
         if self.graph is None:
             self._capture(x_s, x_t)
+            self._graph_key = key
         self._static[0].copy_(x_s, non_blocking=True)
         self._static[1].copy_(x_t, non_blocking=True)
         self._draw_ctrl()
@@ -261,6 +288,7 @@ class IRFDTrainer:
         """Resume from a checkpoint written by save_checkpoint OR by the reference's train.py; returns the dictionary
         (the caller restores optimizer_D / epoch / config, which are outside the hot path)."""
         ckpt = torch.load(path, map_location=map_location or self.device, weights_only=False)
+        self.graph = None  # the graph holds the encoders' bf16 repacks as constants: always recapture after a load
         self.model.load_state_dict(ckpt["model_state_dict"])  # copies INTO the flat parameter views
         ops.invalidate_packed(list(self.model.parameters()))
         if ckpt.get("optimizer_G"):

@@ -386,6 +386,10 @@ def test_golden_train_step_bn_buffers_and_losses(cuda_device):
     net = P.IRFD()
     O.perturb_noise_weights(net.Gd)
     net = net.to(cuda_device).train()
+    # the reference ran on the CPU, so every random draw of its G step came from the CPU generator, in this order:
+    # swap randint; per Gd call rand(1), randn_like(features), randint, 13 noise planes.  Feed the product the same.
+    net.Gd.latent_fn = lambda f: torch.randn(f.shape, dtype=f.dtype).to(f.device)
+    net.Gd.synthesis.noise_fn = lambda b, h, w, device: torch.randn(b, 1, h, w).to(device)
     x_s, x_t = O.synthetic_pair(2)
     xs = x_s.to(cuda_device).requires_grad_(True)
     xt = x_t.to(cuda_device).requires_grad_(True)
@@ -400,13 +404,65 @@ def test_golden_train_step_bn_buffers_and_losses(cuda_device):
     e_m = O.rel_l2(sd["Ei.1.running_mean"], gold["bn_buffers"]["Ei.1.running_mean"])
     e_v = O.rel_l2(sd["Ei.1.running_var"], gold["bn_buffers"]["Ei.1.running_var"])
     e_f = max(O.rel_l2(a, b) for a, b in zip(out[2:8], gold["feat"]))
+    e_lid = abs(l_id.item() - gold["l_identity"]) / abs(gold["l_identity"])
+    e_lrec = abs(l_rec.item() - gold["l_recon"]) / abs(gold["l_recon"])
     print(f"[parity] golden train step: stem BN running mean {e_m:.3e} var {e_v:.3e}; features {e_f:.3e}; "
-          f"l_identity {l_id.item():.4e} (ref {gold['l_identity']:.4e})")
-    assert e_m < 1e-2 and e_v < 1e-2
-    assert e_f < 0.25  # train-mode conditioning
-    assert abs(l_id.item() - gold["l_identity"]) <= 0.3 * abs(gold["l_identity"])
-    got = {n for n, p in net.named_parameters() if p.grad is not None}
+          f"l_identity rel {e_lid:.3e} (ref {gold['l_identity']:.4e}); l_recon rel {e_lrec:.3e} (ref {gold['l_recon']:.4e})")
+    assert e_m < 6e-3 and e_v < 1e-4          # measured 2.6e-3 / 7e-6
+    assert e_f < GOLD_TRAIN_BOUNDS["feat"]    # train-mode conditioning at random init
+    assert e_lid < GOLD_TRAIN_BOUNDS["l_id"] and e_lrec < GOLD_TRAIN_BOUNDS["l_rec"]
+    named = dict(net.named_parameters())
+    got = {n for n, p in named.items() if p.grad is not None}
     assert set(gold["grad_norms"]) == got, (set(gold["grad_norms"]) ^ got)  # same 560 tensors receive gradients
+    # gradient VALUES against the unmodified reference: norms of every tensor, element slices of the pinned ones.
+    # The features entering Gd already differ by e_f (bf16 through the random-init train-mode encoders), so these
+    # bounds reflect that operating point; tests/test_gpu_train_parity.py is the tight, conditioned comparison.
+    worst = {"Gd": ("", 0.0), "enc": ("", 0.0)}
+    ratios = {"Gd": [], "enc": []}
+    for n, gn in gold["grad_norms"].items():
+        grp = "Gd" if n.startswith("Gd.") else "enc"
+        ratios[grp].append(abs(named[n].grad.double().norm().item() / max(gn, 1e-300) - 1.0))
+    for n, gs in gold["grad_slices"].items():
+        sl = GRAD_SLICES[n]
+        mine = named[n].grad if sl is None else named[n].grad[sl]
+        e = O.rel_l2(mine, gs)
+        grp = "Gd" if n.startswith("Gd.") else "enc"
+        if e > worst[grp][1]:
+            worst[grp] = (n, e)
+        print(f"[parity]   golden grad slice {n:50s} rel-L2 {e:.3e}")
+    for grp in ("Gd", "enc"):
+        r = sorted(ratios[grp])
+        print(f"[parity] golden grad norms {grp}: |ratio-1| median {r[len(r) // 2]:.3e} worst {r[-1]:.3e}; "
+              f"worst slice {worst[grp][1]:.3e} ({worst[grp][0]})")
+        assert r[len(r) // 2] < GOLD_TRAIN_BOUNDS[grp + "_norm_median"]
+        assert worst[grp][1] < GOLD_TRAIN_BOUNDS[grp + "_slice_worst"]
+
+
+# provisional until measured on B200 (then <= 2x measured)
+GOLD_TRAIN_BOUNDS = {"feat": 0.2, "l_id": 0.3, "l_rec": 0.5, "Gd_norm_median": 1.0, "Gd_slice_worst": 2.0,
+                     "enc_norm_median": 1.0, "enc_slice_worst": 2.0}
+
+# the element slices oracle/make_golden.py stored (same table)
+GRAD_SLICES = {
+    "Gd.synthesis.to_rgb.weight": None,
+    "Gd.synthesis.to_rgb.bias": None,
+    "Gd.synthesis.layers.5.conv2.weight": (slice(0, 4), slice(0, 8)),
+    "Gd.synthesis.layers.5.noise2.weight": None,
+    "Gd.synthesis.layers.2.conv1.bias": None,
+    "Gd.synthesis.layers.0.style_mod1.linear.weight": (slice(0, 4), slice(0, 32)),
+    "Gd.synthesis.style_mod.linear.bias": None,
+    "Gd.synthesis.const_input": None,
+    "Gd.synthesis.bias": None,
+    "Gd.mapping.0.weight": (slice(0, 4), slice(0, 64)),
+    "Gd.mapping.7.bias": None,
+    "Ei.0.weight": (slice(0, 8),),
+    "Ei.1.weight": None,
+    "Ei.4.0.conv1.weight": (slice(0, 8), slice(0, 16)),
+    "Ei.4.0.downsample.1.bias": None,
+    "Ee.5.0.conv2.weight": (slice(0, 4), slice(0, 8)),
+    "Ep.7.2.conv3.weight": (slice(0, 4), slice(0, 32)),
+    "Ep.7.2.bn3.weight": None,
+}
 
 
 def test_synthesis_512_and_encoder_512(cuda_device):

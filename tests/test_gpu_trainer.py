@@ -34,7 +34,7 @@ def test_routing_kernels_bit_exact(cuda_device):
         coef = torch.ones(14, 1, 1, device=dev)
         coef[:8] *= 0.7
         ref = coef * ref
-        ref[cut:] = w2.unsqueeze(0).repeat(14, 1, 1)[cut:] * coef[cut:]
+        ref[cut:] = w2.unsqueeze(0).repeat(14, 1, 1)[cut:]  # styleganv1.py:553: w2's rows are NOT truncated
         assert torch.allclose(rows, ref, rtol=1e-7, atol=0)
         d = torch.randn(14, 4, 512, generator=g).to(dev)
         dw = ops.style_rows_bwd(d, 0.7, 8)
