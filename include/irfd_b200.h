@@ -66,6 +66,19 @@ int irfd_conv_gemm_style_split(const void* x, int n, int h, int w, int cin, cons
                                const float* noise, const float* sp1, const float* s1, int force_block_n,
                                irfd_stream_t stream);
 
+/* Grouped launches: the three ResNet-50 encoders of IRFD (model.py:33-35, 84-90) run the same layer shapes on the same
+ * images with different weights, so one launch per layer serves all three.  wk stacks `wgroups` weight sets along its
+ * rows ([wgroups*cout][k*k*cin]); the n images are split evenly, group-major ([wgroups][n/wgroups] images); each
+ * group must cover a whole number of 128-pixel tiles.  a_shared != 0 (ksize 1 only): x holds one group's rows and is
+ * read by every group (the stem's im2col matrix).  mode 0 (plain) or 1 (stats; partials stay [m_tiles][cout]).
+ * The affine variant takes scale/shift as [wgroups][cout]. */
+int irfd_conv_gemm_grouped(const void* x, int n, int h, int w, int cin, const void* wk, int cout, int ksize, void* out,
+                           int mode, float* stat_sum, float* stat_sq, int wgroups, int a_shared, int force_block_n,
+                           irfd_stream_t stream);
+int irfd_conv_gemm_affine_grouped(const void* x, int n, int h, int w, int cin, const void* wk, int cout, int ksize,
+                                  void* out, const float* scale, const float* shift, const void* res, int relu,
+                                  int wgroups, int a_shared, int force_block_n, irfd_stream_t stream);
+
 /* Affine variant (mode 3): y = act(acc*scale[c] + shift[c] [+ res[pixel,c]]) -> bf16; relu: 0 none, 1 ReLU,
  * 2 leaky ReLU(0.2) (the discriminator's conv + bias + leaky_relu, styleganv1.py:662-669,689-694, with scale = 1).  Folds an eval-mode
  * BatchNorm2d (scale/shift from irfd_bn_eval_affine), the ReLU and the Bottleneck residual add into the conv
@@ -123,6 +136,25 @@ int irfd_bn_backward(const void* g1, const void* g2, const void* act, const void
                      long long workspace_bytes, irfd_stream_t stream);
 /* mask: act != NULL -> (act > 0);  act == NULL and beta != NULL -> recomputed as gamma*xhat + beta > 0 (a BN+ReLU
  * without residual, saves reading the activation);  both NULL -> g already masked. */
+
+/* Parameter SETS: the same BatchNorm layer of the three IRFD encoders (model.py:33-35: Ei, Ee, Ep are three
+ * independent ResNet-50s fed the same images) normalised by ONE launch sequence.  The statistic groups are stacked
+ * set-major along the row axis ([nsets][groups per set] x rows-per-group); batch statistics (mean/rstd, and the
+ * workspace c1/c2) are per group, gamma/beta/running buffers/dgamma/dbeta per set, passed as HOST arrays of `nsets`
+ * device pointers (read at call time).  irfd_bn_finalize_sets takes groups PER SET, the other two the TOTAL group count. */
+int irfd_bn_finalize_sets(const float* psum, const float* psq, int tiles, int c, long long count, float eps,
+                          float momentum, float* mean, float* rstd, float* const* running_mean,
+                          float* const* running_var, int running_updates, int groups, int nsets,
+                          irfd_stream_t stream);
+int irfd_bn_apply_sets(const void* z, const float* mean, const float* rstd, const float* const* gamma,
+                       const float* const* beta, const void* res, const float* mean2, const float* rstd2,
+                       const float* const* gamma2, const float* const* beta2, void* out, long long rows, int c,
+                       int relu, int groups, int nsets, irfd_stream_t stream);
+int irfd_bn_backward_sets(const void* g1, const void* g2, const void* act, const void* z, const float* mean,
+                          const float* rstd, const float* const* gamma, const float* const* beta, void* dz,
+                          void* g_out, float* const* dgamma, float* const* dbeta, float grad_beta, int batch_stats,
+                          long long rows, int c, int groups, int nsets, void* workspace, long long workspace_bytes,
+                          irfd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Layout / gather kernels for the strided ResNet convs and pooling (torchvision resnet.py:197-205, 133-137, 241).

@@ -13,6 +13,17 @@ namespace irfd {
 // flight per thread; accumulation in double, fixed summation order (bit-deterministic).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kMaxGroups = 4;
+// Parameter SETS: several BatchNorm layers of identical shape normalised by one launch sequence (the same layer of the
+// three IRFD encoders, model.py:33-35).  Statistic group y (blockIdx.y) belongs to set y / groups_per_set; per-channel
+// parameters, running buffers and parameter gradients are per set (pointer arrays passed by value), batch statistics
+// per group.
+constexpr int kMaxSets = 4;
+struct FSet {
+  const float* p[kMaxSets];
+};
+struct FSetM {
+  float* p[kMaxSets];
+};
 constexpr int kFinCh = 8;       // channels per block
 constexpr int kFinLanes = 128;  // partial-row lanes per block (1024 threads)
 constexpr int kFinBatch = 8;    // loads in flight per thread per stream
@@ -66,8 +77,8 @@ __device__ __forceinline__ void fin_block_sums(double& a, double& b, double (*sa
 
 __global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int tiles, int C, double count,
-                   float eps, float momentum, float* __restrict__ mean, float* __restrict__ rstd, float* running_mean,
-                   float* running_var, int running_updates, int groups) {
+                   float eps, float momentum, float* __restrict__ mean, float* __restrict__ rstd, FSetM running_mean_s,
+                   FSetM running_var_s, int running_updates, int groups) {
   // statistic groups (e.g. the source and the target half of a paired encoder pass) are processed one after the
   // other so the running buffers can be updated in call order by the same thread.
   __shared__ double s_sum[32][kFinCh];
@@ -75,6 +86,13 @@ bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq
   const int cl = threadIdx.x & (kFinCh - 1);
   const int lane = threadIdx.x / kFinCh;
   const int c = blockIdx.x * kFinCh + cl;  // C % 8 == 0 on this path
+  // parameter set = blockIdx.y: its `groups` statistic groups are consecutive
+  psum += (size_t)blockIdx.y * groups * tiles * C;
+  psq += (size_t)blockIdx.y * groups * tiles * C;
+  mean += (size_t)blockIdx.y * groups * C;
+  rstd += (size_t)blockIdx.y * groups * C;
+  float* running_mean = running_mean_s.p[blockIdx.y];
+  float* running_var = running_var_s.p[blockIdx.y];
   double gm[kMaxGroups], gv[kMaxGroups];
 #pragma unroll
   for (int g = 0; g < kMaxGroups; ++g) {
@@ -156,14 +174,14 @@ __global__ void bn_eval_rstd_kernel(const float* __restrict__ running_var, float
 struct BnAffine {
   const float* mean;
   const float* rstd;
-  const float* gamma;
-  const float* beta;
+  FSet gamma;
+  FSet beta;
 };
 
 template <int RES_MODE>  // 0 none, 1 identity tensor, 2 second BN branch
 __global__ void __launch_bounds__(kRvThreads)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ z, BnAffine p1, const __nv_bfloat16* __restrict__ res, BnAffine p2,
-                __nv_bfloat16* __restrict__ out, long long rows, int C, int rows_per_blk, int relu) {
+                __nv_bfloat16* __restrict__ out, long long rows, int C, int rows_per_blk, int relu, int gps) {
   constexpr int RB = 8;  // rows per thread in flight: 8 (z only) or 16 (z + residual) 16-byte loads
   RowVec rv(C);
   if (!rv.active) return;
@@ -184,8 +202,9 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z, BnAffine p1, const __nv_bfl
     float m[8], r[8], g[8], b[8];
     loadf8(p1.mean + rv.cv * 8, m);
     loadf8(p1.rstd + rv.cv * 8, r);
-    loadf8(p1.gamma + rv.cv * 8, g);
-    loadf8(p1.beta + rv.cv * 8, b);
+    const int set = blockIdx.y / gps;
+    loadf8(p1.gamma.p[set] + rv.cv * 8, g);
+    loadf8(p1.beta.p[set] + rv.cv * 8, b);
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       sc[t] = g[t] * r[t];
@@ -194,8 +213,8 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z, BnAffine p1, const __nv_bfl
     if (RES_MODE == 2) {
       loadf8(p2.mean + rv.cv * 8, m);
       loadf8(p2.rstd + rv.cv * 8, r);
-      loadf8(p2.gamma + rv.cv * 8, g);
-      loadf8(p2.beta + rv.cv * 8, b);
+      loadf8(p2.gamma.p[set] + rv.cv * 8, g);
+      loadf8(p2.beta.p[set] + rv.cv * 8, b);
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         sc2[t] = g[t] * r[t];
@@ -276,10 +295,11 @@ template <bool HAS_G2, int MASK>
 __global__ void __launch_bounds__(kRvThreads, 2)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
                      const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ z,
-                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, float* __restrict__ partial, long long rows, int C,
-                     int rows_per_blk) {
+                     const float* __restrict__ mean, const float* __restrict__ rstd, FSet gamma_s, FSet beta_s,
+                     float* __restrict__ partial, long long rows, int C, int rows_per_blk, int gps) {
   constexpr int RB = kRowBatch;  // measured: 8 rows for the two-tensor instances is slower (register pressure)
+  const float* __restrict__ gamma = gamma_s.p[blockIdx.y / gps];
+  const float* __restrict__ beta = beta_s.p[blockIdx.y / gps];
   extern __shared__ float red_smem[];
   RowVec rv(C);
   {
@@ -339,14 +359,19 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
 }
 
 __global__ void __launch_bounds__(1024)
-bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, double count, float* __restrict__ dgamma,
-                       float* __restrict__ dbeta, float beta_acc, float* __restrict__ c1, float* __restrict__ c2,
-                       int batch_stats, int groups) {
+bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, double count, FSetM dgamma_s, FSetM dbeta_s,
+                       float beta_acc, float* __restrict__ c1, float* __restrict__ c2, int batch_stats, int groups) {
   __shared__ double s0s[32][kFinCh];
   __shared__ double s1s[32][kFinCh];
   const int cl = threadIdx.x & (kFinCh - 1);
   const int lane = threadIdx.x / kFinCh;
   const int c = blockIdx.x * kFinCh + cl;
+  // parameter set = blockIdx.y (its `groups` statistic groups are consecutive)
+  partial += (size_t)blockIdx.y * groups * nblk * 2 * C;
+  c1 += (size_t)blockIdx.y * groups * C;
+  c2 += (size_t)blockIdx.y * groups * C;
+  float* __restrict__ dgamma = dgamma_s.p[blockIdx.y];
+  float* __restrict__ dbeta = dbeta_s.p[blockIdx.y];
   double tot0 = 0.0, tot1 = 0.0;
   for (int g = 0; g < groups; ++g) {
     const float* pg = partial + (size_t)g * nblk * 2 * C + c;
@@ -371,13 +396,14 @@ template <bool HAS_G2, int MASK, bool G_OUT>
 __global__ void __launch_bounds__(kRvThreads, 2)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
                     const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ z,
-                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, const float* __restrict__ c1, const float* __restrict__ c2,
-                    __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ g_out, long long rows, int C,
-                    int rows_per_blk) {
+                    const float* __restrict__ mean, const float* __restrict__ rstd, FSet gamma_s, FSet beta_s,
+                    const float* __restrict__ c1, const float* __restrict__ c2, __nv_bfloat16* __restrict__ dz,
+                    __nv_bfloat16* __restrict__ g_out, long long rows, int C, int rows_per_blk, int gps) {
   constexpr int RB = kRowBatch;
   RowVec rv(C);
   if (!rv.active) return;
+  const float* __restrict__ gamma = gamma_s.p[blockIdx.y / gps];
+  const float* __restrict__ beta = beta_s.p[blockIdx.y / gps];
   {
     const size_t goff = (size_t)blockIdx.y * rows * C;
     g1 += goff;
@@ -439,47 +465,78 @@ struct BnBwdLaunch {
   size_t smem;
   cudaStream_t stream;
   const __nv_bfloat16 *g1, *g2, *act, *z;
-  const float *mean, *rstd, *gamma, *beta;
+  const float *mean, *rstd;
+  FSet gamma, beta;
   float *partial, *c1, *c2;
   __nv_bfloat16 *dz, *g_out;
-  float *dgamma, *dbeta;
+  FSetM dgamma, dbeta;
   float grad_beta;
   int batch_stats;
   long long grows;
-  int c, rpb, nblk, groups;
+  int c, rpb, nblk, groups;  // groups = TOTAL statistic groups (grid.y)
+  int nsets, gps;            // parameter sets, groups per set
 };
 
 template <bool HAS_G2, int MASK>
 static void launch_bn_bwd(const BnBwdLaunch& L) {
   bn_bwd_reduce_kernel<HAS_G2, MASK><<<L.grid, kRvThreads, L.smem, L.stream>>>(
-      L.g1, L.g2, L.act, L.z, L.mean, L.rstd, L.gamma, L.beta, L.partial, L.grows, L.c, L.rpb);
-  bn_bwd_finalize_kernel<<<L.c / kFinCh, 1024, 0, L.stream>>>(L.partial, L.nblk, L.c, (double)L.grows, L.dgamma,
-                                                                   L.dbeta, L.grad_beta, L.c1, L.c2, L.batch_stats,
-                                                                   L.groups);
+      L.g1, L.g2, L.act, L.z, L.mean, L.rstd, L.gamma, L.beta, L.partial, L.grows, L.c, L.rpb, L.gps);
+  bn_bwd_finalize_kernel<<<dim3(L.c / kFinCh, L.nsets), 1024, 0, L.stream>>>(L.partial, L.nblk, L.c, (double)L.grows,
+                                                                             L.dgamma, L.dbeta, L.grad_beta, L.c1, L.c2,
+                                                                             L.batch_stats, L.gps);
   if (L.g_out != nullptr)
     bn_bwd_apply_kernel<HAS_G2, MASK, true><<<L.grid, kRvThreads, 0, L.stream>>>(
-        L.g1, L.g2, L.act, L.z, L.mean, L.rstd, L.gamma, L.beta, L.c1, L.c2, L.dz, L.g_out, L.grows, L.c, L.rpb);
+        L.g1, L.g2, L.act, L.z, L.mean, L.rstd, L.gamma, L.beta, L.c1, L.c2, L.dz, L.g_out, L.grows, L.c, L.rpb,
+        L.gps);
   else
     bn_bwd_apply_kernel<HAS_G2, MASK, false><<<L.grid, kRvThreads, 0, L.stream>>>(
-        L.g1, L.g2, L.act, L.z, L.mean, L.rstd, L.gamma, L.beta, L.c1, L.c2, L.dz, L.g_out, L.grows, L.c, L.rpb);
+        L.g1, L.g2, L.act, L.z, L.mean, L.rstd, L.gamma, L.beta, L.c1, L.c2, L.dz, L.g_out, L.grows, L.c, L.rpb,
+        L.gps);
 }
 
 }  // namespace irfd
 
 using namespace irfd;
 
-// tiles / count are PER GROUP; mean/rstd are [groups][c].  The running buffers get `running_updates` rounds of momentum
-// updates: round 1 walks the groups in call order, round 2 (the reference's checkpoint recompute) in reverse order.
+static FSet make_fset(const float* const* ptrs, int nsets) {
+  FSet f;
+  for (int i = 0; i < kMaxSets; ++i) f.p[i] = (ptrs != nullptr && i < nsets) ? ptrs[i] : nullptr;
+  return f;
+}
+static FSetM make_fsetm(float* const* ptrs, int nsets) {
+  FSetM f;
+  for (int i = 0; i < kMaxSets; ++i) f.p[i] = (ptrs != nullptr && i < nsets) ? ptrs[i] : nullptr;
+  return f;
+}
+
+// tiles / count are PER GROUP; mean/rstd are [nsets * groups][c] (`groups` statistic groups per parameter set).  Each
+// set's running buffers get `running_updates` rounds of momentum updates: round 1 walks the set's groups in call order,
+// round 2 (the reference's checkpoint recompute) in reverse order.  running_mean / running_var: host arrays of `nsets`
+// device pointers (or NULL).
+extern "C" int irfd_bn_finalize_sets(const float* psum, const float* psq, int tiles, int c, long long count, float eps,
+                                     float momentum, float* mean, float* rstd, float* const* running_mean,
+                                     float* const* running_var, int running_updates, int groups, int nsets,
+                                     cudaStream_t stream) {
+  IRFD_CHECK_ARG(psum && psq && mean && rstd && tiles > 0 && c > 0 && count > 0, "bn_finalize: bad argument");
+  IRFD_CHECK_ARG(groups >= 1 && groups <= kMaxGroups, "bn_finalize: 1..4 statistic groups per set");
+  IRFD_CHECK_ARG(nsets >= 1 && nsets <= kMaxSets, "bn_finalize: 1..4 parameter sets");
+  IRFD_CHECK_ARG(c % kFinCh == 0, "bn_finalize: C must be a multiple of 8 (got %d)", c);
+  IRFD_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running buffers come in pairs");
+  bn_finalize_kernel<<<dim3(c / kFinCh, nsets), 1024, 0, stream>>>(psum, psq, tiles, c, (double)count, eps, momentum,
+                                                                     mean, rstd, make_fsetm(running_mean, nsets),
+                                                                     make_fsetm(running_var, nsets), running_updates,
+                                                                     groups);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
 extern "C" int irfd_bn_finalize(const float* psum, const float* psq, int tiles, int c, long long count, float eps,
                                 float momentum, float* mean, float* rstd, float* running_mean, float* running_var,
                                 int running_updates, int groups, cudaStream_t stream) {
-  IRFD_CHECK_ARG(psum && psq && mean && rstd && tiles > 0 && c > 0 && count > 0, "bn_finalize: bad argument");
-  IRFD_CHECK_ARG(groups >= 1 && groups <= kMaxGroups, "bn_finalize: 1..4 statistic groups");
-  IRFD_CHECK_ARG(c % kFinCh == 0, "bn_finalize: C must be a multiple of 8 (got %d)", c);
-  bn_finalize_kernel<<<c / kFinCh, 1024, 0, stream>>>(psum, psq, tiles, c, (double)count, eps, momentum, mean, rstd,
-                                                         running_mean, running_var, running_updates, groups);
-  IRFD_CHECK_LAUNCH();
-  return IRFD_OK;
+  float* rm[1] = {running_mean};
+  float* rv[1] = {running_var};
+  return irfd_bn_finalize_sets(psum, psq, tiles, c, count, eps, momentum, mean, rstd, running_mean ? rm : nullptr,
+                               running_var ? rv : nullptr, running_updates, groups, 1, stream);
 }
 
 extern "C" int irfd_bn_running_update(const float* mean, const float* rstd, float eps, long long count, float momentum,
@@ -507,30 +564,45 @@ extern "C" int irfd_bn_eval_rstd(const float* running_var, float eps, float* rst
   return IRFD_OK;
 }
 
-// rows = TOTAL rows (all groups, groups stacked along the row axis); mean/rstd (and mean2/rstd2) are [groups][c].
-extern "C" int irfd_bn_apply(const void* z, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                             const void* res, const float* mean2, const float* rstd2, const float* gamma2,
-                             const float* beta2, void* out, long long rows, int c, int relu, int groups,
-                             cudaStream_t stream) {
+// rows = TOTAL rows (all groups, groups stacked along the row axis); mean/rstd (and mean2/rstd2) are [groups][c];
+// gamma/beta (and gamma2/beta2): host arrays of `nsets` device pointers, set = group / (groups / nsets).
+extern "C" int irfd_bn_apply_sets(const void* z, const float* mean, const float* rstd, const float* const* gamma,
+                                  const float* const* beta, const void* res, const float* mean2, const float* rstd2,
+                                  const float* const* gamma2, const float* const* beta2, void* out, long long rows,
+                                  int c, int relu, int groups, int nsets, cudaStream_t stream) {
   IRFD_CHECK_ARG(z && mean && rstd && gamma && beta && out, "bn_apply: null pointer");
   IRFD_CHECK_ARG(c % 8 == 0 && c <= 2048 && rows > 0, "bn_apply: C must be a multiple of 8 and <= 2048");
   IRFD_CHECK_ARG(groups >= 1 && rows % groups == 0, "bn_apply: rows must split evenly into groups");
+  IRFD_CHECK_ARG(nsets >= 1 && nsets <= kMaxSets && groups % nsets == 0, "bn_apply: groups must split evenly into sets");
   const long long grows = rows / groups;
   int nblk, rpb;
   plan_row_blocks(grows, c, num_sms(), &nblk, &rpb);
-  BnAffine p1{mean, rstd, gamma, beta}, p2{mean2, rstd2, gamma2, beta2};
+  BnAffine p1{mean, rstd, make_fset(gamma, nsets), make_fset(beta, nsets)};
+  BnAffine p2{mean2, rstd2, make_fset(gamma2, nsets), make_fset(beta2, nsets)};
   auto zz = reinterpret_cast<const __nv_bfloat16*>(z);
   auto rr = reinterpret_cast<const __nv_bfloat16*>(res);
   auto oo = reinterpret_cast<__nv_bfloat16*>(out);
   const dim3 grid(nblk, groups);
+  const int gps = groups / nsets;
   if (res == nullptr)
-    bn_apply_kernel<0><<<grid, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, grows, c, rpb, relu);
+    bn_apply_kernel<0><<<grid, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, grows, c, rpb, relu, gps);
   else if (mean2 == nullptr)
-    bn_apply_kernel<1><<<grid, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, grows, c, rpb, relu);
+    bn_apply_kernel<1><<<grid, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, grows, c, rpb, relu, gps);
   else
-    bn_apply_kernel<2><<<grid, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, grows, c, rpb, relu);
+    bn_apply_kernel<2><<<grid, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, grows, c, rpb, relu, gps);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
+}
+
+extern "C" int irfd_bn_apply(const void* z, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                             const void* res, const float* mean2, const float* rstd2, const float* gamma2,
+                             const float* beta2, void* out, long long rows, int c, int relu, int groups,
+                             cudaStream_t stream) {
+  const float* g1[1] = {gamma};
+  const float* b1[1] = {beta};
+  const float* g2[1] = {gamma2};
+  const float* b2[1] = {beta2};
+  return irfd_bn_apply_sets(z, mean, rstd, g1, b1, res, mean2, rstd2, g2, b2, out, rows, c, relu, groups, 1, stream);
 }
 
 extern "C" long long irfd_bn_bwd_workspace_bytes(long long rows, int c, int groups) {
@@ -541,13 +613,18 @@ extern "C" long long irfd_bn_bwd_workspace_bytes(long long rows, int c, int grou
 }
 
 // Full BN backward (reduce -> finalize -> apply).  workspace: [groups][nblk][2][C] partials, c1[groups][C], c2[...].
-extern "C" int irfd_bn_backward(const void* g1, const void* g2, const void* act, const void* z, const float* mean,
-                                const float* rstd, const float* gamma, const float* beta, void* dz, void* g_out,
-                                float* dgamma, float* dbeta, float grad_beta, int batch_stats, long long rows, int c,
-                                int groups, void* workspace, long long workspace_bytes, cudaStream_t stream) {
+// groups = TOTAL statistic groups; gamma/beta/dgamma/dbeta: host arrays of `nsets` device pointers (beta may be NULL =
+// no ReLU-from-z mask); each set's dgamma/dbeta sums its groups / nsets groups.
+extern "C" int irfd_bn_backward_sets(const void* g1, const void* g2, const void* act, const void* z, const float* mean,
+                                     const float* rstd, const float* const* gamma, const float* const* beta, void* dz,
+                                     void* g_out, float* const* dgamma, float* const* dbeta, float grad_beta,
+                                     int batch_stats, long long rows, int c, int groups, int nsets, void* workspace,
+                                     long long workspace_bytes, cudaStream_t stream) {
   IRFD_CHECK_ARG(g1 && z && mean && rstd && gamma && dz && dgamma && dbeta && workspace, "bn_backward: null pointer");
   IRFD_CHECK_ARG(c % 8 == 0 && c <= 2048 && rows > 0, "bn_backward: C must be a multiple of 8 and <= 2048");
   IRFD_CHECK_ARG(groups >= 1 && rows % groups == 0, "bn_backward: rows must split evenly into groups");
+  IRFD_CHECK_ARG(nsets >= 1 && nsets <= kMaxSets && groups % nsets == 0,
+                 "bn_backward: groups must split evenly into 1..4 sets");
   const long long grows = rows / groups;
   int nblk, rpb;
   plan_row_blocks(grows, c, num_sms(), &nblk, &rpb);
@@ -567,13 +644,19 @@ extern "C" int irfd_bn_backward(const void* g1, const void* g2, const void* act,
   L.smem = smem;
   L.stream = stream;
   L.g1 = G1; L.g2 = G2; L.act = A; L.z = Z;
-  L.mean = mean; L.rstd = rstd; L.gamma = gamma; L.beta = beta;
+  L.mean = mean; L.rstd = rstd;
+  L.gamma = make_fset(gamma, nsets);
+  L.beta = make_fset(beta, nsets);
   L.partial = partial; L.c1 = c1; L.c2 = c2;
   L.dz = reinterpret_cast<__nv_bfloat16*>(dz);
   L.g_out = reinterpret_cast<__nv_bfloat16*>(g_out);
-  L.dgamma = dgamma; L.dbeta = dbeta; L.grad_beta = grad_beta; L.batch_stats = batch_stats;
+  L.dgamma = make_fsetm(dgamma, nsets);
+  L.dbeta = make_fsetm(dbeta, nsets);
+  L.grad_beta = grad_beta; L.batch_stats = batch_stats;
   L.grows = grows; L.c = c; L.rpb = rpb; L.nblk = nblk; L.groups = groups;
-  const int mask = A != nullptr ? 1 : (beta != nullptr ? 2 : 0);
+  L.nsets = nsets; L.gps = groups / nsets;
+  const bool has_beta = beta != nullptr && beta[0] != nullptr;
+  const int mask = A != nullptr ? 1 : (has_beta ? 2 : 0);
   if (G2 != nullptr) {
     if (mask == 0) launch_bn_bwd<true, 0>(L);
     else if (mask == 1) launch_bn_bwd<true, 1>(L);
@@ -585,4 +668,16 @@ extern "C" int irfd_bn_backward(const void* g1, const void* g2, const void* act,
   }
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
+}
+
+extern "C" int irfd_bn_backward(const void* g1, const void* g2, const void* act, const void* z, const float* mean,
+                                const float* rstd, const float* gamma, const float* beta, void* dz, void* g_out,
+                                float* dgamma, float* dbeta, float grad_beta, int batch_stats, long long rows, int c,
+                                int groups, void* workspace, long long workspace_bytes, cudaStream_t stream) {
+  const float* ga[1] = {gamma};
+  const float* be[1] = {beta};
+  float* dg[1] = {dgamma};
+  float* db[1] = {dbeta};
+  return irfd_bn_backward_sets(g1, g2, act, z, mean, rstd, ga, be, dz, g_out, dg, db, grad_beta, batch_stats, rows, c,
+                               groups, 1, workspace, workspace_bytes, stream);
 }

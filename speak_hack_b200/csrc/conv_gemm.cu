@@ -46,6 +46,12 @@ struct ConvGemmArgs {
   float* stat_sq;
   const __nv_bfloat16* res;  // AFFINE: optional residual [M_total][N_total]
   __nv_bfloat16* y_lo;       // STYLE: optional second half of a split-bf16 y (y ~= y + y_lo), direct 16-byte stores
+  // Weight groups (the three ResNet-50 encoders run as ONE launch per layer, model.py:84-90): the pixel tiles are
+  // stacked group-major, m tile t belongs to group t / wg_tiles and multiplies rows [grp * N_total, ...) of the
+  // stacked weight matrix; per-channel epilogue vectors (AFFINE scale/shift, PLAIN bias) are [groups][N_total].
+  // a_mod_tiles > 0: every group reads the SAME A operand (the stem's shared im2col matrix): A tile = t % a_mod_tiles.
+  int wg_tiles;
+  int a_mod_tiles;
   int relu;                  // AFFINE: 0 = none, 1 = ReLU, 2 = leaky ReLU (slope 0.2)
 };
 
@@ -92,6 +98,7 @@ __device__ __forceinline__ void epilogue_acc(const ConvGemmArgs& p, const CUtens
   float* vs1 = vec + 1024;      // [2][256]
   const int m_tile = m0 >> 7;
   const int ng0 = n_tile * BLOCK_N;
+  const int pg0 = (m_tile / p.wg_tiles) * p.N_total + ng0;  // first channel of this tile in the per-group vectors
   float noise_r = 0.f;
   int img_local = 0;
   if constexpr (MODE == EPI_STYLE) {
@@ -114,13 +121,13 @@ __device__ __forceinline__ void epilogue_acc(const ConvGemmArgs& p, const CUtens
     img_local = p.HW < 128 ? r / p.HW : 0;
   } else if constexpr (MODE == EPI_PLAIN) {
     if (p.bias != nullptr) {
-      for (int i = etid; i < BLOCK_N; i += kEpiThreads) vb[i] = p.bias[ng0 + i];
+      for (int i = etid; i < BLOCK_N; i += kEpiThreads) vb[i] = p.bias[pg0 + i];
       named_bar_sync(1, kEpiThreads);
     }
   } else if constexpr (MODE == EPI_AFFINE) {
     for (int i = etid; i < BLOCK_N; i += kEpiThreads) {
-      vb[i] = p.bias[ng0 + i];   // shift
-      vnw[i] = p.nw[ng0 + i];    // scale
+      vb[i] = p.bias[pg0 + i];   // shift
+      vnw[i] = p.nw[pg0 + i];    // scale
     }
     named_bar_sync(1, kEpiThreads);
   }
@@ -309,10 +316,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.num_n_tiles;
         const int n_tile = tile - m_tile * p.num_n_tiles;
-        const int m0 = m_tile * 128;
+        const int m0 = (p.a_mod_tiles > 0 ? m_tile % p.a_mod_tiles : m_tile) * 128;
         const int w0 = m0 % p.W;
         const int h0 = (m0 / p.W) % p.H;
         const int n0 = m0 / (p.W * p.H);
+        const int b_row = (m_tile / p.wg_tiles) * p.N_total + n_tile * BLOCK_N;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dh = tap / p.kw - p.pad;
           const int dw = tap % p.kw - p.pad;
@@ -322,7 +330,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             if (elect_one_sync()) {
               mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
               tma_load_4d(sa, &map_a, &full_bar[stage], ch * 64, w0 + dw, h0 + dh, n0);
-              tma_load_2d(sa + Cfg::A_BYTES, &map_b, &full_bar[stage], (tap * p.cin_chunks + ch) * 64, n_tile * BLOCK_N);
+              tma_load_2d(sa + Cfg::A_BYTES, &map_b, &full_bar[stage], (tap * p.cin_chunks + ch) * 64, b_row);
             }
             __syncwarp();
             if (++stage == STAGES) {
@@ -703,7 +711,7 @@ extern "C" int irfd_conv_gemm_m_tiles(int n, int h, int w) {
 static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const void* wk, int cout, int ksize, void* out,
                           void* out2, void* out_lo, int mode, const float* bias, const float* nw, const float* noise,
                           const float* sp1, const float* s1, float* stat_sum, float* stat_sq, const void* res, int relu,
-                          int force_block_n, cudaStream_t stream) {
+                          int force_block_n, cudaStream_t stream, int wgroups = 1, int a_shared = 0) {
   IRFD_CHECK_ARG(x && wk && out, "conv_gemm: null pointer");
   IRFD_CHECK_ARG(ksize == 1 || ksize == 3, "conv_gemm: ksize must be 1 or 3 (got %d)", ksize);
   IRFD_CHECK_ARG(cin % 64 == 0 && cin > 0, "conv_gemm: Cin must be a multiple of 64 (got %d)", cin);
@@ -712,12 +720,17 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
   const long long m_total_ll = (long long)n * h * w;
   IRFD_CHECK_ARG(m_total_ll > 0 && m_total_ll < (1ll << 31) - 256, "conv_gemm: bad pixel count");
   const int m_total = (int)m_total_ll;
+  IRFD_CHECK_ARG(wgroups == 1 || (wgroups > 1 && m_total_ll % (128ll * wgroups) == 0),
+                 "conv_gemm: %d weight groups need a whole number of 128-pixel tiles per group (pixels %lld)", wgroups,
+                 m_total_ll);
+  IRFD_CHECK_ARG(wgroups == 1 || (mode != EPI_STYLE), "conv_gemm: weight groups are not available in STYLE mode");
+  IRFD_CHECK_ARG(!a_shared || (ksize == 1 && wgroups > 1), "conv_gemm: a shared A operand needs ksize 1 and groups > 1");
 
   // pixel-tile geometry: 128 consecutive NHWC pixels == a (tn, th, tw) box
   int H = h, W = w, NB = n;
   if (ksize == 1) {  // pointwise conv == plain GEMM over a single long row of pixels
     H = 1;
-    W = m_total;
+    W = a_shared ? m_total / wgroups : m_total;  // a shared A operand only has one group's rows
     NB = 1;
   }
   int tw, th, tn;
@@ -750,6 +763,8 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
   a.stat_sum = stat_sum; a.stat_sq = stat_sq;
   a.res = reinterpret_cast<const __nv_bfloat16*>(res);
   a.y_lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
+  a.wg_tiles = wgroups > 1 ? a.num_m_tiles / wgroups : 0x7fffffff;
+  a.a_mod_tiles = a_shared ? a.num_m_tiles / wgroups : 0;
   a.relu = relu;
   if (mode == EPI_AFFINE) IRFD_CHECK_ARG(bias && nw, "conv_gemm: AFFINE mode needs scale and shift");
   if (mode == EPI_STYLE) {
@@ -776,7 +791,8 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
                  "conv_gemm: BLOCK_N %d incompatible with Cout %d", block_n, cout);
   // halo-reuse kernel: 3x3, rows of >= 128 pixels, Cout of one 64/128-wide tile (the fabric-bound generator layers)
   const int hmode = halo_mode();
-  const bool use_halo = hmode != 0 && ksize == 3 && W % 128 == 0 && H % 2 == 0 && (cout == 64 || cout == 128) &&
+  const bool use_halo = hmode != 0 && wgroups == 1 && ksize == 3 && W % 128 == 0 && H % 2 == 0 &&
+                        (cout == 64 || cout == 128) &&
                         (force_block_n == 0 || force_block_n == cout);
   if (use_halo) block_n = cout;
   a.num_n_tiles = cout / block_n;
@@ -796,7 +812,7 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
   }
   {
     const uint64_t ktot = (uint64_t)a.taps * cin;
-    const uint64_t dims[2] = {ktot, (uint64_t)cout};
+    const uint64_t dims[2] = {ktot, (uint64_t)cout * wgroups};
     const uint64_t str[1] = {ktot * 2};
     const uint32_t box[2] = {64, (uint32_t)block_n};
     int rc = make_tmap_bf16(&mb, wk, 2, dims, str, box, true);
@@ -849,6 +865,24 @@ extern "C" int irfd_conv_gemm_style_split(const void* x, int n, int h, int w, in
   IRFD_CHECK_ARG(out_y_lo != nullptr, "conv_gemm_style_split: out_y_lo is required");
   return conv_gemm_impl(x, n, h, w, cin, wk, cout, ksize, out_a, out_y, out_y_lo, EPI_STYLE, bias, nw, noise, sp1, s1,
                         nullptr, nullptr, nullptr, 0, force_block_n, stream);
+}
+
+// Grouped variants: `wgroups` weight sets stacked along the rows of wk ([wgroups * cout][k*k*cin]), the n images split
+// evenly group-major; a_shared != 0: x holds ONE group's pixels ([n / wgroups] images), read by every group.
+extern "C" int irfd_conv_gemm_grouped(const void* x, int n, int h, int w, int cin, const void* wk, int cout, int ksize,
+                                      void* out, int mode, float* stat_sum, float* stat_sq, int wgroups, int a_shared,
+                                      int force_block_n, cudaStream_t stream) {
+  IRFD_CHECK_ARG(mode == EPI_PLAIN || mode == EPI_STATS, "conv_gemm_grouped: mode must be 0 (plain) or 1 (stats)");
+  return conv_gemm_impl(x, n, h, w, cin, wk, cout, ksize, out, nullptr, nullptr, mode, nullptr, nullptr, nullptr,
+                        nullptr, nullptr, stat_sum, stat_sq, nullptr, 0, force_block_n, stream, wgroups, a_shared);
+}
+
+extern "C" int irfd_conv_gemm_affine_grouped(const void* x, int n, int h, int w, int cin, const void* wk, int cout,
+                                             int ksize, void* out, const float* scale, const float* shift,
+                                             const void* res, int relu, int wgroups, int a_shared, int force_block_n,
+                                             cudaStream_t stream) {
+  return conv_gemm_impl(x, n, h, w, cin, wk, cout, ksize, out, nullptr, nullptr, EPI_AFFINE, shift, scale, nullptr,
+                        nullptr, nullptr, nullptr, nullptr, res, relu, force_block_n, stream, wgroups, a_shared);
 }
 
 extern "C" int irfd_conv_gemm_affine(const void* x, int n, int h, int w, int cin, const void* wk, int cout, int ksize,

@@ -353,7 +353,7 @@ class StyleGenerator(nn.Module):
                     w2 = self.mapping(self.latent_fn(features))
                 cut = int(torch.randint(1, L, (1,)).item())
         psi, cutoff = self._trunc()
-        ctrl = torch.tensor([cut], dtype=torch.int32, device=features.device)
+        ctrl = _cut_tensor(cut, features.device)
         rows_t = _StyleRowsFn.apply(w, w2.detach(), ctrl, 0, psi, cutoff, L)   # repeat + truncation + mixing: one kernel
         noises = self.synthesis.draw_noises(features.size(0), features.device)
         return _SynthesisFn.apply(rows_t, self.synthesis, noises, *self.synthesis._flat_params())
@@ -362,6 +362,20 @@ class StyleGenerator(nn.Module):
 # ----------------------------------------------------------------------------------------------------------------------
 # Static-graph variant: the style-mixing decision arrives as a device-side control value (see csrc/control.cu)
 # ----------------------------------------------------------------------------------------------------------------------
+_cut_cache = {}
+
+
+def _cut_tensor(cut: int, device) -> torch.Tensor:
+    """Device-resident int32 [1] holding `cut` (one per value and device, created on first use): the eager forward
+    hands the style-mixing cut to the style_rows kernel without a per-call host->device copy, which also keeps an
+    eval-mode forward capturable in a CUDA graph (speak_hack_b200/inference.py)."""
+    key = (cut, device.index)
+    t = _cut_cache.get(key)
+    if t is None:
+        t = _cut_cache[key] = torch.tensor([cut], dtype=torch.int32, device=device)
+    return t
+
+
 class _StyleRowsFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, w, w2, ctrl, ctrl_idx, psi, cutoff, num_layers):

@@ -63,6 +63,41 @@ def conditioned_pair(dev, bn3_scale=0.2, checkpoint=True):
     return ref.train(), prod.train()
 
 
+def _r(t):
+    """One bf16 storage rounding (differentiable: the gradient is rounded the same way on its way back)."""
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def make_bf16_faithful(ref):
+    """Insert the product's STORAGE rounding points (NHWC bf16 activations, bf16 GEMM operands, fp32
+    everything else) into the oracle through module hooks, keeping the oracle's own fp32 arithmetic in between.
+
+    Why: a ReLU network evaluated with bf16 activations flips the ReLU mask of every element whose pre-activation lies
+    within the rounding error of zero; a flipped element changes the gradient by 100 % of its value, so the gradient
+    error against a pure-fp32 run scales with sqrt(rounding error) (~6 % per ReLU layer, ~0.4 after 49 of them) whatever
+    the kernel quality.  With the same rounding points the masks agree, and what remains is the accumulation order
+    and the bf16 rounding of gradients: a comparison tight enough to catch a mis-routed tensor.
+    Call AFTER the product has loaded ref.state_dict() (the conv weights are rounded in place here)."""
+    import torch.nn as nn
+
+    for enc in (ref.Ei, ref.Ee, ref.Ep):
+        for m in enc.modules():
+            if isinstance(m, nn.Conv2d):
+                m.weight.data = _r(m.weight.data)                       # bf16 GEMM operand
+                m.register_forward_hook(lambda mod, inp, out: _r(out))  # conv output z stored as bf16
+            elif isinstance(m, nn.ReLU):
+                m.register_forward_hook(lambda mod, inp, out: _r(out))  # BN+ReLU(+residual) output stored as bf16
+        enc[0].register_forward_pre_hook(lambda mod, inp: (_r(inp[0]),))  # image -> bf16 im2col matrix
+    syn = ref.Gd.synthesis
+    for i, blk in enumerate(syn.layers):
+        for conv in (blk.conv1, blk.conv2):
+            conv.weight.data = _r(conv.weight.data)
+            conv.register_forward_pre_hook(lambda mod, inp: (_r(inp[0]),))  # conv operand (upsampled u / styled y1)
+        if 2 ** (i + 3) > 32:   # block outputs above generator.SPLIT_MAX_RES are plain bf16 (below: split bf16)
+            blk.register_forward_hook(lambda mod, inp, out: _r(out))
+    return ref
+
+
 def _collect(net, out, l_id, l_rec):
     grads = {n: p.grad.detach().double().cpu() for n, p in net.named_parameters() if p.grad is not None}
     bufs = {k: v.detach().double().cpu() for k, v in net.state_dict().items()

@@ -74,9 +74,11 @@ def test_generator_forward_eval(cuda_device, nets):
     err = O.rel_l2(img, img_ref)
     print(f"[parity] Gd eval forward rel-L2 = {err:.3e} (|img| max {img_ref.abs().max():.3e})")
     assert img.shape == (2, 3, 256, 256) and img.dtype == torch.float32
-    # 13 un-normalised layers: an ideal bf16-operand / fp32-storage kernel sits at 6.6e-3..8e-3; bf16
-    # activation storage adds one more rounding per upsample.  Per-kernel parity (test_gpu_conv_gemm) is < 4e-3.
-    assert err < 1.5e-2
+    # 13 un-normalised layers.  An IDEAL bf16-operand / fp32-storage evaluation of the oracle on exactly these inputs
+    # sits at 9.87e-3 (scripts/gd_floor.py: the oracle with only its conv operands rounded), so the north_star's 1e-2
+    # is the floor of the operand precision here, not a kernel property; measured 1.04e-2 (the block outputs up to
+    # 32^2 are kept as split bf16 so the upsample does not add a second rounding; 64^2/128^2 outputs are plain bf16).
+    assert err < 1.3e-2
 
 
 def test_generator_backward_train(cuda_device, nets):
@@ -111,10 +113,10 @@ def test_generator_backward_train(cuda_device, nets):
             worst = (name, e)
         # 13 layers of bf16 dz/dy roundings on the way back; noise-weight grads are sums of products with zero-mean
         # noise (cancellation), the least well-conditioned reductions on this path
-        assert e < (0.15 if "noise" in name else 5e-2), (name, e)
+        assert e < (0.15 if "noise" in name else 5e-2), (name, e)   # measured 9.1e-2 / 4.1e-2
     ef = O.rel_l2(fp.grad, fr.grad)
     print(f"[parity] Gd backward: worst param-grad rel-L2 {worst[1]:.3e} ({worst[0]}); d/dfeatures {ef:.3e}")
-    assert ef < 5e-2
+    assert ef < 2e-2  # measured 1.0e-2
     ref.Gd.style_mixing_prob = 0.9
     prod.Gd.style_mixing_prob = 0.9
 
@@ -141,7 +143,7 @@ def test_encoder_eval_and_train_forward(cuda_device, nets):
     torch.cuda.synchronize()
     e_train = O.rel_l2(f, f_ref)
     print(f"[parity] encoder train-mode features rel-L2 = {e_train:.3e} (ideal bf16 kernel: 7.5e-2, SURVEY §7)")
-    assert e_train < 0.2
+    assert e_train < 0.15  # measured 8.6e-2
     # BN running buffers after one train-mode forward (first layers are well conditioned)
     ps, rs = prod.Ee.state_dict(), ref.Ee.state_dict()
     assert O.rel_l2(ps["1.running_mean"], rs["1.running_mean"]) < 1e-2
@@ -263,7 +265,7 @@ def test_encoder_backward_train_in_context(cuda_device):
     e_b, e_w = O.rel_l2(pr["7.2.bn3.bias"].grad, rr["7.2.bn3.bias"].grad), O.rel_l2(pr["7.2.bn3.weight"].grad,
                                                                                      rr["7.2.bn3.weight"].grad)
     print(f"[parity] last-BN grads vs torch fp32: dbeta {e_b:.3e}, dgamma {e_w:.3e}; loss {lr.item():.5e} / {lp.item():.5e}")
-    assert e_b < 0.15 and e_w < 0.3
+    assert e_b < 9e-2 and e_w < 0.25  # measured 4.6e-2 / 1.4e-1
     assert all(torch.isfinite(p.grad).all() for p in enc.parameters())
 
 
@@ -310,8 +312,8 @@ def test_irfd_forward_swap_bit_exact_and_losses(cuda_device, nets):
     # features: 53 conv+BN layers with bf16 storage of both the raw conv output and the normalised activation.
     # images: the un-normalised generator multiplies 13 (style+1) factors, so a relative feature error d shows up as
     # ~10 d in the image (conditioning of the reference model; the generator alone on exact features is ~1e-2).
-    assert e_feat < 3e-2
-    assert e_img < 0.25
+    assert e_feat < 3e-2   # measured 2.0e-2
+    assert e_img < 4e-2    # measured 1.9e-2
     # softmax over logits of O(100) magnitude (fresh-BN eval features): compare the winning class and its mass
     for got, want in ((o[8].cpu(), o_ref[8]), (o[9].cpu(), o_ref[9])):
         assert got.shape == want.shape and torch.allclose(got.sum(1), torch.ones(2), atol=1e-5)
@@ -337,8 +339,8 @@ def test_golden_eval_features(cuda_device):
     errs = [O.rel_l2(a, b) for a, b in zip(out[2:8], gold["feat"])]
     e_img = O.rel_l2(out[0][..., ::8, ::8], gold["img"][0]["sub"])
     print(f"[parity] golden (reference) eval: features max {max(errs):.3e}, image {e_img:.3e}")
-    assert max(errs) < 1e-2   # north_star bound for bf16 paths (measured 3.9e-3 with BN folded into the conv epilogues)
-    assert e_img < 0.1        # 13 multiplicative style layers amplify the feature error ~10x (measured 4.2e-2)
+    assert max(errs) < 8e-3   # north_star bound for bf16 paths is 1e-2; measured 3.9e-3 (BN folded into the conv epilogues)
+    assert e_img < 8e-2       # 13 multiplicative style layers amplify the feature error ~10x (measured 4.1e-2)
 
 
 def test_paired_encoder_pass_equals_two_calls(cuda_device):
@@ -439,8 +441,13 @@ def test_golden_train_step_bn_buffers_and_losses(cuda_device):
 
 
 # provisional until measured on B200 (then <= 2x measured)
-GOLD_TRAIN_BOUNDS = {"feat": 0.2, "l_id": 0.3, "l_rec": 0.5, "Gd_norm_median": 1.0, "Gd_slice_worst": 2.0,
-                     "enc_norm_median": 1.0, "enc_slice_worst": 2.0}
+# measured on B200: features 8.1e-2, l_identity 3.8e-2, l_recon 5.1e-2, Gd gradient norms median 5.3e-2, worst Gd slice
+# 0.51 (mapping.0.weight, behind 8 dense layers and the whole synthesis backward), encoder norms median 0.11.  Encoder
+# gradient ELEMENTS against a pure-fp32 reference are dominated by ReLU-mask flips of the bf16 forward (error ~
+# sqrt(rounding error) per ReLU layer, tests/parity_util.py) and sit at O(1): the bound only guards finiteness/scale;
+# tests/test_gpu_train_parity.py::test_train_step_vs_bf16_faithful_oracle is the tight element-wise check.
+GOLD_TRAIN_BOUNDS = {"feat": 0.16, "l_id": 8e-2, "l_rec": 0.1, "Gd_norm_median": 0.1, "Gd_slice_worst": 1.0,
+                     "enc_norm_median": 0.22, "enc_slice_worst": 2.0}
 
 # the element slices oracle/make_golden.py stored (same table)
 GRAD_SLICES = {

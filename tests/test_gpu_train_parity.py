@@ -42,11 +42,45 @@ def test_conditioned_train_step_all_gradients(cuda_device):
             assert v[0] < med_b and v[1] < worst_b, (k, v)
 
 
-# (median, worst) rel-L2 bounds per gradient group; scalars for the rest.  Provisional until measured on B200.
+def test_train_step_vs_bf16_faithful_oracle(cuda_device):
+    """The routing check proper: the oracle with the product's storage rounding points inserted (parity_util.
+    make_bf16_faithful), random-init weights as the reference constructs them (NO conditioning), one G train step.
+    Masks agree, so every one of the 560 gradient tensors is compared at a bound that a mis-routed tensor cannot meet."""
+    import irfd_oracle as O
+    from parity_util import conditioned_pair, g_step_oracle, g_step_product, grad_report, make_bf16_faithful
+
+    dev = cuda_device
+    ref, prod = conditioned_pair(dev, bn3_scale=1.0)
+    make_bf16_faithful(ref)
+    x_s, x_t = O.synthetic_pair(2)
+    r = g_step_oracle(ref, x_s, x_t, noise_seed=43, device="cpu")
+    p = g_step_product(prod, x_s, x_t, noise_seed=43, device=dev)
+    print("[parity] G train step, product vs bf16-faithful CPU oracle (same rounding points), 2 pairs @256^2")
+    rep = grad_report(r, p, verbose=True)
+    assert rep["same_grad_set"] and rep["counters_equal"]
+    assert rep["feat"] < FAITHFUL["feat"] and rep["img"] < FAITHFUL["img"]
+    assert rep["loss_id"] < FAITHFUL["loss"] and rep["loss_rec"] < FAITHFUL["loss"]
+    assert rep["running_mean"] < FAITHFUL["running"] and rep["running_var"] < FAITHFUL["running"]
+    for k, v in rep.items():
+        if isinstance(v, tuple):
+            med_b, worst_b = FAITHFUL["Gd" if k.startswith("Gd") else "enc"]
+            assert v[0] < med_b and v[1] < worst_b, (k, v)
+
+
+# provisional until measured on B200
+FAITHFUL = {"feat": 5e-2, "img": 0.2, "loss": 5e-2, "running": 5e-2, "Gd": (0.2, 0.5), "enc": (0.3, 0.6)}
+
+
+# (median, worst) rel-L2 bounds per gradient group; scalars for the rest.  All <= 2x the values measured on B200:
+# features 6.0e-3, images 1.2e-2, l_identity 1.2e-3, l_recon 2.8e-3, running mean/var 4.1e-3 / 3.5e-3,
+# Gd.mapping 4.9e-2 / 6.6e-2, Gd.synthesis 1.3e-2 / 4.1e-2, Gd.noise 5.9e-2 / 1.2e-1.
+# Encoder gradients against the PURE-fp32 oracle: median 0.32 (layer4) .. 0.50 (stem), worst 0.69 — flat over depth
+# and the same for bn3 gamma x 0.05 (0.24 .. 0.32): it is not compounding rounding but the ReLU-mask flips of a bf16
+# forward (see parity_util.make_bf16_faithful); test_train_step_vs_bf16_faithful_oracle is the sharp check.
 BOUNDS = {
-    "feat": 2e-2, "img": 0.2, "loss_id": 5e-2, "loss_rec": 5e-2, "running_mean": 2e-2, "running_var": 2e-2,
-    "Gd.mapping": (0.2, 0.5), "Gd.synthesis": (0.2, 0.5), "Gd.noise": (0.3, 0.6),
-    "stem": (0.5, 0.8), "layer1": (0.5, 0.8), "layer2": (0.5, 0.8), "layer3": (0.5, 0.8), "layer4": (0.5, 0.8),
+    "feat": 1.2e-2, "img": 2.4e-2, "loss_id": 3e-3, "loss_rec": 6e-3, "running_mean": 8e-3, "running_var": 7e-3,
+    "Gd.mapping": (0.1, 0.13), "Gd.synthesis": (2.7e-2, 8e-2), "Gd.noise": (0.12, 0.24),
+    "stem": (1.0, 1.1), "layer1": (0.95, 1.3), "layer2": (0.93, 1.1), "layer3": (0.85, 1.0), "layer4": (0.66, 0.83),
 }
 
 
