@@ -435,14 +435,12 @@ def run_native(args):
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
 
     # ---- roofline pass: per-launch CUDA events around every tensor-core GEMM launch (same stream), few steps
-    # serialise the three encoder streams for this pass: an event pair on one stream would otherwise also time the
-    # kernels that happen to run concurrently on the others
-    model._enc_streams = [torch.cuda.current_stream(dev)] * 3
-    trainer.buckets.producer_streams = []
+    # (the whole step runs on one stream, so an event pair times exactly the launch between its two records)
     ops.gemm_timing_begin()
     rsteps = min(args.steps, 3)
     for _ in range(rsteps):
-        trainer.train_step_eager(x_s, x_t)      # eager: per-launch events cannot be recorded inside a graph replay
+        # the captured step's own launch sequence, kernel by kernel (events cannot be recorded inside a graph replay)
+        (trainer.train_step_static_eager if trainer.use_cuda_graph else trainer.train_step_eager)(x_s, x_t)
     torch.cuda.synchronize()
     fam = ops.gemm_timing_end()
     if rank != 0:
@@ -625,8 +623,6 @@ def run_native_infer(args):
     checksum = float(host_out[(args.steps - 1) & 1][0].double().abs().mean())
 
     # ---- roofline pass: eager launches, per-launch CUDA events around every tensor-core GEMM (one stream)
-    if hasattr(model, "_enc_streams"):
-        model._enc_streams = [torch.cuda.current_stream(dev)] * 3
     ops.gemm_timing_begin()
     rsteps = min(args.steps, 3)
     with torch.no_grad():

@@ -142,6 +142,9 @@ int irfd_bn_backward(const void* g1, const void* g2, const void* act, const void
  * set-major along the row axis ([nsets][groups per set] x rows-per-group); batch statistics (mean/rstd, and the
  * workspace c1/c2) are per group, gamma/beta/running buffers/dgamma/dbeta per set, passed as HOST arrays of `nsets`
  * device pointers (read at call time).  irfd_bn_finalize_sets takes groups PER SET, the other two the TOTAL group count. */
+int irfd_bn_eval_affine_sets(const float* const* running_mean, const float* const* running_var,
+                             const float* const* gamma, const float* const* beta, float eps, float* scale, float* shift,
+                             int c, int nsets, irfd_stream_t stream); /* scale/shift: [nsets][c] */
 int irfd_bn_finalize_sets(const float* psum, const float* psq, int tiles, int c, long long count, float eps,
                           float momentum, float* mean, float* rstd, float* const* running_mean,
                           float* const* running_var, int running_updates, int groups, int nsets,
@@ -228,14 +231,17 @@ int irfd_merge_style_grad(const float* dsp1, const float* ds1, float* dstyle, in
  * Device-side routing (lets a whole training step be one static CUDA graph).  The random decisions are still drawn
  * from the CPU generator in the reference's order and uploaded as ctrl (int32): ctrl[0] = swap_type (model.py:98),
  * ctrl[1+g] = first style-mixed row of generator call g, or L when that call does not mix (styleganv1.py:548-552).
- *   irfd_style_rows_fwd: rows_t[l][b][k] = coef(l) * (l >= ctrl[ctrl_idx] ? w2 : w)[b][k], coef = psi for l < cutoff
- *                        (styleganv1.py:536-553);  _bwd: dw = sum_l coef(l)*drows_t[l] (all rows, as in the reference,
+ *   irfd_style_rows_fwd: rows_t[l][b][k] = l >= ctrl[ctrl_idx] ? w2[b][k] : coef(l) * w[b][k], coef = psi for l < cutoff
+ *                        (styleganv1.py:536-553: truncation applies to w only, mixed rows are w2's untruncated rows);  _bwd: dw = sum_l coef(l)*drows_t[l] (all rows, as in the reference,
  *                        whose no_grad overwrite keeps routing the mixed rows' gradient into the mapping output).
  *   irfd_swap_cat_fwd  : S<->T swap of code type ctrl[0] + concat [identity|emotion|pose] -> [b, 3c] (model.py:97-108),
  *                        pure copies (bit-exact);  _bwd scatters the two gradients back to the six codes.
  */
 int irfd_style_rows_fwd(const float* w, const float* w2, const int* ctrl, int ctrl_idx, float psi, int cutoff,
                         float* rows_t, int l, int b, int k, irfd_stream_t stream);
+/* two generator calls stacked along the batch: rows [0, b_first) use ctrl[ctrl_idx], rows [b_first, b) ctrl[ctrl_idx+1] */
+int irfd_style_rows_pair_fwd(const float* w, const float* w2, const int* ctrl, int ctrl_idx, float psi, int cutoff,
+                             float* rows_t, int l, int b, int k, int b_first, irfd_stream_t stream);
 int irfd_style_rows_bwd(const float* drows_t, float psi, int cutoff, float* dw, int l, int b, int k,
                         irfd_stream_t stream);
 int irfd_swap_cat_fwd(const float* fi_s, const float* fe_s, const float* fp_s, const float* fi_t, const float* fe_t,

@@ -162,6 +162,17 @@ __global__ void bn_eval_affine_kernel(const float* __restrict__ running_mean, co
   shift[c] = beta[c] - running_mean[c] * sc;
 }
 
+// the same for `gridDim.y` parameter sets: scale/shift are [nsets][C]
+__global__ void bn_eval_affine_sets_kernel(FSet running_mean, FSet running_var, FSet gamma, FSet beta, float eps,
+                                           float* __restrict__ scale, float* __restrict__ shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int s = blockIdx.y;
+  const float sc = gamma.p[s][c] * rsqrtf(running_var.p[s][c] + eps);
+  scale[(size_t)s * C + c] = sc;
+  shift[(size_t)s * C + c] = beta.p[s][c] - running_mean.p[s][c] * sc;
+}
+
 // eval mode: rstd from the running variance
 __global__ void bn_eval_rstd_kernel(const float* __restrict__ running_var, float eps, float* __restrict__ rstd, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -553,6 +564,18 @@ extern "C" int irfd_bn_eval_affine(const float* running_mean, const float* runni
                                    cudaStream_t stream) {
   IRFD_CHECK_ARG(running_mean && running_var && gamma && beta && scale && shift && c > 0, "bn_eval_affine: bad argument");
   bn_eval_affine_kernel<<<(c + 255) / 256, 256, 0, stream>>>(running_mean, running_var, gamma, beta, eps, scale, shift, c);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_bn_eval_affine_sets(const float* const* running_mean, const float* const* running_var,
+                                        const float* const* gamma, const float* const* beta, float eps, float* scale,
+                                        float* shift, int c, int nsets, cudaStream_t stream) {
+  IRFD_CHECK_ARG(running_mean && running_var && gamma && beta && scale && shift && c > 0, "bn_eval_affine_sets: bad argument");
+  IRFD_CHECK_ARG(nsets >= 1 && nsets <= kMaxSets, "bn_eval_affine_sets: 1..4 parameter sets");
+  bn_eval_affine_sets_kernel<<<dim3((c + 255) / 256, nsets), 256, 0, stream>>>(
+      make_fset(running_mean, nsets), make_fset(running_var, nsets), make_fset(gamma, nsets), make_fset(beta, nsets), eps,
+      scale, shift, c);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }

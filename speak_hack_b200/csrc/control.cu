@@ -11,14 +11,16 @@ namespace irfd {
 // rows_t[l][b][k] = l >= cut ? w2[b][k] : coef(l) * w[b][k],  coef(l) = psi for l < cutoff else 1
 // (styleganv1.py:536-553: repeat -> truncation coefficients on w ONLY -> rows >= mix_layer overwritten with the
 // UNtruncated rows of w2)
+// split_bk: batch rows are two generator calls stacked (source pairs, then target pairs): elements j >= split_bk of a
+// row belong to the second call and read its cut from ctrl[ctrl_idx + 1] (split_bk == BK: one call).
 __global__ void style_rows_fwd_kernel(const float* __restrict__ w, const float* __restrict__ w2,
                                       const int* __restrict__ ctrl, int ctrl_idx, float psi, int cutoff,
-                                      float* __restrict__ rows_t, int L, int BK) {
+                                      float* __restrict__ rows_t, int L, int BK, int split_bk) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)L * BK) return;
   const int l = i / BK;
   const int j = i - (size_t)l * BK;
-  const int cut = ctrl[ctrl_idx];
+  const int cut = ctrl[ctrl_idx + (j >= split_bk ? 1 : 0)];
   const float coef = l < cutoff ? psi : 1.f;
   rows_t[i] = l >= cut ? w2[j] : coef * w[j];
 }
@@ -74,14 +76,21 @@ __global__ void swap_cat_bwd_kernel(const float* __restrict__ dgen_s, const floa
 
 using namespace irfd;
 
-extern "C" int irfd_style_rows_fwd(const float* w, const float* w2, const int* ctrl, int ctrl_idx, float psi,
-                                   int cutoff, float* rows_t, int l, int b, int k, cudaStream_t stream) {
+extern "C" int irfd_style_rows_pair_fwd(const float* w, const float* w2, const int* ctrl, int ctrl_idx, float psi,
+                                        int cutoff, float* rows_t, int l, int b, int k, int b_first,
+                                        cudaStream_t stream) {
   IRFD_CHECK_ARG(w && w2 && ctrl && rows_t && l > 0 && b > 0 && k > 0, "style_rows_fwd: bad argument");
+  IRFD_CHECK_ARG(b_first > 0 && b_first <= b, "style_rows_fwd: b_first must be in 1..b");
   const size_t total = (size_t)l * b * k;
   style_rows_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(w, w2, ctrl, ctrl_idx, psi, cutoff, rows_t,
-                                                                            l, b * k);
+                                                                            l, b * k, b_first * k);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
+}
+
+extern "C" int irfd_style_rows_fwd(const float* w, const float* w2, const int* ctrl, int ctrl_idx, float psi,
+                                   int cutoff, float* rows_t, int l, int b, int k, cudaStream_t stream) {
+  return irfd_style_rows_pair_fwd(w, w2, ctrl, ctrl_idx, psi, cutoff, rows_t, l, b, k, b, stream);
 }
 
 extern "C" int irfd_style_rows_bwd(const float* drows_t, float psi, int cutoff, float* dw, int l, int b, int k,

@@ -1,13 +1,15 @@
 """Data-parallel gradient exchange for the IRFD trainer: bucketed all-reduce(avg) overlapped with backward.
 
 The reference delegates multi-GPU training to HF accelerate -> torch DDP (train.py:333-338, 399-401): batch-sharded
-replicas, per-rank BatchNorm statistics (no SyncBN), gradients averaged by all-reduce.  Here the exchange is explicit:
-one process per GPU, `torch.distributed` (NCCL over NVLink 5 / NVSwitch on the GPU box; gloo on CPU for the tests),
-each bucket all-reduced on a side stream as soon as the backward pass has finished producing it.
+replicas, per-rank BatchNorm statistics (no SyncBN), gradients averaged by all-reduce, BatchNorm buffers broadcast from
+rank 0 (DDP's `broadcast_buffers=True` default).  Here the exchange is explicit: one process per GPU,
+`torch.distributed` (NCCL over NVLink 5 / NVSwitch on the GPU box; gloo on CPU for the tests).  Every bucket is a FLAT
+fp32 gradient buffer the backward kernels write into directly (trainer.py), all-reduced in place on a side stream as
+soon as the backward pass has finished producing it — no flatten / unflatten copies.
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import Dict, List, Optional
 
 import torch
 import torch.distributed as dist
@@ -18,110 +20,109 @@ def world_size() -> int:
 
 
 class GradBuckets:
-    """Launch/finish pairs of asynchronous averaged all-reduces.
+    """Launch/finish pairs of asynchronous averaged all-reduces over flat buffers (in place).
 
-    launch(tensors)      : flatten `tensors` into one buffer and all-reduce it (result copied back on finish()).
-    launch(flat=buffer)  : all-reduce an already-flat buffer in place.
     On CUDA the collective runs on a dedicated stream ordered after the work already enqueued on the current stream;
-    on CPU (gloo) it runs synchronously.
-    """
+    on CPU (gloo) it runs synchronously.  `enabled = False` turns launches into no-ops (bench.py's dp_check captures a
+    second, communication-free graph to obtain the per-rank gradients)."""
 
     def __init__(self, device: torch.device):
         self.world = world_size()
         self.device = device
         self.cuda = device.type == "cuda"
         self.comm_stream = torch.cuda.Stream(device) if (self.cuda and self.world > 1) else None
-        # streams (besides the current one) that may have produced the gradients of a bucket: the encoders' backward
-        # passes run on their own streams (model.IRFD.encoder_streams)
-        self.producer_streams = []
-        self._pending = []
+        self.enabled = True
+        self._pending = 0
         self.launched_bytes = 0
 
-    def launch(self, tensors: Optional[List[torch.Tensor]] = None, flat: Optional[torch.Tensor] = None) -> None:
-        if self.world == 1:
+    def launch(self, flat: torch.Tensor) -> None:
+        if self.world == 1 or not self.enabled or flat is None or flat.numel() == 0:
             return
-        unflatten = None
-        if flat is None:
-            if not tensors:
-                return
-            flat = torch.cat([t.reshape(-1) for t in tensors])
-            unflatten = list(tensors)
         self.launched_bytes += flat.numel() * flat.element_size()
         if self.cuda:
             ready = torch.cuda.Event()
             ready.record()
-            for ps in self.producer_streams:
-                self.comm_stream.wait_stream(ps)
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ready)
                 flat.record_stream(self.comm_stream)
-                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-                flat.mul_(1.0 / self.world)
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
         else:
             dist.all_reduce(flat, op=dist.ReduceOp.SUM)
             flat.mul_(1.0 / self.world)
-        self._pending.append((flat, unflatten))
+        self._pending += 1
 
     def finish(self) -> None:
-        """Make the averaged gradients visible to the current stream and scatter them back into their tensors."""
-        if self.world == 1:
+        """Make the averaged gradients visible to the current stream."""
+        if self.world == 1 or not self._pending:
             return
         if self.cuda:
-            cur = torch.cuda.current_stream()
-            cur.wait_stream(self.comm_stream)
-            for ps in self.producer_streams:  # gradients that were not bucketed are still produced there
-                cur.wait_stream(ps)
-        for flat, unflatten in self._pending:
-            if unflatten is not None:
-                off, views = 0, []
-                for t in unflatten:
-                    views.append(flat[off: off + t.numel()].view_as(t))
-                    off += t.numel()
-                torch._foreach_copy_(unflatten, views)
-        self._pending = []
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self._pending = 0
 
 
 class BucketSchedule:
     """Decides WHEN each bucket is complete during IRFD's backward.
 
-    Backward runs the two generator calls first, then the six encoder passes in reverse forward order
-    (Ep(x_t), Ee(x_t), Ei(x_t), Ep(x_s), Ee(x_s), Ei(x_s)).  Encoder passes call `pre()` when they start — every
-    gradient produced by earlier autograd nodes has been accumulated by then — and `post(enc)` when they end.
-      * the generator bucket is launched at the first `pre()`;
-      * encoder E's bucket is launched at the first `pre()`/`final()` after E's second pass.
+    Backward runs the generator first, then the lockstep encoder pass from ResNet stage 4 down to the stem
+    (encoder_group._EncoderGroupFn.backward reports "pre", one "stage" event per finished stage, "post"):
+      * the generator bucket (all of Gd) is launched when the encoder backward starts;
+      * the bucket of stage s (that stage's parameters of all three encoders) when stage s has been written, so only
+        the small stem bucket is left exposed after the last backward kernel.
+    `final()` launches whatever has not been launched (per-encoder fallback path) and waits for the collectives.
     """
 
-    def __init__(self, buckets: GradBuckets, gd_flat_grad: torch.Tensor, encoders: List[torch.nn.Module]):
+    def __init__(self, buckets: GradBuckets, gd_flat_grad: torch.Tensor, stage_flats: Dict[int, torch.Tensor]):
         self.buckets = buckets
         self.gd_flat_grad = gd_flat_grad
-        self.encoders = encoders
+        self.stage_flats = stage_flats  # {stage index (7 = layer4 ... 4 = layer1, 3 = stem): flat gradient buffer}
         self.reset()
 
     def reset(self):
         self.gd_launched = False
-        self.passes = {id(e): 0 for e in self.encoders}
-        self.launched = {id(e): False for e in self.encoders}
+        self.launched = {k: False for k in self.stage_flats}
         self.order: List[str] = []
 
-    def pre(self):
-        self._launch_ready(final=False)
-
-    def post(self, enc, passes: int = 1):
-        """`passes` = how many of the reference's per-image encoder calls this backward covered (2 for a paired pass)."""
-        self.passes[id(enc)] += passes
+    def on_event(self, kind: str, stage: Optional[int]) -> None:
+        if kind == "pre":
+            self._launch_gd()
+        elif kind == "stage":
+            self._launch_gd()
+            self._launch_stage(stage)
 
     def final(self):
-        self._launch_ready(final=True)
+        self._launch_gd()
+        for k in sorted(self.stage_flats, reverse=True):
+            self._launch_stage(k)
         self.buckets.finish()
 
-    def _launch_ready(self, final: bool):
+    def _launch_gd(self):
         if not self.gd_launched:
             self.gd_launched = True
-            self.buckets.launch(flat=self.gd_flat_grad)
+            self.buckets.launch(self.gd_flat_grad)
             self.order.append("Gd")
-        for i, e in enumerate(self.encoders):
-            if (self.passes[id(e)] >= 2 or final) and not self.launched[id(e)]:
-                self.launched[id(e)] = True
-                gs = [p.grad for p in e.parameters() if p.grad is not None]
-                self.buckets.launch(gs)
-                self.order.append(f"E{i}")
+
+    def _launch_stage(self, k):
+        if k in self.launched and not self.launched[k]:
+            self.launched[k] = True
+            self.buckets.launch(self.stage_flats[k])
+            self.order.append(f"S{k}")
+
+
+def broadcast_buffers(modules, src: int = 0) -> None:
+    """DDP's `broadcast_buffers=True` (the reference's default, train.py:399): every rank takes rank `src`'s BatchNorm
+    running buffers.  DDP does this before every forward; the buffers do not enter train-mode arithmetic, so doing it
+    once before an evaluation or a checkpoint leaves every rank with exactly the state DDP would have (rank `src`'s
+    own trajectory)."""
+    if world_size() == 1:
+        return
+    bufs = [b for m in modules for b in m.buffers()]
+    by_dtype: Dict[torch.dtype, List[torch.Tensor]] = {}
+    for b in bufs:
+        by_dtype.setdefault(b.dtype, []).append(b)
+    for group in by_dtype.values():
+        flat = torch.cat([b.reshape(-1) for b in group])
+        dist.broadcast(flat, src=src)
+        off = 0
+        for b in group:
+            b.copy_(flat[off: off + b.numel()].view_as(b))
+            off += b.numel()

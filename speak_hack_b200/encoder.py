@@ -203,8 +203,6 @@ class _EncoderFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dfeat):
         enc, S = ctx.enc, ctx.S
-        if enc._bwd_pre_cb is not None:  # data-parallel trainer: launch gradient buckets that are complete by now
-            enc._bwd_pre_cb()
         train, G = ctx.train, ctx.G
         grads = {}
         dfeat = dfeat.contiguous().view(dfeat.shape[0], -1).to(torch.float32)
@@ -256,8 +254,6 @@ class _EncoderFn(torch.autograd.Function):
         m0 = dz0.numel() // 64
         grads[enc[0].weight] = ops.conv_wgrad(col0.view(1, 1, m0, 192), dz0.view(1, 1, m0, 64), 1, reduce_cin=147,
                                               reduce_taps=1, out_shape=(64, 3, 7, 7))
-        if enc._bwd_post_cb is not None:
-            enc._bwd_post_cb(enc, ctx.G)
         ctx.S = None
         # dL/dx of the stem is not produced: nothing on the IRFD path consumes the image gradient (train.py only sets
         # requires_grad on the batch as a side effect of the R1 penalty).
@@ -288,8 +284,6 @@ class ResNet50Encoder(nn.Sequential):
                 nn.init.constant_(m.weight, 1)
                 nn.init.constant_(m.bias, 0)
         self._recompute_bn_update = False
-        self._bwd_pre_cb = None
-        self._bwd_post_cb = None
 
     def _flat_params(self) -> List[nn.Parameter]:
         return [p for p in self.parameters()]

@@ -378,19 +378,23 @@ def _cut_tensor(cut: int, device) -> torch.Tensor:
 
 class _StyleRowsFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, w, w2, ctrl, ctrl_idx, psi, cutoff, num_layers):
+    def forward(ctx, w, w2, ctrl, ctrl_idx, psi, cutoff, num_layers, b_first=None):
         ctx.cfg = (psi, cutoff)
-        return ops.style_rows_fwd(w.contiguous(), w2.contiguous(), ctrl, ctrl_idx, psi, cutoff, num_layers)
+        return ops.style_rows_fwd(w.contiguous(), w2.contiguous(), ctrl, ctrl_idx, psi, cutoff, num_layers, b_first)
 
     @staticmethod
     def backward(ctx, drows):
         psi, cutoff = ctx.cfg
-        return ops.style_rows_bwd(drows.contiguous(), psi, cutoff), None, None, None, None, None, None
+        return ops.style_rows_bwd(drows.contiguous(), psi, cutoff), None, None, None, None, None, None, None
 
 
-def _generator_forward_static(self: StyleGenerator, features, ctrl, ctrl_idx):
+def _generator_forward_static(self: StyleGenerator, features, ctrl, ctrl_idx, b_first=None):
     """Same math as StyleGenerator.forward with the mixing cut read on the device: ctrl[ctrl_idx] = first mixed row
-    (== num_layers for "no mixing").  w2 is always computed so the launch sequence is identical every step."""
+    (== num_layers for "no mixing").  w2 is always computed so the launch sequence is identical every step.
+    b_first: `features` stacks TWO generator calls along the batch (IRFD: source pairs then target pairs, model.py:
+    110-114); rows [0, b_first) mix at ctrl[ctrl_idx], the rest at ctrl[ctrl_idx + 1].  The generator has no batch
+    statistics, so one stacked call computes exactly what the two calls would (twice the GEMM rows per launch, one
+    weight-gradient pass instead of two)."""
     if features.dim() > 2:
         features = features.flatten(1)
     features = features.to(torch.float32)
@@ -402,7 +406,7 @@ def _generator_forward_static(self: StyleGenerator, features, ctrl, ctrl_idx):
     else:
         w2 = w.detach()  # eval / mixing disabled: the cut is always L, w2 is never read
     psi, cutoff = self._trunc()
-    rows_t = _StyleRowsFn.apply(w, w2, ctrl, ctrl_idx, psi, cutoff, L)
+    rows_t = _StyleRowsFn.apply(w, w2, ctrl, ctrl_idx, psi, cutoff, L, b_first)
     noises = self.synthesis.draw_noises(features.size(0), features.device)
     return _SynthesisFn.apply(rows_t, self.synthesis, noises, *self.synthesis._flat_params())
 

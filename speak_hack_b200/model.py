@@ -9,7 +9,6 @@ the reference's order and the [B,6144] concatenation, which is a bit-exact copy)
 from __future__ import annotations
 
 import logging
-import os
 
 import torch
 import torch.nn as nn
@@ -17,6 +16,7 @@ import torch.nn as nn
 from . import ops
 from .discriminator import StyleDiscriminator
 from .encoder import ResNet50Encoder
+from .encoder_group import EncoderGroup
 from .generator import StyleGenerator
 
 
@@ -24,24 +24,32 @@ class _MSEFn(torch.autograd.Function):
     """nn.MSELoss(reduction='mean') on fp32 CUDA tensors (model.py:206, 358, 367)."""
 
     @staticmethod
-    def forward(ctx, a, b):
+    def forward(ctx, a, b, scale):
         a = a.contiguous().to(torch.float32)
         b = b.contiguous().to(torch.float32)
         ctx.save_for_backward(a, b)
-        return ops.mse_fwd(a, b).view(())
+        ctx.scale = scale
+        out = ops.mse_fwd(a, b)
+        if scale != 1.0:
+            out = ops.scale_copy(out, scale)
+        return out.view(())
 
     @staticmethod
     def backward(ctx, g):
         a, b = ctx.saved_tensors
-        need_a, need_b = ctx.needs_input_grad
-        da, db = ops.mse_bwd(a, b, g.contiguous().view(1).to(torch.float32), need_da=need_a, need_db=need_b)
-        return da, db
+        need_a, need_b = ctx.needs_input_grad[:2]
+        gs = g.contiguous().view(1).to(torch.float32)
+        if ctx.scale != 1.0:
+            gs = ops.scale_copy(gs, ctx.scale)
+        da, db = ops.mse_bwd(a, b, gs, need_da=need_a, need_db=need_b)
+        return da, db, None
 
 
-def mse_loss(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+def mse_loss(a: torch.Tensor, b: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """scale * mean((a - b)^2) (nn.MSELoss, model.py:206, 358, 367); scale folds a sum of equally sized MSE terms."""
     if a.shape != b.shape:
         raise ValueError(f"mse_loss: shape mismatch {tuple(a.shape)} vs {tuple(b.shape)}")
-    return _MSEFn.apply(a, b)
+    return _MSEFn.apply(a, b, float(scale))
 
 
 class IRFD(nn.Module):
@@ -89,54 +97,39 @@ class IRFD(nn.Module):
         with torch.no_grad():
             return enc(x)
 
-    def encoder_streams(self, device):
-        """Three side streams (one per encoder), created on first use."""
-        st = getattr(self, "_enc_streams", None)
-        if st is None or st[0].device != device:
-            if os.environ.get("IRFD_NO_ENC_STREAMS"):  # profiling aid: serialise everything on the current stream
-                st = [torch.cuda.current_stream(device)] * 3
-            else:
-                st = [torch.cuda.Stream(device) for _ in range(3)]
-            self._enc_streams = st
-        return st
+    @property
+    def encoder_group(self):
+        """Lockstep runner of the three encoders (encoder_group.EncoderGroup), created on first use."""
+        grp = self.__dict__.get("_encoder_group")
+        if grp is None or grp.encoders != [self.Ei, self.Ee, self.Ep]:
+            grp = EncoderGroup([self.Ei, self.Ee, self.Ep])
+            self.__dict__["_encoder_group"] = grp
+        return grp
 
     def _encode_all(self, x_s, x_t):
-        """The six encoder passes of model.py:84-90.  When shapes allow, source and target go through each encoder as
-        ONE launch sequence with two BatchNorm statistic groups: numerically the same as Ei(x_s) followed by Ei(x_t)
-        (per-call batch statistics, running buffers updated in that order), at half the kernel launches."""
+        """The six encoder passes of model.py:84-90.  When shapes allow, the three encoders run in lockstep on the
+        stacked source+target batch: ONE launch per layer (grouped GEMM over the three weight sets, BatchNorm over
+        3 encoders x 2 statistic groups) — numerically the same as Ei(x_s), Ee(x_s), Ep(x_s), Ei(x_t), ... (per-call
+        batch statistics, each encoder's running buffers updated source first), at a sixth of the kernel launches."""
         same = x_s.shape == x_t.shape and x_s.requires_grad == x_t.requires_grad and x_s.is_cuda
-        if same and x_s.dim() == 4 and (x_s.size(0) * (x_s.size(2) // 32) * (x_s.size(3) // 32)) % 128 == 0:
-            B = x_s.size(0)
+        grp = self.encoder_group
+        diff = torch.is_grad_enabled() and x_s.requires_grad
+        if same and x_s.dim() == 4 and (grp.encoders[0].training or not diff):
             x = torch.cat([x_s, x_t], dim=0)  # cat keeps requires_grad (SURVEY Q2 semantics)
-            # The three encoders are independent: run them on three streams (fork/join by events, capturable in a
-            # CUDA graph) so the many small, tail-dominated kernels of one encoder overlap with the others'.  Autograd
-            # replays each encoder's backward on the stream its forward ran on.
-            cur = torch.cuda.current_stream(x.device)
-            streams = self.encoder_streams(x.device)
-            cols = ops.im2col_stem(x.detach().contiguous().to(torch.float32), 192)  # shared by the three stems
-            fork = torch.cuda.Event()
-            fork.record(cur)
-            feats = []
-            for enc, st in zip((self.Ei, self.Ee, self.Ep), streams):
-                st.wait_event(fork)
-                x.record_stream(st)
-                cols.record_stream(st)
-                with torch.cuda.stream(st):
-                    if torch.is_grad_enabled() and x.requires_grad:
+            if grp.can_run(x, 2):
+                B = x_s.size(0)
+                if diff:
+                    for enc in grp.encoders:
                         enc._recompute_bn_update = enc.training
-                        try:
-                            f = enc.forward_groups(x, 2, cols)
-                        finally:
+                    try:
+                        f = grp(x, 2)
+                    finally:
+                        for enc in grp.encoders:
                             enc._recompute_bn_update = False
-                    else:
-                        with torch.no_grad():
-                            f = enc.forward_groups(x, 2, cols)
-                f.record_stream(cur)
-                feats.append(f)
-            for st in streams:
-                cur.wait_stream(st)
-            (fi_s, fi_t), (fe_s, fe_t), (fp_s, fp_t) = [(f[:B], f[B:]) for f in feats]
-            return fi_s, fe_s, fp_s, fi_t, fe_t, fp_t
+                else:
+                    with torch.no_grad():
+                        f = grp(x, 2)
+                return f[0, :B], f[1, :B], f[2, :B], f[0, B:], f[1, B:], f[2, B:]
         return (self._encode(self.Ei, x_s), self._encode(self.Ee, x_s), self._encode(self.Ep, x_s),
                 self._encode(self.Ei, x_t), self._encode(self.Ee, x_t), self._encode(self.Ep, x_t))
 
@@ -209,7 +202,7 @@ class IRFDLoss(nn.Module):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# Static-graph variant of IRFD.forward (used by trainer.IRFDTrainer(use_cuda_graph=True))
+# Static-graph variant of IRFD.forward (used by trainer.IRFDTrainer(use_cuda_graph=True) and inference.IRFDInference)
 # ----------------------------------------------------------------------------------------------------------------------
 class _SwapCatFn(torch.autograd.Function):
     """Device-side S<->T swap + concat: ctrl[0] = swap_type.  Pure copies (bit-exact), see csrc/control.cu."""
@@ -228,30 +221,64 @@ class _SwapCatFn(torch.autograd.Function):
         return (None,) + tuple(o.view(s) for o, s in zip(outs, ctx.shapes))
 
 
+class _SwapCatStackedFn(torch.autograd.Function):
+    """The same on the stacked layout of the lockstep encoder pass: f [3, 2B, C, 1, 1] (encoder-major; source rows then
+    target rows) -> gen [2B, 3C] whose first B rows are the source generator input and the rest the target's
+    (model.py:97-114).  Backward scatters into ONE [3, 2B, C] gradient buffer (six slices written by one kernel)."""
+
+    @staticmethod
+    def forward(ctx, ctrl, f):
+        e, n2, c = f.shape[0], f.shape[1], f.shape[2]
+        b = n2 // 2
+        f2 = f.reshape(e, n2, c)
+        gen = torch.empty((n2, e * c), dtype=torch.float32, device=f.device)
+        ops.swap_cat_fwd([f2[0, :b], f2[1, :b], f2[2, :b], f2[0, b:], f2[1, b:], f2[2, b:]], ctrl, out=gen)
+        ctx.ctrl, ctx.shape = ctrl, f.shape
+        return gen
+
+    @staticmethod
+    def backward(ctx, dgen):
+        dgen = dgen.contiguous()
+        e, n2, c = ctx.shape[0], ctx.shape[1], ctx.shape[2]
+        b = n2 // 2
+        df = torch.empty((e, n2, c), dtype=torch.float32, device=dgen.device)
+        ops.swap_cat_bwd(dgen[:b], dgen[b:], ctx.ctrl, c,
+                         outs=[df[0, :b], df[1, :b], df[2, :b], df[0, b:], df[1, b:], df[2, b:]])
+        return None, df.view(ctx.shape)
+
+
 def _irfd_forward_static(self: IRFD, x_s, x_t, ctrl):
     """IRFD.forward with the swap / style-mixing decisions taken on the device from `ctrl` (int32 [3]).
     Returns (x_s_recon, x_t_recon, fi_s, fi_t) with fi_* UNswapped (the identity MSE is symmetric in them)."""
-    fi_s, fe_s, fp_s, fi_t, fe_t, fp_t = self._encode_all(x_s, x_t)
-    gen_s, gen_t = _SwapCatFn.apply(ctrl, fi_s, fe_s, fp_s, fi_t, fe_t, fp_t)
-    # the two generator calls are independent: run them on two streams (autograd replays each backward on the same
-    # stream); the weight repacks they share are built before the fork
-    dev = gen_s.device
-    cur = torch.cuda.current_stream(dev)
-    st_a, st_b = self.encoder_streams(dev)[:2]
-    self.Gd.synthesis.prepack(backward=torch.is_grad_enabled())
-    fork = torch.cuda.Event()
-    fork.record(cur)
-    outs = []
-    for g, st, idx in ((gen_s, st_a, 1), (gen_t, st_b, 2)):
-        st.wait_event(fork)
-        g.record_stream(st)
-        with torch.cuda.stream(st):
-            img = self.Gd.forward_static(g, ctrl, idx)
-        img.record_stream(cur)
-        outs.append(img)
-    cur.wait_stream(st_a)
-    cur.wait_stream(st_b)
-    return outs[0], outs[1], fi_s, fi_t
+    img, f, b = self.forward_static_stacked(torch.cat([x_s, x_t], dim=0), ctrl)
+    return img[:b], img[b:], f[0, :b], f[0, b:]
+
+
+def _irfd_forward_static_stacked(self: IRFD, x, ctrl):
+    """The whole forward on the stacked batch x = [x_s; x_t] ([2B, 3, H, W]): the three encoders in lockstep (one launch
+    per layer), device-side swap + concat, ONE generator call over the 2B stacked codes.
+    Returns (images [2B, 3, R, R] (source reconstructions first), features [3, 2B, 2048, 1, 1] unswapped, B)."""
+    grp = self.encoder_group
+    b = x.size(0) // 2
+    diff = torch.is_grad_enabled() and x.requires_grad
+    if not grp.can_run(x, 2) or (diff and not grp.encoders[0].training):
+        raise ops._lib.IrfdError(f"IRFD.forward_static: batch {tuple(x.shape)} cannot run as one lockstep encoder pass "
+                                 "(needs pairs x (H/32) x (W/32) to be a multiple of 128); use IRFD.forward")
+    if diff:
+        for enc in grp.encoders:
+            enc._recompute_bn_update = enc.training
+        try:
+            f = grp(x, 2)
+        finally:
+            for enc in grp.encoders:
+                enc._recompute_bn_update = False
+    else:
+        with torch.no_grad():
+            f = grp(x, 2)
+    gen = _SwapCatStackedFn.apply(ctrl, f)
+    img = self.Gd.forward_static(gen, ctrl, 1, b_first=b)
+    return img, f, b
 
 
 IRFD.forward_static = _irfd_forward_static
+IRFD.forward_static_stacked = _irfd_forward_static_stacked

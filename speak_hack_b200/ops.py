@@ -5,6 +5,7 @@ Activations are NHWC bf16 tensors; parameters and reductions are fp32.
 """
 from __future__ import annotations
 
+import ctypes
 import weakref
 from typing import Optional
 
@@ -174,6 +175,72 @@ def conv_gemm_affine(x, wk, ksize, scale, shift, res=None, relu=True, force_bloc
     return out
 
 
+def conv_gemm_grouped(x, wk, ksize, mode=EPI_PLAIN, wgroups=3, a_shared=False, rows=None, force_block_n=0):
+    """One launch for `wgroups` weight sets (the three IRFD encoders).  x [N,H,W,Cin] bf16 stacks the groups' images
+    group-major (N = wgroups * images per group); wk [wgroups*Cout, k*k*Cin].  a_shared: x is a 2-D [rows_per_group, K]
+    matrix read by every group (the stem's im2col); the output then has wgroups * rows_per_group rows.
+    Returns out (mode 0) or (out, stat_sum, stat_sq) (mode 1; partials are [m_tiles, Cout], group-major tiles)."""
+    lib = _lib.load()
+    _chk(x, BF16, "x")
+    _chk(wk, BF16, "wk")
+    if wk.shape[0] % wgroups:
+        raise _lib.IrfdError(f"conv_gemm_grouped: {wk.shape[0]} weight rows do not split into {wgroups} groups")
+    cout = wk.shape[0] // wgroups
+    if a_shared:
+        m_g, cin = x.shape
+        n, h, w = 1, 1, m_g * wgroups
+        out = torch.empty((m_g * wgroups, cout), dtype=BF16, device=x.device)
+    else:
+        n, h, w, cin = x.shape
+        out = torch.empty((n, h, w, cout), dtype=BF16, device=x.device)
+    if wk.shape[1] != ksize * ksize * cin:
+        raise _lib.IrfdError(f"wk shape {tuple(wk.shape)} does not match ksize={ksize}, cin={cin}")
+    m = n * h * w
+    ssum = ssq = None
+    if mode == EPI_STATS:
+        mt = lib.irfd_conv_gemm_m_tiles(n, h, w)
+        ssum = torch.empty((mt, cout), dtype=F32, device=x.device)
+        ssq = torch.empty((mt, cout), dtype=F32, device=x.device)
+    nbytes = 2.0 * m * cin / (wgroups if a_shared else 1) + 2.0 * m * cout + 2.0 * wgroups * cin * cout * ksize * ksize
+    with _timed("conv_gemm_kernel (tcgen05 fprop/dgrad)", 2.0 * m * cout * cin * ksize * ksize, nbytes):
+        _call("irfd_conv_gemm_grouped", x.data_ptr(), n, h, w, cin, wk.data_ptr(), cout, ksize, out.data_ptr(), mode,
+              _ptr(ssum), _ptr(ssq), wgroups, 1 if a_shared else 0, force_block_n, _stream())
+    if mode == EPI_STATS:
+        return out, ssum, ssq
+    return out
+
+
+def conv_gemm_affine_grouped(x, wk, ksize, scale, shift, res=None, relu=True, wgroups=3, a_shared=False,
+                             force_block_n=0):
+    """Grouped conv with y = act(acc*scale[g] + shift[g] [+ res]) in the epilogue; scale/shift are [wgroups, Cout]."""
+    _chk(x, BF16, "x")
+    _chk(wk, BF16, "wk")
+    _chk(scale, F32, "scale")
+    _chk(shift, F32, "shift")
+    cout = wk.shape[0] // wgroups
+    if a_shared:
+        m_g, cin = x.shape
+        n, h, w = 1, 1, m_g * wgroups
+        out = torch.empty((m_g * wgroups, cout), dtype=BF16, device=x.device)
+    else:
+        n, h, w, cin = x.shape
+        out = torch.empty((n, h, w, cout), dtype=BF16, device=x.device)
+    if scale.numel() != wgroups * cout or shift.numel() != wgroups * cout:
+        raise _lib.IrfdError("conv_gemm_affine_grouped: scale/shift must be [wgroups, Cout]")
+    if res is not None:
+        _chk(res, BF16, "res")
+        if res.numel() != out.numel():
+            raise _lib.IrfdError("conv_gemm_affine_grouped: residual shape mismatch")
+    m = n * h * w
+    nbytes = (2.0 * m * cin / (wgroups if a_shared else 1) + 2.0 * m * cout * (2 if res is not None else 1)
+              + 2.0 * wgroups * cin * cout * ksize * ksize)
+    with _timed("conv_gemm_kernel (tcgen05 fprop/dgrad)", 2.0 * m * cout * cin * ksize * ksize, nbytes):
+        _call("irfd_conv_gemm_affine_grouped", x.data_ptr(), n, h, w, cin, wk.data_ptr(), cout, ksize, out.data_ptr(),
+              scale.data_ptr(), shift.data_ptr(), _ptr(res), int(relu), wgroups, 1 if a_shared else 0, force_block_n,
+              _stream())
+    return out
+
+
 def bn_eval_affine(bn):
     """(scale, shift) of an eval-mode nn.BatchNorm2d, cached on nothing: two tiny launches per call."""
     c = bn.weight.numel()
@@ -220,7 +287,10 @@ _pack_cache = {}
 def invalidate_packed(params) -> None:
     """Drop cached bf16 repacks of `params` (call after updating them through a raw pointer, e.g. irfd_adam_step)."""
     ptrs = {p.data_ptr() for p in params}
-    for key in [k for k in _pack_cache if k[0] in ptrs]:
+    def hit(k0):  # single-weight entries key on one pointer, stacked entries on a tuple of pointers
+        return any(q in ptrs for q in k0) if isinstance(k0, tuple) else k0 in ptrs
+
+    for key in [k for k in _pack_cache if hit(k[0])]:
         del _pack_cache[key]
 
 
@@ -239,7 +309,25 @@ def pack_conv_weight(w: torch.Tensor, mode: int, kpad: int = 0) -> torch.Tensor:
     return packed
 
 
-def _pack_conv_weight(w: torch.Tensor, mode: int, kpad: int = 0) -> torch.Tensor:
+def pack_conv_weights_stacked(ws, mode: int, kpad: int = 0) -> torch.Tensor:
+    """Packed bf16 operands of several same-shape conv weights stacked along the rows ([len(ws)*rows, K]) for the
+    grouped launches; cached until any of the weights changes (same validity rule as pack_conv_weight)."""
+    key = (tuple(w.data_ptr() for w in ws), mode, kpad, tuple(ws[0].shape))
+    vers = tuple(w._version for w in ws)
+    hit = _pack_cache.get(key)
+    if hit is not None and hit[0] == vers and all(r() is w for r, w in zip(hit[2], ws)):
+        return hit[1]
+    o, i, kh, kw = ws[0].shape
+    taps = kh * kw
+    rows, cols = {PACK_FPROP: (o, taps * i), PACK_DGRAD: (i, taps * o), PACK_DCOL: (taps * i, o)}.get(mode, (o, kpad))
+    dst = torch.empty((len(ws) * rows, cols), dtype=BF16, device=ws[0].device)
+    for e, w in enumerate(ws):
+        _pack_conv_weight(w, mode, kpad, out=dst[e * rows: (e + 1) * rows])
+    _pack_cache[key] = (vers, dst, [weakref.ref(w) for w in ws])
+    return dst
+
+
+def _pack_conv_weight(w: torch.Tensor, mode: int, kpad: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _chk(w, F32, "w")
     o, i, kh, kw = w.shape
     taps = kh * kw
@@ -251,7 +339,9 @@ def _pack_conv_weight(w: torch.Tensor, mode: int, kpad: int = 0) -> torch.Tensor
         shape = (taps * i, o)
     else:
         shape = (o, kpad)
-    dst = torch.empty(shape, dtype=BF16, device=w.device)
+    dst = out if out is not None else torch.empty(shape, dtype=BF16, device=w.device)
+    if tuple(dst.shape) != tuple(shape) or not dst.is_contiguous():
+        raise _lib.IrfdError(f"_pack_conv_weight: destination {tuple(dst.shape)} != {tuple(shape)}")
     _call("irfd_pack_conv_weight", w.data_ptr(), dst.data_ptr(), o, i, taps, mode, kpad, _stream())
     return dst
 
@@ -324,6 +414,86 @@ def _bn_backward_call(g1, g2, act, z, mean, rstd, gamma, beta, dz, g_out, dgamma
           gamma.data_ptr(), _ptr(beta), dz.data_ptr(), _ptr(g_out), dgamma.data_ptr(), dbeta.data_ptr(), 0.0,
           1 if batch_stats else 0, rows, c, groups,
           ws.data_ptr(), ws.numel(), _stream(), launches=3)
+
+
+def _ptr_array(tensors):
+    """Host array of device pointers (one per parameter set) for the *_sets entry points; None when no tensor given."""
+    if tensors is None:
+        return None
+    return (ctypes.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+
+
+def bn_eval_affine_sets(bns):
+    """(scale, shift) [nsets, C] of eval-mode nn.BatchNorm2d layers of one shape, one launch."""
+    c = bns[0].weight.numel()
+    dev = bns[0].weight.device
+    scale = torch.empty((len(bns), c), dtype=F32, device=dev)
+    shift = torch.empty((len(bns), c), dtype=F32, device=dev)
+    _call("irfd_bn_eval_affine_sets", _ptr_array([b.running_mean for b in bns]), _ptr_array([b.running_var for b in bns]),
+          _ptr_array([b.weight for b in bns]), _ptr_array([b.bias for b in bns]), float(bns[0].eps), scale.data_ptr(),
+          shift.data_ptr(), c, len(bns), _stream())
+    return scale, shift
+
+
+def bn_finalize_sets(ssum, ssq, count, eps, momentum, running_means, running_vars, running_updates, groups, nsets):
+    """`nsets` BatchNorm layers of one shape (same layer of the three encoders) x `groups` statistic groups each.
+    ssum/ssq: [tiles, C] with the tiles stacked set-major, group-major inside a set.  count = rows PER GROUP.
+    Returns mean, rstd [nsets*groups, C]; each set's running buffers are updated in place."""
+    tiles, c = ssum.shape
+    tot = groups * nsets
+    if tiles % tot:
+        raise _lib.IrfdError(f"bn_finalize_sets: {tiles} tiles do not split into {nsets} sets x {groups} groups")
+    mean = torch.empty((tot, c), dtype=F32, device=ssum.device)
+    rstd = torch.empty((tot, c), dtype=F32, device=ssum.device)
+    _call("irfd_bn_finalize_sets", ssum.data_ptr(), ssq.data_ptr(), tiles // tot, c, int(count), eps, momentum,
+          mean.data_ptr(), rstd.data_ptr(), _ptr_array(running_means), _ptr_array(running_vars), running_updates, groups,
+          nsets, _stream())
+    return mean, rstd
+
+
+def bn_apply_sets(z, mean, rstd, gammas, betas, res=None, bn2=None, relu=True, groups=1):
+    """out = [relu](BN(z) [+ res | + BN2(res)]) with per-set gamma/beta lists (len = nsets) and per-group statistics
+    (`groups` = TOTAL statistic groups); bn2 = (mean2, rstd2, gammas2, betas2)."""
+    _chk(z, BF16, "z")
+    c = z.shape[-1]
+    rows = z.numel() // c
+    out = torch.empty_like(z)
+    m2 = r2 = g2 = b2 = None
+    if bn2 is not None:
+        m2, r2, g2, b2 = bn2
+    _call("irfd_bn_apply_sets", z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _ptr_array(gammas), _ptr_array(betas),
+          _ptr(res), _ptr(m2), _ptr(r2), _ptr_array(g2) if g2 is not None else _ptr_array([None] * len(gammas)),
+          _ptr_array(b2) if b2 is not None else _ptr_array([None] * len(gammas)), out.data_ptr(), rows, c,
+          1 if relu else 0, groups, len(gammas), _stream())
+    return out
+
+
+def bn_backward_sets(g1, g2, act, z, mean, rstd, gammas, betas=None, dgammas=None, dbetas=None, want_g_out=False,
+                     batch_stats=True, groups=1):
+    """BN backward for `len(gammas)` parameter sets in one launch sequence.  dgammas/dbetas: optional lists of [C] fp32
+    output tensors (written, not accumulated); allocated as one [nsets, C] tensor each when omitted.
+    Returns dz, dgamma(s), dbeta(s) [, masked g]."""
+    lib = _lib.load()
+    c = z.shape[-1]
+    rows = z.numel() // c
+    nsets = len(gammas)
+    dz = torch.empty_like(z)
+    g_out = torch.empty_like(z) if want_g_out else None
+    if dgammas is None:
+        dg_all = torch.empty((nsets, c), dtype=F32, device=z.device)
+        db_all = torch.empty((nsets, c), dtype=F32, device=z.device)
+        dgammas, dbetas = list(dg_all.unbind(0)), list(db_all.unbind(0))
+    ws = workspace(lib.irfd_bn_bwd_workspace_bytes(rows, c, groups), z.device)
+    n_in = 2 + (g2 is not None) + (act is not None)
+    nbytes = 2.0 * rows * c * (2 * n_in + 1 + (1 if want_g_out else 0))
+    with _timed("bn_backward (reduce+finalize+apply, HBM)", nbytes):
+        _call("irfd_bn_backward_sets", g1.data_ptr(), _ptr(g2), _ptr(act), z.data_ptr(), mean.data_ptr(),
+              rstd.data_ptr(), _ptr_array(gammas), _ptr_array(betas) if betas is not None else None, dz.data_ptr(),
+              _ptr(g_out), _ptr_array(dgammas), _ptr_array(dbetas), 0.0, 1 if batch_stats else 0, rows, c, groups, nsets,
+              ws.data_ptr(), ws.numel(), _stream(), launches=3)
+    if want_g_out:
+        return dz, dgammas, dbetas, g_out
+    return dz, dgammas, dbetas
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -624,11 +794,12 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, total_sumsq=None, max_nor
 # ----------------------------------------------------------------------------------------------------------------------
 # device-side routing (static-graph mode)
 # ----------------------------------------------------------------------------------------------------------------------
-def style_rows_fwd(w, w2, ctrl, ctrl_idx, psi, cutoff, num_layers):
+def style_rows_fwd(w, w2, ctrl, ctrl_idx, psi, cutoff, num_layers, b_first=None):
+    """b_first: the batch stacks two generator calls; rows [0, b_first) use ctrl[ctrl_idx], the rest ctrl[ctrl_idx+1]."""
     b, k = w.shape
     rows_t = torch.empty((num_layers, b, k), dtype=F32, device=w.device)
-    _call("irfd_style_rows_fwd", w.data_ptr(), w2.data_ptr(), ctrl.data_ptr(), ctrl_idx, psi, cutoff,
-          rows_t.data_ptr(), num_layers, b, k, _stream())
+    _call("irfd_style_rows_pair_fwd", w.data_ptr(), w2.data_ptr(), ctrl.data_ptr(), ctrl_idx, psi, cutoff,
+          rows_t.data_ptr(), num_layers, b, k, b if b_first is None else b_first, _stream())
     return rows_t
 
 
@@ -639,19 +810,26 @@ def style_rows_bwd(drows_t, psi, cutoff):
     return dw
 
 
-def swap_cat_fwd(feats, ctrl):
-    """feats = (fi_s, fe_s, fp_s, fi_t, fe_t, fp_t), each [B, C] fp32 contiguous."""
+def swap_cat_fwd(feats, ctrl, out=None):
+    """feats = (fi_s, fe_s, fp_s, fi_t, fe_t, fp_t), each [B, C] fp32 contiguous.  out: optional [2B, 3C] buffer whose
+    halves receive the source and the target generator inputs (one stacked generator call)."""
     b, c = feats[0].shape
-    gen_s = torch.empty((b, 3 * c), dtype=F32, device=feats[0].device)
-    gen_t = torch.empty_like(gen_s)
+    if out is not None:
+        _chk(out, F32, "out")
+        gen_s, gen_t = out[:b], out[b:]
+    else:
+        gen_s = torch.empty((b, 3 * c), dtype=F32, device=feats[0].device)
+        gen_t = torch.empty_like(gen_s)
     _call("irfd_swap_cat_fwd", *[f.data_ptr() for f in feats], ctrl.data_ptr(), gen_s.data_ptr(), gen_t.data_ptr(), b,
           c, _stream())
     return gen_s, gen_t
 
 
-def swap_cat_bwd(dgen_s, dgen_t, ctrl, c):
+def swap_cat_bwd(dgen_s, dgen_t, ctrl, c, outs=None):
+    """outs: optional six [B, C] fp32 destinations (e.g. slices of one stacked feature-gradient buffer)."""
     b = dgen_s.shape[0]
-    outs = [torch.empty((b, c), dtype=F32, device=dgen_s.device) for _ in range(6)]
+    if outs is None:
+        outs = [torch.empty((b, c), dtype=F32, device=dgen_s.device) for _ in range(6)]
     _call("irfd_swap_cat_bwd", dgen_s.data_ptr(), dgen_t.data_ptr(), ctrl.data_ptr(), *[o.data_ptr() for o in outs], b,
           c, _stream())
     return outs

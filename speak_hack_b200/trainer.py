@@ -5,22 +5,35 @@ statistics, like the reference under accelerate/DDP without SyncBN); gradients a
 overlapped with backward (dp.py); Adam (train.py:346: Gd.parameters() only, lr 2e-4) is one fused kernel over a flat
 parameter buffer, optionally preceded by clip_grad_norm_ over ALL model parameters (train.py:207-208).
 
-`use_cuda_graph=True` captures the WHOLE step (zero_grad, forward, losses, backward, all-reduce, Adam: ~3,700 kernel
-launches) into one CUDA graph.  The reference's CPU-generator decisions (swap type, style-mixing cuts) are still drawn
-on the host in the reference's order every step, but reach the kernels through a 3-int control tensor
-(csrc/control.cu) so the launch sequence is static.  Differences from eager mode: the style-mixing latent w2 is
-computed every step (one extra randn_like draw on the device generator when the reference would not mix), and the
-encoders' bf16 weight repacks are captured as constants (encoders have no optimizer in the reference, train.py:346).
+Loss: l_identity + l_recon, the differentiable terms of the reference's criterion (model.py:356-372; the pose and
+emotion terms carry no gradient) — SURVEY §8(d) config 3.  The reference's G step additionally adds
+`stylegan_loss_weight * BCE(D(x_recon), real)` (train.py:197-203); pass `adv_weight` to include it: D(x_s_recon) and
+D(x_t_recon) run through the native discriminator, their gradient reaches Gd, and D's own parameter gradients (which
+the reference's clip_grad_norm_ over model.parameters() also sees) enter the clipping norm.
+
+Gradient buffers are flat: all of Gd in one fp32 buffer, the encoders in one buffer per ResNet stage holding that
+stage's parameters of Ei, Ee and Ep.  The lockstep encoder backward (encoder_group.py) writes every encoder gradient
+straight into its slot (no autograd accumulation kernels), and each buffer is one all-reduce bucket.
+
+`use_cuda_graph=True` captures the WHOLE step (zero_grad, forward, losses, backward, all-reduce, Adam) into one CUDA
+graph on ONE stream (plus the communication stream).  The reference's CPU-generator decisions (swap type, style-mixing
+cuts) are still drawn on the host in the reference's order every step, but reach the kernels through a 3-int control
+tensor (csrc/control.cu) so the launch sequence is static.  Differences from eager mode: source and target images live
+in one stacked [2B,3,H,W] buffer, the two generator calls run as ONE call over the 2B stacked codes (the generator has
+no batch statistics), and the encoders' bf16 weight repacks are captured as constants (encoders have no optimizer in
+the reference, train.py:346).
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import Dict, List, Optional
 
 import torch
 
 from . import ops
-from .dp import BucketSchedule, GradBuckets
+from .dp import BucketSchedule, GradBuckets, broadcast_buffers
 from .model import IRFD, mse_loss
+
+STAGES = (7, 6, 5, 4, 3)  # ResNet50Encoder child indices 7..4 = layer4..layer1; 3 stands for the stem (children 0, 1)
 
 
 def flatten_parameters(params: List[torch.nn.Parameter]):
@@ -39,13 +52,58 @@ def flatten_parameters(params: List[torch.nn.Parameter]):
     return flat, gflat
 
 
+def _stage_of(name: str) -> int:
+    idx = int(name.split(".")[0])
+    return idx if idx >= 4 else 3
+
+
+def flat_encoder_gradients(encoders) -> (Dict[int, torch.Tensor], Dict[torch.nn.Parameter, torch.Tensor]):
+    """One flat fp32 gradient buffer per ResNet stage (all encoders' parameters of that stage, encoder after encoder);
+    every parameter's .grad becomes a view of its slot.  Returns ({stage: flat}, {parameter: view})."""
+    dev = next(encoders[0].parameters()).device
+    by_stage: Dict[int, List[torch.nn.Parameter]] = {k: [] for k in STAGES}
+    for enc in encoders:
+        for name, p in enc.named_parameters():
+            by_stage[_stage_of(name)].append(p)
+    flats, targets = {}, {}
+    for k, ps in by_stage.items():
+        flat = torch.zeros(sum(p.numel() for p in ps), dtype=torch.float32, device=dev)
+        off = 0
+        for p in ps:
+            v = flat[off: off + p.numel()].view_as(p)
+            p.grad = v
+            targets[p] = v
+            off += p.numel()
+        flats[k] = flat
+    return flats, targets
+
+
+class _BCELogitsFn(torch.autograd.Function):
+    """mean(BCEWithLogits(x, target)) for a constant target in {0, 1} on a [B, 1] logit tensor (train.py:200-201).
+    B values: evaluated with the fp32 softplus form, gradient (sigmoid(x) - t) / B."""
+
+    @staticmethod
+    def forward(ctx, logits, target: float):
+        x = logits.detach().to(torch.float32)
+        ctx.save_for_backward(x)
+        ctx.target = target
+        return (torch.clamp(x, min=0) - x * target + torch.log1p(torch.exp(-x.abs()))).mean()
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return g * (torch.sigmoid(x) - ctx.target) / x.numel(), None
+
+
 class IRFDTrainer:
     def __init__(self, model: IRFD, lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8,
-                 grad_clip: Optional[float] = None, encoder_grads: bool = True, use_cuda_graph: bool = False):
+                 grad_clip: Optional[float] = None, encoder_grads: bool = True, use_cuda_graph: bool = False,
+                 adv_weight: Optional[float] = None):
         self.model = model
         self.lr, self.betas, self.eps = lr, betas, eps
         self.grad_clip = grad_clip
         self.encoder_grads = encoder_grads
+        self.adv_weight = adv_weight
         self.gd_params = list(model.Gd.parameters())
         self.flat, self.gflat = flatten_parameters(self.gd_params)
         self._gd_conv_weights = [p for p in self.gd_params if p.dim() == 4 and p.shape[-1] == 3]
@@ -54,11 +112,11 @@ class IRFDTrainer:
         self.step_count = 0
         self.encoders = [model.Ei, model.Ee, model.Ep]
         self.device = self.flat.device
+        self.stage_flats, self._enc_targets = flat_encoder_gradients(self.encoders)
+        self._enc_params = [p for e in self.encoders for p in e.parameters()]
         self.buckets = GradBuckets(self.device)
-        if self.device.type == "cuda":
-            self.buckets.producer_streams = list(model.encoder_streams(self.device))
         self.world = self.buckets.world
-        self.schedule = BucketSchedule(self.buckets, self.gflat, self.encoders)
+        self.schedule = BucketSchedule(self.buckets, self.gflat, self.stage_flats)
         self.last_losses = None
         # static-graph state
         self.use_cuda_graph = use_cuda_graph
@@ -71,59 +129,87 @@ class IRFDTrainer:
                            if self.device.type == "cuda" else [])
         self._ctrl_slot = 0
         self._graph_key = None
+        self.last_ctrl = None
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._static = None
 
     # ---------------------------------------------------------------------------------------------- shared pieces
-    def zero_grad(self):
+    def zero_grad(self, encoders_direct: bool = True):
+        """Gd gradients are accumulated by autograd into the flat buffer: zero it.  Encoder gradients are overwritten by
+        the lockstep backward; only the per-encoder fallback path (autograd accumulation) needs them zeroed."""
         self.gflat.zero_()
-        for enc in self.encoders:
-            for p in enc.parameters():
+        if self.adv_weight is not None:
+            for p in self.model.D.parameters():
                 p.grad = None
+        for p in self._enc_params:  # keep .grad pointing into the flat stage buffers
+            if p.grad is not self._enc_targets[p]:
+                p.grad = self._enc_targets[p]
+        if not encoders_direct:
+            for f in self.stage_flats.values():
+                f.zero_()
+
+    def _direct(self, x_s) -> bool:
+        """Will a batch of this shape run as ONE lockstep encoder pass (source and target stacked) that writes its
+        gradients in place?  Mirrors IRFD._encode_all / EncoderGroup.can_run for 2 statistic groups of x_s.size(0)."""
+        ok = (x_s.is_cuda and x_s.dim() == 4 and x_s.shape[1] == 3 and x_s.shape[2] % 32 == 0 and x_s.shape[3] % 32 == 0
+              and (x_s.size(0) * (x_s.shape[2] // 32) * (x_s.shape[3] // 32)) % 128 == 0)
+        return bool(ok and self.encoder_grads and all(e.training for e in self.encoders))
 
     def _backward_and_update(self, loss, static: bool):
+        grp = self.model.encoder_group
         if self.world > 1:
             self.schedule.reset()
-            for e in self.encoders:
-                e._bwd_pre_cb, e._bwd_post_cb = self.schedule.pre, self.schedule.post
+            grp._bwd_cb = self.schedule.on_event
         try:
             loss.backward()
         finally:
-            for e in self.encoders:
-                e._bwd_pre_cb = e._bwd_post_cb = None
+            grp._bwd_cb = None
         if self.world > 1:
             self.schedule.final()
         self.step_count += 1
         total_sumsq = None
         if self.grad_clip is not None:
             total_sumsq = ops.sumsq(self.gflat)
-            for enc in self.encoders:
-                for p in enc.parameters():
+            for f in self.stage_flats.values():
+                ops.sumsq(f, out=total_sumsq, out_beta=1.0)
+            if self.adv_weight is not None:  # clip_grad_norm_(model.parameters()) also sees D's gradients
+                for p in self.model.D.parameters():
                     if p.grad is not None:
-                        ops.sumsq(p.grad.reshape(-1), out=total_sumsq, out_beta=1.0)
+                        ops.sumsq(p.grad.reshape(-1).contiguous(), out=total_sumsq, out_beta=1.0)
         ops.adam_step(self.flat, self.gflat, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps,
                       self.step_count, total_sumsq=total_sumsq, max_norm=self.grad_clip or 0.0,
                       step_dev=self.step_dev if static else None)
         ops.invalidate_packed(self._gd_conv_weights)  # Adam wrote through the flat buffer: bf16 repacks are stale
 
-    def _prep_inputs(self, x_s, x_t):
-        if self.encoder_grads:
-            # train.py's R1 penalty leaves requires_grad=True on the batch, which is what lets the reference's
-            # reentrant checkpoints differentiate the encoders
-            return x_s.detach().requires_grad_(True), x_t.detach().requires_grad_(True)
-        return x_s.detach(), x_t.detach()
+    def _prep(self, x):
+        # train.py's R1 penalty leaves requires_grad=True on the batch, which is what lets the reference's reentrant
+        # checkpoints differentiate the encoders (SURVEY Q2)
+        return x.detach().requires_grad_(True) if self.encoder_grads else x.detach()
+
+    def _adversarial(self, recon):
+        """stylegan_loss_weight * mean over the two reconstructions of BCE(D(x_recon), real) (train.py:197-203)."""
+        d = self.model.D(recon)
+        return _BCELogitsFn.apply(d, 1.0)
 
     # ---------------------------------------------------------------------------------------------- eager step
     def train_step_eager(self, x_s: torch.Tensor, x_t: torch.Tensor):
         """zero_grad -> forward -> MSE losses -> backward (+ overlapped all-reduce) -> [clip] -> Adam on Gd."""
-        self.zero_grad()
-        x_s, x_t = self._prep_inputs(x_s, x_t)
-        out = self.model(x_s, x_t)
-        x_s_recon, x_t_recon, fi_s, _, _, fi_t = out[:6]
-        l_identity = mse_loss(fi_s, fi_t)
-        l_recon = mse_loss(x_s.detach(), x_s_recon) + mse_loss(x_t.detach(), x_t_recon)
-        loss = l_identity + l_recon
-        self._backward_and_update(loss, static=False)
+        direct = self._direct(x_s)
+        self.zero_grad(encoders_direct=direct)
+        grp = self.model.encoder_group
+        grp.grad_targets = self._enc_targets if direct else None
+        try:
+            x_s, x_t = self._prep(x_s), self._prep(x_t)
+            out = self.model(x_s, x_t)
+            x_s_recon, x_t_recon, fi_s, _, _, fi_t = out[:6]
+            l_identity = mse_loss(fi_s, fi_t)
+            l_recon = mse_loss(x_s.detach(), x_s_recon) + mse_loss(x_t.detach(), x_t_recon)
+            loss = l_identity + l_recon
+            if self.adv_weight is not None:
+                loss = loss + self.adv_weight * 0.5 * (self._adversarial(x_s_recon) + self._adversarial(x_t_recon))
+            self._backward_and_update(loss, static=False)
+        finally:
+            grp.grad_targets = None
         self.last_losses = (l_identity.detach(), l_recon.detach())
         return loss.detach()
 
@@ -152,30 +238,46 @@ class IRFDTrainer:
         self.last_ctrl = tuple(vals)
 
     def _static_body(self):
-        xs, xt, loss_out, lid_out, lrec_out = self._static
-        self.zero_grad()
-        x_s, x_t = self._prep_inputs(xs, xt)
-        x_s_recon, x_t_recon, fi_s, fi_t = self.model.forward_static(x_s, x_t, self.ctrl)
-        l_identity = mse_loss(fi_s, fi_t)
-        l_recon = mse_loss(xs, x_s_recon) + mse_loss(xt, x_t_recon)
-        loss = l_identity + l_recon
-        self._backward_and_update(loss, static=True)
+        x_all, loss_out, lid_out, lrec_out = self._static
+        b = x_all.size(0) // 2
+        self.zero_grad(encoders_direct=True)
+        grp = self.model.encoder_group
+        grp.grad_targets = self._enc_targets
+        try:
+            x = self._prep(x_all)
+            img, f, _ = self.model.forward_static_stacked(x, self.ctrl)
+            l_identity = mse_loss(f[0, :b], f[0, b:])
+            # MSE(x_s, x_s_recon) + MSE(x_t, x_t_recon) with equally sized halves == 2 * MSE over the stacked batch
+            l_recon = mse_loss(x_all, img, scale=2.0)
+            loss = l_identity + l_recon
+            if self.adv_weight is not None:
+                loss = loss + self.adv_weight * self._adversarial(img)  # mean over 2B logits == (BCE_s + BCE_t) / 2
+            self._backward_and_update(loss, static=True)
+        finally:
+            grp.grad_targets = None
         loss_out.copy_(loss.detach())
         lid_out.copy_(l_identity.detach())
         lrec_out.copy_(l_recon.detach())
 
     def _capture(self, x_s, x_t):
         dev = self.device
-        self._static = (torch.empty_like(x_s), torch.empty_like(x_t), torch.zeros((), device=dev),
-                        torch.zeros((), device=dev), torch.zeros((), device=dev))
-        self._static[0].copy_(x_s)
-        self._static[1].copy_(x_t)
+        if not self._direct(x_s):
+            raise ops._lib.IrfdError(
+                f"IRFDTrainer(use_cuda_graph=True): batch {tuple(x_s.shape)} cannot run as one lockstep encoder pass "
+                "(pairs x (H/32) x (W/32) must be a multiple of 128, encoders in train mode with gradients); use the "
+                "eager step")
+        b = x_s.size(0)
+        x_all = torch.empty((2 * b,) + tuple(x_s.shape[1:]), dtype=torch.float32, device=dev)
+        self._static = (x_all, torch.zeros((), device=dev), torch.zeros((), device=dev), torch.zeros((), device=dev))
+        x_all[:b].copy_(x_s)
+        x_all[b:].copy_(x_t)
         self.step_dev.fill_(self.step_count)
         # The warm-up passes below are real steps; snapshot everything they mutate (Gd parameters, Adam moments, BN
         # running buffers, step counters, both RNG streams) and put it back, so capturing is invisible to training.
         snap = [t.clone() for t in (self.flat, self.m, self.v)]
-        bufs = [b for e in self.encoders for b in e.buffers()]
-        snap_bufs = [b.clone() for b in bufs]
+        bufs = [bf for e in self.encoders for bf in e.buffers()]
+        bufs += [bf for bf in self.model.D.buffers()] if self.adv_weight is not None else []
+        snap_bufs = [bf.clone() for bf in bufs]
         snap_step = self.step_count
         cpu_rng, cuda_rng = torch.get_rng_state(), torch.cuda.get_rng_state(dev)
         side = torch.cuda.Stream(dev)
@@ -187,19 +289,20 @@ class IRFDTrainer:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         before = ops.launch_count
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
             self._static_body()
-        self.graph_launches = ops.launch_count - before
+        launches = ops.launch_count - before
         # the captured pass was only recorded, not executed; the warm-up passes are rolled back
         for t, c in zip((self.flat, self.m, self.v), snap):
             t.copy_(c)
-        for b, c in zip(bufs, snap_bufs):
-            b.copy_(c)
+        for bf, c in zip(bufs, snap_bufs):
+            bf.copy_(c)
         self.step_count = snap_step
         self.step_dev.fill_(snap_step)
         torch.set_rng_state(cpu_rng)
         torch.cuda.set_rng_state(cuda_rng, dev)
+        return graph, launches
 
     def _graph_state(self, x_s):
         """What a captured graph bakes in besides the buffers it owns: the train/eval mode of every sub-network, the
@@ -208,28 +311,48 @@ class IRFDTrainer:
         m = self.model
         enc_ver = tuple(e[0].weight._version for e in self.encoders)
         return (m.training, m.Gd.training, tuple(e.training for e in self.encoders), tuple(x_s.shape), enc_ver,
-                float(m.Gd.style_mixing_prob))
+                float(m.Gd.style_mixing_prob), self.buckets.enabled)
 
     def train_step_graph(self, x_s: torch.Tensor, x_t: torch.Tensor):
         key = self._graph_state(x_s)
         if self.graph is not None and key != self._graph_key:
             self.graph = None
         if self.graph is None:
-            self._capture(x_s, x_t)
+            self.graph, self.graph_launches = self._capture(x_s, x_t)
             self._graph_key = key
-        self._static[0].copy_(x_s, non_blocking=True)
-        self._static[1].copy_(x_t, non_blocking=True)
+        b = x_s.size(0)
+        self._static[0][:b].copy_(x_s, non_blocking=True)   # straight into the stacked static batch: no torch.cat
+        self._static[0][b:].copy_(x_t, non_blocking=True)
         self._draw_ctrl()
         self.graph.replay()
         self.step_count += 1
         ops.launch_count += self.graph_launches
-        self.last_losses = (self._static[3], self._static[4])
-        return self._static[2]
+        self.last_losses = (self._static[2], self._static[3])
+        return self._static[1]
+
+    def train_step_static_eager(self, x_s: torch.Tensor, x_t: torch.Tensor):
+        """The launch sequence of the captured step, launched kernel by kernel (bench.py times every GEMM launch with
+        CUDA events this way: events cannot be recorded inside a graph replay).  Needs a captured graph."""
+        if self.graph is None:
+            self.graph, self.graph_launches = self._capture(x_s, x_t)
+            self._graph_key = self._graph_state(x_s)
+        b = x_s.size(0)
+        self._static[0][:b].copy_(x_s, non_blocking=True)
+        self._static[0][b:].copy_(x_t, non_blocking=True)
+        self._draw_ctrl()
+        self.step_dev.fill_(self.step_count)
+        self._static_body()
+        return self._static[1]
 
     def train_step(self, x_s: torch.Tensor, x_t: torch.Tensor):
         if self.use_cuda_graph:
             return self.train_step_graph(x_s, x_t)
         return self.train_step_eager(x_s, x_t)
+
+    def sync_buffers(self) -> None:
+        """DDP `broadcast_buffers=True` (train.py:399 default): every rank takes rank 0's BatchNorm running buffers.
+        Call before evaluating or checkpointing a data-parallel run (save_checkpoint does)."""
+        broadcast_buffers(self.encoders)
 
     # ---------------------------------------------------------------------------------------------- checkpoints
     # The reference saves {'model_state_dict', 'optimizer_G', 'optimizer_D', 'epoch', 'resolution', 'config'}
@@ -280,6 +403,7 @@ class IRFDTrainer:
 
     def save_checkpoint(self, path: str, epoch: int = 0, config=None, optimizer_d: Optional[dict] = None) -> None:
         """Writes the reference's checkpoint dictionary (train.py:232-240); loadable by the reference's resume code."""
+        self.sync_buffers()
         torch.save({"model_state_dict": self.model.state_dict(), "optimizer_G": self.optimizer_state_dict(),
                     "optimizer_D": optimizer_d if optimizer_d is not None else {}, "epoch": epoch,
                     "resolution": getattr(self.model, "current_resolution", 256), "config": config}, path)

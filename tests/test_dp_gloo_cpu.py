@@ -1,5 +1,6 @@
-"""CPU, world_size 2 over gloo: the data-parallel gradient exchange (dp.py) — bucket averaging, scatter-back into the
-original gradient tensors, launch order during a simulated IRFD backward, and shard-average == full-batch gradient."""
+"""CPU, world_size 2 over gloo: the data-parallel gradient exchange (dp.py) — in-place averaging of flat buckets, launch
+order during a simulated IRFD backward (generator bucket, then one bucket per ResNet stage), DDP-style buffer broadcast,
+and shard-average == full-batch gradient."""
 import os
 import socket
 
@@ -24,30 +25,43 @@ def _worker(rank, world, port, q):
     try:
         from speak_hack_b200.dp import BucketSchedule, GradBuckets
 
+        from speak_hack_b200.dp import broadcast_buffers
+
         dev = torch.device("cpu")
-        # --- 1. flat bucket + list bucket are averaged; list bucket is scattered back into the same tensors
+        # --- 1. flat buckets are averaged in place; views into them see the result; disabled buckets stay local
         b = GradBuckets(dev)
         flat = torch.full((10,), float(rank + 1))
-        g1, g2 = torch.full((3, 2), float(rank)), torch.arange(4.0) * (rank + 1)
-        b.launch(flat=flat)
-        b.launch([g1, g2])
+        view = flat[2:6].view(2, 2)            # a parameter's .grad living inside the flat bucket
+        b.launch(flat)
         b.finish()
-        ok1 = torch.allclose(flat, torch.full((10,), 1.5)) and torch.allclose(g1, torch.full((3, 2), 0.5)) and \
-            torch.allclose(g2, torch.arange(4.0) * 1.5)
+        ok1 = torch.allclose(flat, torch.full((10,), 1.5)) and torch.allclose(view, torch.full((2, 2), 1.5))
+        b.enabled = False
+        local = torch.full((4,), float(rank))
+        b.launch(local)
+        b.finish()
+        ok1 = ok1 and torch.equal(local, torch.full((4,), float(rank)))
 
-        # --- 2. schedule: simulated backward order Ep_t, Ee_t, Ei_t, Ep_s, Ee_s, Ei_s
-        encs = [torch.nn.Linear(4, 4) for _ in range(3)]  # stand-ins for Ei, Ee, Ep
-        for e in encs:
-            for p in e.parameters():
-                p.grad = torch.full_like(p, float(rank + 1))
+        # --- 2. schedule: the lockstep encoder backward reports pre, stage 7..4, stage 3 (stem), post
         gd = torch.full((7,), float(2 * rank))
-        sched = BucketSchedule(GradBuckets(dev), gd, encs)
-        for e in (encs[2], encs[1], encs[0], encs[2], encs[1], encs[0]):
-            sched.pre()
-            sched.post(e)
+        stages = {k: torch.full((5,), float(rank + k)) for k in (7, 6, 5, 4, 3)}
+        sched = BucketSchedule(GradBuckets(dev), gd, stages)
+        sched.on_event("pre", None)
+        for k in (7, 6, 5, 4, 3):
+            sched.on_event("stage", k)
+        sched.on_event("post", None)
         sched.final()
-        ok2 = sched.order == ["Gd", "E2", "E1", "E0"] and torch.allclose(gd, torch.full((7,), 1.0)) and all(
-            torch.allclose(p.grad, torch.full_like(p, 1.5)) for e in encs for p in e.parameters())
+        ok2 = sched.order == ["Gd", "S7", "S6", "S5", "S4", "S3"] and torch.allclose(gd, torch.full((7,), 1.0)) and all(
+            torch.allclose(v, torch.full((5,), k + 0.5)) for k, v in stages.items())
+        # fallback path (no events): final() launches everything
+        sched2 = BucketSchedule(GradBuckets(dev), torch.full((3,), float(rank)), {7: torch.full((2,), float(rank))})
+        sched2.final()
+        ok2 = ok2 and sched2.order == ["Gd", "S7"] and torch.allclose(sched2.gd_flat_grad, torch.full((3,), 0.5))
+        # DDP broadcast_buffers: every rank ends with rank 0's BatchNorm buffers (float and integer ones)
+        bn = torch.nn.BatchNorm2d(3)
+        bn.running_mean.fill_(float(rank + 1))
+        bn.num_batches_tracked.fill_(rank + 4)
+        broadcast_buffers([bn])
+        ok2 = ok2 and torch.equal(bn.running_mean, torch.ones(3)) and int(bn.num_batches_tracked) == 4
 
         # --- 3. property: mean of per-shard gradients == gradient of the mean loss over the global batch
         torch.manual_seed(0)
@@ -58,7 +72,13 @@ def _worker(rank, world, port, q):
         loss = torch.nn.functional.mse_loss(model(x[shard]), y[shard])
         loss.backward()
         b3 = GradBuckets(dev)
-        b3.launch([p.grad for p in model.parameters()])
+        params = list(model.parameters())
+        flat3 = torch.cat([p.grad.reshape(-1) for p in params])
+        off = 0
+        for p in params:  # re-home the gradients as views of one flat bucket, like the trainer does
+            p.grad = flat3[off: off + p.numel()].view_as(p)
+            off += p.numel()
+        b3.launch(flat3)
         b3.finish()
         ok3 = all(torch.allclose(p.grad, f, atol=1e-6) for p, f in zip(model.parameters(), full))
         q.put((rank, ok1, ok2, ok3))
@@ -88,6 +108,6 @@ def test_single_process_is_a_noop():
 
     b = GradBuckets(torch.device("cpu"))
     t = torch.ones(3)
-    b.launch([t])
+    b.launch(t)
     b.finish()
     assert b.world == 1 and torch.equal(t, torch.ones(3))

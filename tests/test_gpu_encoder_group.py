@@ -1,0 +1,261 @@
+"""-m gpu: the lockstep encoder pass (encoder_group.EncoderGroup) and its kernels — one launch per layer for the three
+IRFD encoders — against the per-encoder path it replaces.  Same kernels, same tiles, same per-tile summation order:
+forward results must be BIT-identical, gradients equal up to the fp32 order of the split-K / reduction partials."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).contiguous()
+
+
+@pytest.mark.parametrize("ksize,cin,cout,hw,n", [(1, 64, 256, 16, 6), (3, 64, 64, 16, 6), (1, 256, 128, 8, 12),
+                                                 (3, 128, 128, 8, 12)])
+def test_grouped_conv_equals_separate_calls(cuda_device, ksize, cin, cout, hw, n):
+    from speak_hack_b200 import ops
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(ksize * 100 + cin)
+    E = 3
+    x = _bf(torch.randn(n, hw, hw, cin, generator=g).to(dev))                      # E groups of n/E images
+    ws = [torch.randn(cout, cin, ksize, ksize, generator=g).to(dev) * 0.05 for _ in range(E)]
+    wk = ops.pack_conv_weights_stacked(ws, ops.PACK_FPROP)
+    out, s, q = ops.conv_gemm_grouped(x, wk, ksize, ops.EPI_STATS, wgroups=E)
+    plain = ops.conv_gemm_grouped(x, wk, ksize, ops.EPI_PLAIN, wgroups=E)
+    ne = n // E
+    tiles = s.shape[0] // E
+    for e in range(E):
+        o1, s1, q1 = ops.conv_gemm(x[e * ne:(e + 1) * ne], ops._pack_conv_weight(ws[e], ops.PACK_FPROP), ksize,
+                                   ops.EPI_STATS)
+        assert torch.equal(out[e * ne:(e + 1) * ne], o1) and torch.equal(plain[e * ne:(e + 1) * ne], o1)
+        assert torch.equal(s[e * tiles:(e + 1) * tiles], s1) and torch.equal(q[e * tiles:(e + 1) * tiles], q1)
+    # affine epilogue with per-group scale/shift and a residual
+    scale = torch.rand(E, cout, generator=g).to(dev) + 0.5
+    shift = torch.randn(E, cout, generator=g).to(dev)
+    res = _bf(torch.randn(n, hw, hw, cout, generator=g).to(dev))
+    aff = ops.conv_gemm_affine_grouped(x, wk, ksize, scale, shift, res=res, relu=True, wgroups=E)
+    for e in range(E):
+        a1 = ops.conv_gemm_affine(x[e * ne:(e + 1) * ne], ops._pack_conv_weight(ws[e], ops.PACK_FPROP), ksize,
+                                  scale[e].contiguous(), shift[e].contiguous(), res=res[e * ne:(e + 1) * ne], relu=True)
+        assert torch.equal(aff[e * ne:(e + 1) * ne], a1)
+
+
+def test_grouped_conv_shared_operand(cuda_device):
+    """The stem: one im2col matrix read by all three weight sets."""
+    from speak_hack_b200 import ops
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(5)
+    col = _bf(torch.randn(512, 192, generator=g).to(dev))
+    ws = [torch.randn(64, 3, 7, 7, generator=g).to(dev) * 0.05 for _ in range(3)]
+    wk = ops.pack_conv_weights_stacked(ws, ops.PACK_FLAT, kpad=192)
+    out, s, q = ops.conv_gemm_grouped(col, wk, 1, ops.EPI_STATS, wgroups=3, a_shared=True)
+    assert out.shape == (3 * 512, 64)
+    for e in range(3):
+        o1, s1, q1 = ops.gemm_rows(col, ops.pack_conv_weight(ws[e], ops.PACK_FLAT, kpad=192), ops.EPI_STATS)
+        assert torch.equal(out[e * 512:(e + 1) * 512], o1)
+        assert torch.equal(s[e * 4:(e + 1) * 4], s1) and torch.equal(q[e * 4:(e + 1) * 4], q1)
+
+
+def test_bn_sets_equal_separate_calls(cuda_device):
+    from speak_hack_b200 import ops
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(9)
+    E, G, rows_g, c = 3, 2, 256, 128
+    rows = E * G * rows_g
+    z = _bf(torch.randn(rows, c, generator=g).to(dev) * 2 + 0.3)
+    res = _bf(torch.randn(rows, c, generator=g).to(dev))
+    gam = [torch.rand(c, generator=g).to(dev) + 0.5 for _ in range(E)]
+    bet = [torch.randn(c, generator=g).to(dev) * 0.1 for _ in range(E)]
+    # statistics per 128-row tile, like the conv epilogue produces them
+    zt = z.float().view(-1, 128, c)
+    ssum, ssq = zt.sum(1).contiguous(), (zt * zt).sum(1).contiguous()
+    rm = [torch.zeros(c, device=dev) for _ in range(E)]
+    rv = [torch.ones(c, device=dev) for _ in range(E)]
+    mean, rstd = ops.bn_finalize_sets(ssum, ssq, rows_g, 1e-5, 0.1, rm, rv, 2, G, E)
+    out = ops.bn_apply_sets(z, mean, rstd, gam, bet, res=res, relu=True, groups=E * G)
+    g1 = _bf(torch.randn(rows, c, generator=g).to(dev))
+    dz, dgs, dbs, gm = ops.bn_backward_sets(g1, None, out, z, mean, rstd, gam, None, want_g_out=True, groups=E * G)
+    dz2, dgs2, dbs2 = ops.bn_backward_sets(g1, None, None, z, mean, rstd, gam, bet, groups=E * G)
+    per = G * rows_g
+    tp = per // 128
+    for e in range(E):
+        sl = slice(e * per, (e + 1) * per)
+        rm1, rv1 = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+        m1, r1 = ops.bn_finalize(ssum[e * tp:(e + 1) * tp].contiguous(), ssq[e * tp:(e + 1) * tp].contiguous(), rows_g,
+                                 1e-5, 0.1, rm1, rv1, 2, G)
+        assert torch.equal(mean[e * G:(e + 1) * G], m1) and torch.equal(rstd[e * G:(e + 1) * G], r1)
+        assert torch.equal(rm[e], rm1) and torch.equal(rv[e], rv1)
+        o1 = ops.bn_apply(z[sl], m1, r1, gam[e], bet[e], res=res[sl], relu=True, groups=G)
+        assert torch.equal(out[sl], o1)
+        d1, dg1, db1, gm1 = ops.bn_backward(g1[sl], None, o1, z[sl], m1, r1, gam[e], want_g_out=True, groups=G)
+        assert torch.equal(dz[sl], d1) and torch.equal(gm[sl], gm1)
+        assert torch.equal(dgs[e], dg1) and torch.equal(dbs[e], db1)
+        d2, dg2, db2 = ops.bn_backward(g1[sl], None, None, z[sl], m1, r1, gam[e], groups=G, beta=bet[e])
+        assert torch.equal(dz2[sl], d2) and torch.equal(dgs2[e], dg2) and torch.equal(dbs2[e], db2)
+    sc, sh = ops.bn_eval_affine_sets([_FakeBN(rm[e], rv[e], gam[e], bet[e]) for e in range(E)])
+    for e in range(E):
+        s1, h1 = ops.bn_eval_affine(_FakeBN(rm[e], rv[e], gam[e], bet[e]))
+        assert torch.equal(sc[e], s1) and torch.equal(sh[e], h1)
+
+
+class _FakeBN:
+    def __init__(self, rm, rv, w, b):
+        self.running_mean, self.running_var, self.weight, self.bias, self.eps = rm, rv, w, b, 1e-5
+
+
+def _three_encoders(dev, seed=3):
+    import speak_hack_b200 as P
+
+    torch.manual_seed(seed)
+    a = [P.ResNet50Encoder().to(dev).train() for _ in range(3)]
+    b = [P.ResNet50Encoder().to(dev).train() for _ in range(3)]
+    for x, y in zip(a, b):
+        y.load_state_dict(x.state_dict())
+    return a, b
+
+
+def test_encoder_group_train_equals_three_passes(cuda_device):
+    """Features and BN buffers bit-identical to three forward_groups calls; all 3 x 161 parameter gradients equal; the
+    in-place gradient targets receive exactly what autograd would have been handed."""
+    import irfd_oracle as O
+    from speak_hack_b200.encoder_group import EncoderGroup
+
+    dev = cuda_device
+    sep, grouped = _three_encoders(dev)
+    x_s, x_t = O.synthetic_pair(2, seed=21)
+    x = torch.cat([x_s, x_t]).to(dev)
+    w = torch.randn(3, 4, 2048, 1, 1, generator=torch.Generator().manual_seed(1)).to(dev)
+    xa = x.clone().requires_grad_(True)
+    for e in sep:
+        e._recompute_bn_update = True
+    fs = torch.stack([e.forward_groups(xa, 2) for e in sep])
+    (fs * w).sum().backward()
+    grp = EncoderGroup(grouped)
+    for e in grouped:
+        e._recompute_bn_update = True
+    xb = x.clone().requires_grad_(True)
+    fg = grp(xb, 2)
+    (fg * w).sum().backward()
+    torch.cuda.synchronize()
+    assert fg.shape == (3, 4, 2048, 1, 1) and torch.equal(fg, fs)
+    worst = 0.0
+    for e1, e2 in zip(sep, grouped):
+        sd1, sd2 = e1.state_dict(), e2.state_dict()
+        for k in sd1:
+            if "running" in k or "num_batches" in k:
+                assert torch.equal(sd1[k], sd2[k]), k
+        for (n1, p1), (_, p2) in zip(e1.named_parameters(), e2.named_parameters()):
+            assert p2.grad is not None, n1
+            worst = max(worst, O.rel_l2(p2.grad, p1.grad))
+    print(f"[parity] lockstep vs separate encoder passes: worst param-grad rel-L2 {worst:.3e}")
+    assert worst < 1e-5
+    # in-place targets: same values, nothing returned to autograd
+    targets = {p: torch.full_like(p, float("nan")) for e in grouped for p in e.parameters()}
+    ref_grads = {p: p.grad.clone() for e in grouped for p in e.parameters()}
+    for e in grouped:
+        for p in e.parameters():
+            p.grad = None
+    grp.grad_targets = targets
+    events = []
+    grp._bwd_cb = lambda kind, stage: events.append((kind, stage))
+    (grp(x.clone().requires_grad_(True), 2) * w).sum().backward()
+    torch.cuda.synchronize()
+    grp.grad_targets, grp._bwd_cb = None, None
+    assert all(p.grad is None for e in grouped for p in e.parameters())
+    assert all(torch.equal(targets[p], ref_grads[p]) for p in targets)
+    assert events == [("pre", None), ("stage", 7), ("stage", 6), ("stage", 5), ("stage", 4), ("stage", 3), ("post", None)]
+
+
+def test_encoder_group_inference_equals_three_passes(cuda_device):
+    import irfd_oracle as O
+    from speak_hack_b200.encoder_group import EncoderGroup
+
+    dev = cuda_device
+    sep, grouped = _three_encoders(dev, seed=4)
+    x_s, x_t = O.synthetic_pair(2, seed=22)
+    x = torch.cat([x_s, x_t]).to(dev)
+    with torch.no_grad():   # give the running buffers non-trivial values first (identical on both sides)
+        for e1, e2 in zip(sep, grouped):
+            e1(x)
+            e2.load_state_dict(e1.state_dict())
+    for e in sep + grouped:
+        e.eval()
+    with torch.no_grad():
+        fs = torch.stack([e(x) for e in sep])
+        fg = EncoderGroup(grouped)(x, 2)
+    torch.cuda.synchronize()
+    assert torch.equal(fg, fs)
+
+
+def test_static_stacked_forward_equals_eager_forward(cuda_device):
+    """IRFD.forward_static_stacked (lockstep encoders + ONE generator call over the 2B stacked codes) against
+    IRFD.forward (two generator calls), same weights, swap draw and noise planes: the images must be bit-identical."""
+    import irfd_oracle as O
+    import speak_hack_b200 as P
+
+    dev = cuda_device
+    torch.manual_seed(O.WEIGHT_SEED)
+    net = P.IRFD()
+    O.perturb_noise_weights(net.Gd)
+    net = net.to(dev).train()
+    net.Gd.style_mixing_prob = 0.0
+    x_s, x_t = O.synthetic_pair(2)
+    xs, xt = x_s.to(dev), x_t.to(dev)
+    g = torch.Generator().manual_seed(77)
+    L, res, planes = net.Gd.synthesis.num_layers, 4, []
+    planes.append(torch.randn(4, 1, 4, 4, generator=g))
+    for _ in net.Gd.synthesis.layers:
+        res *= 2
+        planes += [torch.randn(4, 1, res, res, generator=g), torch.randn(4, 1, res, res, generator=g)]
+    state = {"i": 0, "half": None}
+
+    def noise(b, h, w, device):
+        t = planes[state["i"] % len(planes)]
+        state["i"] += 1
+        if b == 4:
+            return t.to(device)
+        return t[:2].to(device) if state["half"] == 0 else t[2:].to(device)
+
+    net.Gd.synthesis.noise_fn = noise
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    for swap in range(3):
+        net.load_state_dict(sd)
+        ctrl = torch.tensor([swap, L, L], dtype=torch.int32, device=dev)
+        state["i"] = 0
+        with torch.no_grad():
+            img, f, b = net.forward_static_stacked(torch.cat([xs, xt]), ctrl)
+        net.load_state_dict(sd)
+        # eager: reproduce the same swap through the CPU generator draw
+        seed = next(s for s in range(100) if (torch.manual_seed(s), int(torch.randint(0, 3, (1,))))[1] == swap)
+        torch.manual_seed(seed)
+        orig = net.Gd.forward
+
+        def gd_call(feat, _orig=orig):
+            state["half"] = 0 if state["half"] is None else 1
+            state["i"] = 0
+            return _orig(feat)
+
+        net.Gd.forward = gd_call
+        state["half"] = None
+        try:
+            with torch.no_grad():
+                out = net(xs, xt)
+        finally:
+            net.Gd.forward = orig
+            state["half"] = None
+        torch.cuda.synchronize()
+        assert torch.equal(img[:b], out[0]) and torch.equal(img[b:], out[1]), f"swap {swap}"
+        got = [out[2], out[3], out[4], out[5], out[6], out[7]]
+        want = [f[0, :b], f[1, :b], f[2, :b], f[0, b:], f[1, b:], f[2, b:]]
+        want[swap], want[3 + swap] = want[3 + swap], want[swap]
+        assert all(torch.equal(a, c) for a, c in zip(got, want))
