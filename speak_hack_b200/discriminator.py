@@ -3,30 +3,37 @@
 Same classes, constructor signatures and state_dict keys as the reference (`D.*`, spectral-norm `weight_orig / weight_u /
 weight_v`), so checkpoints move both ways and a seeded construction consumes the RNG identically.
 
-On CUDA tensors the forward and the first-order backward (gradient w.r.t. the image AND all parameters) run on the
-sm_100a kernels as one autograd node: `irfd_from_rgb_fwd` for the 1x1 RGB stem, the tcgen05 implicit-GEMM convs with
-the `+ bias -> leaky_relu(0.2)` tail fused as their epilogue (3x3 stride 1 directly, 3x3 stride 2 through the same
-NHWC im2col the encoders use), NHWC bf16 activations, fp32 dense head.  That is what the reference's generator step
-needs from D (train.py:197-201: `D(x_recon)` -> BCE -> backward into Gd) and what the real/fake terms of its D step need
-(train.py:160-175).
+Forward, first-order backward (gradient w.r.t. the image AND all parameters) and the second-order path of the R1
+penalty run on the sm_100a kernels: `irfd_from_rgb_fwd` for the 1x1 RGB stem, the tcgen05 implicit-GEMM convs with the
+`+ bias -> leaky_relu(0.2)` tail fused as their epilogue (3x3 stride 1 directly, 3x3 stride 2 through the same NHWC
+im2col the encoders use), NHWC bf16 activations, fp32 dense head.  That covers the reference's generator step
+(train.py:197-201: `D(x_recon)` -> BCE -> backward into Gd) and its discriminator step (train.py:157-183).
 
-The R1 penalty (train.py:246-255) differentiates THROUGH the image gradient (`create_graph=True`).  The native node is
-once-differentiable, so a generic `torch.autograd.grad(..., create_graph=True)` over it is not available; instead
-`D.r1_penalty(real_img)` / `compute_r1_reg(D, real_img)` below compute the penalty and its parameter gradients directly
-(`_R1Fn`: forward, dgrad chain, masked forward chain, one wgrad per layer).  `use_native = False` selects the
-reference's PyTorch composition for callers that insist on a generic double backward.
+R1 (train.py:246-255) differentiates THROUGH the image gradient: `torch.autograd.grad(D(x).sum(), x,
+create_graph=True)` followed by a backward of `grad.pow(2).sum()`.  The reference's own `compute_r1_reg` works on this
+module unchanged: when `_DiscFn.backward` runs with grad mode enabled (create_graph=True) it returns the image gradient
+as the output of a second autograd node, `_DiscGradFn`, whose backward is the closed-form second-order chain.  D is
+piecewise linear in x, so with the leaky-ReLU masks m_l of the forward pass held fixed
+
+    g_{l-1} = C_l^T (m_l * g_l)                         (image-gradient chain, u_l = m_l * g_l)
+    d<g_x, p_x>/dW_l = wgrad(input = p_{l-1}, output gradient = u_l),   p_l = m_l * (C_l p_{l-1})
+
+i.e. one masked forward chain on p_x (the gradient arriving at g_x) and one wgrad per layer, all on the same kernels
+as the first-order path.  Biases only enter through the masks: their second-order gradient is zero, and so is the
+image's.  `D.r1_penalty(x)` is the same computation fused into one node (it skips the first-order weight gradients a
+generic double backward cannot know it does not need).
 
 Spectral normalisation itself (one power iteration on each [Cout, Cin*k*k] matrix, styleganv1.py:643-654 via
 torch.nn.utils.spectral_norm) stays in its torch hook: it is parameter preparation — a few mat-vecs per layer, like the
 fp32 -> bf16 weight repack — and keeping the hook keeps `weight_u / weight_v` updates and the backward through sigma
-exactly the reference's.
+exactly the reference's.  There is no PyTorch composition of the network in this module: inputs the kernels cannot
+take (CPU tensors, other resolutions, channel counts that are not multiples of 64) raise.
 """
 from __future__ import annotations
 
 import numpy as np
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 from torch.autograd.function import once_differentiable
 from torch.nn.utils import spectral_norm
 
@@ -40,8 +47,8 @@ class DiscriminatorBlock(nn.Module):
         self.conv2 = spectral_norm(nn.Conv2d(in_channels, out_channels, kernel_size=3, padding=1, stride=2))
 
     def forward(self, x):
-        x = F.leaky_relu(self.conv1(x), 0.2)
-        return F.leaky_relu(self.conv2(x), 0.2)
+        raise ops._lib.IrfdError("DiscriminatorBlock runs fused inside StyleDiscriminator (NHWC bf16 activations between "
+                                 "its convs); call StyleDiscriminator")
 
 
 def _normalized_weight(m: nn.Module) -> torch.Tensor:
@@ -158,6 +165,67 @@ def _disc_backward(S, nblocks, wb, dout, need_dx=True, need_dw=True, keep_u=Fals
     return dx, grads, (U if keep_u else None)
 
 
+def _second_order_chain(S, U, nblocks, wb, px, dout):
+    """Given p_x (fp32 [B,3,H,W], the gradient arriving at the image gradient g_x), the forward record S and the masked
+    upstream gradients U of the first-order chain, returns (grads aligned with wb, d<g_x,p_x>/d dout [B,1])."""
+    acts, hdn = S["acts"], S["hdn"]
+    grads = [None] * len(wb)
+    px = px.contiguous().to(torch.float32)
+    c0 = acts[0].shape[-1]
+    w_rgb = wb[0].reshape(c0, 3).contiguous()
+    _, dwt, _ = ops.to_rgb_bwd(px, U["rgb"], w_rgb.t().contiguous())
+    grads[0] = dwt.view(3, c0).t().contiguous().view_as(wb[0])
+    p, _ = ops.bias_lrelu_bwd(ops.from_rgb_fwd(px, w_rgb, None, lrelu=False), acts[0])
+    for bi in range(nblocks):
+        j = 2 + 4 * bi
+        w1, w2 = wb[j], wb[j + 2]
+        y1, y2 = acts[2 * bi + 1], acts[2 * bi + 2]
+        cin, cout = w1.shape[0], w2.shape[0]
+        u1, u2 = U["blk"][bi]
+        grads[j] = ops.conv_wgrad(p, u1, 3)
+        p, _ = ops.bias_lrelu_bwd(ops.conv_gemm(p, _pack(w1, ops.PACK_FPROP), 3), y1)
+        pcol = ops.im2col_3x3s2(p)
+        m2 = pcol.shape[0]
+        grads[j + 2] = ops.conv_wgrad(pcol.view(1, 1, m2, 9 * cin), u2.view(1, 1, m2, cout), 1, reduce_cin=cin,
+                                      reduce_taps=9, out_shape=(cout, cin, 3, 3))
+        q = ops.gemm_rows(pcol, _pack(w2, ops.PACK_FPROP)).view(y2.shape)
+        p, _ = ops.bias_lrelu_bwd(q, y2)
+    i = 2 + 4 * nblocks
+    grads[i] = ops.conv_wgrad(p, U["final"], 3)
+    p, _ = ops.bias_lrelu_bwd(ops.conv_gemm(p, _pack(wb[i], ops.PACK_FPROP), 3), acts[-1])
+    ppool = ops.avgpool_fwd(p)
+    wd0, wd1 = wb[i + 2].contiguous(), wb[i + 4].contiguous()
+    t = ops.linear_fwd(ppool, wd0, None, 1.0, 1.0, lrelu=False)
+    _, grads[i + 2], _ = ops.linear_bwd(U["head"], ppool, wd0, 1.0, 1.0, need_dx=False, has_bias=False)
+    pdh = ops.lrelu_bwd(t, hdn)
+    dout = dout.contiguous().to(torch.float32)
+    _, grads[i + 4], _ = ops.linear_bwd(dout, pdh, wd1, 1.0, 1.0, need_dx=False, has_bias=False)
+    d_dout = ops.linear_fwd(pdh, wd1, None, 1.0, 1.0, lrelu=False)
+    return grads, d_dout
+
+
+class _DiscGradFn(torch.autograd.Function):
+    """The image gradient of D as a differentiable function of (dout, weights): forward = the first-order dgrad chain,
+    backward = _second_order_chain.  Created by _DiscFn.backward when it runs under create_graph=True."""
+
+    @staticmethod
+    def forward(ctx, dout, holder, nblocks, *wb):
+        dx, grads, U = _disc_backward(holder["S"], nblocks, wb, dout, need_dx=True, need_dw=holder["need_dw"],
+                                      keep_u=True)
+        holder["grads"] = grads
+        ctx.S, ctx.U, ctx.nblocks, ctx.wb = holder["S"], U, nblocks, wb
+        ctx.save_for_backward(dout)
+        return dx
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, ddx):
+        (dout,) = ctx.saved_tensors
+        grads, d_dout = _second_order_chain(ctx.S, ctx.U, ctx.nblocks, ctx.wb, ddx, dout)
+        ctx.S = ctx.U = None
+        return (d_dout, None, None) + tuple(grads)
+
+
 class _DiscFn(torch.autograd.Function):
     """forward(x [B,3,H,W] fp32, nblocks, w_rgb, b_rgb, (w1, b1, w2, b2) x nblocks, w_final, b_final, wd0, bd0, wd1, bd1)
     -> logits [B,1] fp32.  The weights are the spectrally normalised ones (autograd continues into weight_orig)."""
@@ -167,66 +235,33 @@ class _DiscFn(torch.autograd.Function):
         out, S = _disc_forward(x, nblocks, wb)
         ctx.nblocks, ctx.S, ctx.wb = nblocks, S, wb
         ctx.need_dx = ctx.needs_input_grad[0]
+        ctx.need_dw = any(ctx.needs_input_grad[2:])
         return out
 
     @staticmethod
-    @once_differentiable  # a create_graph=True caller gets an error, not a silently constant image gradient
     def backward(ctx, dout):
-        dx, grads, _ = _disc_backward(ctx.S, ctx.nblocks, ctx.wb, dout, need_dx=ctx.need_dx)
+        if torch.is_grad_enabled() and ctx.need_dx:
+            # create_graph=True (train.py:250-252): the image gradient must remain a function of the weights
+            holder = {"S": ctx.S, "need_dw": ctx.need_dw}
+            dx = _DiscGradFn.apply(dout, holder, ctx.nblocks, *ctx.wb)
+            return (dx, None) + tuple(holder["grads"])
+        dx, grads, _ = _disc_backward(ctx.S, ctx.nblocks, ctx.wb, dout, need_dx=ctx.need_dx, need_dw=ctx.need_dw)
         ctx.S = None
         return (dx, None) + tuple(grads)
 
 
 class _R1Fn(torch.autograd.Function):
-    """R1 penalty  mean_b || d D(x).sum() / dx ||^2  (train.py:246-255) with its gradient w.r.t. the (normalised)
-    weights, without a generic double backward: D is piecewise linear in x, so with the leaky-ReLU masks m_l of the
-    forward pass held fixed the image gradient is the chain  g_{l-1} = C_l^T (m_l * g_l)  and
-
-        dR1/dW_l = wgrad(input = p_{l-1}, output gradient = u_l),   u_l = m_l * g_l,   p_l = m_l * (C_l p_{l-1}),   p_x = 2 g_x / B
-
-    i.e. one forward, one dgrad chain (u_l, g_x), one masked forward chain on p, one wgrad per layer — all on the same
-    kernels as the first-order path.  Biases only enter through the masks: their R1 gradient is zero."""
+    """R1 penalty  mean_b || d D(x).sum() / dx ||^2  (train.py:246-255) and its gradient w.r.t. the (normalised) weights
+    as ONE node: forward, dgrad chain (no first-order weight gradients), second-order chain with p_x = 2 g_x / B."""
 
     @staticmethod
     def forward(ctx, x, nblocks, *wb):
         bsz = x.shape[0]
         out, S = _disc_forward(x, nblocks, wb)
-        dev = out.device
         dout = torch.ones_like(out)
         gx, _, U = _disc_backward(S, nblocks, wb, dout, need_dx=True, need_dw=False, keep_u=True)
         pen = ops.sumsq(gx) / bsz
-        acts, hdn = S["acts"], S["hdn"]
-        grads = [None] * len(wb)
-        px = ops.scale_copy(gx, 2.0 / bsz)
-        c0 = acts[0].shape[-1]
-        w_rgb = wb[0].reshape(c0, 3).contiguous()
-        _, dwt, _ = ops.to_rgb_bwd(px, U["rgb"], w_rgb.t().contiguous())
-        grads[0] = dwt.view(3, c0).t().contiguous().view_as(wb[0])
-        p, _ = ops.bias_lrelu_bwd(ops.from_rgb_fwd(px, w_rgb, None, lrelu=False), acts[0])
-        for bi in range(nblocks):
-            j = 2 + 4 * bi
-            w1, w2 = wb[j], wb[j + 2]
-            y1, y2 = acts[2 * bi + 1], acts[2 * bi + 2]
-            cin, cout = w1.shape[0], w2.shape[0]
-            u1, u2 = U["blk"][bi]
-            grads[j] = ops.conv_wgrad(p, u1, 3)
-            p, _ = ops.bias_lrelu_bwd(ops.conv_gemm(p, _pack(w1, ops.PACK_FPROP), 3), y1)
-            pcol = ops.im2col_3x3s2(p)
-            m2 = pcol.shape[0]
-            grads[j + 2] = ops.conv_wgrad(pcol.view(1, 1, m2, 9 * cin), u2.view(1, 1, m2, cout), 1, reduce_cin=cin,
-                                          reduce_taps=9, out_shape=(cout, cin, 3, 3))
-            q = ops.gemm_rows(pcol, _pack(w2, ops.PACK_FPROP)).view(y2.shape)
-            p, _ = ops.bias_lrelu_bwd(q, y2)
-        i = 2 + 4 * nblocks
-        grads[i] = ops.conv_wgrad(p, U["final"], 3)
-        p, _ = ops.bias_lrelu_bwd(ops.conv_gemm(p, _pack(wb[i], ops.PACK_FPROP), 3), acts[-1])
-        ppool = ops.avgpool_fwd(p)
-        wd0, wd1 = wb[i + 2].contiguous(), wb[i + 4].contiguous()
-        t = ops.linear_fwd(ppool, wd0, None, 1.0, 1.0, lrelu=False)
-        _, grads[i + 2], _ = ops.linear_bwd(U["head"], ppool, wd0, 1.0, 1.0, need_dx=False, has_bias=False)
-        pdh = ops.lrelu_bwd(t, hdn)
-        _, grads[i + 4], _ = ops.linear_bwd(dout, pdh, wd1, 1.0, 1.0, need_dx=False, has_bias=False)
-        ctx.grads = grads
+        ctx.grads, _ = _second_order_chain(S, U, nblocks, wb, ops.scale_copy(gx, 2.0 / bsz), dout)
         del S, U
         return pen.view(())
 
@@ -253,10 +288,9 @@ class StyleDiscriminator(nn.Module):
         self.adaptive_pool = nn.AdaptiveAvgPool2d((1, 1))
         self.dense0 = spectral_norm(nn.Linear(nf(1), nf(0)))
         self.dense1 = spectral_norm(nn.Linear(nf(0), 1))
-        self.use_native = True  # CUDA inputs run on libirfd_b200.so; set False for double-backward (R1) callers
 
     def _native_ok(self, x) -> bool:
-        if not (self.use_native and x.is_cuda and x.dim() == 4 and x.shape[1] == 3):
+        if not (x.is_cuda and x.dim() == 4 and x.shape[1] == 3):
             return False
         # every conv input must map onto the GEMM tiles (64-channel multiples, 128-pixel tile geometry)
         if x.shape[2] != x.shape[3] or x.shape[2] != 2 ** self.resolution_log2 or self.fromrgb.weight_orig.shape[0] % 64:
@@ -274,37 +308,27 @@ class StyleDiscriminator(nn.Module):
         return wb
 
     def r1_penalty(self, real_img):
-        """`compute_r1_reg(D, real_img)` of train.py:246-255 on the sm_100a path: the penalty (scalar) with gradients
+        """`compute_r1_reg(D, real_img)` of train.py:246-255 fused into one node: the penalty (scalar) with gradients
         w.r.t. the parameters.  Like the reference it marks the batch as requiring grad and runs the
         spectral-norm hooks once (one power iteration in train mode, as `D(real_img)` would)."""
         real_img.requires_grad_(True)
-        if not self._native_ok(real_img):
-            raise ops._lib.IrfdError(f"StyleDiscriminator.r1_penalty: input {tuple(real_img.shape)} on {real_img.device} "
-                                     "does not fit the sm_100a path")
+        self._require_native(real_img, "r1_penalty")
         return _R1Fn.apply(real_img.detach(), len(self.blocks), *self._weights_and_biases())
 
-    def forward(self, x):
-        if self._native_ok(x):
-            return _DiscFn.apply(x, len(self.blocks), *self._weights_and_biases())
-        if self.use_native:  # no silent fallback: the native path either runs or the call fails
+    def _require_native(self, x, what):
+        if not self._native_ok(x):  # no fallback: the sm_100a path either runs or the call fails
             raise ops._lib.IrfdError(
-                f"StyleDiscriminator: input {tuple(x.shape)} on {x.device} does not fit the sm_100a path (CUDA, square "
-                "images of the constructed resolution, 64-channel multiples); set use_native=False to run the "
-                "reference's PyTorch composition (needed for the R1 double backward)")
-        # use_native=False, chosen by the caller (R1 double backward): the reference's own PyTorch composition
-        x = F.leaky_relu(self.fromrgb(x), 0.2)
-        for block in self.blocks:
-            x = block(x)
-        x = F.leaky_relu(self.final_conv(x), 0.2)
-        x = self.adaptive_pool(x).flatten(1)
-        x = F.leaky_relu(self.dense0(x), 0.2)
-        return self.dense1(x)
+                f"StyleDiscriminator.{what}: input {tuple(x.shape)} on {x.device} does not fit the sm_100a path (CUDA, "
+                f"square {2 ** self.resolution_log2}x{2 ** self.resolution_log2} RGB images, 64-channel multiples)")
+
+    def forward(self, x):
+        self._require_native(x, "forward")
+        return _DiscFn.apply(x, len(self.blocks), *self._weights_and_biases())
 
 
 def compute_r1_reg(D: StyleDiscriminator, real_img):
-    """train.py:246-255.  Native when D is; otherwise the reference's double backward through the PyTorch composition."""
-    if D.use_native:
-        return D.r1_penalty(real_img)
+    """train.py:246-255, verbatim semantics: the generic double backward, which the native node supports.
+    (`D.r1_penalty(real_img)` computes the same value and gradients in one fused node.)"""
     real_img = real_img.requires_grad_(True)
     real_pred = D(real_img)
     grad_real = torch.autograd.grad(outputs=real_pred.sum(), inputs=real_img, create_graph=True)[0]

@@ -91,11 +91,7 @@ def test_discriminator_interface_and_no_silent_fallback(net):
 
     with pytest.raises(IrfdError):
         net.D(torch.zeros(1, 3, 256, 256))
-    # ... unless the caller explicitly selects the reference's PyTorch composition (R1 double-backward path)
-    net.D.use_native = False
-    try:
-        with torch.no_grad():
-            out = net.D(torch.zeros(1, 3, 256, 256))
-    finally:
-        net.D.use_native = True
-    assert out.shape == (1, 1)
+    # ... and there is no PyTorch composition to fall back to
+    assert not hasattr(net.D, "use_native")
+    with pytest.raises(IrfdError):
+        net.D.blocks[0](torch.zeros(1, 64, 8, 8))

@@ -52,11 +52,13 @@ def test_discriminator_native_matches_torch(cuda_device, train_mode):
     against the same module run as plain PyTorch fp32; in train mode the power-iteration buffers advance identically."""
     from speak_hack_b200.discriminator import StyleDiscriminator
 
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import irfd_oracle as O
+
     dev = cuda_device
     torch.manual_seed(0)
     d_nat = StyleDiscriminator().to(dev)
-    d_ref = StyleDiscriminator().to(dev)
-    d_ref.use_native = False
+    d_ref = O.StyleDiscriminatorRef().to(dev)   # the oracle's plain-PyTorch fp32 restatement, same state_dict keys
     g = torch.Generator().manual_seed(1)
     x = (torch.rand(2, 3, 256, 256, generator=g) * 2 - 1).to(dev)
     # Freshly constructed u / v give a random sigma estimate (weights up to 1e3 x too large per layer, gradients of
@@ -123,16 +125,19 @@ def test_discriminator_matches_oracle_from_state_dict(cuda_device):
 
 
 def test_r1_penalty_native_matches_double_backward(cuda_device):
-    """`compute_r1_reg` (train.py:246-255): the native second-order chain (dgrad chain, masked forward chain, wgrads)
-    against torch's generic double backward through the PyTorch composition: penalty value and every weight gradient
+    """`compute_r1_reg` (train.py:246-255, the reference's generic create_graph=True double backward) running on the
+    NATIVE node (first-order chain -> _DiscGradFn -> second-order chain) and the fused `D.r1_penalty`, both against
+    torch's double backward through the oracle's PyTorch composition: penalty value and every weight gradient
     (through the spectral normalisation); the biases get no gradient in either (they only move the masks)."""
     from speak_hack_b200.discriminator import StyleDiscriminator, compute_r1_reg
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import irfd_oracle as O
 
     dev = cuda_device
     torch.manual_seed(0)
     d_nat = StyleDiscriminator().to(dev)
-    d_ref = StyleDiscriminator().to(dev)
-    d_ref.use_native = False
+    d_ref = O.StyleDiscriminatorRef().to(dev)
     g = torch.Generator().manual_seed(1)
     x = (torch.rand(2, 3, 256, 256, generator=g) * 2 - 1).to(dev)
     d_ref.train()
@@ -160,11 +165,26 @@ def test_r1_penalty_native_matches_double_backward(cuda_device):
         worst = max(worst, e)
         assert e < 8e-2, (k, e)
     print(f"[disc] R1 native {float(rn):.6e} vs torch {float(rr):.6e}, worst weight-grad rel-L2 {worst:.3e}")
-    # a generic double backward over the native node must fail loudly instead of returning a constant
+    # the fused node computes the same penalty and the same gradients as the generic double backward
+    gen_grads = {k: p.grad.clone() for k, p in d_nat.named_parameters() if p.grad is not None}
+    d_nat.zero_grad(set_to_none=True)
+    rf = d_nat.r1_penalty(x.clone())
+    rf.backward()
+    torch.cuda.synchronize()
+    assert abs(float(rf) - float(rn)) <= 1e-6 * abs(float(rn))
+    for k, p in d_nat.named_parameters():
+        if not k.endswith("bias"):
+            assert rel_l2(p.grad, gen_grads[k]) < 1e-5, k
+    # the reference's literal call pattern (train.py:246-255), nothing imported from the package
     xg = x.clone().requires_grad_(True)
-    gimg = torch.autograd.grad(d_nat(xg).sum(), xg, create_graph=True)[0]
-    with pytest.raises(RuntimeError):
-        gimg.pow(2).sum().backward()
+    pred = d_nat(xg)
+    gimg = torch.autograd.grad(outputs=pred.sum(), inputs=xg, create_graph=True)[0]
+    pen = gimg.pow(2).reshape(gimg.shape[0], -1).sum(1).mean()
+    d_nat.zero_grad(set_to_none=True)
+    pen.backward()
+    torch.cuda.synchronize()
+    assert abs(float(pen) - float(rn)) <= 1e-6 * abs(float(rn))
+    assert xg.grad is None or float(xg.grad.abs().max()) == 0.0  # D is piecewise linear in x
 
 
 def test_discriminator_and_r1_against_reference_golden(cuda_device):
