@@ -434,6 +434,38 @@ def run_native(args):
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
 
+    # ---- N > 1: on-hardware check of the exchange (reference semantics: DDP averages the per-rank gradients,
+    # train.py:399-401).  One step through the captured graph WITH its NCCL buckets, then — from the same parameters,
+    # BN buffers, CPU draws and device RNG seed — one step through a second graph captured WITHOUT communication; the
+    # per-rank gradients of the second are all-gathered and their mean compared with the first's buffers.
+    dp_check = None
+    if world > 1 and trainer.use_cuda_graph:
+        snap = trainer.snapshot()
+
+        def seeded_step():
+            torch.manual_seed(1234)
+            torch.cuda.manual_seed(4321)
+            trainer.train_step(x_s, x_t)
+            torch.cuda.synchronize()
+            return [g.clone() for g in trainer.gradient_buffers()]
+
+        averaged = seeded_step()
+        trainer.restore(snap)
+        trainer.buckets.enabled = False          # changes the graph key: the step is recaptured without collectives
+        local = seeded_step()
+        trainer.buckets.enabled = True
+        trainer.restore(snap)
+        worst = 0.0
+        for a, l in zip(averaged, local):
+            parts = [torch.empty_like(l) for _ in range(world)]
+            dist.all_gather(parts, l)
+            mean = torch.stack([p.double() for p in parts]).mean(0)
+            worst = max(worst, float((a.double() - mean).norm() / mean.norm().clamp_min(1e-300)))
+        t = torch.tensor([worst], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dp_check = {"max_rel_l2_vs_mean_of_rank_gradients": float(t.item()), "buffers": len(averaged),
+                    "elements": int(sum(a.numel() for a in averaged))}
+
     # ---- roofline pass: per-launch CUDA events around every tensor-core GEMM launch (same stream), few steps
     # (the whole step runs on one stream, so an event pair times exactly the launch between its two records)
     ops.gemm_timing_begin()
@@ -468,6 +500,8 @@ def run_native(args):
         "clocks": clocks,
         "roofline": roofline,
     }
+    if dp_check is not None:
+        line["dp_check"] = dp_check
     if world == 1 and not args.no_cpu_baseline:
         try:
             val, done, threads, dt = cpu_train_steps(args.cpu_sample, 3, 1, budget_s=90.0)

@@ -349,6 +349,25 @@ class IRFDTrainer:
             return self.train_step_graph(x_s, x_t)
         return self.train_step_eager(x_s, x_t)
 
+    def snapshot(self):
+        """Everything a step mutates (Gd parameters, Adam moments, BN buffers, step counters), for restore()."""
+        bufs = [bf for e in self.encoders for bf in e.buffers()]
+        return ([t.clone() for t in (self.flat, self.m, self.v)], [bf.clone() for bf in bufs], self.step_count)
+
+    def restore(self, snap) -> None:
+        tensors, bufs, step = snap
+        for t, c in zip((self.flat, self.m, self.v), tensors):
+            t.copy_(c)
+        for bf, c in zip([bf for e in self.encoders for bf in e.buffers()], bufs):
+            bf.copy_(c)
+        self.step_count = step
+        self.step_dev.fill_(step)
+        ops.invalidate_packed(self._gd_conv_weights)
+
+    def gradient_buffers(self):
+        """The flat gradient buffers in bucket order: all of Gd, then the encoders' stages 4..1 and the stem."""
+        return [self.gflat] + [self.stage_flats[k] for k in STAGES]
+
     def sync_buffers(self) -> None:
         """DDP `broadcast_buffers=True` (train.py:399 default): every rank takes rank 0's BatchNorm running buffers.
         Call before evaluating or checkpointing a data-parallel run (save_checkpoint does)."""
