@@ -101,6 +101,14 @@ long long irfd_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout, int
 int irfd_conv_wgrad(const void* x, const void* dy, int n, int h, int w, int cin, int cout, int ksize, float* dw,
                     float beta, int reduce_cin, int reduce_taps, void* workspace, long long workspace_bytes,
                     irfd_stream_t stream);
+/* `groups` weight gradients (the same layer of the three IRFD encoders) in one launch pair: x / dy stack the groups'
+ * images group-major (n = TOTAL images; 2-D row matrices pass n = 1, h = 1, w = total rows), dw is a HOST array of
+ * `groups` device pointers.  x_shared != 0 (ksize 1): x holds ONE group's rows read by every group (the stem's im2col
+ * matrix).  Fewer split-K partials than `groups` separate launches (the CTAs of all groups share the one wave). */
+long long irfd_wgrad_workspace_bytes_grouped(int n, int h, int w, int cin, int cout, int ksize, int groups);
+int irfd_conv_wgrad_grouped(const void* x, const void* dy, int n, int h, int w, int cin, int cout, int ksize,
+                            float* const* dw, float beta, int reduce_cin, int reduce_taps, int groups, int x_shared,
+                            void* workspace, long long workspace_bytes, irfd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * BatchNorm2d around the encoder convs (torch.nn.BatchNorm2d in torchvision Bottleneck, resnet.py:143-164).

@@ -23,7 +23,16 @@ struct WgradArgs {
   int num_kb, kb_per_split;
   int taps, kw, pad, cin_chunks, num_atoms;
   int H, W;
-  float* partial;  // [splits][K_total][N_total]
+  float* partial;  // [groups][splits][K_total][N_total]
+  // Weight groups (the same layer of the three IRFD encoders in ONE launch): the pixel range is stacked group-major,
+  // group g owns k-blocks [g * num_kb, (g + 1) * num_kb) and its own partial block; x_shared: every group reads the
+  // SAME x rows (the stem's shared im2col matrix), only dY is stacked.
+  int groups, x_shared;
+};
+
+constexpr int kMaxWgGroups = 4;
+struct WgDst {
+  float* p[kMaxWgGroups];
 };
 
 constexpr int kWgThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
@@ -57,16 +66,20 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // work item
+  // work item: (group, k-pair, n tile, split)
   int item = blockIdx.x;
   const int split = item % p.splits;
   item /= p.splits;
   const int n_tile = item % p.num_n_tiles;
-  const int pair = item / p.num_n_tiles;
-  const int kb_begin = split * p.kb_per_split;
+  item /= p.num_n_tiles;
+  const int pair = item % p.num_pairs;
+  const int grp = item / p.num_pairs;
+  int kb_begin = split * p.kb_per_split;
   int kb_end = kb_begin + p.kb_per_split;
   if (kb_end > p.num_kb) kb_end = p.num_kb;
   const int my_kb = kb_end > kb_begin ? kb_end - kb_begin : 0;
+  const int kb_off = grp * p.num_kb;             // dY (and x unless shared) are stacked group-major
+  const int kb_off_x = p.x_shared ? 0 : kb_off;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -104,10 +117,11 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = kb_begin; kb < kb_end; ++kb) {
-      const int p0 = kb * 64;
-      const int w0 = p0 % p.W;
-      const int h0 = (p0 / p.W) % p.H;
-      const int n0 = p0 / (p.W * p.H);
+      const int p0 = (kb + kb_off) * 64;
+      const int px = (kb + kb_off_x) * 64;
+      const int w0 = px % p.W;
+      const int h0 = (px / p.W) % p.H;
+      const int n0 = px / (p.W * p.H);
       mbar_wait(&empty_bar[stage], phase ^ 1);
       uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
       uint8_t* sb = sa + Cfg::A_BYTES;
@@ -157,7 +171,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const int atom_i = r >> 6;
     const bool valid = (pair * 2 + atom_i) < p.num_atoms;
     const size_t krow = (size_t)pair * 128 + r;
-    float* dst = p.partial + ((size_t)split * p.K_total + krow) * p.N_total + (size_t)n_tile * BLOCK_N;
+    float* dst = p.partial + (((size_t)grp * p.splits + split) * p.K_total + krow) * p.N_total + (size_t)n_tile * BLOCK_N;
     if (my_kb > 0) {
       mbar_wait(done_bar, 0);
       tc_fence_after();
@@ -194,9 +208,11 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 // pure load latency per launch on the 1x1 layers.
 template <int LANES>  // split lanes per output: 256 threads = (256 / LANES) consecutive outputs x LANES
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int K_total, int N_total,
-                    int cin, int taps, float beta) {
+wgrad_reduce_kernel(const float* __restrict__ partial, WgDst dws, int splits, int K_total, int N_total, int cin,
+                    int taps, float beta) {
   constexpr int OUTS = 256 / LANES;
+  float* __restrict__ dw = dws.p[blockIdx.y];  // weight group = blockIdx.y
+  partial += (size_t)blockIdx.y * splits * K_total * N_total;
   __shared__ float part[LANES][OUTS + 1];
   const int o = threadIdx.x % OUTS, w = threadIdx.x / OUTS;
   const size_t idx = (size_t)blockIdx.x * OUTS + o;  // over [K_total][N_total], n fastest
@@ -238,9 +254,11 @@ wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, i
 // tile transposed on the fly, then each n row is written as 32*taps contiguous floats.
 template <int TAPS>
 __global__ void __launch_bounds__(256)
-wgrad_reduce_transpose_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int K_total,
-                              int N_total, int cin, float beta) {
+wgrad_reduce_transpose_kernel(const float* __restrict__ partial, WgDst dws, int splits, int K_total, int N_total,
+                              int cin, float beta) {
   constexpr int ROW = 32 * TAPS;
+  float* __restrict__ dw = dws.p[blockIdx.z];  // weight group = blockIdx.z
+  partial += (size_t)blockIdx.z * splits * K_total * N_total;
   __shared__ float tile[32][ROW + 1];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // tx -> n within the tile, ty -> (tap, c) lane
   const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -271,28 +289,28 @@ wgrad_reduce_transpose_kernel(const float* __restrict__ partial, float* __restri
 }
 
 // few splits: one thread per output; many splits (1x1 layers, halo kernel: up to 148): 8 lanes share the walk
-static void launch_wgrad_reduce(const float* partial, float* dw, int splits, int K_total, int N_total, int cin, int taps,
-                                float beta, cudaStream_t stream) {
+static void launch_wgrad_reduce(const float* partial, const WgDst& dws, int groups, int splits, int K_total, int N_total,
+                                int cin, int taps, float beta, cudaStream_t stream) {
   const size_t total = (size_t)K_total * N_total;
   // the transposing kernel needs whole 32 x 32 tiles and the plain k = tap*cin + c layout (no padded K tail)
   const bool tileable = cin % 32 == 0 && N_total % 32 == 0 && K_total == cin * taps && (taps == 9 || taps == 1);
   if (splits <= 6 && tileable && total >= (size_t)1 << 18) {
-    const dim3 grid(N_total / 32, cin / 32);
+    const dim3 grid(N_total / 32, cin / 32, groups);
     if (taps == 9)
-      wgrad_reduce_transpose_kernel<9><<<grid, 256, 0, stream>>>(partial, dw, splits, K_total, N_total, cin, beta);
+      wgrad_reduce_transpose_kernel<9><<<grid, 256, 0, stream>>>(partial, dws, splits, K_total, N_total, cin, beta);
     else
-      wgrad_reduce_transpose_kernel<1><<<grid, 256, 0, stream>>>(partial, dw, splits, K_total, N_total, cin, beta);
+      wgrad_reduce_transpose_kernel<1><<<grid, 256, 0, stream>>>(partial, dws, splits, K_total, N_total, cin, beta);
     return;
   }
   if (splits <= 6)
-    wgrad_reduce_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(partial, dw, splits, K_total, N_total,
-                                                                                cin, taps, beta);
+    wgrad_reduce_kernel<1><<<dim3((unsigned)((total + 255) / 256), groups), 256, 0, stream>>>(
+        partial, dws, splits, K_total, N_total, cin, taps, beta);
   else if (splits <= 24)
-    wgrad_reduce_kernel<4><<<(unsigned)((total + 63) / 64), 256, 0, stream>>>(partial, dw, splits, K_total, N_total, cin,
-                                                                              taps, beta);
+    wgrad_reduce_kernel<4><<<dim3((unsigned)((total + 63) / 64), groups), 256, 0, stream>>>(
+        partial, dws, splits, K_total, N_total, cin, taps, beta);
   else
-    wgrad_reduce_kernel<8><<<(unsigned)((total + 31) / 32), 256, 0, stream>>>(partial, dw, splits, K_total, N_total, cin,
-                                                                              taps, beta);
+    wgrad_reduce_kernel<8><<<dim3((unsigned)((total + 31) / 32), groups), 256, 0, stream>>>(
+        partial, dws, splits, K_total, N_total, cin, taps, beta);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -314,7 +332,8 @@ struct WgHaloArgs {
   int hblocks, wsegs;        // H / TH, W / TW
   int spr_shift;             // log2(16-pixel segments per block row)
   int a_tx_bytes;            // (TH + 2) * (TW + 2) * 128
-  float* partial;            // [splits][K_total][N_total]
+  float* partial;            // [groups][splits][K_total][N_total]
+  int groups;                // weight groups stacked along the images (see WgradArgs); num_kb is PER GROUP
 };
 
 constexpr int kWhA = 50176;   // halo stage (<= 3 x 130 lines), 1024-aligned
@@ -339,11 +358,14 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   const int split = item % p.splits;
   item /= p.splits;
   const int n_tile = item % p.num_n_tiles;
-  const int chunk = item / p.num_n_tiles;
+  item /= p.num_n_tiles;
+  const int chunk = item % p.chunks;
+  const int grp = item / p.chunks;
   const int kb_begin = split * p.kb_per_split;
   int kb_end = kb_begin + p.kb_per_split;
   if (kb_end > p.num_kb) kb_end = p.num_kb;
   const int my_kb = kb_end > kb_begin ? kb_end - kb_begin : 0;
+  const int kb_off = grp * p.num_kb;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWhStages; ++i) {
@@ -369,7 +391,8 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     __syncwarp();
     int stage = 0;
     uint32_t phase = 0;
-    for (int kb = kb_begin; kb < kb_end; ++kb) {
+    for (int kbl = kb_begin; kbl < kb_end; ++kbl) {
+      const int kb = kbl + kb_off;
       const int wseg = kb % p.wsegs;
       const int t = kb / p.wsegs;
       const int hb = t % p.hblocks;
@@ -438,7 +461,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     for (int pr = 0; pr < 5; ++pr) {
       const int tap = 2 * pr + (q4 >> 1);
       const size_t krow = (size_t)tap * p.cin + (size_t)chunk * 64 + ci;
-      float* dst = p.partial + ((size_t)split * p.K_total + krow) * p.N_total + (size_t)n_tile * 64;
+      float* dst = p.partial + (((size_t)grp * p.splits + split) * p.K_total + krow) * p.N_total + (size_t)n_tile * 64;
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
@@ -466,7 +489,30 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 }
 
 // Geometry of the halo wgrad for a [n, h, w] image batch; false when the shape is not eligible.
-static bool wgrad_halo_plan(int n, int h, int w, int cin, int cout, int ksize, WgHaloArgs* a) {
+// Split count for `groups` weight groups sharing one launch: the CTAs of all groups must fit ONE wave when possible;
+// otherwise pick the count whose (waves x k-blocks per split) is smallest (a few CTAs spilling into a second wave
+// double the kernel time), smaller counts winning ties (fewer fp32 partials).
+static int grouped_splits(int base_per_group, int groups, int num_kb, int max_splits) {
+  const int sms = num_sms();
+  if (max_splits < 1) max_splits = 1;
+  int fit = sms / (base_per_group * groups);
+  if (fit >= 1) return fit < max_splits ? fit : max_splits;
+  int best = 1;
+  long long best_cost = -1;
+  for (int s = 1; s <= max_splits && s <= 8; ++s) {
+    const long long ctas = (long long)base_per_group * groups * s;
+    const long long waves = (ctas + sms - 1) / sms;
+    const long long cost = waves * ((num_kb + s - 1) / s) * 16 + s;  // + s: partial traffic breaks ties
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = s;
+    }
+  }
+  return best;
+}
+
+// n = images PER GROUP
+static bool wgrad_halo_plan(int n, int h, int w, int cin, int cout, int ksize, WgHaloArgs* a, int groups = 1) {
   const char* e = getenv("IRFD_WGRAD_HALO");
   if (e && atoi(e) == 0) return false;
   if (ksize != 3 || w < 16 || w % 16 != 0 || cin % 64 != 0 || cout % 64 != 0) return false;
@@ -497,10 +543,16 @@ static bool wgrad_halo_plan(int n, int h, int w, int cin, int cout, int ksize, W
   while ((1 << sh) < spr) ++sh;
   a->spr_shift = sh;
   a->a_tx_bytes = (TH + 2) * (TW + 2) * 128;
+  a->groups = groups;
   const int base = a->chunks * a->num_n_tiles;
-  int splits = num_sms() / base;  // one CTA per SM is resident: the launch must fit one wave
-  if (splits > a->num_kb) splits = a->num_kb;
-  if (splits < 1) splits = 1;
+  int splits;
+  if (groups == 1) {
+    splits = num_sms() / base;  // one CTA per SM is resident: the launch must fit one wave
+    if (splits > a->num_kb) splits = a->num_kb;
+    if (splits < 1) splits = 1;
+  } else {
+    splits = grouped_splits(base, groups, a->num_kb, a->num_kb);
+  }
   a->kb_per_split = (a->num_kb + splits - 1) / splits;
   a->splits = (a->num_kb + a->kb_per_split - 1) / a->kb_per_split;
   return true;
@@ -519,14 +571,17 @@ static int launch_wgrad(const CUtensorMap& mx, const CUtensorMap& mdy, const Wgr
     }
     configured = true;
   }
-  const int grid = a.num_pairs * a.num_n_tiles * a.splits;
+  const int grid = a.groups * a.num_pairs * a.num_n_tiles * a.splits;
   kern<<<grid, kWgThreads, Cfg::SMEM_BYTES, stream>>>(mx, mdy, a);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }
 
-static void wgrad_plan(int n, int h, int w, int cin, int cout, int ksize, WgradArgs* a, int* block_n) {
+// n = images PER GROUP
+static void wgrad_plan(int n, int h, int w, int cin, int cout, int ksize, WgradArgs* a, int* block_n, int groups = 1) {
   const long long m_total = (long long)n * h * w;
+  a->groups = groups;
+  a->x_shared = 0;
   a->M_total = (int)m_total;
   a->N_total = cout;
   a->taps = ksize * ksize;
@@ -542,10 +597,15 @@ static void wgrad_plan(int n, int h, int w, int cin, int cout, int ksize, WgradA
   // One CTA per SM is resident (200 KB of pipeline stages), so the launch must fit ONE wave: rounding the split count
   // up left a second wave of a handful of CTAs (e.g. 153 = 148 + 5) that doubled the kernel time.
   const int base = a->num_pairs * a->num_n_tiles;
-  int splits = (kWgWaves * num_sms()) / base;
   const int max_splits = (a->num_kb + kWgMinKb - 1) / kWgMinKb;  // at least kWgMinKb k-blocks (64 pixels each) per split
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
+  int splits;
+  if (groups == 1) {
+    splits = (kWgWaves * num_sms()) / base;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  } else {
+    splits = grouped_splits(base, groups, a->num_kb, max_splits);
+  }
   a->kb_per_split = (a->num_kb + splits - 1) / splits;
   a->splits = (a->num_kb + a->kb_per_split - 1) / a->kb_per_split;
 }
@@ -554,36 +614,52 @@ static void wgrad_plan(int n, int h, int w, int cin, int cout, int ksize, WgradA
 
 using namespace irfd;
 
-extern "C" long long irfd_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout, int ksize) {
+static long long wgrad_ws_bytes(int n_g, int h, int w, int cin, int cout, int ksize, int groups) {
   WgHaloArgs ha;
-  if (wgrad_halo_plan(n, h, w, cin, cout, ksize, &ha)) return (long long)ha.splits * ha.K_total * ha.N_total * 4;
+  if (wgrad_halo_plan(n_g, h, w, cin, cout, ksize, &ha, groups))
+    return (long long)groups * ha.splits * ha.K_total * ha.N_total * 4;
   WgradArgs a;
   int bn;
-  wgrad_plan(n, h, w, cin, cout, ksize, &a, &bn);
-  return (long long)a.splits * a.K_total * a.N_total * 4;
+  wgrad_plan(n_g, h, w, cin, cout, ksize, &a, &bn, groups);
+  return (long long)groups * a.splits * a.K_total * a.N_total * 4;
 }
 
-extern "C" int irfd_conv_wgrad(const void* x, const void* dy, int n, int h, int w, int cin, int cout, int ksize,
-                               float* dw, float beta, int reduce_cin, int reduce_taps, void* workspace,
-                               long long workspace_bytes, cudaStream_t stream) {
-  IRFD_CHECK_ARG(x && dy && dw && workspace, "conv_wgrad: null pointer");
+extern "C" long long irfd_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout, int ksize) {
+  return wgrad_ws_bytes(n, h, w, cin, cout, ksize, 1);
+}
+
+// n = TOTAL images (all groups); with x_shared, n/h/w describe dY's stacked rows and x holds one group's rows
+extern "C" long long irfd_wgrad_workspace_bytes_grouped(int n, int h, int w, int cin, int cout, int ksize, int groups) {
+  if (groups < 1 || groups > kMaxWgGroups) return -1;
+  if (n % groups == 0) return wgrad_ws_bytes(n / groups, h, w, cin, cout, ksize, groups);
+  return wgrad_ws_bytes(1, 1, (int)(((long long)n * h * w) / groups), cin, cout, ksize, groups);  // 2-D row matrices
+}
+
+static int conv_wgrad_impl(const void* x, const void* dy, int n, int h, int w, int cin, int cout, int ksize,
+                           const WgDst& dws, int groups, int x_shared, float beta, int reduce_cin, int reduce_taps,
+                           void* workspace, long long workspace_bytes, cudaStream_t stream) {
+  // n, h, w: geometry of ONE group
+  IRFD_CHECK_ARG(x && dy && workspace, "conv_wgrad: null pointer");
   IRFD_CHECK_ARG(ksize == 1 || ksize == 3, "conv_wgrad: ksize must be 1 or 3");
   IRFD_CHECK_ARG(cin % 64 == 0 && cout % 64 == 0, "conv_wgrad: channels must be multiples of 64");
+  IRFD_CHECK_ARG(!x_shared || ksize == 1, "conv_wgrad: a shared x operand needs ksize 1");
+  const long long m_group = (long long)n * h * w;
+  IRFD_CHECK_ARG(groups == 1 || m_group % 128 == 0, "conv_wgrad: grouped launches need 128-pixel multiples per group");
   WgHaloArgs ha;
-  if (wgrad_halo_plan(n, h, w, cin, cout, ksize, &ha)) {
-    IRFD_CHECK_ARG(workspace_bytes >= (long long)ha.splits * ha.K_total * ha.N_total * 4,
+  if (!x_shared && wgrad_halo_plan(n, h, w, cin, cout, ksize, &ha, groups)) {
+    IRFD_CHECK_ARG(workspace_bytes >= (long long)groups * ha.splits * ha.K_total * ha.N_total * 4,
                    "conv_wgrad: workspace too small");
     ha.partial = reinterpret_cast<float*>(workspace);
     CUtensorMap mx, mdy;
     {
-      const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+      const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n * groups};
       const uint64_t str[3] = {(uint64_t)cin * 2, (uint64_t)w * cin * 2, (uint64_t)h * w * cin * 2};
       const uint32_t box[4] = {64, (uint32_t)(ha.TW + 2), (uint32_t)(ha.TH + 2), 1};
       int rc = make_tmap_bf16(&mx, x, 4, dims, str, box, true);
       if (rc) return rc;
     }
     {
-      const uint64_t dims[2] = {(uint64_t)cout, (uint64_t)((long long)n * h * w)};
+      const uint64_t dims[2] = {(uint64_t)cout, (uint64_t)(m_group * groups)};
       const uint64_t str[1] = {(uint64_t)cout * 2};
       const uint32_t box[2] = {64, 128};
       int rc = make_tmap_bf16(&mdy, dy, 2, dims, str, box, true);
@@ -598,22 +674,25 @@ extern "C" int irfd_conv_wgrad(const void* x, const void* dy, int n, int h, int 
       }
       configured = true;
     }
-    wgrad_halo_kernel<<<ha.chunks * ha.num_n_tiles * ha.splits, kWgThreads, kWhSmem, stream>>>(mx, mdy, ha);
+    wgrad_halo_kernel<<<groups * ha.chunks * ha.num_n_tiles * ha.splits, kWgThreads, kWhSmem, stream>>>(mx, mdy, ha);
     IRFD_CHECK_LAUNCH();
-    launch_wgrad_reduce(ha.partial, dw, ha.splits, ha.K_total, ha.N_total, reduce_cin > 0 ? reduce_cin : cin,
+    launch_wgrad_reduce(ha.partial, dws, groups, ha.splits, ha.K_total, ha.N_total, reduce_cin > 0 ? reduce_cin : cin,
                         reduce_cin > 0 ? reduce_taps : 9, beta, stream);
     IRFD_CHECK_LAUNCH();
     return IRFD_OK;
   }
   WgradArgs a;
   int block_n;
-  wgrad_plan(n, h, w, cin, cout, ksize, &a, &block_n);
-  IRFD_CHECK_ARG(workspace_bytes >= (long long)a.splits * a.K_total * a.N_total * 4, "conv_wgrad: workspace too small");
+  wgrad_plan(n, h, w, cin, cout, ksize, &a, &block_n, groups);
+  a.x_shared = x_shared;
+  IRFD_CHECK_ARG(workspace_bytes >= (long long)groups * a.splits * a.K_total * a.N_total * 4,
+                 "conv_wgrad: workspace too small");
   a.partial = reinterpret_cast<float*>(workspace);
 
-  int H = h, W = w, NB = n;
+  const int xg = x_shared ? 1 : groups;  // groups stacked in x
+  int H = h, W = w, NB = n * xg;
   if (ksize == 1) {
-    H = 1; W = a.M_total; NB = 1;
+    H = 1; W = (int)(m_group * xg); NB = 1;
   }
   int tw, th, tn;
   if (W >= 64) {
@@ -642,7 +721,7 @@ extern "C" int irfd_conv_wgrad(const void* x, const void* dy, int n, int h, int 
     if (rc) return rc;
   }
   {
-    const uint64_t dims[2] = {(uint64_t)cout, (uint64_t)a.M_total};
+    const uint64_t dims[2] = {(uint64_t)cout, (uint64_t)(m_group * groups)};
     const uint64_t str[1] = {(uint64_t)cout * 2};
     const uint32_t box[2] = {64, 64};
     int rc = make_tmap_bf16(&mdy, dy, 2, dims, str, box, true);
@@ -655,8 +734,40 @@ extern "C" int irfd_conv_wgrad(const void* x, const void* dy, int n, int h, int 
     default: rc = launch_wgrad<256>(mx, mdy, a, stream); break;
   }
   if (rc) return rc;
-  launch_wgrad_reduce(a.partial, dw, a.splits, a.K_total, a.N_total, reduce_cin > 0 ? reduce_cin : cin,
+  launch_wgrad_reduce(a.partial, dws, groups, a.splits, a.K_total, a.N_total, reduce_cin > 0 ? reduce_cin : cin,
                       reduce_cin > 0 ? reduce_taps : a.taps, beta, stream);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
+}
+
+extern "C" int irfd_conv_wgrad(const void* x, const void* dy, int n, int h, int w, int cin, int cout, int ksize,
+                               float* dw, float beta, int reduce_cin, int reduce_taps, void* workspace,
+                               long long workspace_bytes, cudaStream_t stream) {
+  IRFD_CHECK_ARG(dw != nullptr, "conv_wgrad: null pointer");
+  WgDst dws;
+  for (int i = 0; i < kMaxWgGroups; ++i) dws.p[i] = i == 0 ? dw : nullptr;
+  return conv_wgrad_impl(x, dy, n, h, w, cin, cout, ksize, dws, 1, 0, beta, reduce_cin, reduce_taps, workspace,
+                         workspace_bytes, stream);
+}
+
+// `groups` weight gradients in one launch pair: x [n, h, w, cin] and dy [n, h, w, cout] stack the groups' images
+// group-major (n = TOTAL images, n % groups == 0; 2-D row matrices pass n = 1, h = 1, w = total rows); dw is a HOST
+// array of `groups` device pointers (one OIHW fp32 gradient each).  x_shared != 0 (ksize 1): x holds ONE group's rows,
+// read by every group (the stem's im2col matrix); n/h/w then describe dy.
+extern "C" int irfd_conv_wgrad_grouped(const void* x, const void* dy, int n, int h, int w, int cin, int cout, int ksize,
+                                       float* const* dw, float beta, int reduce_cin, int reduce_taps, int groups,
+                                       int x_shared, void* workspace, long long workspace_bytes, cudaStream_t stream) {
+  IRFD_CHECK_ARG(dw != nullptr && groups >= 1 && groups <= kMaxWgGroups, "conv_wgrad_grouped: 1..4 groups");
+  WgDst dws;
+  for (int i = 0; i < kMaxWgGroups; ++i) dws.p[i] = i < groups ? dw[i] : nullptr;
+  for (int i = 0; i < groups; ++i) IRFD_CHECK_ARG(dws.p[i] != nullptr, "conv_wgrad_grouped: null gradient pointer");
+  int ng = n, hg = h, wg = w;
+  if (n % groups == 0) {
+    ng = n / groups;
+  } else {  // 2-D row matrix [1, 1, rows, K]
+    IRFD_CHECK_ARG(n == 1 && h == 1 && w % groups == 0, "conv_wgrad_grouped: rows do not split into groups");
+    wg = w / groups;
+  }
+  return conv_wgrad_impl(x, dy, ng, hg, wg, cin, cout, ksize, dws, groups, x_shared, beta, reduce_cin, reduce_taps,
+                         workspace, workspace_bytes, stream);
 }

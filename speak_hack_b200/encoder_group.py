@@ -12,8 +12,9 @@ of the tensor peak, 18-55 us launches against 6-26 us bounds).  `EncoderGroup` r
   (`irfd_bn_*_sets`): per-call batch statistics and running-buffer updates exactly as E x groups separate
   nn.BatchNorm2d calls (the reference calls each encoder on x_s and then on x_t);
 * layout kernels (maxpool, stride-2 gathers, pools) are per image and run on the stacked tensor unchanged;
-* weight gradients are one split-K launch per encoder on its slice of the stacked tensors (those launches already fill
-  the machine), written straight into the caller's gradient buffers when `grad_targets` is set.
+* weight gradients are one grouped split-K launch per layer (`irfd_conv_wgrad_grouped`: the CTAs of the three encoders
+  share the single wave, a third of the fp32 partials), written straight into the caller's gradient buffers when
+  `grad_targets` is set.
 
 Numerically the grouped pass is the per-encoder pass: same kernels, same tiles, same summation order per tile
 (tests/test_gpu_encoder_group.py: features and BN buffers bit-identical, parameter gradients equal).
@@ -204,17 +205,9 @@ class _EncoderGroupFn(torch.autograd.Function):
             return (r[0], r[3]) if want_g_out else r[0]
 
         def wgrad(convs, xx, dy, ksize, **kw):
-            """One split-K launch per encoder on its slice of the stacked activations."""
-            ne = xx.shape[0] // E if xx.dim() == 4 and xx.shape[0] % E == 0 and "rows" not in kw else None
-            for e, c in enumerate(convs):
-                if ne is not None:
-                    xe, dye = xx[e * ne: (e + 1) * ne], dy[e * ne: (e + 1) * ne]
-                else:  # 2-D row matrices viewed as [1, 1, rows, K]
-                    rows = kw["rows"]
-                    xe = xx[e * rows: (e + 1) * rows].view(1, 1, rows, xx.shape[-1])
-                    dye = dy[e * rows: (e + 1) * rows].view(1, 1, rows, dy.shape[-1])
-                ops.conv_wgrad(xe, dye, ksize, dw=tgt(c.weight), beta=0.0, reduce_cin=kw.get("reduce_cin", 0),
-                               reduce_taps=kw.get("reduce_taps", 0))
+            """All E weight gradients of one layer in one split-K launch pair (the CTAs of the three encoders share the
+            wave, so each encoder needs a third of the fp32 partials three separate launches would write)."""
+            ops.conv_wgrad_grouped(xx, dy, ksize, [tgt(c.weight) for c in convs], **kw)
 
         cur_li = None
         for rec in reversed(S["blocks"]):
@@ -233,8 +226,7 @@ class _EncoderGroupFn(torch.autograd.Function):
                 d_a1 = ops.conv_gemm_grouped(dz2, _stack_pack([b.conv2 for b in blks], ops.PACK_DGRAD), 3, wgroups=E)
             else:
                 m2 = dz2.numel() // planes
-                wgrad([b.conv2 for b in blks], col2, dz2.view(m2, planes), 1, rows=m2 // E, reduce_cin=planes,
-                      reduce_taps=9)
+                wgrad([b.conv2 for b in blks], col2, dz2.view(m2, planes), 1, reduce_cin=planes, reduce_taps=9)
                 dcol = ops.conv_gemm_grouped(dz2.view(1, 1, m2, planes),
                                              _stack_pack([b.conv2 for b in blks], ops.PACK_DCOL), 1, wgroups=E)
                 d_a1 = ops.col2im_3x3s2(dcol.view(m2, 9 * planes), nb, hh, ww, planes)
@@ -257,10 +249,9 @@ class _EncoderGroupFn(torch.autograd.Function):
         col0, z0, st0, a0, arg0 = S["stem"]
         d_a0 = ops.maxpool_bwd(g, arg0, g2)
         dz0 = bn_bwd([e[1] for e in encs], st0, d_a0, None, a0, z0, mask_from_z=True)
-        m0 = dz0.numel() // 64 // E
-        for e, enc in enumerate(encs):  # the stem's im2col matrix is shared: every encoder reads the same rows
-            ops.conv_wgrad(col0.view(1, 1, m0, 192), dz0.view(E * m0, 64)[e * m0: (e + 1) * m0].view(1, 1, m0, 64), 1,
-                           dw=tgt(enc[0].weight), beta=0.0, reduce_cin=147, reduce_taps=1)
+        # the stem's im2col matrix is shared: every encoder reads the same rows
+        ops.conv_wgrad_grouped(col0, dz0.view(-1, 64), 1, [tgt(e[0].weight) for e in encs], x_shared=True, reduce_cin=147,
+                               reduce_taps=1)
         if cb is not None:
             cb("stage", 3)   # the stem (Sequential indices 0, 1)
             cb("post", None)

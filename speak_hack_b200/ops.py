@@ -281,6 +281,33 @@ def conv_wgrad(x, dy, ksize, dw=None, beta=0.0, reduce_cin=0, reduce_taps=0, out
     return dw
 
 
+def conv_wgrad_grouped(x, dy, ksize, dws, x_shared=False, reduce_cin=0, reduce_taps=0):
+    """Weight gradients of `len(dws)` weight groups (the same layer of the three encoders) in ONE launch pair.
+    x [N,H,W,Cin] / dy [N,H,W,Cout] stack the groups' images group-major (2-D [rows, K] matrices are accepted too);
+    x_shared: x is one group's [rows, K] matrix read by every group.  dws: fp32 OIHW destinations (overwritten)."""
+    lib = _lib.load()
+    _chk(x, BF16, "x")
+    _chk(dy, BF16, "dy")
+    groups = len(dws)
+    for d in dws:
+        _chk(d, F32, "dw")
+    cin, cout = x.shape[-1], dy.shape[-1]
+    if dy.dim() == 4 and not x_shared:
+        n, h, w = dy.shape[0], dy.shape[1], dy.shape[2]
+    else:
+        n, h, w = 1, 1, dy.numel() // cout
+    need = lib.irfd_wgrad_workspace_bytes_grouped(n, h, w, cin, cout, ksize, groups)
+    if need < 0:
+        raise _lib.IrfdError(f"conv_wgrad_grouped: {groups} groups not supported")
+    ws = workspace(need, x.device)
+    m = n * h * w
+    nbytes = 2.0 * m * cout + 2.0 * m * cin / (groups if x_shared else 1) + 4.0 * groups * cin * cout * ksize * ksize
+    with _timed("wgrad_gemm_kernel (tcgen05 split-K + reduce)", 2.0 * m * cout * cin * ksize * ksize, nbytes):
+        _call("irfd_conv_wgrad_grouped", x.data_ptr(), dy.data_ptr(), n, h, w, cin, cout, ksize, _ptr_array(dws), 0.0,
+              reduce_cin, reduce_taps, groups, 1 if x_shared else 0, ws.data_ptr(), ws.numel(), _stream(), launches=2)
+    return dws
+
+
 _pack_cache = {}
 
 

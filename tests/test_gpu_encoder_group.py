@@ -65,6 +65,36 @@ def test_grouped_conv_shared_operand(cuda_device):
         assert torch.equal(s[e * 4:(e + 1) * 4], s1) and torch.equal(q[e * 4:(e + 1) * 4], q1)
 
 
+@pytest.mark.parametrize("ksize,cin,cout,hw,n", [(1, 256, 64, 16, 6), (3, 64, 64, 64, 6), (3, 128, 128, 8, 12),
+                                                 (1, 512, 2048, 8, 12)])
+def test_grouped_wgrad_equals_separate_calls(cuda_device, ksize, cin, cout, hw, n):
+    """One grouped split-K launch pair for three weight gradients == three launches on the slices (the split count
+    differs, so the fp32 partials are summed in a different order: equal to ~1e-6, not bit for bit)."""
+    import irfd_oracle as O
+    from speak_hack_b200 import ops
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(ksize * 10 + cin)
+    E = 3
+    x = _bf(torch.randn(n, hw, hw, cin, generator=g).to(dev))
+    dy = _bf(torch.randn(n, hw, hw, cout, generator=g).to(dev))
+    dws = [torch.full((cout, cin, ksize, ksize), float("nan"), device=dev) for _ in range(E)]
+    ops.conv_wgrad_grouped(x, dy, ksize, dws)
+    ne = n // E
+    for e in range(E):
+        ref = ops.conv_wgrad(x[e * ne:(e + 1) * ne], dy[e * ne:(e + 1) * ne], ksize)
+        assert O.rel_l2(dws[e], ref) < 2e-6, (e, O.rel_l2(dws[e], ref))
+    # shared x operand (the stem): 2-D matrices, zero-padded K tail dropped by reduce_cin
+    col = _bf(torch.randn(512, 192, generator=g).to(dev))
+    dz = _bf(torch.randn(3 * 512, 64, generator=g).to(dev))
+    dws = [torch.empty((64, 3, 7, 7), device=dev) for _ in range(E)]
+    ops.conv_wgrad_grouped(col, dz, 1, dws, x_shared=True, reduce_cin=147, reduce_taps=1)
+    for e in range(E):
+        ref = ops.conv_wgrad(col.view(1, 1, 512, 192), dz[e * 512:(e + 1) * 512].view(1, 1, 512, 64), 1, reduce_cin=147,
+                             reduce_taps=1, out_shape=(64, 3, 7, 7))
+        assert O.rel_l2(dws[e], ref) < 2e-6
+
+
 def test_bn_sets_equal_separate_calls(cuda_device):
     from speak_hack_b200 import ops
 
@@ -172,7 +202,7 @@ def test_encoder_group_train_equals_three_passes(cuda_device):
     torch.cuda.synchronize()
     grp.grad_targets, grp._bwd_cb = None, None
     assert all(p.grad is None for e in grouped for p in e.parameters())
-    assert all(torch.equal(targets[p], ref_grads[p]) for p in targets)
+    assert all(torch.equal(targets[p], ref_grads[p]) for p in targets)  # same launches, same order: bit-identical
     assert events == [("pre", None), ("stage", 7), ("stage", 6), ("stage", 5), ("stage", 4), ("stage", 3), ("post", None)]
 
 
