@@ -468,6 +468,7 @@ def run_native(args):
 
     # ---- roofline pass: per-launch CUDA events around every tensor-core GEMM launch (same stream), few steps
     # (the whole step runs on one stream, so an event pair times exactly the launch between its two records)
+    ops.use_side_stream = False                  # weight gradients on the main stream: every launch timed alone
     ops.gemm_timing_begin()
     rsteps = min(args.steps, 3)
     for _ in range(rsteps):

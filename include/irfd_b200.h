@@ -188,6 +188,10 @@ int irfd_maxpool_bwd(const void* dout, const void* dout2, const void* argmax, vo
                      irfd_stream_t stream); /* dout2 (optional) is added to dout before routing */
 int irfd_avgpool_fwd(const void* a, float* out, int n, int hw, int c, irfd_stream_t stream);
 int irfd_avgpool_bwd(const float* dfeat, void* g, int n, int hw, int c, irfd_stream_t stream);
+/* NCHW fp32 [b,c,hw] <-> NHWC bf16 [b,hw,c_pad] (c_pad >= c; padded channels are zero): the standalone forwards of the
+ * reference's per-layer modules (styleganv1.py:612-635 SynthesisBlock) enter and leave the NHWC kernels through these. */
+int irfd_nchw_to_nhwc_bf16(const float* in, void* out, int b, int c, int hw, int c_pad, irfd_stream_t stream);
+int irfd_nhwc_bf16_to_nchw(const void* in, float* out, int b, int c, int hw, int c_pad, irfd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Synthesis-network pieces that are not conv epilogues (styleganv1.py:593-635).
@@ -209,6 +213,11 @@ int irfd_const_input_split_fwd(const float* cst, const float* bias, const float*
                                const float* sp1, const float* s1, void* a0, void* y0, void* y0_lo, int b, int c,
                                irfd_stream_t stream);
 int irfd_upsample2x_bwd(const void* dout, void* din, int b, int h, int w, int c, irfd_stream_t stream);
+/* standalone ApplyNoise (styleganv1.py:453-456) and ApplyStyle (:463-468) on NCHW fp32: out = x + w[c]*noise[b,hw];
+ * out = x*(style[b,c]+1) + style[b,C+c] */
+int irfd_apply_noise_nchw(const float* x, const float* w, const float* noise, float* out, int b, int c, int hw,
+                          irfd_stream_t stream);
+int irfd_apply_style_nchw(const float* x, const float* style, float* out, int b, int c, int hw, irfd_stream_t stream);
 long long irfd_style_bwd_workspace_bytes(int b, int hw, int c);
 int irfd_style_bwd(const void* dy, const void* a, const float* noise, const float* sp1, void* dz, float* ds1,
                    float* dsp1, float* dbias, float* dnw, int b, int hw, int c, void* workspace,

@@ -277,6 +277,44 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ dfeat, __nv_bfloat1
   store8(g + (size_t)pix * C + v * 8, f);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// NCHW fp32 <-> NHWC bf16 (the reference's module interfaces are NCHW fp32; the kernels work on NHWC bf16).  Used by
+// the standalone forwards of the per-layer modules (SynthesisBlock, ApplyNoise, ApplyStyle); the fused paths never
+// materialise NCHW activations.  32 x 32 (channel x pixel) tiles through shared memory: coalesced on both sides.
+// c_pad >= c: channels [c, c_pad) of the NHWC tensor are written as zero (64-channel GEMM tiles) / ignored.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int HW, int c_pad) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, p = p0 + tx;
+    tile[i][tx] = (c < C && p < HW) ? in[((size_t)b * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int p = p0 + i, c = c0 + tx;
+    if (p < HW && c < c_pad) out[((size_t)b * HW + p) * c_pad + c] = __float2bfloat16(tile[tx][i]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int C, int HW, int c_pad) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int p = p0 + i, c = c0 + tx;
+    tile[i][tx] = (p < HW && c < c_pad) ? __bfloat162float(in[((size_t)b * HW + p) * c_pad + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, p = p0 + tx;
+    if (c < C && p < HW) out[((size_t)b * C + c) * HW + p] = tile[tx][i];
+  }
+}
+
 }  // namespace irfd
 
 using namespace irfd;
@@ -374,6 +412,22 @@ extern "C" int irfd_avgpool_bwd(const float* dfeat, void* g, int n, int hw, int 
   const size_t total = (size_t)n * hw * (c / 8);
   CHECK_TOTAL32(total);
   avgpool_bwd_kernel<<<GRID1D(total)>>>(dfeat, BF(g), n, hw, c);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_nchw_to_nhwc_bf16(const float* in, void* out, int b, int c, int hw, int c_pad, cudaStream_t stream) {
+  IRFD_CHECK_ARG(in && out && b > 0 && c > 0 && hw > 0 && c_pad >= c, "nchw_to_nhwc_bf16: bad argument");
+  nchw_to_nhwc_kernel<<<dim3((hw + 31) / 32, (c_pad + 31) / 32, b), 256, 0, stream>>>(
+      in, reinterpret_cast<__nv_bfloat16*>(out), c, hw, c_pad);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_nhwc_bf16_to_nchw(const void* in, float* out, int b, int c, int hw, int c_pad, cudaStream_t stream) {
+  IRFD_CHECK_ARG(in && out && b > 0 && c > 0 && hw > 0 && c_pad >= c, "nhwc_bf16_to_nchw: bad argument");
+  nhwc_to_nchw_kernel<<<dim3((hw + 31) / 32, (c_pad + 31) / 32, b), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(in), out, c, hw, c_pad);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }

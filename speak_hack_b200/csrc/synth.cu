@@ -425,6 +425,33 @@ __global__ void to_rgb_bwd_finalize_kernel(const float* __restrict__ partial, in
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Standalone ApplyNoise / ApplyStyle on the reference's own layout (NCHW fp32, styleganv1.py:453-468): the fused
+// path applies both inside the conv epilogue; these serve direct calls of the two modules.
+//   noise: out = x + w[c] * noise[b, hw]          style: out = x * (style[b, c] + 1) + style[b, C + c]
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void apply_noise_nchw_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                        const float* __restrict__ noise, float* __restrict__ out, int C, int HW,
+                                        size_t total) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int hw = (int)(i % HW);
+  const size_t bc = i / HW;
+  const int c = (int)(bc % C);
+  const size_t b = bc / C;
+  out[i] = x[i] + w[c] * noise[b * HW + hw];
+}
+
+__global__ void apply_style_nchw_kernel(const float* __restrict__ x, const float* __restrict__ style,
+                                        float* __restrict__ out, int C, int HW, size_t total) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const size_t bc = i / HW;
+  const int c = (int)(bc % C);
+  const size_t b = bc / C;
+  out[i] = x[i] * (style[b * 2 * C + c] + 1.f) + style[b * 2 * C + C + c];
+}
+
 }  // namespace irfd
 
 using namespace irfd;
@@ -545,6 +572,24 @@ extern "C" int irfd_to_rgb_bwd(const float* drgb, const void* y, const float* w,
                                                                            rpb);
   IRFD_CHECK_LAUNCH();
   to_rgb_bwd_finalize_kernel<<<(3 * c + 3 + 127) / 128, 128, 0, stream>>>(partial, nblk, c, dw, dbias);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_apply_noise_nchw(const float* x, const float* w, const float* noise, float* out, int b, int c, int hw,
+                                     cudaStream_t stream) {
+  IRFD_CHECK_ARG(x && w && noise && out && b > 0 && c > 0 && hw > 0, "apply_noise_nchw: bad argument");
+  const size_t total = (size_t)b * c * hw;
+  apply_noise_nchw_kernel<<<GRID1D(total)>>>(x, w, noise, out, c, hw, total);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
+extern "C" int irfd_apply_style_nchw(const float* x, const float* style, float* out, int b, int c, int hw,
+                                     cudaStream_t stream) {
+  IRFD_CHECK_ARG(x && style && out && b > 0 && c > 0 && hw > 0, "apply_style_nchw: bad argument");
+  const size_t total = (size_t)b * c * hw;
+  apply_style_nchw_kernel<<<GRID1D(total)>>>(x, style, out, c, hw, total);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }

@@ -32,6 +32,9 @@ class GradBuckets:
         self.cuda = device.type == "cuda"
         self.comm_stream = torch.cuda.Stream(device) if (self.cuda and self.world > 1) else None
         self.enabled = True
+        # callable returning the streams (besides the current one) that may still be producing the gradients of the
+        # bucket being launched: the weight-gradient side stream while it has un-joined work (ops.SideStream)
+        self.producers = lambda: []
         self._pending = 0
         self.launched_bytes = 0
 
@@ -42,6 +45,8 @@ class GradBuckets:
         if self.cuda:
             ready = torch.cuda.Event()
             ready.record()
+            for ps in self.producers():
+                self.comm_stream.wait_stream(ps)
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ready)
                 flat.record_stream(self.comm_stream)

@@ -204,10 +204,14 @@ class _EncoderGroupFn(torch.autograd.Function):
                                      want_g_out=want_g_out, batch_stats=True, groups=GT)
             return (r[0], r[3]) if want_g_out else r[0]
 
+        side = ops.side_stream(dfeat.device)
+
         def wgrad(convs, xx, dy, ksize, **kw):
             """All E weight gradients of one layer in one split-K launch pair (the CTAs of the three encoders share the
-            wave, so each encoder needs a third of the fp32 partials three separate launches would write)."""
-            ops.conv_wgrad_grouped(xx, dy, ksize, [tgt(c.weight) for c in convs], **kw)
+            wave, so each encoder needs a third of the fp32 partials three separate launches would write), on the side
+            stream: the tensor-bound wgrad overlaps the HBM-bound BatchNorm backward of the next layer."""
+            dws = [tgt(c.weight) for c in convs]   # allocated on the main stream
+            side.launch(lambda: ops.conv_wgrad_grouped(xx, dy, ksize, dws, **kw), xx, dy, *dws)
 
         cur_li = None
         for rec in reversed(S["blocks"]):
@@ -250,8 +254,8 @@ class _EncoderGroupFn(torch.autograd.Function):
         d_a0 = ops.maxpool_bwd(g, arg0, g2)
         dz0 = bn_bwd([e[1] for e in encs], st0, d_a0, None, a0, z0, mask_from_z=True)
         # the stem's im2col matrix is shared: every encoder reads the same rows
-        ops.conv_wgrad_grouped(col0, dz0.view(-1, 64), 1, [tgt(e[0].weight) for e in encs], x_shared=True, reduce_cin=147,
-                               reduce_taps=1)
+        wgrad([e[0] for e in encs], col0, dz0.view(-1, 64), 1, x_shared=True, reduce_cin=147, reduce_taps=1)
+        side.join()
         if cb is not None:
             cb("stage", 3)   # the stem (Sequential indices 0, 1)
             cb("post", None)

@@ -64,26 +64,46 @@ class FC(nn.Module):
         return _FCFn.apply(x, self.weight, self.bias, float(self.w_lrmul), float(self.b_lrmul), True)
 
 
+def _standalone_only_forward(name: str, *tensors) -> None:
+    """The per-layer modules below exist for their parameters (state_dict layout) — SynthesisNetwork runs them fused,
+    with its own hand-written backward.  Called on their own they run the same kernels forward-only."""
+    for t in tensors:
+        if not t.is_cuda:
+            raise ops._lib.IrfdError(f"{name}: CUDA tensors only (no CPU fallback on the IRFD hot path)")
+    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+        raise ops._lib.IrfdError(f"{name}: the standalone forward is not differentiable; run it under torch.no_grad() "
+                                 "or call SynthesisNetwork / StyleGenerator (fused forward + backward)")
+
+
 class ApplyNoise(nn.Module):
-    """Parameter holder for the per-channel noise weight (styleganv1.py:448-456); applied inside the conv epilogue."""
+    """styleganv1.py:448-456.  Inside SynthesisNetwork the noise is added in the conv epilogue; a direct call runs the
+    standalone NCHW fp32 kernel (forward only)."""
 
     def __init__(self, channels):
         super().__init__()
         self.weight = nn.Parameter(torch.zeros(channels))
 
-    def forward(self, x, noise=None):  # pragma: no cover - fused path is used instead
-        raise RuntimeError("ApplyNoise is fused into SynthesisNetwork's conv epilogue; call SynthesisNetwork/StyleGenerator")
+    def forward(self, x, noise=None):
+        _standalone_only_forward("ApplyNoise", x, self.weight)
+        x = x.contiguous().to(torch.float32)
+        if noise is None:  # same draw as the reference (styleganv1.py:455)
+            noise = torch.randn(x.size(0), 1, x.size(2), x.size(3), device=x.device, dtype=x.dtype)
+        return ops.apply_noise_nchw(x, self.weight.detach(), noise.to(x.device, torch.float32).contiguous())
 
 
 class ApplyStyle(nn.Module):
-    """Parameter holder for the style affine FC (styleganv1.py:458-468); applied inside the conv epilogue."""
+    """styleganv1.py:458-468.  Inside SynthesisNetwork the affine runs in the conv epilogue; a direct call runs the FC
+    and the standalone NCHW fp32 kernel (forward only)."""
 
     def __init__(self, latent_size, channels, use_wscale):
         super().__init__()
         self.linear = FC(latent_size, channels * 2, gain=1.0, use_wscale=use_wscale)
 
-    def forward(self, x, latent):  # pragma: no cover
-        raise RuntimeError("ApplyStyle is fused into SynthesisNetwork's conv epilogue; call SynthesisNetwork/StyleGenerator")
+    def forward(self, x, latent):
+        _standalone_only_forward("ApplyStyle", x, latent, self.linear.weight)
+        with torch.no_grad():
+            style = self.linear(latent.contiguous().to(torch.float32))
+        return ops.apply_style_nchw(x.contiguous().to(torch.float32), style)
 
 
 class SynthesisBlock(nn.Module):
@@ -99,8 +119,28 @@ class SynthesisBlock(nn.Module):
         self.style_mod2 = ApplyStyle(512, out_channels, use_wscale=True)
         self.upsample = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=False)
 
-    def forward(self, x, w):  # pragma: no cover
-        raise RuntimeError("SynthesisBlock runs fused inside SynthesisNetwork; call SynthesisNetwork/StyleGenerator")
+    def forward(self, x, w):
+        """styleganv1.py:623-635 on its own: x [B,Cin,H,W] fp32, w [B,2,512] -> [B,Cout,2H,2W] fp32.  Forward only
+        (SynthesisNetwork is the differentiable, fused path); same kernels: bilinear x2, two tcgen05 convs with the
+        noise / leaky-ReLU / style epilogue, NHWC bf16 in between."""
+        _standalone_only_forward("SynthesisBlock", x, w, self.conv1.weight)
+        x = x.contiguous().to(torch.float32)
+        b, cin, h, wd = x.shape
+        cout = self.conv1.weight.shape[0]
+        cip, cop = _cpad(cin), _cpad(cout)
+        lin1, lin2 = self.style_mod1.linear, self.style_mod2.linear
+        with torch.no_grad():
+            u = ops.upsample2x_fwd(ops.nchw_to_nhwc(x, cip))
+            y = u
+            for conv, noise_w, lin, row in ((self.conv1, self.noise1.weight, lin1, 0), (self.conv2, self.noise2.weight, lin2, 1)):
+                st = ops.linear_fwd(w[:, row].contiguous().to(torch.float32), lin.weight, lin.bias, float(lin.w_lrmul),
+                                    float(lin.b_lrmul), lrelu=True)
+                sp1, s1 = ops.split_style(st, cout)
+                noise = torch.randn(b, 1, 2 * h, 2 * wd, device=x.device, dtype=torch.float32).reshape(-1)
+                _, y = ops.conv_gemm(y, _packed(conv.weight, conv.weight, ops.PACK_FPROP, cop, y.shape[-1]), 3,
+                                     ops.EPI_STYLE, bias=_pad_to(conv.bias, 0, cop), nw=_pad_to(noise_w, 0, cop),
+                                     noise=noise, sp1=_pad_to(sp1, 1, cop), s1=_pad_to(s1, 1, cop))
+            return ops.nhwc_to_nchw(y, cout)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -212,6 +252,17 @@ class _SynthesisFn(torch.autograd.Function):
                     t = t.narrow(d, 0, n)
             return t.contiguous()
 
+        side = ops.side_stream(dimg.device)
+
+        def wgrad(xx, dz, co, ci):
+            """conv weight gradient on the side stream (overlaps the HBM-bound style backward of the next layer); the
+            zero-padded 32-channel layers of a 512^2 network stay on the main stream (they need a crop afterwards)."""
+            if xx.shape[-1] != ci or dz.shape[-1] != co:
+                return crop(ops.conv_wgrad(xx, dz, 3), co, ci)
+            dw = torch.empty((co, ci, 3, 3), dtype=torch.float32, device=xx.device)
+            side.launch(lambda: ops.conv_wgrad(xx, dz, 3, dw=dw, beta=0.0), xx, dz, dw)
+            return dw
+
         rgb_w = params[-2]
         cl = ctx.y_last.shape[-1]
         dy, drgb_w, grads[-1] = ops.to_rgb_bwd(dimg, ctx.y_last, _pad_to(rgb_w, 1, cl).contiguous())
@@ -226,17 +277,18 @@ class _SynthesisFn(torch.autograd.Function):
             dz2, ds1_2, dsp1_2, db2, dnw2 = ops.style_bwd(dy, a2, n2, sp1_2)
             grads[base + 3], grads[base + 5] = crop(db2, cout), crop(dnw2, cout)
             style_backward(dsp1_2, ds1_2, st2, 2 * i + 2, s2w, base + 8, base + 9, cout)
-            grads[base + 2] = crop(ops.conv_wgrad(y1, dz2, 3), cout, cout)
+            grads[base + 2] = wgrad(y1, dz2, cout, cout)
             dy1 = ops.conv_gemm(dz2, _packed(blk.conv2.weight, w2, ops.PACK_DGRAD, cp, cp), 3, ops.EPI_PLAIN)
             dz1, ds1_1, dsp1_1, db1, dnw1 = ops.style_bwd(dy1, a1, n1, sp1_1)
             grads[base + 1], grads[base + 4] = crop(db1, cout), crop(dnw1, cout)
             style_backward(dsp1_1, ds1_1, st1, 2 * i + 1, s1w, base + 6, base + 7, cout)
-            grads[base + 0] = crop(ops.conv_wgrad(u, dz1, 3), cout, cin)
+            grads[base + 0] = wgrad(u, dz1, cout, cin)
             du = ops.conv_gemm(dz1, _packed(blk.conv1.weight, w1, ops.PACK_DGRAD, cp, u.shape[-1]), 3, ops.EPI_PLAIN)
             dy = ops.upsample2x_bwd(du)
         a0, noise0, sp1_0, st0 = saved["const"]
         dsp1_0, ds1_0, grads[0], grads[1], grads[4] = ops.const_input_bwd(dy, a0, noise0, sp1_0)
         style_backward(dsp1_0, ds1_0, st0, 0, params[2], 2, 3, params[0].shape[1])
+        side.join()
         ctx.saved = None
         return (drows, None, None) + tuple(grads)
 

@@ -94,6 +94,53 @@ class _timed:
         return False
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# Side stream for weight-gradient launches
+# ----------------------------------------------------------------------------------------------------------------------
+# In a backward pass the weight gradient of a layer is off the critical path: dz feeds (a) the wgrad GEMM and (b) the
+# dgrad GEMM -> BatchNorm / style backward of the next layer.  (a) is tensor-bound, the BN / style passes in (b) are
+# HBM-bound, and a persistent GEMM CTA (one per SM, ~210 KB of shared memory) leaves room for a row-streaming block on
+# the same SM, so running (a) on a second stream hides most of it.  Fork/join are events, capturable in a CUDA graph.
+use_side_stream = True
+_side_streams = {}
+
+
+class SideStream:
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device)
+        self.keep = []       # tensors the side stream still reads/writes: kept alive (no allocator reuse) until join()
+        self.active = False
+
+    def launch(self, fn, *keep):
+        """Run fn() (kernel launches only, no allocations) on the side stream, ordered after everything enqueued so far
+        on the current stream."""
+        if not use_side_stream:
+            fn()
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            fn()
+        self.keep.extend(keep)
+        self.active = True
+
+    def join(self):
+        """Order the current stream after the side stream's work; release the kept tensors."""
+        if self.active:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self.active = False
+        self.keep.clear()
+
+
+def side_stream(device) -> SideStream:
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    s = _side_streams.get(key)
+    if s is None:
+        s = _side_streams[key] = SideStream(device)
+    return s
+
+
 _workspace = {}
 _workspace_retired = []  # outgrown buffers stay alive: a captured CUDA graph may still hold their addresses
 
@@ -677,6 +724,49 @@ def to_rgb_bwd(drgb, y, w):
     _call("irfd_to_rgb_bwd", drgb.data_ptr(), y.data_ptr(), w.data_ptr(), dy.data_ptr(), dw.data_ptr(),
           dbias.data_ptr(), b, h * wd, c, ws.data_ptr(), ws.numel(), _stream(), launches=2)
     return dy, dw, dbias
+
+
+def nchw_to_nhwc(x: torch.Tensor, c_pad: Optional[int] = None) -> torch.Tensor:
+    """[B,C,H,W] fp32 -> [B,H,W,c_pad] bf16 (channels >= C zero)."""
+    _chk(x, F32, "x")
+    b, c, h, w = x.shape
+    cp = c if c_pad is None else c_pad
+    out = torch.empty((b, h, w, cp), dtype=BF16, device=x.device)
+    _call("irfd_nchw_to_nhwc_bf16", x.data_ptr(), out.data_ptr(), b, c, h * w, cp, _stream())
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, c: Optional[int] = None) -> torch.Tensor:
+    """[B,H,W,c_pad] bf16 -> [B,c,H,W] fp32 (first c channels)."""
+    _chk(x, BF16, "x")
+    b, h, w, cp = x.shape
+    c = cp if c is None else c
+    out = torch.empty((b, c, h, w), dtype=F32, device=x.device)
+    _call("irfd_nhwc_bf16_to_nchw", x.data_ptr(), out.data_ptr(), b, c, h * w, cp, _stream())
+    return out
+
+
+def apply_noise_nchw(x, w, noise):
+    _chk(x, F32, "x")
+    _chk(w, F32, "w")
+    _chk(noise, F32, "noise")
+    b, c, h, wd = x.shape
+    if noise.numel() != b * h * wd or w.numel() != c:
+        raise _lib.IrfdError("apply_noise_nchw: noise must be [B,1,H,W] and weight [C]")
+    out = torch.empty_like(x)
+    _call("irfd_apply_noise_nchw", x.data_ptr(), w.data_ptr(), noise.data_ptr(), out.data_ptr(), b, c, h * wd, _stream())
+    return out
+
+
+def apply_style_nchw(x, style):
+    _chk(x, F32, "x")
+    _chk(style, F32, "style")
+    b, c, h, wd = x.shape
+    if tuple(style.shape) != (b, 2 * c):
+        raise _lib.IrfdError(f"apply_style_nchw: style must be [B, 2C] = {(b, 2 * c)}, got {tuple(style.shape)}")
+    out = torch.empty_like(x)
+    _call("irfd_apply_style_nchw", x.data_ptr(), style.data_ptr(), out.data_ptr(), b, c, h * wd, _stream())
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -115,6 +115,9 @@ class IRFDTrainer:
         self.stage_flats, self._enc_targets = flat_encoder_gradients(self.encoders)
         self._enc_params = [p for e in self.encoders for p in e.parameters()]
         self.buckets = GradBuckets(self.device)
+        if self.device.type == "cuda":
+            side = ops.side_stream(self.device)
+            self.buckets.producers = lambda: [side.stream] if side.active else []
         self.world = self.buckets.world
         self.schedule = BucketSchedule(self.buckets, self.gflat, self.stage_flats)
         self.last_losses = None

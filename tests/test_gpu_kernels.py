@@ -1,7 +1,12 @@
 """-m gpu: every memory-bound kernel of libirfd_b200.so against the torch fp32 op it replaces (same inputs)."""
+import os
+import sys
+
 import pytest
 import torch
 import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
@@ -486,3 +491,74 @@ def test_upsample_borders(cuda_device, b, h, w, c):
     torch.cuda.synchronize()
     (dr,) = torch.autograd.grad(ref, xr, nchw(dout.float()))
     assert rel_l2(nchw(din.float()), dr) < BF16_TOL
+
+
+def test_standalone_generator_modules(cuda_device):
+    """ApplyNoise / ApplyStyle / SynthesisBlock called directly (reference-visible classes, styleganv1.py:448-468,
+    612-635): same arithmetic as the oracle's modules, forward only; a differentiable call raises instead of returning a
+    tensor without a graph."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import irfd_oracle as O
+    import speak_hack_b200 as P
+    from speak_hack_b200._lib import IrfdError
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(2, 64, 16, 16, generator=g).to(dev)
+    an = P.ApplyNoise(64).to(dev)
+    with torch.no_grad():
+        an.weight.copy_(torch.randn(64, generator=g))
+    noise = torch.randn(2, 1, 16, 16, generator=g).to(dev)
+    with torch.no_grad():
+        out = an(x, noise)
+    assert torch.allclose(out, x + an.weight.view(1, -1, 1, 1) * noise, rtol=1e-6, atol=1e-6)
+    torch.manual_seed(5)
+    with torch.no_grad():
+        out2 = an(x, None)   # noise drawn like the reference: torch.randn(B,1,H,W) on the device generator
+    torch.manual_seed(5)
+    ref_noise = torch.randn(2, 1, 16, 16, device=dev)
+    assert torch.allclose(out2, x + an.weight.view(1, -1, 1, 1) * ref_noise, rtol=1e-6, atol=1e-6)
+    with pytest.raises(IrfdError):
+        an(x.clone().requires_grad_(True), noise)
+
+    torch.manual_seed(1)
+    ref_style = O.ApplyStyleRef(512, 64)
+    st = P.ApplyStyle(512, 64, use_wscale=True)
+    st.load_state_dict(ref_style.state_dict())
+    st = st.to(dev)
+    lat = torch.randn(2, 512, generator=g)
+    with torch.no_grad():
+        want = ref_style(x.cpu(), lat)
+        got = st(x, lat.to(dev))
+    assert rel_l2(got.cpu(), want) < 1e-5
+
+    torch.manual_seed(2)
+    ref_blk = O.SynthesisBlockRef(128, 64)
+    O.perturb_noise_weights(ref_blk)   # noise1/noise2 weights away from zero
+    blk = P.SynthesisBlock(128, 64, 5)
+    blk.load_state_dict(ref_blk.state_dict(), strict=False)
+    blk = blk.to(dev)
+    xin = torch.randn(2, 128, 16, 16, generator=g)
+    w = torch.randn(2, 2, 512, generator=g) * 0.3
+    bank = []
+
+    def draw(b, h, wd, device, dtype):
+        t = torch.randn(b, 1, h, wd, generator=g)
+        bank.append(t)
+        return t
+
+    with torch.no_grad():
+        want = ref_blk(xin, w, draw)
+    it = iter(bank)
+    orig_randn = torch.randn
+    torch.randn = lambda *a, **k: next(it).to(k.get("device", "cpu"))   # feed the block the oracle's noise planes
+    try:
+        with torch.no_grad():
+            got = blk(xin.to(dev), w.to(dev))
+    finally:
+        torch.randn = orig_randn
+    torch.cuda.synchronize()
+    assert got.shape == (2, 64, 32, 32) and got.dtype == torch.float32
+    e = rel_l2(got.cpu(), want)
+    print(f"[parity] standalone SynthesisBlock vs oracle rel-L2 {e:.3e}")
+    assert e < 8e-3

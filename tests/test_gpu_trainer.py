@@ -75,7 +75,7 @@ def test_graph_step_matches_eager_step(cuda_device):
         assert tr.step_count == 3
         assert torch.isfinite(tr.flat).all() and all(l == l for l in seq)
         if graph:
-            assert tr.graph is not None and tr.graph_launches > 1000
+            assert tr.graph is not None and tr.graph_launches > 500   # lockstep encoders: ~730 launches per step
     print(f"[trainer] eager losses {losses[False]} | graph losses {losses[True]}")
     assert abs(losses[False][0] - losses[True][0]) <= 1e-3 * abs(losses[False][0])
 
