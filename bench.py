@@ -52,7 +52,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=0, help="units (pairs / images) per GPU; 0 = the config's own")
     ap.add_argument("--global-batch", type=int, default=0, help="total pairs over all GPUs (config 4: 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
+    ap.add_argument("--no-graph", action="store_true", help="the step's launch sequence launched kernel by kernel "
+                    "instead of as one CUDA graph (profiling: ncu lists the same kernels the graph replays)")
     ap.add_argument("--cpu-sample", type=int, default=8, help="pairs per CPU-baseline step")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -358,6 +359,8 @@ def run_native(args):
     torch.manual_seed(0)                        # identical weights on every rank
     model = P.IRFD().to(dev).train()
     trainer = IRFDTrainer(model, lr=2e-4, use_cuda_graph=not args.no_graph)
+    if args.no_graph:
+        trainer.train_step = trainer.train_step_static_eager
     g = torch.Generator().manual_seed(7 + rank)  # each rank its own shard of the global batch
     host_s = (torch.rand(B, 3, 256, 256, generator=g) * 2 - 1).pin_memory()
     host_t = (torch.rand(B, 3, 256, 256, generator=g) * 2 - 1).pin_memory()
@@ -473,7 +476,7 @@ def run_native(args):
     rsteps = min(args.steps, 3)
     for _ in range(rsteps):
         # the captured step's own launch sequence, kernel by kernel (events cannot be recorded inside a graph replay)
-        (trainer.train_step_static_eager if trainer.use_cuda_graph else trainer.train_step_eager)(x_s, x_t)
+        trainer.train_step_static_eager(x_s, x_t)
     torch.cuda.synchronize()
     fam = ops.gemm_timing_end()
     if rank != 0:

@@ -490,6 +490,11 @@ struct BnBwdLaunch {
 
 template <bool HAS_G2, int MASK>
 static void launch_bn_bwd(const BnBwdLaunch& L) {
+  // co-residency with the side-stream weight-gradient GEMMs (see host_util.h)
+  prefer_max_shared_carveout(reinterpret_cast<const void*>(&bn_bwd_reduce_kernel<HAS_G2, MASK>));
+  prefer_max_shared_carveout(reinterpret_cast<const void*>(&bn_bwd_apply_kernel<HAS_G2, MASK, true>));
+  prefer_max_shared_carveout(reinterpret_cast<const void*>(&bn_bwd_apply_kernel<HAS_G2, MASK, false>));
+  prefer_max_shared_carveout(reinterpret_cast<const void*>(&bn_bwd_finalize_kernel));
   bn_bwd_reduce_kernel<HAS_G2, MASK><<<L.grid, kRvThreads, L.smem, L.stream>>>(
       L.g1, L.g2, L.act, L.z, L.mean, L.rstd, L.gamma, L.beta, L.partial, L.grows, L.c, L.rpb, L.gps);
   bn_bwd_finalize_kernel<<<dim3(L.c / kFinCh, L.nsets), 1024, 0, L.stream>>>(L.partial, L.nblk, L.c, (double)L.grows,

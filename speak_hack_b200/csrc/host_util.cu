@@ -1,5 +1,8 @@
 #include "host_util.h"
 
+#include <mutex>
+#include <unordered_set>
+
 #include <stdarg.h>
 #include <string.h>
 
@@ -69,5 +72,15 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 }  // namespace irfd
 
 extern "C" const char* irfd_last_error(void) { return irfd::g_last_error; }
+
+namespace irfd {
+void prefer_max_shared_carveout(const void* kernel) {
+  static std::mutex mu;
+  static std::unordered_set<const void*> done;
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.insert(kernel).second)
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+}  // namespace irfd
 
 extern "C" int irfd_abi_version(void) { return IRFD_ABI_VERSION; }

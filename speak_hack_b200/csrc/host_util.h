@@ -22,6 +22,12 @@ void set_last_error(const char* fmt, ...);
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, bool swizzle128);
 
+// Ask for the maximum shared-memory carveout for a (memory-bound, small-smem) kernel.  An SM can only run kernels of
+// ONE L1/shared split at a time, and the persistent GEMM kernels configure the SMs for ~227 KB of shared memory; a
+// row-streaming kernel left on the default split cannot become co-resident with a weight-gradient GEMM running on the
+// side stream (ops.SideStream) until the SM drains.  These kernels stream with 16-byte loads and do not rely on L1.
+void prefer_max_shared_carveout(const void* kernel);
+
 #define IRFD_CHECK_ARG(cond, ...)            \
   do {                                       \
     if (!(cond)) {                           \

@@ -275,7 +275,11 @@ style_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __re
       }
     }
   }
-  block_reduce_rows<4>(rv, C, acc, red_smem, partial + ((size_t)b * gridDim.x + blockIdx.x) * 4 * C, (size_t)C);
+  // two rounds of two sums: 16 KB of shared memory instead of 32, so a block fits beside a weight-gradient GEMM CTA
+  float* dst = partial + ((size_t)b * gridDim.x + blockIdx.x) * 4 * C;
+  block_reduce_rows<2>(rv, C, *reinterpret_cast<float(*)[2][8]>(&acc[0]), red_smem, dst, (size_t)C);
+  __syncthreads();
+  block_reduce_rows<2>(rv, C, *reinterpret_cast<float(*)[2][8]>(&acc[2]), red_smem, dst + 2 * (size_t)C, (size_t)C);
 }
 
 __global__ void __launch_bounds__(1024)
@@ -505,6 +509,7 @@ extern "C" int irfd_upsample2x_fwd(const void* in, void* out, int b, int h, int 
 extern "C" int irfd_upsample2x_bwd(const void* dout, void* din, int b, int h, int w, int c, cudaStream_t stream) {
   IRFD_CHECK_ARG(dout && din && c % 8 == 0, "upsample2x_bwd: bad argument");
   IRFD_CHECK_ARG(b > 0 && h > 0 && w > 0 && (long long)w * c < (1ll << 24), "upsample2x_bwd: bad shape");
+  prefer_max_shared_carveout(reinterpret_cast<const void*>(&upsample2x_bwd_kernel));
   upsample2x_bwd_kernel<<<dim3((unsigned)(b * h), (unsigned)((w * (c / 8) + 255) / 256)), 256, 0, stream>>>(
       CBF(dout), BF(din), b, h, w, c);
   IRFD_CHECK_LAUNCH();
@@ -537,7 +542,9 @@ extern "C" int irfd_style_bwd(const void* dy, const void* a, const float* noise,
   style_plan(hw, c, b, &chunks, &rpb);
   IRFD_CHECK_ARG(workspace_bytes >= (long long)b * chunks * 4 * c * 4, "style_bwd: workspace too small");
   float* partial = reinterpret_cast<float*>(workspace);
-  style_bwd_kernel<<<dim3(chunks, b), kRvThreads, 4 * 2048 * sizeof(float), stream>>>(CBF(dy), CBF(a), noise, sp1,
+  prefer_max_shared_carveout(reinterpret_cast<const void*>(&style_bwd_kernel));
+  prefer_max_shared_carveout(reinterpret_cast<const void*>(&style_bwd_finalize_kernel));
+  style_bwd_kernel<<<dim3(chunks, b), kRvThreads, 2 * 2048 * sizeof(float), stream>>>(CBF(dy), CBF(a), noise, sp1,
                                                                                      BF(dz), partial, hw, c, rpb);
   IRFD_CHECK_LAUNCH();
   style_bwd_finalize_kernel<<<(c + 31) / 32, 1024, 0, stream>>>(partial, b, chunks, c, ds1, dsp1, dbias, dnw);

@@ -222,26 +222,28 @@ class _EncoderGroupFn(torch.autograd.Function):
             nb, hh, ww, _cin = xin.shape
             planes = a1.shape[-1]
             dz3, gmask = bn_bwd([b.bn3 for b in blks], st3, g, g2, out, z3, want_g_out=True)
-            wgrad([b.conv3 for b in blks], a2, dz3, 1)
+            # dgrad first, wgrad second: the persistent dgrad takes the SMs, the wgrad (side stream) follows it and
+            # runs beside the BatchNorm backward that consumes the dgrad's output
             d_a2 = ops.conv_gemm_grouped(dz3, _stack_pack([b.conv3 for b in blks], ops.PACK_DGRAD), 1, wgroups=E)
+            wgrad([b.conv3 for b in blks], a2, dz3, 1)
             dz2 = bn_bwd([b.bn2 for b in blks], st2, d_a2, None, a2, z2, mask_from_z=True)
             if blks[0].stride == 1:
-                wgrad([b.conv2 for b in blks], a1, dz2, 3)
                 d_a1 = ops.conv_gemm_grouped(dz2, _stack_pack([b.conv2 for b in blks], ops.PACK_DGRAD), 3, wgroups=E)
+                wgrad([b.conv2 for b in blks], a1, dz2, 3)
             else:
                 m2 = dz2.numel() // planes
-                wgrad([b.conv2 for b in blks], col2, dz2.view(m2, planes), 1, reduce_cin=planes, reduce_taps=9)
                 dcol = ops.conv_gemm_grouped(dz2.view(1, 1, m2, planes),
                                              _stack_pack([b.conv2 for b in blks], ops.PACK_DCOL), 1, wgroups=E)
+                wgrad([b.conv2 for b in blks], col2, dz2.view(m2, planes), 1, reduce_cin=planes, reduce_taps=9)
                 d_a1 = ops.col2im_3x3s2(dcol.view(m2, 9 * planes), nb, hh, ww, planes)
             dz1 = bn_bwd([b.bn1 for b in blks], st1, d_a1, None, a1, z1, mask_from_z=True)
-            wgrad([b.conv1 for b in blks], xin, dz1, 1)
             d_in = ops.conv_gemm_grouped(dz1, _stack_pack([b.conv1 for b in blks], ops.PACK_DGRAD), 1, wgroups=E)
+            wgrad([b.conv1 for b in blks], xin, dz1, 1)
             if blks[0].downsample is not None:
                 dzd = bn_bwd([b.downsample[1] for b in blks], std, gmask, None, None, zd)
-                wgrad([b.downsample[0] for b in blks], xs, dzd, 1)
                 d_xs = ops.conv_gemm_grouped(dzd, _stack_pack([b.downsample[0] for b in blks], ops.PACK_DGRAD), 1,
                                              wgroups=E)
+                wgrad([b.downsample[0] for b in blks], xs, dzd, 1)
                 if blks[0].stride == 2:
                     g, g2 = ops.scatter_add_s2(d_in, d_xs), None
                 else:

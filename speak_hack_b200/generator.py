@@ -277,13 +277,13 @@ class _SynthesisFn(torch.autograd.Function):
             dz2, ds1_2, dsp1_2, db2, dnw2 = ops.style_bwd(dy, a2, n2, sp1_2)
             grads[base + 3], grads[base + 5] = crop(db2, cout), crop(dnw2, cout)
             style_backward(dsp1_2, ds1_2, st2, 2 * i + 2, s2w, base + 8, base + 9, cout)
-            grads[base + 2] = wgrad(y1, dz2, cout, cout)
             dy1 = ops.conv_gemm(dz2, _packed(blk.conv2.weight, w2, ops.PACK_DGRAD, cp, cp), 3, ops.EPI_PLAIN)
+            grads[base + 2] = wgrad(y1, dz2, cout, cout)   # after the dgrad: runs beside the next style_bwd
             dz1, ds1_1, dsp1_1, db1, dnw1 = ops.style_bwd(dy1, a1, n1, sp1_1)
             grads[base + 1], grads[base + 4] = crop(db1, cout), crop(dnw1, cout)
             style_backward(dsp1_1, ds1_1, st1, 2 * i + 1, s1w, base + 6, base + 7, cout)
-            grads[base + 0] = wgrad(u, dz1, cout, cin)
             du = ops.conv_gemm(dz1, _packed(blk.conv1.weight, w1, ops.PACK_DGRAD, cp, u.shape[-1]), 3, ops.EPI_PLAIN)
+            grads[base + 0] = wgrad(u, dz1, cout, cin)
             dy = ops.upsample2x_bwd(du)
         a0, noise0, sp1_0, st0 = saved["const"]
         dsp1_0, ds1_0, grads[0], grads[1], grads[4] = ops.const_input_bwd(dy, a0, noise0, sp1_0)

@@ -262,18 +262,26 @@ class IRFDTrainer:
         lid_out.copy_(l_identity.detach())
         lrec_out.copy_(l_recon.detach())
 
-    def _capture(self, x_s, x_t):
+    def _ensure_static(self, x_s):
+        """The stacked static batch [x_s; x_t] and the three loss scalars the static step reads / writes."""
         dev = self.device
         if not self._direct(x_s):
             raise ops._lib.IrfdError(
-                f"IRFDTrainer(use_cuda_graph=True): batch {tuple(x_s.shape)} cannot run as one lockstep encoder pass "
-                "(pairs x (H/32) x (W/32) must be a multiple of 128, encoders in train mode with gradients); use the "
-                "eager step")
+                f"IRFDTrainer static step: batch {tuple(x_s.shape)} cannot run as one lockstep encoder pass (pairs x "
+                "(H/32) x (W/32) must be a multiple of 128, encoders in train mode with gradients); use "
+                "train_step_eager")
         b = x_s.size(0)
-        x_all = torch.empty((2 * b,) + tuple(x_s.shape[1:]), dtype=torch.float32, device=dev)
-        self._static = (x_all, torch.zeros((), device=dev), torch.zeros((), device=dev), torch.zeros((), device=dev))
-        x_all[:b].copy_(x_s)
-        x_all[b:].copy_(x_t)
+        shape = (2 * b,) + tuple(x_s.shape[1:])
+        if self._static is None or tuple(self._static[0].shape) != shape:
+            self._static = (torch.empty(shape, dtype=torch.float32, device=dev), torch.zeros((), device=dev),
+                            torch.zeros((), device=dev), torch.zeros((), device=dev))
+
+    def _capture(self, x_s, x_t):
+        dev = self.device
+        self._ensure_static(x_s)
+        b = x_s.size(0)
+        self._static[0][:b].copy_(x_s)
+        self._static[0][b:].copy_(x_t)
         self.step_dev.fill_(self.step_count)
         # The warm-up passes below are real steps; snapshot everything they mutate (Gd parameters, Adam moments, BN
         # running buffers, step counters, both RNG streams) and put it back, so capturing is invisible to training.
@@ -335,10 +343,8 @@ class IRFDTrainer:
 
     def train_step_static_eager(self, x_s: torch.Tensor, x_t: torch.Tensor):
         """The launch sequence of the captured step, launched kernel by kernel (bench.py times every GEMM launch with
-        CUDA events this way: events cannot be recorded inside a graph replay).  Needs a captured graph."""
-        if self.graph is None:
-            self.graph, self.graph_launches = self._capture(x_s, x_t)
-            self._graph_key = self._graph_state(x_s)
+        CUDA events this way — events cannot be recorded inside a graph replay — and ncu lists its launches)."""
+        self._ensure_static(x_s)
         b = x_s.size(0)
         self._static[0][:b].copy_(x_s, non_blocking=True)
         self._static[0][b:].copy_(x_t, non_blocking=True)
@@ -348,6 +354,8 @@ class IRFDTrainer:
         return self._static[1]
 
     def train_step(self, x_s: torch.Tensor, x_t: torch.Tensor):
+        """use_cuda_graph: one graph replay.  Otherwise the reference-ordered eager step (IRFD.forward: two generator
+        calls, the reference's RNG consumption order)."""
         if self.use_cuda_graph:
             return self.train_step_graph(x_s, x_t)
         return self.train_step_eager(x_s, x_t)

@@ -44,13 +44,16 @@ def test_conditioned_train_step_all_gradients(cuda_device):
 
 def test_train_step_vs_bf16_faithful_oracle(cuda_device):
     """The routing check proper: the oracle with the product's storage rounding points inserted (parity_util.
-    make_bf16_faithful), random-init weights as the reference constructs them (NO conditioning), one G train step.
-    Masks agree, so every one of the 560 gradient tensors is compared at a bound that a mis-routed tensor cannot meet."""
+    make_bf16_faithful) on the conditioned weights (bn3 gamma x 0.2), one G train step.  With the same rounding points
+    the ReLU masks agree, so every one of the 560 gradient tensors is compared at a bound a mis-routed tensor cannot
+    meet.  (Without the conditioning even this oracle drifts: scripts/faithful_probe.py shows the 1.7e-5 difference the
+    fp32 accumulation order leaves after the stem conv growing ~1.3x per layer to 0.3 in layer4 — the random-init
+    train-mode stack is chaotic at that depth)"""
     import irfd_oracle as O
     from parity_util import conditioned_pair, g_step_oracle, g_step_product, grad_report, make_bf16_faithful
 
     dev = cuda_device
-    ref, prod = conditioned_pair(dev, bn3_scale=1.0)
+    ref, prod = conditioned_pair(dev, bn3_scale=0.2)
     make_bf16_faithful(ref)
     x_s, x_t = O.synthetic_pair(2)
     r = g_step_oracle(ref, x_s, x_t, noise_seed=43, device="cpu")
