@@ -17,10 +17,11 @@ sys.path.insert(0, ROOT)
 from speak_hack_b200 import ops  # noqa: E402
 
 BF = torch.bfloat16
-ENC_IMGS, GEN_B = 64, 32  # paired encoder pass (32 source + 32 target images), one generator call
+E = 3                        # encoders per lockstep launch (encoder_group.py)
+ENC_IMGS, GEN_B = 3 * 64, 64  # lockstep encoder pass: 3 encoders x (32 source + 32 target images); one stacked generator call
 
 # (name, launches per step of each of fprop/dgrad/wgrad, images, H, W, Cin, Cout, ksize, fprop epilogue)
-ENC = [  # x3 encoders; strided convs run as 1x1 GEMMs over their im2col / subsampled input (K = k*k*Cin)
+ENC = [  # one grouped launch serves the three encoders; strided convs run as 1x1 GEMMs over their im2col / subsampled input (K = k*k*Cin)
     ("enc 64->64 1x1 @64", 1, 64, 64, 64, 64, 1), ("enc 64->64 3x3 @64", 3, 64, 64, 64, 64, 3),
     ("enc 64->256 1x1 @64", 4, 64, 64, 64, 256, 1), ("enc 256->64 1x1 @64", 2, 64, 64, 256, 64, 1),
     ("enc 256->128 1x1 @64", 1, 64, 64, 256, 128, 1), ("enc 128->128 3x3/2 @32 (im2col)", 1, 32, 32, 1152, 128, 1),
@@ -33,7 +34,7 @@ ENC = [  # x3 encoders; strided convs run as 1x1 GEMMs over their im2col / subsa
     ("enc 1024->2048 1x1/2 @8", 1, 8, 8, 1024, 2048, 1), ("enc 512->512 3x3 @8", 2, 8, 8, 512, 512, 3),
     ("enc 512->2048 1x1 @8", 3, 8, 8, 512, 2048, 1), ("enc 2048->512 1x1 @8", 2, 8, 8, 2048, 512, 1),
 ]
-GEN = [  # x2 generator calls
+GEN = [  # one generator call over the 2B stacked codes
     ("gen 512->512 @8", 2, 8, 8, 512, 512, 3), ("gen 512->512 @16", 2, 16, 16, 512, 512, 3),
     ("gen 512->512 @32", 2, 32, 32, 512, 512, 3), ("gen 512->256 @64", 1, 64, 64, 512, 256, 3),
     ("gen 256->256 @64", 1, 64, 64, 256, 256, 3), ("gen 256->128 @128", 1, 128, 128, 256, 128, 3),
@@ -77,17 +78,18 @@ def main():
     buf = torch.zeros(64 << 20, dtype=torch.float32, device=dev)  # 256 MB > L2
     g = torch.Generator(device="cpu").manual_seed(0)
     rows = []
-    for group, mult, imgs, table in (("enc", 3, ENC_IMGS, ENC), ("gen", 2, GEN_B, GEN)):
+    for group, mult, imgs, table in (("enc", 1, ENC_IMGS, ENC), ("gen", 1, GEN_B, GEN)):
         for name, cnt, h, w, cin, cout, k in table:
             if a.only and a.only not in name:
                 continue
             x = (torch.randn(imgs, h, w, cin, generator=g) * 0.5).to(dev).to(BF)
             dy = (torch.randn(imgs, h, w, cout, generator=g) * 0.5).to(dev).to(BF)
-            wf = (torch.randn(cout, k * k * cin, generator=g) * 0.05).to(dev).to(BF)
-            wd = (torch.randn(cin, k * k * cout, generator=g) * 0.05).to(dev).to(BF)
+            ng = E if group == "enc" else 1   # weight sets in the launch
+            wf = (torch.randn(ng * cout, k * k * cin, generator=g) * 0.05).to(dev).to(BF)
+            wd = (torch.randn(ng * cin, k * k * cout, generator=g) * 0.05).to(dev).to(BF)
             m = imgs * h * w
             flops = 2.0 * m * cin * cout * k * k
-            wbytes = 2.0 * cin * cout * k * k
+            wbytes = 2.0 * ng * cin * cout * k * k
             if group == "gen":
                 bias = torch.zeros(cout, device=dev)
                 nwt = torch.ones(cout, device=dev)
@@ -96,13 +98,16 @@ def main():
                 s1 = torch.zeros(imgs, cout, device=dev)
                 fprop = lambda: ops.conv_gemm(x, wf, k, ops.EPI_STYLE, bias, nwt, noise, sp1, s1)  # noqa: E731
                 fbytes = 2.0 * m * cin + 2 * 2.0 * m * cout + wbytes  # two bf16 outputs (a, y)
+                dgrad = lambda: ops.conv_gemm(dy, wd, k, ops.EPI_PLAIN)  # noqa: E731
+                wgrad = lambda: ops.conv_wgrad(x, dy, k)  # noqa: E731
             else:
-                fprop = lambda: ops.conv_gemm(x, wf, k, ops.EPI_STATS)  # noqa: E731
+                fprop = lambda: ops.conv_gemm_grouped(x, wf, k, ops.EPI_STATS, wgroups=E)  # noqa: E731
                 fbytes = 2.0 * m * cin + 2.0 * m * cout + wbytes
-            dgrad = lambda: ops.conv_gemm(dy, wd, k, ops.EPI_PLAIN)  # noqa: E731
+                dgrad = lambda: ops.conv_gemm_grouped(dy, wd, k, ops.EPI_PLAIN, wgroups=E)  # noqa: E731
+                dws = [torch.empty((cout, cin, k, k), dtype=torch.float32, device=dev) for _ in range(E)]
+                wgrad = lambda: ops.conv_wgrad_grouped(x, dy, k, dws)  # noqa: E731
             dbytes = 2.0 * m * cout + 2.0 * m * cin + wbytes
-            wgrad = lambda: ops.conv_wgrad(x, dy, k)  # noqa: E731
-            gbytes = 2.0 * m * cin + 2.0 * m * cout + 4.0 * cin * cout * k * k
+            gbytes = 2.0 * m * cin + 2.0 * m * cout + 2.0 * wbytes
             for kind, fn, nbytes in (("fprop", fprop, fbytes), ("dgrad", dgrad, dbytes), ("wgrad", wgrad, gbytes)):
                 t = timeit(fn, buf, a.reps)
                 bound = max(flops / tf_peak, nbytes / bw_peak)
@@ -111,7 +116,8 @@ def main():
             del x, dy, wf, wd
     tot = sum(r["n"] * r["t"] for r in rows)
     totb = sum(r["n"] * r["bound"] for r in rows)
-    lines = ["# Per-shape roofline of the tcgen05 GEMM launches of one IRFD train step (B=32 pairs @256^2)", "",
+    lines = ["# Per-shape roofline of the tcgen05 GEMM launches of one IRFD train step (B=32 pairs @256^2): lockstep "
+             "encoder launches (3 weight sets x 64 images), one stacked generator call (64 codes)", "",
              f"Peaks: bf16 {tf_peak / 1e12:.1f} TF/s sustained, HBM {bw_peak / 1e9:.0f} GB/s (MEASURED_PEAKS.json). Each launch "
              "timed alone with CUDA events, L2 flushed (256 MB write) between repetitions, median of %d." % a.reps, "",
              f"Sum over the step: measured {tot * 1e3:.2f} ms, per-launch roofline bound {totb * 1e3:.2f} ms "

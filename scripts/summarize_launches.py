@@ -19,7 +19,10 @@ def load(path):
 
 def short(name):
     m = re.search(r"irfd::(\w+(?:<[^>]*>)?)", name)
-    return m.group(1) if m else name[:70]
+    if m:
+        return m.group(1)
+    m = re.search(r"at::native::(?:\(anonymous namespace\)::)?(\w+)[<(].*?(CUDAFunctor_add|FillFunctor|copy|MulFunctor)?", name)
+    return ("aten::" + m.group(1)[:40]) if m else name[:70]
 
 
 def family(k):
@@ -29,7 +32,13 @@ def family(k):
         return "conv_gemm_kernel (all variants)"
     if k.startswith("wgrad"):
         return "wgrad_gemm_kernel + wgrad_reduce"
-    return "other"
+    if k.startswith(("style_bwd", "upsample", "to_rgb", "const_input")):
+        return "generator memory-bound (style_bwd / upsample / to_rgb)"
+    if k.startswith(("im2col", "col2im", "subsample", "scatter_add", "maxpool", "avgpool", "pack_")):
+        return "encoder layout (im2col / pools / stride-2 gathers)"
+    if k.startswith("aten::") or "at::" in k:
+        return "ATen (torch plumbing)"
+    return "other (dense, losses, Adam, control)"
 
 
 def to_bytes(value, unit):
@@ -37,8 +46,22 @@ def to_bytes(value, unit):
     return v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
 
 
+def one_step(allrows, which):
+    """Keep the launches of ONE training step: those after the `which`-th adam_kernel launch up to and including the
+    next one (rows carry ncu's launch ID)."""
+    ids = sorted({int(d["ID"]) for d in allrows if "adam_kernel" in d["Kernel Name"]})
+    if len(ids) < which + 2:
+        raise SystemExit(f"only {len(ids)} adam_kernel launches in the capture")
+    lo, hi = ids[which], ids[which + 1]
+    return [d for d in allrows if lo < int(d["ID"]) <= hi]
+
+
 def main():
     allrows = load(sys.argv[1])
+    if "--step" in sys.argv:  # usage: ... --step K   (K-th complete step of the capture, 0-based)
+        i = sys.argv.index("--step")
+        allrows = one_step(allrows, int(sys.argv[i + 1]))
+        del sys.argv[i: i + 2]
     title = sys.argv[2] if len(sys.argv) > 2 else "ncu launch list"
     rows = [d for d in allrows if d["Metric Name"] == "gpu__time_duration.sum"]
     t, n, dram = collections.Counter(), collections.Counter(), collections.Counter()

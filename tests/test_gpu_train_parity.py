@@ -66,12 +66,22 @@ def test_train_step_vs_bf16_faithful_oracle(cuda_device):
     assert rep["running_mean"] < FAITHFUL["running"] and rep["running_var"] < FAITHFUL["running"]
     for k, v in rep.items():
         if isinstance(v, tuple):
-            med_b, worst_b = FAITHFUL["Gd" if k.startswith("Gd") else "enc"]
+            med_b, worst_b = FAITHFUL[k if k.startswith("Gd") else "enc"]
             assert v[0] < med_b and v[1] < worst_b, (k, v)
 
 
-# provisional until measured on B200
-FAITHFUL = {"feat": 5e-2, "img": 0.2, "loss": 5e-2, "running": 5e-2, "Gd": (0.2, 0.5), "enc": (0.3, 0.6)}
+# <= 2x measured on B200: features 3.7e-3, images 7.8e-3, l_identity 4.9e-5, l_recon 1.3e-3, running buffers 2.2e-3;
+# Gd.synthesis 4.1e-3 / 3.7e-2, Gd.mapping 3.9e-2 / 5.2e-2, Gd.noise 5.0e-2 / 6.7e-2 (median / worst).
+# Encoder gradients: median 0.25 (layer4) .. 0.35 (layer1), worst 0.56.  Forward and generator agree 2-3x better than
+# with the pure-fp32 oracle, the encoder gradients do not: scripts/numerics_probe_cpu.py shows on the oracle alone that
+# bf16 storage of the forward activations moves these gradients by 0.30-0.35 (ReLU-mask flips; rounding only the
+# gradients costs 4e-3), and two implementations that agree to 4e-3 in the forward do not flip the SAME elements.  The
+# encoder bound therefore only catches a gross mis-routing (uncorrelated gradients sit at 1.4); the sharp routing checks
+# of the encoder backward are test_encoder_backward_eval_end_to_end (eval-mode BN, every gradient, median 2.5e-2),
+# test_encoder_backward_train_in_context (every train-mode launch on its own inputs) and
+# test_encoder_group_train_equals_three_passes (lockstep path bit-identical to the per-encoder path).
+FAITHFUL = {"feat": 8e-3, "img": 1.6e-2, "loss": 3e-3, "running": 5e-3,
+            "Gd.synthesis": (1e-2, 8e-2), "Gd.mapping": (8e-2, 0.11), "Gd.noise": (0.1, 0.14), "enc": (0.7, 1.1)}
 
 
 # (median, worst) rel-L2 bounds per gradient group; scalars for the rest.  All <= 2x the values measured on B200:
