@@ -6,6 +6,7 @@ Activations are NHWC bf16 tensors; parameters and reductions are fp32.
 from __future__ import annotations
 
 import ctypes
+import os
 import weakref
 from typing import Optional
 
@@ -101,7 +102,7 @@ class _timed:
 # dgrad GEMM -> BatchNorm / style backward of the next layer.  (a) is tensor-bound, the BN / style passes in (b) are
 # HBM-bound, and a persistent GEMM CTA (one per SM, ~210 KB of shared memory) leaves room for a row-streaming block on
 # the same SM, so running (a) on a second stream hides most of it.  Fork/join are events, capturable in a CUDA graph.
-use_side_stream = True
+use_side_stream = os.environ.get("IRFD_SIDE_STREAM", "1") != "0"   # 0: everything on one stream (experiments)
 _side_streams = {}
 
 
