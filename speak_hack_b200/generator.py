@@ -194,9 +194,37 @@ class _SynthesisFn(torch.autograd.Function):
             sp1, s1 = ops.split_style(st, c)
             return st, _pad_to(sp1, 1, cp), _pad_to(s1, 1, cp)
 
+        # The 2L-1 style FCs depend only on the latent rows, not on the conv chain: they run on the side stream while
+        # the main stream works through the first layers, each layer waiting (by event) only for its own style.
         c0 = const_input.shape[1]
+        blocks_p = [tuple(next(it) for _ in range(10)) for _ in net.layers]
+        jobs = [(0, sw0, sb0, c0, c0)]
+        for i, bp in enumerate(blocks_p):
+            cout = bp[0].shape[0]
+            jobs += [(2 * i + 1, bp[6], bp[7], cout, _cpad(cout)), (2 * i + 2, bp[8], bp[9], cout, _cpad(cout))]
+        side = ops.side_stream(rows_t.device)
+        styles, events = [], []
+
+        def all_styles():
+            for row, sw, sb, c, cp in jobs:
+                styles.append(style(rows_t[row], sw, sb, c, cp))
+                if ops.use_side_stream:
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    events.append(ev)
+
+        side.launch(all_styles, rows_t)
+        main = torch.cuda.current_stream()
+
+        def take(j):
+            if events:
+                main.wait_event(events[j])
+                for t in styles[j]:
+                    t.record_stream(main)
+            return styles[j]
+
         noise0 = next(ni)
-        st0, sp1_0, s1_0 = style(rows_t[0], sw0, sb0, c0, c0)
+        st0, sp1_0, s1_0 = take(0)
         # The output of a block feeds a bilinear upsample and only then a conv: stored as plain bf16 it would be rounded
         # twice on the way into that conv (once here, once after the interpolation) where the fp32 reference rounds
         # never and an ideal bf16-operand kernel once.  Up to SPLIT_MAX_RES the block output is therefore kept as split
@@ -204,22 +232,24 @@ class _SynthesisFn(torch.autograd.Function):
         a0, y, y_lo = ops.const_input_fwd(const_input, bias0, nw0, noise0, sp1_0, s1_0, split_y=True)
         saved["const"] = (a0, noise0, sp1_0, st0)
         for i, blk in enumerate(net.layers):
-            w1, b1, w2, b2, nw1, nw2, s1w, s1b, s2w, s2b = (next(it) for _ in range(10))
+            w1, b1, w2, b2, nw1, nw2, s1w, s1b, s2w, s2b = blocks_p[i]
             cout = w1.shape[0]
             cp = _cpad(cout)
             u = ops.upsample2x_fwd(y, y_lo)
             n1 = next(ni)
-            st1, sp1_1, s1_1 = style(rows_t[2 * i + 1], s1w, s1b, cout, cp)
+            st1, sp1_1, s1_1 = take(2 * i + 1)
             a1, y1 = ops.conv_gemm(u, _packed(blk.conv1.weight, w1, ops.PACK_FPROP, cp, u.shape[-1]), 3, ops.EPI_STYLE,
                                    bias=_pad_to(b1, 0, cp), nw=_pad_to(nw1, 0, cp), noise=n1, sp1=sp1_1, s1=s1_1)
             n2 = next(ni)
-            st2, sp1_2, s1_2 = style(rows_t[2 * i + 2], s2w, s2b, cout, cp)
+            st2, sp1_2, s1_2 = take(2 * i + 2)
             split = y1.shape[1] <= SPLIT_MAX_RES and i + 1 < len(net.layers)
             r2 = ops.conv_gemm(y1, _packed(blk.conv2.weight, w2, ops.PACK_FPROP, cp, cp), 3, ops.EPI_STYLE,
                                bias=_pad_to(b2, 0, cp), nw=_pad_to(nw2, 0, cp), noise=n2, sp1=sp1_2, s1=s1_2,
                                split_y=split)
             a2, y, y_lo = r2 if split else (r2[0], r2[1], None)
             saved["blocks"].append((u, a1, y1, a2, n1, n2, sp1_1, sp1_2, st1, st2))
+        side.join()
+        it = iter(params[5 + 10 * len(net.layers):])
         rgb_w, rgb_b = next(it), next(it)
         img = ops.to_rgb_fwd(y, _pad_to(rgb_w, 1, y.shape[-1]).contiguous(), rgb_b)
         ctx.net = net
@@ -235,24 +265,29 @@ class _SynthesisFn(torch.autograd.Function):
         dimg = dimg.contiguous()
         wm, bm = float(net.style_mod.linear.w_lrmul), float(net.style_mod.linear.b_lrmul)
         drows = torch.zeros_like(rows_t)
+        side = ops.side_stream(dimg.device)
         nblk = len(net.layers)
         grads: List[Optional[torch.Tensor]] = [None] * len(params)
 
         def style_backward(dsp1, ds1, st, row_idx, sw, gw_i, gb_i, c):
-            if dsp1.shape[1] != c:  # drop the zero-padded channels
-                dsp1, ds1 = dsp1[:, :c].contiguous(), ds1[:, :c].contiguous()
-            dst = ops.merge_style_grad(dsp1, ds1)
-            dz = ops.lrelu_bwd(dst, st)
-            dx, dw, db = ops.linear_bwd(dz, rows_t[row_idx], sw, wm, bm, need_dx=True, dx=drows[row_idx], dx_beta=0.0)
-            grads[gw_i], grads[gb_i] = dw, db
+            """Backward of one style FC (4 tiny launches) on the side stream: it only feeds d(rows) and two parameter
+            gradients, all consumed after the join at the end of this backward."""
+            def run():
+                a, b = dsp1, ds1
+                if a.shape[1] != c:  # drop the zero-padded channels
+                    a, b = a[:, :c].contiguous(), b[:, :c].contiguous()
+                dst = ops.merge_style_grad(a, b)
+                dz = ops.lrelu_bwd(dst, st)
+                dx, dw, db = ops.linear_bwd(dz, rows_t[row_idx], sw, wm, bm, need_dx=True, dx=drows[row_idx], dx_beta=0.0)
+                grads[gw_i], grads[gb_i] = dw, db
+
+            side.launch(run, dsp1, ds1, st)
 
         def crop(t, *sizes):
             for d, n in enumerate(sizes):
                 if t.shape[d] != n:
                     t = t.narrow(d, 0, n)
             return t.contiguous()
-
-        side = ops.side_stream(dimg.device)
 
         def wgrad(xx, dz, co, ci):
             """conv weight gradient on the side stream (overlaps the HBM-bound style backward of the next layer); the
@@ -289,6 +324,11 @@ class _SynthesisFn(torch.autograd.Function):
         dsp1_0, ds1_0, grads[0], grads[1], grads[4] = ops.const_input_bwd(dy, a0, noise0, sp1_0)
         style_backward(dsp1_0, ds1_0, st0, 0, params[2], 2, 3, params[0].shape[1])
         side.join()
+        if ops.use_side_stream:  # gradients allocated by the side stream's launches, consumed by autograd on this one
+            cur = torch.cuda.current_stream()
+            for g_ in grads:
+                if g_ is not None:
+                    g_.record_stream(cur)
         ctx.saved = None
         return (drows, None, None) + tuple(grads)
 
@@ -451,10 +491,21 @@ def _generator_forward_static(self: StyleGenerator, features, ctrl, ctrl_idx, b_
         features = features.flatten(1)
     features = features.to(torch.float32)
     L = self.synthesis.num_layers
+    mixing = self.training and self.style_mixing_prob > 0
+    side = ops.side_stream(features.device)
+    box = []
+    if mixing:  # the mixing latent's mapping pass (8 dependent dense layers, no autograd) runs beside w's on the side stream
+        def second_latent():
+            with torch.no_grad():
+                box.append(self.mapping(self.latent_fn(features)))
+
+        side.launch(second_latent, features)
     w = self.mapping(features)
-    if self.training and self.style_mixing_prob > 0:
-        with torch.no_grad():
-            w2 = self.mapping(self.latent_fn(features))
+    if mixing:
+        side.join()
+        w2 = box[0]
+        if ops.use_side_stream:
+            w2.record_stream(torch.cuda.current_stream())
     else:
         w2 = w.detach()  # eval / mixing disabled: the cut is always L, w2 is never read
     psi, cutoff = self._trunc()
