@@ -38,6 +38,10 @@ CONFIGS = {
     "gen_infer": {"metric": "gd_infer_images_per_sec_256", "unit": "images/s", "flops_per_unit": 56.195e9, "batch": 32},
     # config 5: IRFD inference at 512^2 with SynthesisNetwork(resolution=512), 8 pairs per GPU, replicas only
     "infer512": {"metric": "irfd_infer_pairs_per_sec_512", "unit": "pairs/s", "flops_per_unit": 397.7e9, "batch": 8},
+    # the discriminator step (train.py:157-183).  Per pair: D forward on 4 images (119.2 GF) + their
+    # backward (238.4) + R1 on 2 images (forward, image-gradient chain, second-order forward chain, wgrads: 238.4) +
+    # one IRFD forward under no_grad (176.45) = 772.5 GF (D forward 29.8 GF / image)
+    "d_step": {"metric": "irfd_d_step_pairs_per_sec_256", "unit": "pairs/s", "flops_per_unit": 772.5e9, "batch": 32},
 }
 
 
@@ -221,13 +225,68 @@ CPU_SAMPLE_DESC = {
     "train": "G train step(s) of {u} pair(s) @256^2 (oracle port with reentrant checkpoints, fp32, torch CPU)",
     "gen_infer": "StyleGenerator eval forward(s) on {u} feature rows -> 256^2 images (oracle port, fp32, torch CPU)",
     "infer512": "IRFD eval forward(s) on {u} pair(s) @512^2, SynthesisNetwork(512) (oracle port, fp32, torch CPU)",
+    "d_step": "D train step(s) on {u} pair(s) @256^2 (oracle port: 4 D calls + IRFD forward + 2 R1 double backwards + Adam, "
+              "fp32, torch CPU)",
 }
-CPU_UNITS = {"train": 8, "gen_infer": 8, "infer512": 1}   # bounded sample of the GPU arm's batch, per CPU step
+CPU_UNITS = {"train": 8, "gen_infer": 8, "infer512": 1, "d_step": 1}   # bounded sample of the GPU arm's batch, per CPU step
+
+
+def cpu_d_steps(pairs: int, steps: int, warmup: int, budget_s: float):
+    """Reference D step (train.py:157-183, 246-255) on the host cores with the oracle modules."""
+    import torch
+    import torch.nn.functional as F
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import irfd_oracle as O
+
+    threads = _host_threads()
+    torch.set_num_threads(threads)
+    torch.manual_seed(O.WEIGHT_SEED)
+    net = O.IRFDRef().train()
+    opt = torch.optim.Adam(net.D.parameters(), lr=5e-5)
+    x_s, x_t = O.synthetic_pair(pairs)
+
+    def noisy(x):
+        return x + torch.randn_like(x) * 0.1
+
+    def bce(logits, label):
+        return F.binary_cross_entropy_with_logits(logits, torch.full_like(logits, label))
+
+    def r1(x):
+        x = x.clone().requires_grad_(True)
+        g = torch.autograd.grad(outputs=net.D(x).sum(), inputs=x, create_graph=True)[0]
+        return g.pow(2).reshape(g.shape[0], -1).sum(1).mean()
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = (bce(net.D(noisy(x_s)), 0.9) + bce(net.D(noisy(x_t)), 0.9)) / 2
+        with torch.no_grad():
+            out = net(x_s, x_t)
+        loss = loss + (bce(net.D(noisy(out[0])), 0.1) + bce(net.D(noisy(out[1])), 0.1)) / 2
+        loss = loss + (r1(x_s) + r1(x_t)) / 2
+        loss.backward()
+        opt.step()
+
+    t_start = time.time()
+    for _ in range(warmup):
+        step()
+        if time.time() - t_start > budget_s / 3:
+            break
+    done, t0 = 0, time.time()
+    for _ in range(steps):
+        step()
+        done += 1
+        if time.time() - t_start > budget_s:
+            break
+    dt = time.time() - t0
+    return pairs * done / dt, done, threads, dt
 
 
 def cpu_arm(config: str, units: int, steps: int, warmup: int, budget_s: float):
     if config == "train":
         return cpu_train_steps(units, steps, warmup, budget_s)
+    if config == "d_step":
+        return cpu_d_steps(units, steps, warmup, budget_s)
     return cpu_infer_steps(config, units, steps, warmup, budget_s)
 
 
@@ -260,6 +319,9 @@ WORKLOAD_DESC = {
                  "bilinear x2, to_rgb) @256^2, eval, BASELINE config 2",
     "infer512": "IRFD inference (6 encoder passes on 512^2 images + swap + 2 generator calls with "
                 "SynthesisNetwork(resolution=512)), eval, BASELINE config 5",
+    "d_step": "IRFD discriminator step (4 x D forward/backward on instance-noised real and reconstructed images, IRFD "
+              "forward under no_grad, R1 penalty x2 with its second-order chain, Adam on D) @256^2, train.py:157-183 "
+              "(SURVEY §8(f) N1)",
 }
 
 
@@ -544,7 +606,21 @@ def run_native_infer(args):
     B = args.batch
     torch.manual_seed(0)
     g = torch.Generator().manual_seed(7 + rank)
-    if args.config == "gen_infer":
+    differentiable = args.config == "d_step"
+    if args.config == "d_step":
+        from speak_hack_b200.trainer import IRFDDiscriminatorStep
+
+        model = P.IRFD().to(dev).train()
+        dstep = IRFDDiscriminatorStep(model)
+        host_in = [(torch.rand(B, 3, 256, 256, generator=g) * 2 - 1).pin_memory() for _ in range(2)]
+        dev_in = [t.to(dev) for t in host_in]
+        with torch.no_grad():  # let the spectral-norm power iterations converge (fresh u/v give weights ~1e3 too large)
+            for _ in range(6):
+                model.D(dev_in[0])
+        eager = lambda: dstep.step(*dev_in)                                # noqa: E731
+        runner = lambda a, b: dstep.step(a, b)                            # noqa: E731  (eager launches: no graph)
+        pick = lambda out: [out.reshape(1)]                                # noqa: E731
+    elif args.config == "gen_infer":
         model = P.StyleGenerator(input_dim=6144).to(dev).eval()
         host_in = [(torch.randn(B, 6144, generator=g).abs() * 0.5).pin_memory()]
         dev_in = [t.to(dev) for t in host_in]
@@ -570,6 +646,8 @@ def run_native_infer(args):
     torch.manual_seed(11)
 
     def step(inputs):
+        if differentiable:
+            return runner(*inputs)
         with torch.no_grad():
             return runner(*inputs) if runner is not None else model(*inputs)
 
@@ -661,9 +739,10 @@ def run_native_infer(args):
     checksum = float(host_out[(args.steps - 1) & 1][0].double().abs().mean())
 
     # ---- roofline pass: eager launches, per-launch CUDA events around every tensor-core GEMM (one stream)
+    ops.use_side_stream = False
     ops.gemm_timing_begin()
     rsteps = min(args.steps, 3)
-    with torch.no_grad():
+    with torch.set_grad_enabled(differentiable):
         for _ in range(rsteps):
             eager()
     torch.cuda.synchronize()
@@ -681,7 +760,7 @@ def run_native_infer(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD_DESC[args.config], "units_per_gpu": B, "units_per_step": B * world,
                    "parallelism": f"replicas x{world} (no collective)" if world > 1 else "single GPU",
-                   "launch_mode": "one CUDA graph per forward" if runner is not None else "eager",
+                   "launch_mode": ("eager launches" if differentiable or runner is None else "one CUDA graph per forward"),
                    "l2_policy": "activations of one forward (>1 GB) exceed the 126 MB L2; no explicit flush",
                    "algorithmic_tflop_per_step_per_gpu": cfg["flops_per_unit"] * B / 1e12,
                    "outputs_finite": finite},
@@ -697,7 +776,7 @@ def run_native_infer(args):
     if world == 1 and not args.no_cpu_baseline:
         try:
             u = CPU_UNITS[args.config]
-            val, done, threads, dt = cpu_arm(args.config, u, 3, 1, budget_s=90.0)
+            val, done, threads, dt = cpu_arm(args.config, u, 2 if args.config == "d_step" else 3, 1, budget_s=90.0)
             line["cpu_baseline"] = {"value": val, "unit": cfg["unit"], "cores": threads, "kind": "port",
                                     "sample": f"{done} " + CPU_SAMPLE_DESC[args.config].format(u=u)
                                               + f", {dt:.1f} s after 1 warm-up step"}

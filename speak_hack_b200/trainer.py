@@ -33,6 +33,7 @@ from . import ops
 from .dp import BucketSchedule, GradBuckets, broadcast_buffers
 from .model import IRFD, mse_loss
 
+REAL_LABEL, FAKE_LABEL = 0.9, 0.1   # train.py:145-146 (one-sided label smoothing on both sides)
 STAGES = (7, 6, 5, 4, 3)  # ResNet50Encoder child indices 7..4 = layer4..layer1; 3 stands for the stem (children 0, 1)
 
 
@@ -192,7 +193,7 @@ class IRFDTrainer:
     def _adversarial(self, recon):
         """stylegan_loss_weight * mean over the two reconstructions of BCE(D(x_recon), real) (train.py:197-203)."""
         d = self.model.D(recon)
-        return _BCELogitsFn.apply(d, 1.0)
+        return _BCELogitsFn.apply(d, REAL_LABEL)
 
     # ---------------------------------------------------------------------------------------------- eager step
     def train_step_eager(self, x_s: torch.Tensor, x_t: torch.Tensor):
@@ -448,3 +449,54 @@ class IRFDTrainer:
         if ckpt.get("optimizer_G"):
             self.load_optimizer_state_dict(ckpt["optimizer_G"])
         return ckpt
+
+
+class IRFDDiscriminatorStep:
+    """The reference's discriminator step (train.py:157-183) on the native discriminator.
+
+        D(x_s + n), D(x_t + n)                      -> BCE against real_label 0.9       (instance noise std 0.1)
+        x_recon = model(x_s, x_t)[:2] under no_grad  (train mode: the encoders' BN buffers move, as in the reference)
+        D(x_s_recon + n), D(x_t_recon + n)          -> BCE against fake_label 0.1
+        R1 = (r1(x_s) + r1(x_t)) / 2                 (train.py:246-255; fused second-order node, D.r1_penalty)
+        loss_D = real + fake + r1_weight * R1 -> backward -> Adam(lr 5e-5) on D.parameters()   (train.py:347)
+
+    Every D call is its own forward (one spectral-norm power iteration each, like the reference's six calls).  D's
+    parameters and gradients are views of flat fp32 buffers, so zero_grad and Adam are one launch each.  Eager launches
+    (no CUDA graph: the spectral-norm hooks are torch code); the G step is the graphed path."""
+
+    def __init__(self, model: IRFD, lr: float = 5e-5, betas=(0.9, 0.999), eps: float = 1e-8, r1_weight: float = 1.0,
+                 noise_std: float = 0.1):
+        self.model = model
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.r1_weight, self.noise_std = r1_weight, noise_std
+        self.params = list(model.D.parameters())
+        self.flat, self.gflat = flatten_parameters(self.params)
+        self._grad_views = [p.grad for p in self.params]
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.step_count = 0
+        self.last = None
+
+    def _noisy(self, x):
+        return torch.add(x.detach(), torch.randn_like(x), alpha=self.noise_std)   # add_instance_noise, train.py:148-149
+
+    def step(self, x_s: torch.Tensor, x_t: torch.Tensor):
+        model, D = self.model, self.model.D
+        self.gflat.zero_()
+        for p, v in zip(self.params, self._grad_views):  # keep .grad pointing into the flat buffer
+            if p.grad is not v:
+                p.grad = v
+        d_real_s, d_real_t = D(self._noisy(x_s)), D(self._noisy(x_t))
+        loss_real = 0.5 * (_BCELogitsFn.apply(d_real_s, REAL_LABEL) + _BCELogitsFn.apply(d_real_t, REAL_LABEL))
+        with torch.no_grad():
+            out = model(x_s, x_t)
+        d_fake_s, d_fake_t = D(self._noisy(out[0])), D(self._noisy(out[1]))
+        loss_fake = 0.5 * (_BCELogitsFn.apply(d_fake_s, FAKE_LABEL) + _BCELogitsFn.apply(d_fake_t, FAKE_LABEL))
+        r1 = 0.5 * (D.r1_penalty(x_s) + D.r1_penalty(x_t))
+        loss = loss_real + loss_fake + self.r1_weight * r1
+        loss.backward()
+        self.step_count += 1
+        ops.adam_step(self.flat, self.gflat, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps,
+                      self.step_count)
+        self.last = (loss_real.detach(), loss_fake.detach(), r1.detach())
+        return loss.detach()
