@@ -482,6 +482,9 @@ class IRFDDiscriminatorStep:
 
     def step(self, x_s: torch.Tensor, x_t: torch.Tensor):
         model, D = self.model, self.model.D
+        # the reference's R1 helper marks the batch as requiring grad (train.py:247); do that to private views so the
+        # caller's (possibly reused, in-place refilled) input buffers stay plain tensors
+        x_s, x_t = x_s.detach(), x_t.detach()
         self.gflat.zero_()
         for p, v in zip(self.params, self._grad_views):  # keep .grad pointing into the flat buffer
             if p.grad is not v:
