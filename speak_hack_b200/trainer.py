@@ -100,6 +100,9 @@ class IRFDTrainer:
     def __init__(self, model: IRFD, lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  grad_clip: Optional[float] = None, encoder_grads: bool = True, use_cuda_graph: bool = False,
                  adv_weight: Optional[float] = None):
+        if adv_weight is not None and use_cuda_graph:
+            raise ops._lib.IrfdError("IRFDTrainer: the adversarial term runs the discriminator's spectral-norm hooks "
+                                     "(torch code) every step; use the eager step (use_cuda_graph=False) with adv_weight")
         self.model = model
         self.lr, self.betas, self.eps = lr, betas, eps
         self.grad_clip = grad_clip

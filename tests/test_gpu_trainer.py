@@ -138,3 +138,53 @@ def test_graph_gradients_equal_eager_gradients(cuda_device):
           f"encoder last-BN worst {worst_last[1]:.3e} ({worst_last[0]})")
     assert worst_gd[1] < 1e-5, worst_gd
     assert worst_last[1] < 1e-3, worst_last
+
+
+def test_adversarial_term_and_discriminator_step(cuda_device):
+    """train.py:197-203 (G step with + w * BCE(D(x_recon), 0.9)) and train.py:157-183 (D step) on the native path:
+    the adversarial gradient reaches Gd, D's parameters receive gradients the clip norm sees, the D step moves D only."""
+    import irfd_oracle as O
+    import speak_hack_b200 as P
+    from speak_hack_b200.trainer import IRFDDiscriminatorStep, IRFDTrainer
+
+    dev = cuda_device
+    x_s, x_t = O.synthetic_pair(2)
+    xs, xt = x_s.to(dev), x_t.to(dev)
+    grads = {}
+    for adv in (None, 0.1):
+        torch.manual_seed(O.WEIGHT_SEED)
+        net = P.IRFD().to(dev).train()
+        net.Gd.style_mixing_prob = 0.0
+        with torch.no_grad():   # converge the spectral-norm power iteration (fresh u/v give weights ~1e3 too large)
+            for _ in range(6):
+                net.D(xs)
+        tr = IRFDTrainer(net, lr=2e-4, grad_clip=1.0, adv_weight=adv)
+        torch.manual_seed(7)
+        torch.cuda.manual_seed(7)
+        loss = tr.train_step(xs, xt)
+        torch.cuda.synchronize()
+        assert torch.isfinite(loss) and torch.isfinite(tr.flat).all()
+        grads[adv] = tr.gflat.clone()
+        d_grads = [p.grad for p in net.D.parameters() if p.grad is not None]
+        if adv is None:
+            assert not d_grads
+        else:
+            assert len(d_grads) >= 20 and all(torch.isfinite(g).all() for g in d_grads)
+    rel = float((grads[0.1] - grads[None]).norm() / grads[None].norm())
+    print(f"[trainer] adversarial term changes the Gd gradient by rel {rel:.3e}")
+    assert rel > 0.0
+    with pytest.raises(Exception):
+        IRFDTrainer(net, adv_weight=0.1, use_cuda_graph=True)
+    # D step
+    d_before = {k: v.clone() for k, v in net.D.state_dict().items()}
+    gd_before = net.Gd.mapping[0].weight.detach().clone()
+    ds = IRFDDiscriminatorStep(net, lr=5e-5, r1_weight=1.0)
+    l1 = ds.step(xs, xt)
+    l2 = ds.step(xs, xt)
+    torch.cuda.synchronize()
+    assert torch.isfinite(l1) and torch.isfinite(l2) and ds.step_count == 2
+    assert not xs.requires_grad and not xt.requires_grad       # the caller's buffers are left alone
+    moved = sum(float((net.D.state_dict()[k] - v).abs().sum()) for k, v in d_before.items() if k.endswith("weight_orig"))
+    assert moved > 0.0 and torch.equal(net.Gd.mapping[0].weight, gd_before)
+    print(f"[trainer] D step losses {float(l1):.4e} -> {float(l2):.4e} (real {float(ds.last[0]):.3e}, fake {float(ds.last[1]):.3e}, "
+          f"R1 {float(ds.last[2]):.3e})")
