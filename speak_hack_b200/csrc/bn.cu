@@ -192,20 +192,25 @@ struct BnAffine {
 template <int RES_MODE>  // 0 none, 1 identity tensor, 2 second BN branch
 __global__ void __launch_bounds__(kRvThreads)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ z, BnAffine p1, const __nv_bfloat16* __restrict__ res, BnAffine p2,
-                __nv_bfloat16* __restrict__ out, long long rows, int C, int rows_per_blk, int relu, int gps) {
+                __nv_bfloat16* __restrict__ out, long long rows, int C, int rows_per_blk, int relu, int gps,
+                int reverse) {
   constexpr int RB = 8;  // rows per thread in flight: 8 (z only) or 16 (z + residual) 16-byte loads
   RowVec rv(C);
   if (!rv.active) return;
-  {  // statistic group = blockIdx.y: `rows` rows each, own mean/rstd (gamma/beta shared)
-    const size_t goff = (size_t)blockIdx.y * rows * C;
+  // reverse: the first blocks to be scheduled take the LAST rows — the part of z its producer (the conv epilogue) wrote
+  // last and that is still in the 126 MB L2 — and the rows written last here are the ones the next conv reads first
+  const unsigned bx = reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const unsigned by = reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  {  // statistic group = by: `rows` rows each, own mean/rstd (gamma/beta shared)
+    const size_t goff = (size_t)by * rows * C;
     z += goff;
     out += goff;
     if (RES_MODE != 0) res += goff;
-    p1.mean += (size_t)blockIdx.y * C;
-    p1.rstd += (size_t)blockIdx.y * C;
+    p1.mean += (size_t)by * C;
+    p1.rstd += (size_t)by * C;
     if (RES_MODE == 2) {
-      p2.mean += (size_t)blockIdx.y * C;
-      p2.rstd += (size_t)blockIdx.y * C;
+      p2.mean += (size_t)by * C;
+      p2.rstd += (size_t)by * C;
     }
   }
   float sc[8], sh[8], sc2[8], sh2[8];
@@ -213,7 +218,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z, BnAffine p1, const __nv_bfl
     float m[8], r[8], g[8], b[8];
     loadf8(p1.mean + rv.cv * 8, m);
     loadf8(p1.rstd + rv.cv * 8, r);
-    const int set = blockIdx.y / gps;
+    const int set = by / gps;
     loadf8(p1.gamma.p[set] + rv.cv * 8, g);
     loadf8(p1.beta.p[set] + rv.cv * 8, b);
 #pragma unroll
@@ -233,7 +238,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z, BnAffine p1, const __nv_bfl
       }
     }
   }
-  const long long r0 = (long long)blockIdx.x * rows_per_blk;
+  const long long r0 = (long long)bx * rows_per_blk;
   long long r1 = r0 + rows_per_blk;
   if (r1 > rows) r1 = rows;
   // RB rows per thread per iteration, all loads issued before the first use (memory-level parallelism)
@@ -307,21 +312,25 @@ __global__ void __launch_bounds__(kRvThreads, 2)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
                      const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ z,
                      const float* __restrict__ mean, const float* __restrict__ rstd, FSet gamma_s, FSet beta_s,
-                     float* __restrict__ partial, long long rows, int C, int rows_per_blk, int gps) {
+                     float* __restrict__ partial, long long rows, int C, int rows_per_blk, int gps, int reverse) {
   constexpr int RB = kRowBatch;  // measured: 8 rows for the two-tensor instances is slower (register pressure)
-  const float* __restrict__ gamma = gamma_s.p[blockIdx.y / gps];
-  const float* __restrict__ beta = beta_s.p[blockIdx.y / gps];
+  // reverse: start with the rows the producer of g (a dgrad GEMM, ascending) wrote last: they are still in L2; the
+  // apply pass then runs ascending and starts with what this pass touched last.  Partials stay indexed by row range.
+  const unsigned bx = reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const unsigned by = reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  const float* __restrict__ gamma = gamma_s.p[by / gps];
+  const float* __restrict__ beta = beta_s.p[by / gps];
   extern __shared__ float red_smem[];
   RowVec rv(C);
   {
-    const size_t goff = (size_t)blockIdx.y * rows * C;
+    const size_t goff = (size_t)by * rows * C;
     g1 += goff;
     if (HAS_G2) g2 += goff;
     if (MASK == 1) act += goff;
     z += goff;
-    mean += (size_t)blockIdx.y * C;
-    rstd += (size_t)blockIdx.y * C;
-    partial += (size_t)blockIdx.y * gridDim.x * 2 * C;
+    mean += (size_t)by * C;
+    rstd += (size_t)by * C;
+    partial += (size_t)by * gridDim.x * 2 * C;
   }
   float acc[2][8];
 #pragma unroll
@@ -334,7 +343,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
       loadf8(gamma + rv.cv * 8, ga);
       loadf8(beta + rv.cv * 8, be);
     }
-    const long long r0 = (long long)blockIdx.x * rows_per_blk;
+    const long long r0 = (long long)bx * rows_per_blk;
     long long r1 = r0 + rows_per_blk;
     if (r1 > rows) r1 = rows;
     for (long long r = r0 + rv.row_lane; r < r1; r += (long long)rv.rows_par * RB) {
@@ -366,7 +375,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
       }
     }
   }
-  block_reduce_rows<2>(rv, C, acc, red_smem, partial + (size_t)blockIdx.x * 2 * C, (size_t)C);
+  block_reduce_rows<2>(rv, C, acc, red_smem, partial + (size_t)bx * 2 * C, (size_t)C);
 }
 
 __global__ void __launch_bounds__(1024)
@@ -470,6 +479,15 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* _
   }
 }
 
+// IRFD_ZIGZAG (default 1): reversed traversal of bn_apply / bn_bwd_reduce (L2 reuse across consecutive kernels)
+static int zigzag() {
+  static int v = [] {
+    const char* e = getenv("IRFD_ZIGZAG");
+    return e ? atoi(e) : 1;
+  }();
+  return v;
+}
+
 // Runtime (g2, mask, g_out) -> template instance: reduce -> finalize -> apply on one stream.
 struct BnBwdLaunch {
   dim3 grid;
@@ -496,7 +514,7 @@ static void launch_bn_bwd(const BnBwdLaunch& L) {
   prefer_max_shared_carveout(reinterpret_cast<const void*>(&bn_bwd_apply_kernel<HAS_G2, MASK, false>));
   prefer_max_shared_carveout(reinterpret_cast<const void*>(&bn_bwd_finalize_kernel));
   bn_bwd_reduce_kernel<HAS_G2, MASK><<<L.grid, kRvThreads, L.smem, L.stream>>>(
-      L.g1, L.g2, L.act, L.z, L.mean, L.rstd, L.gamma, L.beta, L.partial, L.grows, L.c, L.rpb, L.gps);
+      L.g1, L.g2, L.act, L.z, L.mean, L.rstd, L.gamma, L.beta, L.partial, L.grows, L.c, L.rpb, L.gps, zigzag());
   bn_bwd_finalize_kernel<<<dim3(L.c / kFinCh, L.nsets), 1024, 0, L.stream>>>(L.partial, L.nblk, L.c, (double)L.grows,
                                                                              L.dgamma, L.dbeta, L.grad_beta, L.c1, L.c2,
                                                                              L.batch_stats, L.gps);
@@ -613,11 +631,11 @@ extern "C" int irfd_bn_apply_sets(const void* z, const float* mean, const float*
   const dim3 grid(nblk, groups);
   const int gps = groups / nsets;
   if (res == nullptr)
-    bn_apply_kernel<0><<<grid, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, grows, c, rpb, relu, gps);
+    bn_apply_kernel<0><<<grid, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, grows, c, rpb, relu, gps, zigzag());
   else if (mean2 == nullptr)
-    bn_apply_kernel<1><<<grid, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, grows, c, rpb, relu, gps);
+    bn_apply_kernel<1><<<grid, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, grows, c, rpb, relu, gps, zigzag());
   else
-    bn_apply_kernel<2><<<grid, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, grows, c, rpb, relu, gps);
+    bn_apply_kernel<2><<<grid, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, grows, c, rpb, relu, gps, zigzag());
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }

@@ -120,42 +120,41 @@ upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
       if constexpr (LO) ql[r][c] = ldg16(in_lo + (size_t)b * H * W * C + v * 8 + ((size_t)hs[r] * W + ws[c]) * C);
     }
   auto fetch = [&](int r, int c, float (&f)[8]) {  // r, c are compile-time after unrolling
-    unpack8(c == 0 ? q[r][0] : (c == 1 ? q[r][1] : q[r][2]), f);
+    unpack8(q[r][c], f);
     if constexpr (LO) {
       float l[8];
-      unpack8(c == 0 ? ql[r][0] : (c == 1 ? ql[r][1] : ql[r][2]), l);
+      unpack8(ql[r][c], l);
 #pragma unroll
       for (int t = 0; t < 8; ++t) f[t] += l[t];
     }
   };
+  // Output column 2w + dx interpolates neighbourhood columns (dx, dx + 1) = (left, centre) / (centre, right) and output
+  // row 2h + dy rows (dy, dy + 1), with ATen's weights: (0.25, 0.75) for the even output, (0.75, 0.25) for the odd one,
+  // (l0, l1) = (1, 0) on the clamped first output (whose i0 is the centre: the neighbourhood's clamped left column holds
+  // the same pixel, so 0 * left + 1 * centre is ATen's 1 * centre + 0 * next).  Per-thread weights, fixed operands: no
+  // per-value selects (ncu, round 2: the select-heavy version was issue-bound at 76 % SM throughput, 2.6 TB/s).
+  const float ax[2] = {w > 0 ? 0.25f : 0.f, 0.75f}, bx[2] = {w > 0 ? 0.75f : 1.f, 0.25f};
+  const float ay[2] = {h > 0 ? 0.25f : 0.f, 0.75f}, by[2] = {h > 0 ? 0.75f : 1.f, 0.25f};
+  float fq[3][3][8];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) fetch(r, c, fq[r][c]);
   // horizontal pass: hl[r][dx] = lx.l0 * row[lx.i0] + lx.l1 * row[lx.i1] for the two output columns 2w, 2w + 1
   float hl[3][2][8];
 #pragma unroll
-  for (int dx = 0; dx < 2; ++dx) {
-    const Lerp lx = lerp_src(2 * w + dx, W);
-    const int c0 = lx.i0 - w + 1, c1 = lx.i1 - w + 1;  // 0..2 into the neighbourhood (border: clamped duplicates)
+  for (int dx = 0; dx < 2; ++dx)
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      float f0[8], f1[8];
-      fetch(r, c0, f0);
-      fetch(r, c1, f1);
+    for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int t = 0; t < 8; ++t) hl[r][dx][t] = lx.l0 * f0[t] + lx.l1 * f1[t];
-    }
-  }
+      for (int t = 0; t < 8; ++t) hl[r][dx][t] = ax[dx] * fq[r][dx][t] + bx[dx] * fq[r][dx + 1][t];
 #pragma unroll
   for (int dy = 0; dy < 2; ++dy) {
-    const Lerp ly = lerp_src(2 * h + dy, H);
-    const int r0 = ly.i0 - h + 1, r1 = ly.i1 - h + 1;
 #pragma unroll
     for (int dx = 0; dx < 2; ++dx) {
       float o[8];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const float a0 = r0 == 0 ? hl[0][dx][t] : (r0 == 1 ? hl[1][dx][t] : hl[2][dx][t]);
-        const float a1 = r1 == 0 ? hl[0][dx][t] : (r1 == 1 ? hl[1][dx][t] : hl[2][dx][t]);
-        o[t] = ly.l0 * a0 + ly.l1 * a1;
-      }
+      for (int t = 0; t < 8; ++t) o[t] = ay[dy] * hl[dy][dx][t] + by[dy] * hl[dy + 1][dx][t];
       store8(out + (((size_t)b * 2 * H + 2 * h + dy) * Wo + 2 * w + dx) * C + v * 8, o);
     }
   }
@@ -221,11 +220,11 @@ upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __r
 //   per (b,c): ds1 = sum_hw dy, dsp1 = sum_hw dy*a ;  per c: dbias = sum dz, dnw = sum dz*noise[b,hw]
 // grid = (chunks, B); partial[b][chunk][4][C]
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRvThreads)
+__global__ void __launch_bounds__(kRvThreads, 2)
 style_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ a,
                  const float* __restrict__ noise, const float* __restrict__ sp1, __nv_bfloat16* __restrict__ dz,
                  float* __restrict__ partial, int HW, int C, int rows_per_blk) {
-  constexpr int RB = 8;  // two streamed tensors: 16 loads of 16 bytes in flight per thread
+  constexpr int RB = 4;  // two streamed tensors: 8 loads of 16 bytes in flight per thread, two blocks per SM
   extern __shared__ float red_smem[];
   RowVec rv(C);
   const int b = blockIdx.y;
@@ -519,7 +518,10 @@ extern "C" int irfd_upsample2x_bwd(const void* dout, void* din, int b, int h, in
 static void style_plan(int hw, int c, int b, int* chunks, int* rpb) {
   int rows_par = kRvThreads / (c / 8);
   if (rows_par < 1) rows_par = 1;
-  long long want = ((long long)num_sms() * row_block_waves() + b - 1) / b;  // chunks per image
+  // grid = chunks x images, two blocks resident per SM: as many chunks per image as still fit ONE wave (ncu, round 2:
+  // ceil(SMs / b) chunks gave 192 blocks at one block per SM = 1.3 waves, the second almost empty)
+  long long want = (2ll * num_sms()) / b;  // chunks per image
+  if (want < 1) want = 1;
   long long r = (hw + want - 1) / want;
   r = ((r + rows_par - 1) / rows_par) * rows_par;
   if (r < rows_par * 4) r = rows_par * 4;
