@@ -198,47 +198,59 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfl
   *reinterpret_cast<uint2*>(arg + (size_t)pix * C + v * 8) = packed;
 }
 
-__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ dout2,
-                                   const uint8_t* __restrict__ arg,
-                                   __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C) {
-  const unsigned Ho = H / 2, Wo = W / 2, vc = C / 8;
-  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;  // host checks total < 2^32
-  if (idx >= (size_t)N * H * W * vc) return;
-  const int v = idx % vc;
-  const unsigned pix = idx / vc;
-  const int w = pix % W, h = (pix / W) % H, n = pix / ((unsigned)W * H);
+// grid = (N*H input rows, segments of W*C/8 vectors): the row decode is per block, the column decode 32-bit.  An input
+// pixel lies in at most 2 x 2 pooling windows (stride 2, kernel 3, pad 1): row h belongs to output row h/2 through tap
+// kh = 1 when h is even, to rows (h+1)/2 (kh = 0) and (h-1)/2 (kh = 2) when it is odd; the candidates are listed once per
+// thread instead of walking 3 x 3 taps with parity tests (ncu, round 2: that version was issue-bound, 1.3 TB/s).
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ dout2,
+                   const uint8_t* __restrict__ arg, __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C) {
+  const unsigned Ho = H / 2, Wo = W / 2, vc = C >> 3;
+  const unsigned i = blockIdx.y * blockDim.x + threadIdx.x;
+  if (i >= (unsigned)W * vc) return;
+  const int w = i / vc, v = i - w * vc;
+  const int n = blockIdx.x / H, h = blockIdx.x - n * H;
+  int oh[2], kh[2], nh = 0, ow[2], kw[2], nw = 0;
+  if (h & 1) {  // ascending tap order, like the 3 x 3 walk it replaces (same summation order)
+    if ((unsigned)((h + 1) >> 1) < Ho) { oh[nh] = (h + 1) >> 1; kh[nh++] = 0; }
+    oh[nh] = (h - 1) >> 1; kh[nh++] = 2;
+  } else {
+    oh[nh] = h >> 1; kh[nh++] = 1;
+  }
+  if (w & 1) {
+    if ((unsigned)((w + 1) >> 1) < Wo) { ow[nw] = (w + 1) >> 1; kw[nw++] = 0; }
+    ow[nw] = (w - 1) >> 1; kw[nw++] = 2;
+  } else {
+    ow[nw] = w >> 1; kw[nw++] = 1;
+  }
   float acc[8];
 #pragma unroll
   for (int t = 0; t < 8; ++t) acc[t] = 0.f;
-  for (int kh = 0; kh < 3; ++kh) {
-    const int th = h - kh + 1;
-    if (th < 0 || (th & 1)) continue;
-    const int oh = th >> 1;
-    if (oh >= Ho) continue;
-    for (int kw = 0; kw < 3; ++kw) {
-      const int tw = w - kw + 1;
-      if (tw < 0 || (tw & 1)) continue;
-      const int ow = tw >> 1;
-      if (ow >= Wo) continue;
-      const size_t op = (((size_t)n * Ho + oh) * Wo + ow) * C + v * 8;
-      const uint2 packed = *reinterpret_cast<const uint2*>(arg + op);
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    if (a >= nh) break;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      if (b >= nw) break;
+      const size_t op = (((size_t)n * Ho + oh[a]) * Wo + ow[b]) * C + v * 8;
+      const uint2 packed = __ldg(reinterpret_cast<const uint2*>(arg + op));
       float g[8];
-      load8(dout + op, g);
+      unpack8(ldg16(dout + op), g);
       if (dout2 != nullptr) {
         float g2[8];
-        load8(dout2 + op, g2);
+        unpack8(ldg16(dout2 + op), g2);
 #pragma unroll
         for (int t = 0; t < 8; ++t) g[t] += g2[t];
       }
-      const int tap = kh * 3 + kw;
+      const unsigned tap = kh[a] * 3 + kw[b];
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
-        const int a = ((t < 4 ? packed.x : packed.y) >> ((t & 3) * 8)) & 0xff;
-        if (a == tap) acc[t] += g[t];
+        const unsigned am = ((t < 4 ? packed.x : packed.y) >> ((t & 3) * 8)) & 0xffu;
+        if (am == tap) acc[t] += g[t];
       }
     }
   }
-  store8(dx + (size_t)pix * C + v * 8, acc);
+  store8(dx + (((size_t)n * H + h) * W + w) * C + v * 8, acc);
 }
 
 // AdaptiveAvgPool2d(1): [N, HW, C] bf16 -> [N, C] fp32 ; backward broadcasts dfeat/HW
@@ -392,10 +404,9 @@ extern "C" int irfd_maxpool_fwd(const void* a, void* out, void* argmax, int n, i
 extern "C" int irfd_maxpool_bwd(const void* dout, const void* dout2, const void* argmax, void* dx, int n, int h, int w,
                                 int c, cudaStream_t stream) {
   IRFD_CHECK_ARG(dout && dx && argmax && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "maxpool_bwd: bad argument");
-  const size_t total = (size_t)n * h * w * (c / 8);
-  CHECK_TOTAL32(total);
-  maxpool_bwd_kernel<<<GRID1D(total)>>>(CBF(dout), CBF(dout2), reinterpret_cast<const uint8_t*>(argmax), BF(dx), n, h,
-                                        w, c);
+  IRFD_CHECK_ARG((long long)w * c < (1ll << 24) && (long long)n * h < (1ll << 31), "maxpool_bwd: bad shape");
+  maxpool_bwd_kernel<<<dim3((unsigned)(n * h), (unsigned)((w * (c / 8) + 255) / 256)), 256, 0, stream>>>(
+      CBF(dout), CBF(dout2), reinterpret_cast<const uint8_t*>(argmax), BF(dx), n, h, w, c);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }

@@ -169,49 +169,87 @@ __device__ __forceinline__ void lerp_adjoint_weights(int i, int in_size, float (
   w[3] = i < in_size - 1 ? 0.25f : 0.f;
 }
 
-// grid = (B*H input rows, segments of W*C/8 vectors)
-__global__ void __launch_bounds__(256)
+// One thread per 2x2 block of INPUT pixels (one 8-channel vector): the four adjoint stencils (4x4 output gradients each)
+// overlap in a 6x6 window, so 36 loads serve 4 results — 9 per result instead of 16 (ncu, round 2: the one-pixel-per-
+// thread version pulled every gradient 4x through L2, 42 % hit rate, 2.3 TB/s).  Row by row: six gradients are combined
+// horizontally into the two input columns, then added into the two input rows with the vertical weights.
+// grid = (B*ceil(H/2) input row pairs, segments of ceil(W/2)*C/8 vectors); odd sizes leave the last pair half empty.
+__global__ void __launch_bounds__(256, 2)
 upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ din, int B, int H, int W,
                       int C) {
-  const unsigned vc = C >> 3, Wo = 2 * W;
+  const unsigned vc = C >> 3, Wo = 2 * W, Ho = 2 * H, W2 = (W + 1) >> 1, H2 = (H + 1) >> 1;
   const unsigned i = blockIdx.y * blockDim.x + threadIdx.x;
-  if (i >= (unsigned)W * vc) return;
-  const int w = i / vc, v = i - w * vc;
-  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
-  float wy[4], wx[4];
-  lerp_adjoint_weights(h, H, wy);
-  lerp_adjoint_weights(w, W, wx);
-  // clamp the coordinates of the zero-weight (non-existent) outputs so that every load is in range: all 16 loads are
-  // then unconditional and in flight together
-  const __nv_bfloat16* base = dout + (size_t)b * (2 * H) * Wo * C + v * 8;
-  uint4 q[4][4];
+  if (i >= W2 * vc) return;
+  const int wb = i / vc, v = i - wb * vc;
+  const int b = blockIdx.x / H2, hb = blockIdx.x - b * H2;
+  const int h0 = 2 * hb, w0 = 2 * wb;
+  float wy[2][4], wx[2][4];
+  lerp_adjoint_weights(h0, H, wy[0]);
+  lerp_adjoint_weights(h0 + 1, H, wy[1]);
+  lerp_adjoint_weights(w0, W, wx[0]);
+  lerp_adjoint_weights(w0 + 1, W, wx[1]);
+  const __nv_bfloat16* base = dout + (size_t)b * Ho * Wo * C + v * 8;
+  float acc[2][2][8];
 #pragma unroll
-  for (int dy = 0; dy < 4; ++dy) {
-    int oh = 2 * h - 1 + dy;
-    oh = oh < 0 ? 0 : (oh > 2 * H - 1 ? 2 * H - 1 : oh);
+  for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int dx = 0; dx < 4; ++dx) {
-      int ow = 2 * w - 1 + dx;
-      ow = ow < 0 ? 0 : (ow > (int)Wo - 1 ? (int)Wo - 1 : ow);
-      q[dy][dx] = ldg16(base + ((size_t)oh * Wo + ow) * C);
-    }
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[a][c][t] = 0.f;
+  int ows[6];
+#pragma unroll
+  for (int dx = 0; dx < 6; ++dx) {  // clamp the coordinates of the non-existent (zero-weight) outputs into range
+    int ow = 2 * w0 - 1 + dx;
+    ows[dx] = ow < 0 ? 0 : (ow > (int)Wo - 1 ? (int)Wo - 1 : ow);
   }
-  float acc[8];
 #pragma unroll
-  for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+  for (int dy = 0; dy < 6; ++dy) {
+    int oh = 2 * h0 - 1 + dy;
+    oh = oh < 0 ? 0 : (oh > (int)Ho - 1 ? (int)Ho - 1 : oh);
+    uint4 q[6];
 #pragma unroll
-  for (int dy = 0; dy < 4; ++dy)
+    for (int dx = 0; dx < 6; ++dx) q[dx] = ldg16(base + ((size_t)oh * Wo + ows[dx]) * C);
+    float cw[2][8];
 #pragma unroll
-    for (int dx = 0; dx < 4; ++dx) {
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) cw[c][t] = 0.f;
+#pragma unroll
+    for (int dx = 0; dx < 6; ++dx) {
       float g[8];
-      unpack8(q[dy][dx], g);
-      const float ww = wy[dy] * wx[dx];
-      if (ww != 0.f) {  // a clamped (non-existent) output must not contribute even when it holds inf/nan
+      unpack8(q[dx], g);
+      // input column c (= w0 + c) receives output columns 2(w0+c)-1 .. 2(w0+c)+2 = window columns 2c .. 2c+3
 #pragma unroll
-        for (int t = 0; t < 8; ++t) acc[t] += ww * g[t];
+      for (int c = 0; c < 2; ++c) {
+        const int k = dx - 2 * c;
+        if (k >= 0 && k < 4) {
+          const float ww = wx[c][k];
+          if (ww != 0.f) {  // a clamped (non-existent) output must not contribute even when it holds inf/nan
+#pragma unroll
+            for (int t = 0; t < 8; ++t) cw[c][t] += ww * g[t];
+          }
+        }
       }
     }
-  store8(din + ((size_t)blockIdx.x * W + w) * C + v * 8, acc);
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {  // input row a (= h0 + a) receives window rows 2a .. 2a+3
+      const int k = dy - 2 * a;
+      if (k >= 0 && k < 4) {
+        const float ww = wy[a][k];
+        if (ww != 0.f) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int t = 0; t < 8; ++t) acc[a][c][t] += ww * cw[c][t];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+      if (h0 + a < H && w0 + c < W) store8(din + (((size_t)b * H + h0 + a) * W + w0 + c) * C + v * 8, acc[a][c]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -509,7 +547,8 @@ extern "C" int irfd_upsample2x_bwd(const void* dout, void* din, int b, int h, in
   IRFD_CHECK_ARG(dout && din && c % 8 == 0, "upsample2x_bwd: bad argument");
   IRFD_CHECK_ARG(b > 0 && h > 0 && w > 0 && (long long)w * c < (1ll << 24), "upsample2x_bwd: bad shape");
   prefer_max_shared_carveout(reinterpret_cast<const void*>(&upsample2x_bwd_kernel));
-  upsample2x_bwd_kernel<<<dim3((unsigned)(b * h), (unsigned)((w * (c / 8) + 255) / 256)), 256, 0, stream>>>(
+  upsample2x_bwd_kernel<<<dim3((unsigned)(b * ((h + 1) / 2)), (unsigned)((((w + 1) / 2) * (c / 8) + 255) / 256)), 256, 0,
+                          stream>>>(
       CBF(dout), BF(din), b, h, w, c);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
