@@ -148,7 +148,7 @@ _workspace_retired = []  # outgrown buffers stay alive: a captured CUDA graph ma
 
 def workspace(nbytes: int, device) -> torch.Tensor:
     """Grow-only scratch buffer (split-K partials, reduction partials), one per (device, stream): every use is
-    stream-ordered, and the three encoders run concurrently on their own streams."""
+    stream-ordered, and the weight-gradient launches run on their own side stream."""
     key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0)
     buf = _workspace.get(key)
     if buf is None or buf.numel() < nbytes:
