@@ -26,6 +26,7 @@ class _FCFn(torch.autograd.Function):
         x = x.contiguous()
         y = ops.linear_fwd(x, weight, bias, wmul, bmul, lrelu)
         ctx.save_for_backward(x, weight, y)
+        ctx.bias = bias
         ctx.cfg = (wmul, bmul, lrelu, bias is not None)
         return y
 
@@ -36,8 +37,10 @@ class _FCFn(torch.autograd.Function):
         dy = dy.contiguous()
         dz = ops.lrelu_bwd(dy, y) if lrelu else dy
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        dx, dw, db = ops.linear_bwd(dz, x, weight, wmul, bmul, need_dx=need_dx, need_dw=need_dw, has_bias=has_bias)
-        return dx, dw, db, None, None, None
+        tw, tb = _target(weight), (_target(ctx.bias) if has_bias else None)
+        dx, dw, db = ops.linear_bwd(dz, x, weight, wmul, bmul, need_dx=need_dx, need_dw=need_dw, has_bias=has_bias,
+                                    dw_out=tw, db_out=tb)
+        return dx, (None if tw is not None else dw), (None if tb is not None else db), None, None, None
 
 
 class FC(nn.Module):
@@ -146,6 +149,17 @@ class SynthesisBlock(nn.Module):
 # ----------------------------------------------------------------------------------------------------------------------
 # Synthesis network as one autograd node
 # ----------------------------------------------------------------------------------------------------------------------
+# {parameter.data_ptr(): fp32 tensor of the parameter's shape} or None.  When set (IRFDTrainer's static step: exactly ONE
+# backward per generator parameter per step), the backward kernels WRITE each parameter gradient there (the trainer's
+# flat gradient buffer) and hand autograd no gradient for it: no accumulation kernels, no zeroing of the buffer.
+GRAD_TARGETS = None
+
+
+def _target(p):
+    t = GRAD_TARGETS
+    return None if t is None else t.get(p.data_ptr())
+
+
 SPLIT_MAX_RES = 32  # block outputs up to this resolution are stored as split bf16 (see _SynthesisFn.forward)
 
 
@@ -269,6 +283,10 @@ class _SynthesisFn(torch.autograd.Function):
         nblk = len(net.layers)
         grads: List[Optional[torch.Tensor]] = [None] * len(params)
 
+        def T(i):
+            """In-place destination of parameter i's gradient (GRAD_TARGETS, the trainer's static step) or None."""
+            return _target(params[i])
+
         def style_backward(dsp1, ds1, st, row_idx, sw, gw_i, gb_i, c):
             """Backward of one style FC (4 tiny launches) on the side stream: it only feeds d(rows) and two parameter
             gradients, all consumed after the join at the end of this backward."""
@@ -278,8 +296,10 @@ class _SynthesisFn(torch.autograd.Function):
                     a, b = a[:, :c].contiguous(), b[:, :c].contiguous()
                 dst = ops.merge_style_grad(a, b)
                 dz = ops.lrelu_bwd(dst, st)
-                dx, dw, db = ops.linear_bwd(dz, rows_t[row_idx], sw, wm, bm, need_dx=True, dx=drows[row_idx], dx_beta=0.0)
-                grads[gw_i], grads[gb_i] = dw, db
+                tw, tb = T(gw_i), T(gb_i)
+                dx, dw, db = ops.linear_bwd(dz, rows_t[row_idx], sw, wm, bm, need_dx=True, dx=drows[row_idx], dx_beta=0.0,
+                                            dw_out=tw, db_out=tb)
+                grads[gw_i], grads[gb_i] = (None if tw is not None else dw), (None if tb is not None else db)
 
             side.launch(run, dsp1, ds1, st)
 
@@ -289,19 +309,36 @@ class _SynthesisFn(torch.autograd.Function):
                     t = t.narrow(d, 0, n)
             return t.contiguous()
 
-        def wgrad(xx, dz, co, ci):
+        def wgrad(xx, dz, co, ci, tgt):
             """conv weight gradient on the side stream (overlaps the HBM-bound style backward of the next layer); the
             zero-padded 32-channel layers of a 512^2 network stay on the main stream (they need a crop afterwards)."""
             if xx.shape[-1] != ci or dz.shape[-1] != co:
-                return crop(ops.conv_wgrad(xx, dz, 3), co, ci)
-            dw = torch.empty((co, ci, 3, 3), dtype=torch.float32, device=xx.device)
+                g_ = crop(ops.conv_wgrad(xx, dz, 3), co, ci)
+                if tgt is None:
+                    return g_
+                tgt.copy_(g_)
+                return None
+            dw = tgt if tgt is not None else torch.empty((co, ci, 3, 3), dtype=torch.float32, device=xx.device)
             side.launch(lambda: ops.conv_wgrad(xx, dz, 3, dw=dw, beta=0.0), xx, dz, dw)
-            return dw
+            return None if tgt is not None else dw
+
+        def place(i, g_):
+            """Hand a gradient that was computed into a temporary (padded layers) to its target, or to autograd."""
+            t = T(i)
+            if t is None:
+                return g_
+            if g_.data_ptr() != t.data_ptr():
+                t.copy_(g_.view_as(t))
+            return None
 
         rgb_w = params[-2]
         cl = ctx.y_last.shape[-1]
-        dy, drgb_w, grads[-1] = ops.to_rgb_bwd(dimg, ctx.y_last, _pad_to(rgb_w, 1, cl).contiguous())
-        grads[-2] = crop(drgb_w, 3, rgb_w.shape[1])
+        np_ = len(params)
+        direct_rgb = cl == rgb_w.shape[1]
+        dy, drgb_w, drgb_b = ops.to_rgb_bwd(dimg, ctx.y_last, _pad_to(rgb_w, 1, cl).contiguous(),
+                                            dw_out=T(np_ - 2) if direct_rgb else None, db_out=T(np_ - 1))
+        grads[-1] = place(np_ - 1, drgb_b)
+        grads[-2] = place(np_ - 2, crop(drgb_w, 3, rgb_w.shape[1]))
         for i in range(nblk - 1, -1, -1):
             base = 5 + 10 * i
             w1, b1, w2, b2, nw1, nw2, s1w, s1b, s2w, s2b = params[base: base + 10]
@@ -309,19 +346,25 @@ class _SynthesisFn(torch.autograd.Function):
             blk = net.layers[i]
             cout, cin = w1.shape[0], w1.shape[1]
             cp = a1.shape[-1]
-            dz2, ds1_2, dsp1_2, db2, dnw2 = ops.style_bwd(dy, a2, n2, sp1_2)
-            grads[base + 3], grads[base + 5] = crop(db2, cout), crop(dnw2, cout)
+            direct = cp == cout  # unpadded layer: the per-channel reductions go straight to their targets
+            dz2, ds1_2, dsp1_2, db2, dnw2 = ops.style_bwd(dy, a2, n2, sp1_2, dbias_out=T(base + 3) if direct else None,
+                                                          dnw_out=T(base + 5) if direct else None)
+            grads[base + 3], grads[base + 5] = place(base + 3, crop(db2, cout)), place(base + 5, crop(dnw2, cout))
             style_backward(dsp1_2, ds1_2, st2, 2 * i + 2, s2w, base + 8, base + 9, cout)
             dy1 = ops.conv_gemm(dz2, _packed(blk.conv2.weight, w2, ops.PACK_DGRAD, cp, cp), 3, ops.EPI_PLAIN)
-            grads[base + 2] = wgrad(y1, dz2, cout, cout)   # after the dgrad: runs beside the next style_bwd
-            dz1, ds1_1, dsp1_1, db1, dnw1 = ops.style_bwd(dy1, a1, n1, sp1_1)
-            grads[base + 1], grads[base + 4] = crop(db1, cout), crop(dnw1, cout)
+            grads[base + 2] = wgrad(y1, dz2, cout, cout, T(base + 2))   # after the dgrad: runs beside the next style_bwd
+            dz1, ds1_1, dsp1_1, db1, dnw1 = ops.style_bwd(dy1, a1, n1, sp1_1, dbias_out=T(base + 1) if direct else None,
+                                                          dnw_out=T(base + 4) if direct else None)
+            grads[base + 1], grads[base + 4] = place(base + 1, crop(db1, cout)), place(base + 4, crop(dnw1, cout))
             style_backward(dsp1_1, ds1_1, st1, 2 * i + 1, s1w, base + 6, base + 7, cout)
             du = ops.conv_gemm(dz1, _packed(blk.conv1.weight, w1, ops.PACK_DGRAD, cp, u.shape[-1]), 3, ops.EPI_PLAIN)
-            grads[base + 0] = wgrad(u, dz1, cout, cin)
+            grads[base + 0] = wgrad(u, dz1, cout, cin, T(base + 0))
             dy = ops.upsample2x_bwd(du)
         a0, noise0, sp1_0, st0 = saved["const"]
-        dsp1_0, ds1_0, grads[0], grads[1], grads[4] = ops.const_input_bwd(dy, a0, noise0, sp1_0)
+        t0 = (T(0), T(1), T(4))
+        dsp1_0, ds1_0, dconst, dbias0, dnw0 = ops.const_input_bwd(dy, a0, noise0, sp1_0,
+                                                                  outs=t0 if all(t is not None for t in t0) else None)
+        grads[0], grads[1], grads[4] = place(0, dconst), place(1, dbias0), place(4, dnw0)
         style_backward(dsp1_0, ds1_0, st0, 0, params[2], 2, 3, params[0].shape[1])
         side.join()
         if ops.use_side_stream:  # gradients allocated by the side stream's launches, consumed by autograd on this one

@@ -656,14 +656,18 @@ def const_input_fwd(cst, bias, nw, noise, sp1, s1, split_y=False):
     return (a0, y0, y0_lo) if split_y else (a0, y0)
 
 
-def const_input_bwd(dy, a0, noise, sp1):
+def const_input_bwd(dy, a0, noise, sp1, outs=None):
+    """outs: optional (dconst, dbias, dnw) fp32 destinations (overwritten)."""
     b, c = sp1.shape
     dev = sp1.device
     dsp1 = torch.empty((b, c), dtype=F32, device=dev)
     ds1 = torch.empty((b, c), dtype=F32, device=dev)
-    dconst = torch.empty((1, c, 4, 4), dtype=F32, device=dev)
-    dbias = torch.empty(c, dtype=F32, device=dev)
-    dnw = torch.empty(c, dtype=F32, device=dev)
+    if outs is not None:
+        dconst, dbias, dnw = outs
+    else:
+        dconst = torch.empty((1, c, 4, 4), dtype=F32, device=dev)
+        dbias = torch.empty(c, dtype=F32, device=dev)
+        dnw = torch.empty(c, dtype=F32, device=dev)
     _call("irfd_const_input_bwd", dy.data_ptr(), a0.data_ptr(), noise.data_ptr(), sp1.data_ptr(), dsp1.data_ptr(),
           ds1.data_ptr(), dconst.data_ptr(), dbias.data_ptr(), dnw.data_ptr(), b, c, _stream())
     return dsp1, ds1, dconst, dbias, dnw
@@ -690,16 +694,17 @@ def upsample2x_bwd(dout: torch.Tensor) -> torch.Tensor:
     return din
 
 
-def style_bwd(dy, a, noise, sp1):
-    """Backward of the fused conv epilogue.  Returns dz (bf16), ds1, dsp1 [B,C], dbias, dnw [C]."""
+def style_bwd(dy, a, noise, sp1, dbias_out=None, dnw_out=None):
+    """Backward of the fused conv epilogue.  Returns dz (bf16), ds1, dsp1 [B,C], dbias, dnw [C] (the last two written
+    into dbias_out / dnw_out when given)."""
     lib = _lib.load()
     b, h, w, c = dy.shape
     dev = dy.device
     dz = torch.empty_like(dy)
     ds1 = torch.empty((b, c), dtype=F32, device=dev)
     dsp1 = torch.empty((b, c), dtype=F32, device=dev)
-    dbias = torch.empty(c, dtype=F32, device=dev)
-    dnw = torch.empty(c, dtype=F32, device=dev)
+    dbias = dbias_out if dbias_out is not None else torch.empty(c, dtype=F32, device=dev)
+    dnw = dnw_out if dnw_out is not None else torch.empty(c, dtype=F32, device=dev)
     ws = workspace(lib.irfd_style_bwd_workspace_bytes(b, h * w, c), dev)
     _call("irfd_style_bwd", dy.data_ptr(), a.data_ptr(), noise.data_ptr(), sp1.data_ptr(), dz.data_ptr(),
           ds1.data_ptr(), dsp1.data_ptr(), dbias.data_ptr(), dnw.data_ptr(), b, h * w, c, ws.data_ptr(), ws.numel(),
@@ -714,13 +719,13 @@ def to_rgb_fwd(y, w, bias):
     return out
 
 
-def to_rgb_bwd(drgb, y, w):
+def to_rgb_bwd(drgb, y, w, dw_out=None, db_out=None):
     lib = _lib.load()
     _chk(drgb, F32, "drgb")
     b, h, wd, c = y.shape
     dy = torch.empty_like(y)
-    dw = torch.empty((3, c, 1, 1), dtype=F32, device=y.device)
-    dbias = torch.empty(3, dtype=F32, device=y.device)
+    dw = dw_out if dw_out is not None else torch.empty((3, c, 1, 1), dtype=F32, device=y.device)
+    dbias = db_out if db_out is not None else torch.empty(3, dtype=F32, device=y.device)
     ws = workspace(lib.irfd_to_rgb_bwd_workspace_bytes(b, h * wd, c), y.device)
     _call("irfd_to_rgb_bwd", drgb.data_ptr(), y.data_ptr(), w.data_ptr(), dy.data_ptr(), dw.data_ptr(),
           dbias.data_ptr(), b, h * wd, c, ws.data_ptr(), ws.numel(), _stream(), launches=2)
@@ -825,16 +830,18 @@ def lrelu_bwd(dy, y):
     return dz
 
 
-def linear_bwd(dz, x, w, wmul=1.0, bmul=1.0, need_dx=True, dx=None, dx_beta=0.0, need_dw=True, has_bias=True):
-    """Returns (dx, dw, db); dx may be accumulated into an existing buffer (dx_beta=1)."""
+def linear_bwd(dz, x, w, wmul=1.0, bmul=1.0, need_dx=True, dx=None, dx_beta=0.0, need_dw=True, has_bias=True, dw_out=None,
+               db_out=None):
+    """Returns (dx, dw, db); dx may be accumulated into an existing buffer (dx_beta=1); dw_out / db_out: optional fp32
+    destinations of the parameter gradients (overwritten), e.g. views of the trainer's flat gradient buffer."""
     b, n = dz.shape
     k = w.shape[1]
     dev = dz.device
     if need_dx and dx is None:
         dx = torch.empty((b, k), dtype=F32, device=dev)
         dx_beta = 0.0
-    dw = torch.empty((n, k), dtype=F32, device=dev) if need_dw else None
-    db = torch.empty(n, dtype=F32, device=dev) if (need_dw and has_bias) else None
+    dw = (dw_out if dw_out is not None else torch.empty((n, k), dtype=F32, device=dev)) if need_dw else None
+    db = (db_out if db_out is not None else torch.empty(n, dtype=F32, device=dev)) if (need_dw and has_bias) else None
     for r0 in range(0, b, 64):  # the kernels keep one accumulator per batch row in registers (<= 64 rows per launch)
         r1 = min(b, r0 + 64)
         _call("irfd_linear_bwd", dz[r0:r1].data_ptr(), _ptr(x[r0:r1]) if x is not None else None, w.data_ptr(),

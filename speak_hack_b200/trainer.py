@@ -110,6 +110,7 @@ class IRFDTrainer:
         self.adv_weight = adv_weight
         self.gd_params = list(model.Gd.parameters())
         self.flat, self.gflat = flatten_parameters(self.gd_params)
+        self._gd_targets = {p.data_ptr(): p.grad for p in self.gd_params}
         self._gd_conv_weights = [p for p in self.gd_params if p.dim() == 4 and p.shape[-1] == 3]
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
@@ -141,10 +142,16 @@ class IRFDTrainer:
         self._static = None
 
     # ---------------------------------------------------------------------------------------------- shared pieces
-    def zero_grad(self, encoders_direct: bool = True):
-        """Gd gradients are accumulated by autograd into the flat buffer: zero it.  Encoder gradients are overwritten by
-        the lockstep backward; only the per-encoder fallback path (autograd accumulation) needs them zeroed."""
-        self.gflat.zero_()
+    def zero_grad(self, encoders_direct: bool = True, gd_direct: bool = False):
+        """Gd gradients are accumulated by autograd into the flat buffer: zero it — unless the step writes them in place
+        (static step: one generator call, generator.GRAD_TARGETS).  Encoder gradients are overwritten by the lockstep
+        backward; only the per-encoder fallback path (autograd accumulation) needs them zeroed."""
+        if not gd_direct:
+            self.gflat.zero_()
+        for p in self.gd_params:  # keep .grad pointing into the flat buffer
+            t = self._gd_targets[p.data_ptr()]
+            if p.grad is not t:
+                p.grad = t
         if self.adv_weight is not None:
             for p in self.model.D.parameters():
                 p.grad = None
@@ -247,9 +254,12 @@ class IRFDTrainer:
     def _static_body(self):
         x_all, loss_out, lid_out, lrec_out = self._static
         b = x_all.size(0) // 2
-        self.zero_grad(encoders_direct=True)
+        from . import generator
+
+        self.zero_grad(encoders_direct=True, gd_direct=True)
         grp = self.model.encoder_group
         grp.grad_targets = self._enc_targets
+        generator.GRAD_TARGETS = self._gd_targets   # ONE generator call per step: its backward writes gflat in place
         try:
             x = self._prep(x_all)
             img, f, _ = self.model.forward_static_stacked(x, self.ctrl)
@@ -262,6 +272,7 @@ class IRFDTrainer:
             self._backward_and_update(loss, static=True)
         finally:
             grp.grad_targets = None
+            generator.GRAD_TARGETS = None
         loss_out.copy_(loss.detach())
         lid_out.copy_(l_identity.detach())
         lrec_out.copy_(l_recon.detach())
