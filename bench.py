@@ -364,7 +364,7 @@ def build_roofline(fam, rsteps):
     peak_bw = float(peaks.get("hbm_gbs", 6650.0))
     traffic = None
     try:  # per-launch DRAM bytes of the dominant family from the committed ncu capture (scripts/ncu_traffic.sh)
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as fh:
             traffic = json.load(fh)
     except Exception:
         pass
@@ -392,8 +392,9 @@ def build_roofline(fam, rsteps):
                                          "achieved_gbs": v["flops"] / (v["ms"] * 1e-3) / 1e9,
                                          "frac_of_measured_hbm": v["flops"] / (v["ms"] * 1e-3) / 1e9 / peak_bw}
                                      for k, v in hbm.items()},
-                    "ncu": "profiles/r1_launches_v3_summary.md, profiles/r1_launches_final2_summary.md, profiles/r1_ncu_shapes_summary.md, "
-                           "profiles/r1_conv_shapes.md (per-shape roofline)"}
+                    "ncu": "profiles/r2_launches_summary.md (launch list with DRAM bytes), profiles/r2_ncu_full_summary.md "
+                           "(--set full of the top kernels), profiles/r2_conv_shapes.md (per-shape roofline), "
+                           "profiles/r2_graph_timeline.md"}
 
     return roofline
 
