@@ -54,6 +54,59 @@ linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, cons
   }
 }
 
+// Long-K variant (the 6144 -> 512 first mapping layer): COLS output columns per block, so the [B, K] activations go
+// through L2 N / COLS times instead of N times (168 us -> the x traffic of 805 MB drops 4x).  Per output the k partition
+// per thread and the reduction order are those of linear_fwd_kernel: bit-identical results.
+template <int ROWS, int COLS>
+__global__ void __launch_bounds__(32 * kFcWarps)
+linear_fwd_cols_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                       float* __restrict__ y, int B, int N, int K, float wmul, float bmul, int lrelu) {
+  __shared__ float part[kFcWarps][ROWS][COLS];
+  const int n0 = blockIdx.x * COLS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b0 = 0; b0 < B; b0 += ROWS) {
+    float acc[ROWS][COLS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) acc[r][c] = 0.f;
+    for (int k = threadIdx.x * 4; k < K; k += 128 * kFcWarps) {
+      float4 wv[COLS];
+#pragma unroll
+      for (int c = 0; c < COLS; ++c)
+        wv[c] = n0 + c < N ? __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + c) * K + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        if (b0 + r < B) {
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)(b0 + r) * K + k));
+#pragma unroll
+          for (int c = 0; c < COLS; ++c) acc[r][c] += xv.x * wv[c].x + xv.y * wv[c].y + xv.z * wv[c].z + xv.w * wv[c].w;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) {
+        const float s = warp_sum(acc[r][c]);
+        if (lane == 0) part[warp][r][c] = s;
+      }
+    __syncthreads();
+    if (threadIdx.x < ROWS * COLS) {
+      const int r = threadIdx.x / COLS, c = threadIdx.x % COLS;
+      if (b0 + r < B && n0 + c < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kFcWarps; ++w) s += part[w][r][c];
+        float v = s * wmul + (bias != nullptr ? bias[n0 + c] * bmul : 0.f);
+        if (lrelu) v = v > 0.f ? v : 0.2f * v;
+        y[(size_t)(b0 + r) * N + n0 + c] = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // dz = dy * (y > 0 ? 1 : 0.2)   (y is the post-activation output; lrelu preserves sign)
 __global__ void lrelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz,
                                  size_t n) {
@@ -109,21 +162,38 @@ linear_dx_kernel(const float* __restrict__ dz, const float* __restrict__ W, floa
 }
 
 // dW[n,k] = beta*dW + wmul * sum_b dz[b,n]*x[b,k] ;  db[n] = beta*db + bmul * sum_b dz[b,n]
-__global__ void linear_dw_kernel(const float* __restrict__ dz, const float* __restrict__ x, float* __restrict__ dW,
-                                 float* __restrict__ db, int B, int N, int K, float wmul, float bmul, float beta) {
+// A thread owns one k and kDwCols consecutive n: x[b][k] is loaded once per b for all of them (the first version gave every
+// n its own block row, so the 64 x K slice of x went through L2 N times: 805 MB and 176 us for the 6144 -> 512 layer).
+// Same summation order per output (b ascending): results are bit-identical to the one-output-per-thread version.
+constexpr int kDwCols = 8;
+__global__ void __launch_bounds__(128)
+linear_dw_kernel(const float* __restrict__ dz, const float* __restrict__ x, float* __restrict__ dW,
+                 float* __restrict__ db, int B, int N, int K, float wmul, float bmul, float beta) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = blockIdx.y;
+  const int n0 = blockIdx.y * kDwCols;
   if (k < K) {
-    float s = 0.f;
-#pragma unroll 8
-    for (int b = 0; b < B; ++b) s += __ldg(dz + (size_t)b * N + n) * __ldg(x + (size_t)b * K + k);
-    float* d = dW + (size_t)n * K + k;
-    *d = (beta != 0.f ? beta * (*d) : 0.f) + wmul * s;
+    float s[kDwCols];
+#pragma unroll
+    for (int j = 0; j < kDwCols; ++j) s[j] = 0.f;
+#pragma unroll 4
+    for (int b = 0; b < B; ++b) {
+      const float xv = __ldg(x + (size_t)b * K + k);
+#pragma unroll
+      for (int j = 0; j < kDwCols; ++j)
+        if (n0 + j < N) s[j] += __ldg(dz + (size_t)b * N + n0 + j) * xv;
+    }
+#pragma unroll
+    for (int j = 0; j < kDwCols; ++j)
+      if (n0 + j < N) {
+        float* d = dW + (size_t)(n0 + j) * K + k;
+        *d = (beta != 0.f ? beta * (*d) : 0.f) + wmul * s[j];
+      }
   }
-  if (db != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
-    float s = 0.f;
-    for (int b = 0; b < B; ++b) s += dz[(size_t)b * N + n];
-    db[n] = (beta != 0.f ? beta * db[n] : 0.f) + bmul * s;
+  if (db != nullptr && blockIdx.x == 0 && threadIdx.x < kDwCols && n0 + (int)threadIdx.x < N) {
+    const int n = n0 + threadIdx.x;
+    float t = 0.f;
+    for (int b = 0; b < B; ++b) t += dz[(size_t)b * N + n];
+    db[n] = (beta != 0.f ? beta * db[n] : 0.f) + bmul * t;
   }
 }
 
@@ -170,6 +240,11 @@ extern "C" int irfd_linear_fwd(const float* x, const float* w, const float* bias
                                float wmul, float bmul, int lrelu, cudaStream_t stream) {
   IRFD_CHECK_ARG(x && w && y && b > 0 && n > 0 && k > 0 && k % 4 == 0, "linear_fwd: bad argument (K %% 4 == 0)");
   const dim3 grid(n), block(32 * kFcWarps);
+  if (k >= 2048 && b > 8) {  // long K: four columns per block (x traffic through L2 / 4)
+    linear_fwd_cols_kernel<16, 4><<<dim3((n + 3) / 4), block, 0, stream>>>(x, w, bias, y, b, n, k, wmul, bmul, lrelu);
+    IRFD_CHECK_LAUNCH();
+    return IRFD_OK;
+  }
   // rows per pass: each pass streams the weight row once, so cover the whole batch in as few passes as possible
   if (b > 16)
     linear_fwd_kernel<32><<<grid, block, 0, stream>>>(x, w, bias, y, b, n, k, wmul, bmul, lrelu);
@@ -201,7 +276,8 @@ extern "C" int irfd_linear_bwd(const float* dz, const float* x, const float* w, 
   }
   if (dw != nullptr) {
     IRFD_CHECK_ARG(x != nullptr, "linear_bwd: dw needs x");
-    linear_dw_kernel<<<dim3((k + 127) / 128, n), 128, 0, stream>>>(dz, x, dw, db, b, n, k, wmul, bmul, dw_beta);
+    linear_dw_kernel<<<dim3((k + 127) / 128, (n + kDwCols - 1) / kDwCols), 128, 0, stream>>>(dz, x, dw, db, b, n, k, wmul, bmul,
+                                                                                      dw_beta);
     IRFD_CHECK_LAUNCH();
   }
   return IRFD_OK;
