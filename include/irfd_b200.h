@@ -159,13 +159,16 @@ int irfd_bn_finalize_sets(const float* psum, const float* psq, int tiles, int c,
                           irfd_stream_t stream);
 int irfd_bn_apply_sets(const void* z, const float* mean, const float* rstd, const float* const* gamma,
                        const float* const* beta, const void* res, const float* mean2, const float* rstd2,
-                       const float* const* gamma2, const float* const* beta2, void* out, long long rows, int c,
-                       int relu, int groups, int nsets, irfd_stream_t stream);
-int irfd_bn_backward_sets(const void* g1, const void* g2, const void* act, const void* z, const float* mean,
-                          const float* rstd, const float* const* gamma, const float* const* beta, void* dz,
-                          void* g_out, float* const* dgamma, float* const* dbeta, float grad_beta, int batch_stats,
-                          long long rows, int c, int groups, int nsets, void* workspace, long long workspace_bytes,
-                          irfd_stream_t stream);
+                       const float* const* gamma2, const float* const* beta2, void* out, void* mask_bits,
+                       long long rows, int c, int relu, int groups, int nsets, irfd_stream_t stream);
+/* mask_bits (optional, relu only): [rows][c/8] bytes, bit t of byte j = out[row][8j+t] > 0.  irfd_bn_backward_sets takes
+ * it in place of the post-ReLU tensor when act_is_bits != 0 (a sixteenth of the bytes on the widest activations).
+ * With g_out != NULL the reduce pass stores the masked gradient and the apply pass reads only g_out and z. */
+int irfd_bn_backward_sets(const void* g1, const void* g2, const void* act, int act_is_bits, const void* z,
+                          const float* mean, const float* rstd, const float* const* gamma, const float* const* beta,
+                          void* dz, void* g_out, float* const* dgamma, float* const* dbeta, float grad_beta,
+                          int batch_stats, long long rows, int c, int groups, int nsets, void* workspace,
+                          long long workspace_bytes, irfd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Layout / gather kernels for the strided ResNet convs and pooling (torchvision resnet.py:197-205, 133-137, 241).

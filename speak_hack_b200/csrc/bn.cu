@@ -192,8 +192,8 @@ struct BnAffine {
 template <int RES_MODE>  // 0 none, 1 identity tensor, 2 second BN branch
 __global__ void __launch_bounds__(kRvThreads)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ z, BnAffine p1, const __nv_bfloat16* __restrict__ res, BnAffine p2,
-                __nv_bfloat16* __restrict__ out, long long rows, int C, int rows_per_blk, int relu, int gps,
-                int reverse) {
+                __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ bits, long long rows, int C, int rows_per_blk,
+                int relu, int gps, int reverse) {
   constexpr int RB = 8;  // rows per thread in flight: 8 (z only) or 16 (z + residual) 16-byte loads
   RowVec rv(C);
   if (!rv.active) return;
@@ -205,6 +205,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z, BnAffine p1, const __nv_bfl
     const size_t goff = (size_t)by * rows * C;
     z += goff;
     out += goff;
+    if (bits != nullptr) bits += goff >> 3;
     if (RES_MODE != 0) res += goff;
     p1.mean += (size_t)by * C;
     p1.rstd += (size_t)by * C;
@@ -272,7 +273,20 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z, BnAffine p1, const __nv_bfl
 #pragma unroll
           for (int t = 0; t < 8; ++t) o[t] = fmaxf(o[t], 0.f);
         }
-        store8(out + off, o);
+        uint4 q;
+        q.x = pack_bf16x2(o[0], o[1]);
+        q.y = pack_bf16x2(o[2], o[3]);
+        q.z = pack_bf16x2(o[4], o[5]);
+        q.w = pack_bf16x2(o[6], o[7]);
+        *reinterpret_cast<uint4*>(out + off) = q;
+        if (bits != nullptr) {  // bit t = (bf16 output of channel cv*8+t) > 0: the ReLU mask the backward pass needs
+          auto pos2 = [](uint32_t w) -> uint32_t {  // two bf16 lanes -> two bits (value > 0)
+            return (((w & 0x7fffu) != 0u && (w & 0x8000u) == 0u) ? 1u : 0u) |
+                   (((w & 0x7fff0000u) != 0u && (w & 0x80000000u) == 0u) ? 2u : 0u);
+          };
+          const uint32_t b = pos2(q.x) | (pos2(q.y) << 2) | (pos2(q.z) << 4) | (pos2(q.w) << 6);
+          bits[(size_t)rr * (C >> 3) + rv.cv] = (uint8_t)b;
+        }
       }
     }
   }
@@ -282,9 +296,13 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z, BnAffine p1, const __nv_bfl
 // Backward.  g = (g1 [+ g2]) * (act > 0) where `act` is the post-ReLU tensor of the forward pass.
 //   reduce  : per-block partials of  sum(g), sum(g * xhat)            xhat = (z - mean) * rstd
 //   finalize: dgamma = sum(g*xhat), dbeta = sum(g); c1 = dbeta/n, c2 = dgamma/n
-//   apply   : dz = gamma*rstd * (g - c1 - xhat*c2)     (+ optional copy of the masked g for the identity shortcut)
+//   apply   : dz = gamma*rstd * (g - c1 - xhat*c2)
+// When the caller wants the masked g (the identity-shortcut gradient of a Bottleneck), the REDUCE pass stores it and the
+// apply pass reads that one tensor back instead of g1, g2 and act again: 4R+1W + 2R+1W tensor passes instead of
+// 4R + 4R+2W on the widest activations of the network.
 // ---------------------------------------------------------------------------------------------------------------
-// MASK: 0 = no ReLU on this BN output, 1 = mask from the saved post-ReLU tensor `act`, 2 = mask recomputed from z.
+// MASK: 0 = no ReLU on this BN output, 1 = mask from the saved post-ReLU tensor `act`, 2 = mask recomputed from z,
+// 3 = mask from the bit plane bn_apply wrote (one byte per 8 channels; `qa.x` carries the byte).
 template <bool HAS_G2, int MASK>
 __device__ __forceinline__ void bn_bwd_masked_grad(const uint4& qg, const uint4& qh, const uint4& qa, const float (&zz)[8],
                                                    const float (&m)[8], const float (&rs)[8], const float (&ga)[8],
@@ -304,15 +322,19 @@ __device__ __forceinline__ void bn_bwd_masked_grad(const uint4& qg, const uint4&
   } else if (MASK == 2) {
 #pragma unroll
     for (int t = 0; t < 8; ++t) g[t] = (ga[t] * ((zz[t] - m[t]) * rs[t]) + be[t]) > 0.f ? g[t] : 0.f;
+  } else if (MASK == 3) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) g[t] = ((qa.x >> t) & 1u) ? g[t] : 0.f;
   }
 }
 
-template <bool HAS_G2, int MASK>
+template <bool HAS_G2, int MASK, bool G_OUT>
 __global__ void __launch_bounds__(kRvThreads, 2)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
                      const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ z,
                      const float* __restrict__ mean, const float* __restrict__ rstd, FSet gamma_s, FSet beta_s,
-                     float* __restrict__ partial, long long rows, int C, int rows_per_blk, int gps, int reverse) {
+                     float* __restrict__ partial, __nv_bfloat16* __restrict__ g_out, long long rows, int C,
+                     int rows_per_blk, int gps, int reverse) {
   constexpr int RB = kRowBatch;  // measured: 8 rows for the two-tensor instances is slower (register pressure)
   // reverse: start with the rows the producer of g (a dgrad GEMM, ascending) wrote last: they are still in L2; the
   // apply pass then runs ascending and starts with what this pass touched last.  Partials stay indexed by row range.
@@ -327,7 +349,9 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
     g1 += goff;
     if (HAS_G2) g2 += goff;
     if (MASK == 1) act += goff;
+    if (MASK == 3) act = reinterpret_cast<const __nv_bfloat16*>(reinterpret_cast<const uint8_t*>(act) + (goff >> 3));
     z += goff;
+    if (G_OUT) g_out += goff;
     mean += (size_t)by * C;
     rstd += (size_t)by * C;
     partial += (size_t)by * gridDim.x * 2 * C;
@@ -357,6 +381,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
           if (HAS_G2) qh[u] = ldg16(g2 + off);
           qz[u] = ldg16(z + off);
           if (MASK == 1) qa[u] = ldg16(act + off);
+          if (MASK == 3) qa[u].x = __ldg(reinterpret_cast<const uint8_t*>(act) + (off >> 3));
         }
       }
 #pragma unroll
@@ -366,6 +391,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
           float g[8], zz[8];
           unpack8(qz[u], zz);
           bn_bwd_masked_grad<HAS_G2, MASK>(qg[u], qh[u], qa[u], zz, m, rs, ga, be, g);
+          if (G_OUT) store8(g_out + (size_t)rr * C + rv.cv * 8, g);
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             acc[0][t] += g[t];
@@ -429,6 +455,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* _
     g1 += goff;
     if (HAS_G2) g2 += goff;
     if (MASK == 1) act += goff;
+    if (MASK == 3) act = reinterpret_cast<const __nv_bfloat16*>(reinterpret_cast<const uint8_t*>(act) + (goff >> 3));
     z += goff;
     dz += goff;
     if (G_OUT) g_out += goff;
@@ -460,6 +487,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* _
         if (HAS_G2) qh[u] = ldg16(g2 + off);
         qz[u] = ldg16(z + off);
         if (MASK == 1) qa[u] = ldg16(act + off);
+        if (MASK == 3) qa[u].x = __ldg(reinterpret_cast<const uint8_t*>(act) + (off >> 3));
       }
     }
 #pragma unroll
@@ -509,22 +537,29 @@ struct BnBwdLaunch {
 template <bool HAS_G2, int MASK>
 static void launch_bn_bwd(const BnBwdLaunch& L) {
   // co-residency with the side-stream weight-gradient GEMMs (see host_util.h)
-  prefer_max_shared_carveout(reinterpret_cast<const void*>(&bn_bwd_reduce_kernel<HAS_G2, MASK>));
-  prefer_max_shared_carveout(reinterpret_cast<const void*>(&bn_bwd_apply_kernel<HAS_G2, MASK, true>));
+  prefer_max_shared_carveout(reinterpret_cast<const void*>(&bn_bwd_reduce_kernel<HAS_G2, MASK, true>));
+  prefer_max_shared_carveout(reinterpret_cast<const void*>(&bn_bwd_reduce_kernel<HAS_G2, MASK, false>));
   prefer_max_shared_carveout(reinterpret_cast<const void*>(&bn_bwd_apply_kernel<HAS_G2, MASK, false>));
+  prefer_max_shared_carveout(reinterpret_cast<const void*>(&bn_bwd_apply_kernel<false, 0, false>));
   prefer_max_shared_carveout(reinterpret_cast<const void*>(&bn_bwd_finalize_kernel));
-  bn_bwd_reduce_kernel<HAS_G2, MASK><<<L.grid, kRvThreads, L.smem, L.stream>>>(
-      L.g1, L.g2, L.act, L.z, L.mean, L.rstd, L.gamma, L.beta, L.partial, L.grows, L.c, L.rpb, L.gps, zigzag());
+  if (L.g_out != nullptr)
+    bn_bwd_reduce_kernel<HAS_G2, MASK, true><<<L.grid, kRvThreads, L.smem, L.stream>>>(
+        L.g1, L.g2, L.act, L.z, L.mean, L.rstd, L.gamma, L.beta, L.partial, L.g_out, L.grows, L.c, L.rpb, L.gps,
+        zigzag());
+  else
+    bn_bwd_reduce_kernel<HAS_G2, MASK, false><<<L.grid, kRvThreads, L.smem, L.stream>>>(
+        L.g1, L.g2, L.act, L.z, L.mean, L.rstd, L.gamma, L.beta, L.partial, nullptr, L.grows, L.c, L.rpb, L.gps,
+        zigzag());
   bn_bwd_finalize_kernel<<<dim3(L.c / kFinCh, L.nsets), 1024, 0, L.stream>>>(L.partial, L.nblk, L.c, (double)L.grows,
                                                                              L.dgamma, L.dbeta, L.grad_beta, L.c1, L.c2,
                                                                              L.batch_stats, L.gps);
-  if (L.g_out != nullptr)
-    bn_bwd_apply_kernel<HAS_G2, MASK, true><<<L.grid, kRvThreads, 0, L.stream>>>(
-        L.g1, L.g2, L.act, L.z, L.mean, L.rstd, L.gamma, L.beta, L.c1, L.c2, L.dz, L.g_out, L.grows, L.c, L.rpb,
+  if (L.g_out != nullptr)  // the masked gradient is already in g_out (bf16, the value its other consumers see)
+    bn_bwd_apply_kernel<false, 0, false><<<L.grid, kRvThreads, 0, L.stream>>>(
+        L.g_out, nullptr, nullptr, L.z, L.mean, L.rstd, L.gamma, L.beta, L.c1, L.c2, L.dz, nullptr, L.grows, L.c, L.rpb,
         L.gps);
   else
     bn_bwd_apply_kernel<HAS_G2, MASK, false><<<L.grid, kRvThreads, 0, L.stream>>>(
-        L.g1, L.g2, L.act, L.z, L.mean, L.rstd, L.gamma, L.beta, L.c1, L.c2, L.dz, L.g_out, L.grows, L.c, L.rpb,
+        L.g1, L.g2, L.act, L.z, L.mean, L.rstd, L.gamma, L.beta, L.c1, L.c2, L.dz, nullptr, L.grows, L.c, L.rpb,
         L.gps);
 }
 
@@ -614,8 +649,8 @@ extern "C" int irfd_bn_eval_rstd(const float* running_var, float eps, float* rst
 // gamma/beta (and gamma2/beta2): host arrays of `nsets` device pointers, set = group / (groups / nsets).
 extern "C" int irfd_bn_apply_sets(const void* z, const float* mean, const float* rstd, const float* const* gamma,
                                   const float* const* beta, const void* res, const float* mean2, const float* rstd2,
-                                  const float* const* gamma2, const float* const* beta2, void* out, long long rows,
-                                  int c, int relu, int groups, int nsets, cudaStream_t stream) {
+                                  const float* const* gamma2, const float* const* beta2, void* out, void* mask_bits,
+                                  long long rows, int c, int relu, int groups, int nsets, cudaStream_t stream) {
   IRFD_CHECK_ARG(z && mean && rstd && gamma && beta && out, "bn_apply: null pointer");
   IRFD_CHECK_ARG(c % 8 == 0 && c <= 2048 && rows > 0, "bn_apply: C must be a multiple of 8 and <= 2048");
   IRFD_CHECK_ARG(groups >= 1 && rows % groups == 0, "bn_apply: rows must split evenly into groups");
@@ -628,14 +663,16 @@ extern "C" int irfd_bn_apply_sets(const void* z, const float* mean, const float*
   auto zz = reinterpret_cast<const __nv_bfloat16*>(z);
   auto rr = reinterpret_cast<const __nv_bfloat16*>(res);
   auto oo = reinterpret_cast<__nv_bfloat16*>(out);
+  auto mb = reinterpret_cast<uint8_t*>(mask_bits);  // optional [rows][c/8] ReLU mask plane for irfd_bn_backward_sets
+  IRFD_CHECK_ARG(mb == nullptr || relu, "bn_apply: a mask plane needs relu");
   const dim3 grid(nblk, groups);
   const int gps = groups / nsets;
   if (res == nullptr)
-    bn_apply_kernel<0><<<grid, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, grows, c, rpb, relu, gps, zigzag());
+    bn_apply_kernel<0><<<grid, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, mb, grows, c, rpb, relu, gps, zigzag());
   else if (mean2 == nullptr)
-    bn_apply_kernel<1><<<grid, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, grows, c, rpb, relu, gps, zigzag());
+    bn_apply_kernel<1><<<grid, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, mb, grows, c, rpb, relu, gps, zigzag());
   else
-    bn_apply_kernel<2><<<grid, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, grows, c, rpb, relu, gps, zigzag());
+    bn_apply_kernel<2><<<grid, kRvThreads, 0, stream>>>(zz, p1, rr, p2, oo, mb, grows, c, rpb, relu, gps, zigzag());
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }
@@ -648,7 +685,8 @@ extern "C" int irfd_bn_apply(const void* z, const float* mean, const float* rstd
   const float* b1[1] = {beta};
   const float* g2[1] = {gamma2};
   const float* b2[1] = {beta2};
-  return irfd_bn_apply_sets(z, mean, rstd, g1, b1, res, mean2, rstd2, g2, b2, out, rows, c, relu, groups, 1, stream);
+  return irfd_bn_apply_sets(z, mean, rstd, g1, b1, res, mean2, rstd2, g2, b2, out, nullptr, rows, c, relu, groups, 1,
+                            stream);
 }
 
 extern "C" long long irfd_bn_bwd_workspace_bytes(long long rows, int c, int groups) {
@@ -661,11 +699,13 @@ extern "C" long long irfd_bn_bwd_workspace_bytes(long long rows, int c, int grou
 // Full BN backward (reduce -> finalize -> apply).  workspace: [groups][nblk][2][C] partials, c1[groups][C], c2[...].
 // groups = TOTAL statistic groups; gamma/beta/dgamma/dbeta: host arrays of `nsets` device pointers (beta may be NULL =
 // no ReLU-from-z mask); each set's dgamma/dbeta sums its groups / nsets groups.
-extern "C" int irfd_bn_backward_sets(const void* g1, const void* g2, const void* act, const void* z, const float* mean,
-                                     const float* rstd, const float* const* gamma, const float* const* beta, void* dz,
-                                     void* g_out, float* const* dgamma, float* const* dbeta, float grad_beta,
-                                     int batch_stats, long long rows, int c, int groups, int nsets, void* workspace,
-                                     long long workspace_bytes, cudaStream_t stream) {
+// act_is_bits: `act` is the [rows][c/8] mask plane irfd_bn_apply_sets wrote, not the post-ReLU tensor.
+extern "C" int irfd_bn_backward_sets(const void* g1, const void* g2, const void* act, int act_is_bits, const void* z,
+                                     const float* mean, const float* rstd, const float* const* gamma,
+                                     const float* const* beta, void* dz, void* g_out, float* const* dgamma,
+                                     float* const* dbeta, float grad_beta, int batch_stats, long long rows, int c,
+                                     int groups, int nsets, void* workspace, long long workspace_bytes,
+                                     cudaStream_t stream) {
   IRFD_CHECK_ARG(g1 && z && mean && rstd && gamma && dz && dgamma && dbeta && workspace, "bn_backward: null pointer");
   IRFD_CHECK_ARG(c % 8 == 0 && c <= 2048 && rows > 0, "bn_backward: C must be a multiple of 8 and <= 2048");
   IRFD_CHECK_ARG(groups >= 1 && rows % groups == 0, "bn_backward: rows must split evenly into groups");
@@ -702,15 +742,17 @@ extern "C" int irfd_bn_backward_sets(const void* g1, const void* g2, const void*
   L.grows = grows; L.c = c; L.rpb = rpb; L.nblk = nblk; L.groups = groups;
   L.nsets = nsets; L.gps = groups / nsets;
   const bool has_beta = beta != nullptr && beta[0] != nullptr;
-  const int mask = A != nullptr ? 1 : (has_beta ? 2 : 0);
+  const int mask = A != nullptr ? (act_is_bits ? 3 : 1) : (has_beta ? 2 : 0);
   if (G2 != nullptr) {
     if (mask == 0) launch_bn_bwd<true, 0>(L);
     else if (mask == 1) launch_bn_bwd<true, 1>(L);
-    else launch_bn_bwd<true, 2>(L);
+    else if (mask == 2) launch_bn_bwd<true, 2>(L);
+    else launch_bn_bwd<true, 3>(L);
   } else {
     if (mask == 0) launch_bn_bwd<false, 0>(L);
     else if (mask == 1) launch_bn_bwd<false, 1>(L);
-    else launch_bn_bwd<false, 2>(L);
+    else if (mask == 2) launch_bn_bwd<false, 2>(L);
+    else launch_bn_bwd<false, 3>(L);
   }
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
@@ -724,6 +766,6 @@ extern "C" int irfd_bn_backward(const void* g1, const void* g2, const void* act,
   const float* be[1] = {beta};
   float* dg[1] = {dgamma};
   float* db[1] = {dbeta};
-  return irfd_bn_backward_sets(g1, g2, act, z, mean, rstd, ga, be, dz, g_out, dg, db, grad_beta, batch_stats, rows, c,
-                               groups, 1, workspace, workspace_bytes, stream);
+  return irfd_bn_backward_sets(g1, g2, act, 0, z, mean, rstd, ga, be, dz, g_out, dg, db, grad_beta, batch_stats, rows,
+                               c, groups, 1, workspace, workspace_bytes, stream);
 }

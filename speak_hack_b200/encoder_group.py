@@ -108,9 +108,9 @@ class _EncoderGroupFn(torch.autograd.Function):
                                               [b.running_mean for b in bns], [b.running_var for b in bns], U, G, E)
             return _Stats(mean, rstd)
 
-        def apply(z, st, bns, relu=True, res=None, bn2=None):
+        def apply(z, st, bns, relu=True, res=None, bn2=None, want_mask=False):
             return ops.bn_apply_sets(z, st.mean, st.rstd, [b.weight for b in bns], [b.bias for b in bns], res=res,
-                                     bn2=bn2, relu=relu, groups=GT)
+                                     bn2=bn2, relu=relu, groups=GT, want_mask=want_mask)
 
         S = {}
         if col0 is None:
@@ -161,11 +161,14 @@ class _EncoderGroupFn(torch.autograd.Function):
                                                      ops.EPI_STATS, wgroups=E)
                     dbn = [b.downsample[1] for b in blks]
                     std = stats(dbn, s, q, nb * ho * wo)
-                    out = apply(z3, st3, bn3, res=zd,
+                    out = apply(z3, st3, bn3, res=zd, want_mask=recorded,
                                 bn2=(std.mean, std.rstd, [b.weight for b in dbn], [b.bias for b in dbn]))
                 else:
-                    out = apply(z3, st3, bn3, res=xin)
-                S["blocks"].append((li, blks, xin, z1, st1, a1, col2, z2, st2, a2, z3, st3, xs, zd, std, out))
+                    out = apply(z3, st3, bn3, res=xin, want_mask=recorded)
+                out, obits = out if recorded else (out, None)
+                # the backward pass needs the block output only as a ReLU mask: keep the bit plane (1/16 of the bytes
+                # to read back), the tensor itself lives on as the next block's input
+                S["blocks"].append((li, blks, xin, z1, st1, a1, col2, z2, st2, a2, z3, st3, xs, zd, std, obits))
                 cur = out
         feat = ops.avgpool_fwd(cur)
         counters = [c for e in encs for c in e._bn_counters()]
@@ -197,11 +200,11 @@ class _EncoderGroupFn(torch.autograd.Function):
             grads[p] = t
             return t
 
-        def bn_bwd(bns, st, g1, g2_, act, z, want_g_out=False, mask_from_z=False):
+        def bn_bwd(bns, st, g1, g2_, act, z, want_g_out=False, mask_from_z=False, act_bits=None):
             r = ops.bn_backward_sets(g1, g2_, None if mask_from_z else act, z, st.mean, st.rstd,
                                      [b.weight for b in bns], [b.bias for b in bns] if mask_from_z else None,
                                      dgammas=[tgt(b.weight) for b in bns], dbetas=[tgt(b.bias) for b in bns],
-                                     want_g_out=want_g_out, batch_stats=True, groups=GT)
+                                     want_g_out=want_g_out, batch_stats=True, groups=GT, act_bits=act_bits)
             return (r[0], r[3]) if want_g_out else r[0]
 
         side = ops.side_stream(dfeat.device)
@@ -215,13 +218,13 @@ class _EncoderGroupFn(torch.autograd.Function):
 
         cur_li = None
         for rec in reversed(S["blocks"]):
-            li, blks, xin, z1, st1, a1, col2, z2, st2, a2, z3, st3, xs, zd, std, out = rec
+            li, blks, xin, z1, st1, a1, col2, z2, st2, a2, z3, st3, xs, zd, std, obits = rec
             if cur_li is not None and li != cur_li and cb is not None:
                 cb("stage", cur_li)  # every gradient of ResNet stage `cur_li` (all encoders) has been written
             cur_li = li
             nb, hh, ww, _cin = xin.shape
             planes = a1.shape[-1]
-            dz3, gmask = bn_bwd([b.bn3 for b in blks], st3, g, g2, out, z3, want_g_out=True)
+            dz3, gmask = bn_bwd([b.bn3 for b in blks], st3, g, g2, None, z3, want_g_out=True, act_bits=obits)
             # dgrad first, wgrad second: the persistent dgrad takes the SMs, the wgrad (side stream) follows it and
             # runs beside the BatchNorm backward that consumes the dgrad's output
             d_a2 = ops.conv_gemm_grouped(dz3, _stack_pack([b.conv3 for b in blks], ops.PACK_DGRAD), 1, wgroups=E)

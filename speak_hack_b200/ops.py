@@ -474,8 +474,7 @@ def bn_backward(g1, g2, act, z, mean, rstd, gamma, want_g_out=False, batch_stats
     dbeta = torch.empty(c, dtype=F32, device=z.device)
     ws = workspace(lib.irfd_bn_bwd_workspace_bytes(rows, c, groups), z.device)
     # algorithmic HBM bytes: both passes read g1 [, g2] [, act], z; the apply pass writes dz [, g_out]
-    n_in = 2 + (g2 is not None) + (act is not None)
-    nbytes = 2.0 * rows * c * (2 * n_in + 1 + (1 if want_g_out else 0))
+    nbytes = _bn_bwd_bytes(rows, c, g2 is not None, 1.0 if act is not None else 0.0, want_g_out)
     with _timed("bn_backward (reduce+finalize+apply, HBM)", nbytes):
         _bn_backward_call(g1, g2, act, z, mean, rstd, gamma, beta, dz, g_out, dgamma, dbeta, batch_stats, rows, c, groups,
                           ws)
@@ -526,27 +525,39 @@ def bn_finalize_sets(ssum, ssq, count, eps, momentum, running_means, running_var
     return mean, rstd
 
 
-def bn_apply_sets(z, mean, rstd, gammas, betas, res=None, bn2=None, relu=True, groups=1):
+def bn_apply_sets(z, mean, rstd, gammas, betas, res=None, bn2=None, relu=True, groups=1, want_mask=False):
     """out = [relu](BN(z) [+ res | + BN2(res)]) with per-set gamma/beta lists (len = nsets) and per-group statistics
-    (`groups` = TOTAL statistic groups); bn2 = (mean2, rstd2, gammas2, betas2)."""
+    (`groups` = TOTAL statistic groups); bn2 = (mean2, rstd2, gammas2, betas2).  want_mask: also return the ReLU mask as
+    a bit plane ([rows, C/8] uint8) for bn_backward_sets(act_bits=...)."""
     _chk(z, BF16, "z")
     c = z.shape[-1]
     rows = z.numel() // c
     out = torch.empty_like(z)
+    bits = torch.empty((rows, c // 8), dtype=torch.uint8, device=z.device) if want_mask else None
     m2 = r2 = g2 = b2 = None
     if bn2 is not None:
         m2, r2, g2, b2 = bn2
     _call("irfd_bn_apply_sets", z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _ptr_array(gammas), _ptr_array(betas),
           _ptr(res), _ptr(m2), _ptr(r2), _ptr_array(g2) if g2 is not None else _ptr_array([None] * len(gammas)),
-          _ptr_array(b2) if b2 is not None else _ptr_array([None] * len(gammas)), out.data_ptr(), rows, c,
+          _ptr_array(b2) if b2 is not None else _ptr_array([None] * len(gammas)), out.data_ptr(), _ptr(bits), rows, c,
           1 if relu else 0, groups, len(gammas), _stream())
-    return out
+    return (out, bits) if want_mask else out
+
+
+def _bn_bwd_bytes(rows, c, has_g2, mask_units, want_g_out):
+    """Algorithmic HBM bytes of reduce + apply.  Without g_out both passes read g1 [, g2] [, mask], z and the apply pass
+    writes dz; with g_out the reduce pass also writes the masked gradient and the apply pass reads only that and z."""
+    n_in = 2 + (1 if has_g2 else 0) + mask_units
+    if want_g_out:
+        return 2.0 * rows * c * (n_in + 1 + 3)
+    return 2.0 * rows * c * (2 * n_in + 1)
 
 
 def bn_backward_sets(g1, g2, act, z, mean, rstd, gammas, betas=None, dgammas=None, dbetas=None, want_g_out=False,
-                     batch_stats=True, groups=1):
+                     batch_stats=True, groups=1, act_bits=None):
     """BN backward for `len(gammas)` parameter sets in one launch sequence.  dgammas/dbetas: optional lists of [C] fp32
-    output tensors (written, not accumulated); allocated as one [nsets, C] tensor each when omitted.
+    output tensors (written, not accumulated); allocated as one [nsets, C] tensor each when omitted.  The ReLU mask comes
+    from `act` (post-ReLU tensor), `act_bits` (bn_apply_sets(want_mask=True)) or is recomputed from z when betas is given.
     Returns dz, dgamma(s), dbeta(s) [, masked g]."""
     lib = _lib.load()
     c = z.shape[-1]
@@ -559,10 +570,13 @@ def bn_backward_sets(g1, g2, act, z, mean, rstd, gammas, betas=None, dgammas=Non
         db_all = torch.empty((nsets, c), dtype=F32, device=z.device)
         dgammas, dbetas = list(dg_all.unbind(0)), list(db_all.unbind(0))
     ws = workspace(lib.irfd_bn_bwd_workspace_bytes(rows, c, groups), z.device)
-    n_in = 2 + (g2 is not None) + (act is not None)
-    nbytes = 2.0 * rows * c * (2 * n_in + 1 + (1 if want_g_out else 0))
+    if act_bits is not None and act is not None:
+        raise _lib.IrfdError("bn_backward_sets: pass act or act_bits, not both")
+    mask_units = 1.0 if act is not None else (1.0 / 16 if act_bits is not None else 0.0)
+    nbytes = _bn_bwd_bytes(rows, c, g2 is not None, mask_units, want_g_out)
     with _timed("bn_backward (reduce+finalize+apply, HBM)", nbytes):
-        _call("irfd_bn_backward_sets", g1.data_ptr(), _ptr(g2), _ptr(act), z.data_ptr(), mean.data_ptr(),
+        _call("irfd_bn_backward_sets", g1.data_ptr(), _ptr(g2), _ptr(act if act_bits is None else act_bits),
+              0 if act_bits is None else 1, z.data_ptr(), mean.data_ptr(),
               rstd.data_ptr(), _ptr_array(gammas), _ptr_array(betas) if betas is not None else None, dz.data_ptr(),
               _ptr(g_out), _ptr_array(dgammas), _ptr_array(dbetas), 0.0, 1 if batch_stats else 0, rows, c, groups, nsets,
               ws.data_ptr(), ws.numel(), _stream(), launches=3)

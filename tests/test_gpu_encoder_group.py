@@ -96,6 +96,7 @@ def test_grouped_wgrad_equals_separate_calls(cuda_device, ksize, cin, cout, hw, 
 
 
 def test_bn_sets_equal_separate_calls(cuda_device):
+    import irfd_oracle as O
     from speak_hack_b200 import ops
 
     dev = cuda_device
@@ -116,6 +117,25 @@ def test_bn_sets_equal_separate_calls(cuda_device):
     g1 = _bf(torch.randn(rows, c, generator=g).to(dev))
     dz, dgs, dbs, gm = ops.bn_backward_sets(g1, None, out, z, mean, rstd, gam, None, want_g_out=True, groups=E * G)
     dz2, dgs2, dbs2 = ops.bn_backward_sets(g1, None, None, z, mean, rstd, gam, bet, groups=E * G)
+    # the ReLU mask as a bit plane (one byte per 8 channels) is the same mask as the post-ReLU tensor
+    outb, bits = ops.bn_apply_sets(z, mean, rstd, gam, bet, res=res, relu=True, groups=E * G, want_mask=True)
+    assert torch.equal(outb, out) and bits.shape == (rows, c // 8)
+    want_bits = ((out.view(rows, c // 8, 8) > 0).to(torch.int32) << torch.arange(8, device=dev, dtype=torch.int32)).sum(-1)
+    assert torch.equal(bits.to(torch.int32), want_bits)
+    g2 = _bf(torch.randn(rows, c, generator=g).to(dev))
+    for gg in (None, g2):
+        for want in (True, False):
+            a = ops.bn_backward_sets(g1, gg, out, z, mean, rstd, gam, None, want_g_out=want, groups=E * G)
+            b = ops.bn_backward_sets(g1, gg, None, z, mean, rstd, gam, None, want_g_out=want, groups=E * G, act_bits=bits)
+            assert torch.equal(a[0], b[0]) and (not want or torch.equal(a[3], b[3]))
+            assert all(torch.equal(x, y) for x, y in zip(a[1] + a[2], b[1] + b[2]))
+    # g_out comes from the reduce pass and the apply pass reads it back (bf16): dz agrees with the fp32-g variant to
+    # one bf16 rounding of g, the parameter gradients exactly
+    a = ops.bn_backward_sets(g1, g2, out, z, mean, rstd, gam, None, want_g_out=True, groups=E * G)
+    b = ops.bn_backward_sets(g1, g2, out, z, mean, rstd, gam, None, want_g_out=False, groups=E * G)
+    assert all(torch.equal(x, y) for x, y in zip(a[1] + a[2], b[1] + b[2]))
+    assert O.rel_l2(a[0].float(), b[0].float()) < 4e-3
+    assert torch.equal(a[3].float(), ((g1.float() + g2.float()) * (out.float() > 0)).to(torch.bfloat16).float())
     per = G * rows_g
     tp = per // 128
     for e in range(E):
