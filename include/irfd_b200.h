@@ -170,6 +170,22 @@ int irfd_bn_backward_sets(const void* g1, const void* g2, const void* act, int a
                           int batch_stats, long long rows, int c, int groups, int nsets, void* workspace,
                           long long workspace_bytes, irfd_stream_t stream);
 
+/* BatchNorm backward with the reduce pass folded into the dgrad GEMM that produces the activation gradient
+ * (torchvision resnet.py:146-152: conv -> bn -> relu -> conv; the second conv's data gradient is the first BN's input):
+ *   irfd_conv_gemm_bnbwd_grouped : out = dgrad(x, wk) * relu-mask(z) (bf16); partial[m tile][2][cout] = per 128-pixel
+ *                                  tile sums of g and g*xhat.  stat_groups = statistic groups of z (multiple of wgroups).
+ *   irfd_bn_backward_finish_sets : dgamma/dbeta from the partials, dz from the masked g and z.  tiles = partial rows per
+ *                                  statistic group; workspace >= 2*groups*c floats. */
+int irfd_conv_gemm_bnbwd_grouped(const void* x, int n, int h, int w, int cin, const void* wk, int cout, int ksize,
+                                 void* out, const void* bn_z, const float* bn_mean, const float* bn_rstd,
+                                 const float* const* bn_gamma, const float* const* bn_beta, float* partial,
+                                 int stat_groups, int wgroups, int force_block_n, irfd_stream_t stream);
+int irfd_bn_backward_finish_sets(const void* g, const void* z, const float* mean, const float* rstd,
+                                 const float* const* gamma, void* dz, float* const* dgamma, float* const* dbeta,
+                                 float grad_beta, int batch_stats, long long rows, int c, int groups, int nsets,
+                                 const float* partial, int tiles, void* workspace, long long workspace_bytes,
+                                 irfd_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Layout / gather kernels for the strided ResNet convs and pooling (torchvision resnet.py:197-205, 133-137, 241).
  *   irfd_pack_conv_weight: fp32 OIHW -> bf16 GEMM operand. mode 0 fprop [o][tap][i]; 1 dgrad [i][flip(tap)][o];

@@ -758,6 +758,42 @@ extern "C" int irfd_bn_backward_sets(const void* g1, const void* g2, const void*
   return IRFD_OK;
 }
 
+// Second half of a BatchNorm backward whose reduce pass ran inside the producing dgrad GEMM's epilogue
+// (irfd_conv_gemm_bnbwd_grouped): g is the MASKED activation gradient, partial [groups][tiles][2][c] the per-tile sums
+// of g and g*xhat.  finalize (dgamma, dbeta, c1, c2) + apply (dz from g and z).  workspace: 2 * groups * c floats.
+extern "C" int irfd_bn_backward_finish_sets(const void* g, const void* z, const float* mean, const float* rstd,
+                                            const float* const* gamma, void* dz, float* const* dgamma,
+                                            float* const* dbeta, float grad_beta, int batch_stats, long long rows,
+                                            int c, int groups, int nsets, const float* partial, int tiles,
+                                            void* workspace, long long workspace_bytes, cudaStream_t stream) {
+  IRFD_CHECK_ARG(g && z && mean && rstd && gamma && dz && dgamma && dbeta && partial && workspace,
+                 "bn_backward_finish: null pointer");
+  IRFD_CHECK_ARG(c % 8 == 0 && c <= 2048 && rows > 0 && tiles > 0, "bn_backward_finish: bad shape");
+  IRFD_CHECK_ARG(groups >= 1 && rows % groups == 0, "bn_backward_finish: rows must split evenly into groups");
+  IRFD_CHECK_ARG(nsets >= 1 && nsets <= kMaxSets && groups % nsets == 0,
+                 "bn_backward_finish: groups must split evenly into 1..4 sets");
+  IRFD_CHECK_ARG(workspace_bytes >= (long long)2 * groups * c * 4, "bn_backward_finish: workspace too small");
+  const long long grows = rows / groups;
+  int nblk, rpb;
+  plan_row_blocks(grows, c, num_sms(), &nblk, &rpb);
+  float* c1 = reinterpret_cast<float*>(workspace);
+  float* c2 = c1 + (size_t)groups * c;
+  const FSet ga = make_fset(gamma, nsets);
+  const FSet be = make_fset(nullptr, nsets);
+  const int gps = groups / nsets;
+  prefer_max_shared_carveout(reinterpret_cast<const void*>(&bn_bwd_apply_kernel<false, 0, false>));
+  prefer_max_shared_carveout(reinterpret_cast<const void*>(&bn_bwd_finalize_kernel));
+  bn_bwd_finalize_kernel<<<dim3(c / kFinCh, nsets), 1024, 0, stream>>>(partial, tiles, c, (double)grows,
+                                                                        make_fsetm(dgamma, nsets),
+                                                                        make_fsetm(dbeta, nsets), grad_beta, c1, c2,
+                                                                        batch_stats, gps);
+  bn_bwd_apply_kernel<false, 0, false><<<dim3(nblk, groups), kRvThreads, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(g), nullptr, nullptr, reinterpret_cast<const __nv_bfloat16*>(z), mean, rstd,
+      ga, be, c1, c2, reinterpret_cast<__nv_bfloat16*>(dz), nullptr, grows, c, rpb, gps);
+  IRFD_CHECK_LAUNCH();
+  return IRFD_OK;
+}
+
 extern "C" int irfd_bn_backward(const void* g1, const void* g2, const void* act, const void* z, const float* mean,
                                 const float* rstd, const float* gamma, const float* beta, void* dz, void* g_out,
                                 float* dgamma, float* dbeta, float grad_beta, int batch_stats, long long rows, int c,

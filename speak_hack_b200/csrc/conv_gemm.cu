@@ -30,7 +30,7 @@
 
 namespace irfd {
 
-enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_STYLE = 2, EPI_AFFINE = 3 };
+enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_STYLE = 2, EPI_AFFINE = 3, EPI_BNBWD = 4 };
 
 struct ConvGemmArgs {
   int M_total, N_total;
@@ -53,6 +53,16 @@ struct ConvGemmArgs {
   int wg_tiles;
   int a_mod_tiles;
   int relu;                  // AFFINE: 0 = none, 1 = ReLU, 2 = leaky ReLU (slope 0.2)
+  // BNBWD: this GEMM is the data gradient of a conv whose INPUT was relu(BN(z)) (torchvision resnet.py:146-152).  Its
+  // epilogue applies the ReLU mask (recomputed from z) to the activation gradient it produces and sums, per channel
+  // and 128-pixel tile, g and g * xhat — the reduce pass of that BatchNorm's backward, which then needs no launch and
+  // no second read of the gradient.  stat_sum receives the partials as [m tile][2][N_total].
+  const __nv_bfloat16* bn_z;  // [M_total][N_total]
+  const float* bn_mean;       // [statistic groups][N_total]
+  const float* bn_rstd;
+  const float* bn_gamma[4];   // per weight group
+  const float* bn_beta[4];
+  int sg_tiles;               // m tiles per statistic group
 };
 
 constexpr int kNumThreads = 320;      // 10 warps
@@ -134,6 +144,13 @@ __device__ __forceinline__ void epilogue_acc(const ConvGemmArgs& p, const CUtens
 #pragma unroll 1
   for (int chunk = 0; chunk < BLOCK_N / 64; ++chunk, ++chunk_counter) {
     uint32_t v[32];
+    uint32_t zw[16];  // BNBWD: this thread's 16 rows x 2 channels of z for the column phase, in flight during the drain
+    if constexpr (MODE == EPI_BNBWD) {
+      const __nv_bfloat16* zp =
+          p.bn_z + (size_t)(m0 + (etid >> 5) * 16) * p.N_total + ng0 + chunk * 64 + 2 * (etid & 31);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) zw[i] = __ldg(reinterpret_cast<const uint32_t*>(zp + (size_t)i * p.N_total));
+    }
     const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc_col + chunk * 64 + half * 32;
     tmem_ld32(taddr, v);
     tmem_ld_wait();
@@ -218,6 +235,60 @@ __device__ __forceinline__ void epilogue_acc(const ConvGemmArgs& p, const CUtens
     }
     fence_proxy_async_smem();
     named_bar_sync(1, kEpiThreads);
+    if constexpr (MODE == EPI_BNBWD) {
+      // column phase on the staged chunk: thread = (channel pair, 16-row group); mask the gradient in place, sum
+      // g and g * xhat over the rows (same expressions as bn_bwd_reduce_kernel<., 2>)
+      const int pr = etid & 31;
+      const int g = etid >> 5;
+      const int cc = ng0 + chunk * 64 + 2 * pr;
+      const int grp = m_tile / p.wg_tiles;
+      const float* gam = grp == 0 ? p.bn_gamma[0] : (grp == 1 ? p.bn_gamma[1] : (grp == 2 ? p.bn_gamma[2] : p.bn_gamma[3]));
+      const float* bet = grp == 0 ? p.bn_beta[0] : (grp == 1 ? p.bn_beta[1] : (grp == 2 ? p.bn_beta[2] : p.bn_beta[3]));
+      const size_t so = (size_t)(m_tile / p.sg_tiles) * p.N_total + cc;
+      const float2 mm = __ldg(reinterpret_cast<const float2*>(p.bn_mean + so));
+      const float2 rs = __ldg(reinterpret_cast<const float2*>(p.bn_rstd + so));
+      const float2 ga = __ldg(reinterpret_cast<const float2*>(gam + cc));
+      const float2 be = __ldg(reinterpret_cast<const float2*>(bet + cc));
+      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int row = g * 16 + i;
+        const int phys = (pr >> 2) ^ (row & 7);
+        uint32_t* cell = reinterpret_cast<uint32_t*>(stg0 + row * 128 + phys * 16 + (pr & 3) * 4);
+        float2 f = unpack_bf16x2(*cell);
+        const float2 z = unpack_bf16x2(zw[i]);
+        const float x0 = (z.x - mm.x) * rs.x, x1 = (z.y - mm.y) * rs.y;
+        f.x = (ga.x * x0 + be.x) > 0.f ? f.x : 0.f;
+        f.y = (ga.y * x1 + be.y) > 0.f ? f.y : 0.f;
+        *cell = pack_bf16x2(f.x, f.y);
+        s0 += f.x;
+        q0 += f.x * x0;
+        s1 += f.y;
+        q1 += f.y * x1;
+      }
+      float* red = vec;  // [8][64][2]
+      red[(g * 64 + 2 * pr) * 2 + 0] = s0;
+      red[(g * 64 + 2 * pr) * 2 + 1] = q0;
+      red[(g * 64 + 2 * pr + 1) * 2 + 0] = s1;
+      red[(g * 64 + 2 * pr + 1) * 2 + 1] = q1;
+      fence_proxy_async_smem();
+      named_bar_sync(1, kEpiThreads);
+      if (warp == 2) {
+        __syncwarp();
+        if (elect_one_sync()) {
+          tma_store_2d(map_out, stg0, ng0 + chunk * 64, m0);
+          tma_store_commit();
+        }
+      }
+      if (etid < 128) {
+        const int ch = etid & 63, which = etid >> 6;
+        float acc = 0.f;
+#pragma unroll
+        for (int gg = 0; gg < 8; ++gg) acc += red[(gg * 64 + ch) * 2 + which];
+        p.stat_sum[((size_t)m_tile * 2 + which) * p.N_total + ng0 + chunk * 64 + ch] = acc;
+      }
+      continue;
+    }
     if (warp == 2) {
       __syncwarp();
       if (elect_one_sync()) {
@@ -708,15 +779,24 @@ extern "C" int irfd_conv_gemm_m_tiles(int n, int h, int w) {
   return (int)((m + 127) / 128);
 }
 
+struct BnBwdFold {  // EPI_BNBWD operands (see ConvGemmArgs)
+  const void* z;
+  const float *mean, *rstd;
+  const float* const* gamma;
+  const float* const* beta;
+  int stat_groups;
+};
+
 static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const void* wk, int cout, int ksize, void* out,
                           void* out2, void* out_lo, int mode, const float* bias, const float* nw, const float* noise,
                           const float* sp1, const float* s1, float* stat_sum, float* stat_sq, const void* res, int relu,
-                          int force_block_n, cudaStream_t stream, int wgroups = 1, int a_shared = 0) {
+                          int force_block_n, cudaStream_t stream, int wgroups = 1, int a_shared = 0,
+                          const BnBwdFold* fold = nullptr) {
   IRFD_CHECK_ARG(x && wk && out, "conv_gemm: null pointer");
   IRFD_CHECK_ARG(ksize == 1 || ksize == 3, "conv_gemm: ksize must be 1 or 3 (got %d)", ksize);
   IRFD_CHECK_ARG(cin % 64 == 0 && cin > 0, "conv_gemm: Cin must be a multiple of 64 (got %d)", cin);
   IRFD_CHECK_ARG(cout % 64 == 0 && cout > 0, "conv_gemm: Cout must be a multiple of 64 (got %d)", cout);
-  IRFD_CHECK_ARG(mode >= 0 && mode <= 3, "conv_gemm: bad mode %d", mode);
+  IRFD_CHECK_ARG(mode >= 0 && mode <= 4, "conv_gemm: bad mode %d", mode);
   const long long m_total_ll = (long long)n * h * w;
   IRFD_CHECK_ARG(m_total_ll > 0 && m_total_ll < (1ll << 31) - 256, "conv_gemm: bad pixel count");
   const int m_total = (int)m_total_ll;
@@ -772,6 +852,27 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
     IRFD_CHECK_ARG(h * w >= 64, "conv_gemm: STYLE mode needs >= 64 pixels per image");
   }
   if (mode == EPI_STATS) IRFD_CHECK_ARG(stat_sum && stat_sq, "conv_gemm: STATS mode needs stat buffers");
+  a.bn_z = nullptr;
+  a.bn_mean = a.bn_rstd = nullptr;
+  for (int i = 0; i < 4; ++i) a.bn_gamma[i] = a.bn_beta[i] = nullptr;
+  a.sg_tiles = 0x7fffffff;
+  if (mode == EPI_BNBWD) {
+    IRFD_CHECK_ARG(fold && fold->z && fold->mean && fold->rstd && fold->gamma && fold->beta && stat_sum,
+                   "conv_gemm: BNBWD mode needs z, mean, rstd, gamma, beta and the partial buffer");
+    IRFD_CHECK_ARG(wgroups <= 4 && m_total % 128 == 0 && fold->stat_groups >= wgroups &&
+                       fold->stat_groups % wgroups == 0 && a.num_m_tiles % fold->stat_groups == 0,
+                   "conv_gemm: BNBWD needs whole 128-pixel tiles per statistic group (%d tiles, %d groups, %d sets)",
+                   a.num_m_tiles, fold->stat_groups, wgroups);
+    a.bn_z = reinterpret_cast<const __nv_bfloat16*>(fold->z);
+    a.bn_mean = fold->mean;
+    a.bn_rstd = fold->rstd;
+    for (int i = 0; i < wgroups; ++i) {
+      IRFD_CHECK_ARG(fold->gamma[i] && fold->beta[i], "conv_gemm: BNBWD gamma/beta pointer %d is null", i);
+      a.bn_gamma[i] = fold->gamma[i];
+      a.bn_beta[i] = fold->beta[i];
+    }
+    a.sg_tiles = a.num_m_tiles / fold->stat_groups;
+  }
 
   int block_n = force_block_n;
   if (block_n == 0) {
@@ -791,7 +892,7 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
                  "conv_gemm: BLOCK_N %d incompatible with Cout %d", block_n, cout);
   // halo-reuse kernel: 3x3, rows of >= 128 pixels, Cout of one 64/128-wide tile (the fabric-bound generator layers)
   const int hmode = halo_mode();
-  const bool use_halo = hmode != 0 && wgroups == 1 && ksize == 3 && W % 128 == 0 && H % 2 == 0 &&
+  const bool use_halo = hmode != 0 && mode != EPI_BNBWD && wgroups == 1 && ksize == 3 && W % 128 == 0 && H % 2 == 0 &&
                         (cout == 64 || cout == 128) &&
                         (force_block_n == 0 || force_block_n == cout);
   if (use_halo) block_n = cout;
@@ -845,6 +946,7 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
     case EPI_STATS: return dispatch_block_n<EPI_STATS>(block_n, ma, mb, mo, mo2, a, stream);
     case EPI_STYLE: return dispatch_block_n<EPI_STYLE>(block_n, ma, mb, mo, mo2, a, stream);
     case EPI_AFFINE: return dispatch_block_n<EPI_AFFINE>(block_n, ma, mb, mo, mo2, a, stream);
+    case EPI_BNBWD: return dispatch_block_n<EPI_BNBWD>(block_n, ma, mb, mo, mo2, a, stream);
   }
   return IRFD_ERR_INVALID_ARGUMENT;
 }
@@ -875,6 +977,20 @@ extern "C" int irfd_conv_gemm_grouped(const void* x, int n, int h, int w, int ci
   IRFD_CHECK_ARG(mode == EPI_PLAIN || mode == EPI_STATS, "conv_gemm_grouped: mode must be 0 (plain) or 1 (stats)");
   return conv_gemm_impl(x, n, h, w, cin, wk, cout, ksize, out, nullptr, nullptr, mode, nullptr, nullptr, nullptr,
                         nullptr, nullptr, stat_sum, stat_sq, nullptr, 0, force_block_n, stream, wgroups, a_shared);
+}
+
+// Data gradient of a conv whose input was relu(BN(z)), with that BatchNorm's backward reduce pass folded into the
+// epilogue: out = dgrad * (gamma*xhat + beta > 0) (bf16), partial[m tile][2][cout] = per-tile sums of g and g*xhat.
+// Finish with irfd_bn_backward_finish_sets.  stat_groups = TOTAL statistic groups of z (a multiple of wgroups).
+extern "C" int irfd_conv_gemm_bnbwd_grouped(const void* x, int n, int h, int w, int cin, const void* wk, int cout,
+                                            int ksize, void* out, const void* bn_z, const float* bn_mean,
+                                            const float* bn_rstd, const float* const* bn_gamma,
+                                            const float* const* bn_beta, float* partial, int stat_groups, int wgroups,
+                                            int force_block_n, cudaStream_t stream) {
+  IRFD_CHECK_ARG(wgroups >= 1 && wgroups <= 4, "conv_gemm_bnbwd: 1..4 weight groups");
+  const BnBwdFold fold{bn_z, bn_mean, bn_rstd, bn_gamma, bn_beta, stat_groups};
+  return conv_gemm_impl(x, n, h, w, cin, wk, cout, ksize, out, nullptr, nullptr, EPI_BNBWD, nullptr, nullptr, nullptr,
+                        nullptr, nullptr, partial, nullptr, nullptr, 0, force_block_n, stream, wgroups, 0, &fold);
 }
 
 extern "C" int irfd_conv_gemm_affine_grouped(const void* x, int n, int h, int w, int cin, const void* wk, int cout,

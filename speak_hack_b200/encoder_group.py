@@ -21,6 +21,7 @@ Numerically the grouped pass is the per-encoder pass: same kernels, same tiles, 
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -28,6 +29,11 @@ import torch.nn as nn
 
 from . import ops
 from .encoder import BN_EPS, BN_MOMENTUM, ResNet50Encoder
+
+
+# IRFD_BN_FOLD (default 1): the reduce pass of bn1 / bn2's backward runs in the epilogue of the dgrad GEMM that produces
+# their activation gradient (irfd_conv_gemm_bnbwd_grouped); 0 = separate reduce launch (experiments, A/B timing).
+fold_bn_reduce = os.environ.get("IRFD_BN_FOLD", "1") != "0"
 
 
 def _stack_pack(convs, mode, kpad=0):
@@ -207,6 +213,20 @@ class _EncoderGroupFn(torch.autograd.Function):
                                      want_g_out=want_g_out, batch_stats=True, groups=GT, act_bits=act_bits)
             return (r[0], r[3]) if want_g_out else r[0]
 
+        def dgrad_bn(dy, convs, ksize, bns, st, z):
+            """Data gradient through `convs` into relu(BN(z)), then that BatchNorm's backward.  Launches the dgrad GEMM
+            and returns the closure that launches the rest (the caller forks the weight gradient in between, so that it
+            runs beside the HBM-bound BN pass) and returns dz."""
+            wk = _stack_pack(convs, ops.PACK_DGRAD)
+            if not fold_bn_reduce:
+                d_a = ops.conv_gemm_grouped(dy, wk, ksize, wgroups=E)
+                return lambda: bn_bwd(bns, st, d_a, None, None, z, mask_from_z=True)
+            gm, part = ops.conv_gemm_bnbwd_grouped(dy, wk, ksize, z, st.mean, st.rstd, [b.weight for b in bns],
+                                                   [b.bias for b in bns], GT)
+            return lambda: ops.bn_backward_finish_sets(gm, z, st.mean, st.rstd, [b.weight for b in bns], part,
+                                                       dgammas=[tgt(b.weight) for b in bns],
+                                                       dbetas=[tgt(b.bias) for b in bns], groups=GT)[0]
+
         side = ops.side_stream(dfeat.device)
 
         def wgrad(convs, xx, dy, ksize, **kw):
@@ -227,19 +247,20 @@ class _EncoderGroupFn(torch.autograd.Function):
             dz3, gmask = bn_bwd([b.bn3 for b in blks], st3, g, g2, None, z3, want_g_out=True, act_bits=obits)
             # dgrad first, wgrad second: the persistent dgrad takes the SMs, the wgrad (side stream) follows it and
             # runs beside the BatchNorm backward that consumes the dgrad's output
-            d_a2 = ops.conv_gemm_grouped(dz3, _stack_pack([b.conv3 for b in blks], ops.PACK_DGRAD), 1, wgroups=E)
+            finish = dgrad_bn(dz3, [b.conv3 for b in blks], 1, [b.bn2 for b in blks], st2, z2)
             wgrad([b.conv3 for b in blks], a2, dz3, 1)
-            dz2 = bn_bwd([b.bn2 for b in blks], st2, d_a2, None, a2, z2, mask_from_z=True)
+            dz2 = finish()
             if blks[0].stride == 1:
-                d_a1 = ops.conv_gemm_grouped(dz2, _stack_pack([b.conv2 for b in blks], ops.PACK_DGRAD), 3, wgroups=E)
+                finish = dgrad_bn(dz2, [b.conv2 for b in blks], 3, [b.bn1 for b in blks], st1, z1)
                 wgrad([b.conv2 for b in blks], a1, dz2, 3)
+                dz1 = finish()
             else:
                 m2 = dz2.numel() // planes
                 dcol = ops.conv_gemm_grouped(dz2.view(1, 1, m2, planes),
                                              _stack_pack([b.conv2 for b in blks], ops.PACK_DCOL), 1, wgroups=E)
                 wgrad([b.conv2 for b in blks], col2, dz2.view(m2, planes), 1, reduce_cin=planes, reduce_taps=9)
                 d_a1 = ops.col2im_3x3s2(dcol.view(m2, 9 * planes), nb, hh, ww, planes)
-            dz1 = bn_bwd([b.bn1 for b in blks], st1, d_a1, None, a1, z1, mask_from_z=True)
+                dz1 = bn_bwd([b.bn1 for b in blks], st1, d_a1, None, a1, z1, mask_from_z=True)
             d_in = ops.conv_gemm_grouped(dz1, _stack_pack([b.conv1 for b in blks], ops.PACK_DGRAD), 1, wgroups=E)
             wgrad([b.conv1 for b in blks], xin, dz1, 1)
             if blks[0].downsample is not None:

@@ -258,6 +258,32 @@ def conv_gemm_grouped(x, wk, ksize, mode=EPI_PLAIN, wgroups=3, a_shared=False, r
     return out
 
 
+def conv_gemm_bnbwd_grouped(dy, wk, ksize, z, mean, rstd, gammas, betas, stat_groups, force_block_n=0):
+    """Data gradient of a conv whose input was relu(BN(z)), with that BatchNorm's backward reduce pass in the epilogue.
+    dy [N,H,W,Cin'] bf16 (groups stacked group-major), wk the stacked dgrad weights [len(gammas)*C, k*k*Cin'], z
+    [N,H,W,C].  Returns (g, partial): g = dgrad * (gamma*xhat+beta > 0) bf16, partial [m_tiles, 2, C] fp32 per-tile sums
+    of g and g*xhat.  Finish with bn_backward_finish_sets."""
+    lib = _lib.load()
+    _chk(dy, BF16, "dy")
+    _chk(wk, BF16, "wk")
+    _chk(z, BF16, "z")
+    wgroups = len(gammas)
+    n, h, w, cin = dy.shape
+    cout = wk.shape[0] // wgroups
+    if wk.shape[0] % wgroups or wk.shape[1] != ksize * ksize * cin or z.shape != (n, h, w, cout):
+        raise _lib.IrfdError(f"conv_gemm_bnbwd_grouped: wk {tuple(wk.shape)} / z {tuple(z.shape)} do not match dy "
+                             f"{tuple(dy.shape)}, ksize={ksize}, {wgroups} groups")
+    m = n * h * w
+    out = torch.empty((n, h, w, cout), dtype=BF16, device=dy.device)
+    partial = torch.empty((lib.irfd_conv_gemm_m_tiles(n, h, w), 2, cout), dtype=F32, device=dy.device)
+    nbytes = 2.0 * m * cin + 2 * 2.0 * m * cout + 2.0 * wgroups * cin * cout * ksize * ksize
+    with _timed("conv_gemm_kernel (tcgen05 fprop/dgrad)", 2.0 * m * cout * cin * ksize * ksize, nbytes):
+        _call("irfd_conv_gemm_bnbwd_grouped", dy.data_ptr(), n, h, w, cin, wk.data_ptr(), cout, ksize, out.data_ptr(),
+              z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _ptr_array(gammas), _ptr_array(betas), partial.data_ptr(),
+              stat_groups, wgroups, force_block_n, _stream())
+    return out, partial
+
+
 def conv_gemm_affine_grouped(x, wk, ksize, scale, shift, res=None, relu=True, wgroups=3, a_shared=False,
                              force_block_n=0):
     """Grouped conv with y = act(acc*scale[g] + shift[g] [+ res]) in the epilogue; scale/shift are [wgroups, Cout]."""
@@ -582,6 +608,28 @@ def bn_backward_sets(g1, g2, act, z, mean, rstd, gammas, betas=None, dgammas=Non
               ws.data_ptr(), ws.numel(), _stream(), launches=3)
     if want_g_out:
         return dz, dgammas, dbetas, g_out
+    return dz, dgammas, dbetas
+
+
+def bn_backward_finish_sets(g, z, mean, rstd, gammas, partial, dgammas=None, dbetas=None, batch_stats=True, groups=1):
+    """Second half of a BN backward whose reduce pass ran in conv_gemm_bnbwd_grouped: g is the masked gradient, partial
+    [groups * tiles, 2, C] the per-tile sums.  Returns dz, dgammas, dbetas."""
+    c = z.shape[-1]
+    rows = z.numel() // c
+    nsets = len(gammas)
+    dz = torch.empty_like(z)
+    if dgammas is None:
+        dg_all = torch.empty((nsets, c), dtype=F32, device=z.device)
+        db_all = torch.empty((nsets, c), dtype=F32, device=z.device)
+        dgammas, dbetas = list(dg_all.unbind(0)), list(db_all.unbind(0))
+    if partial.shape[0] % groups:
+        raise _lib.IrfdError("bn_backward_finish_sets: partial rows do not split into the statistic groups")
+    ws = workspace(2 * groups * c * 4, z.device)
+    with _timed("bn_backward (reduce+finalize+apply, HBM)", 2.0 * rows * c * 3):
+        _call("irfd_bn_backward_finish_sets", g.data_ptr(), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+              _ptr_array(gammas), dz.data_ptr(), _ptr_array(dgammas), _ptr_array(dbetas), 0.0, 1 if batch_stats else 0,
+              rows, c, groups, nsets, partial.data_ptr(), partial.shape[0] // groups, ws.data_ptr(), ws.numel(), _stream(),
+              launches=2)
     return dz, dgammas, dbetas
 
 

@@ -158,6 +158,48 @@ def test_bn_sets_equal_separate_calls(cuda_device):
         assert torch.equal(sc[e], s1) and torch.equal(sh[e], h1)
 
 
+@pytest.mark.parametrize("ksize,cin,cout,hw,n", [(1, 256, 64, 16, 12), (3, 64, 64, 16, 6), (1, 512, 128, 8, 12),
+                                                 (3, 256, 256, 8, 12), (1, 2048, 512, 8, 12)])
+def test_dgrad_with_folded_bn_reduce_equals_separate_passes(cuda_device, ksize, cin, cout, hw, n):
+    """irfd_conv_gemm_bnbwd_grouped + irfd_bn_backward_finish_sets (the BatchNorm backward's reduce pass inside the
+    dgrad epilogue) against dgrad GEMM -> bn_backward_sets(mask recomputed from z): the masked gradient must be
+    bit-identical (same mask expression on the same bf16 values), sums equal up to fp32 summation order."""
+    import irfd_oracle as O
+    from speak_hack_b200 import ops
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(ksize * 1000 + cin + cout)
+    E, G = 3, 2
+    GT = E * G
+    dy = _bf(torch.randn(n, hw, hw, cin, generator=g).to(dev))
+    z = _bf(torch.randn(n, hw, hw, cout, generator=g).to(dev) * 1.5 + 0.2)
+    ws = [torch.randn(cin, cout, ksize, ksize, generator=g).to(dev) * 0.05 for _ in range(E)]   # forward conv: cout -> cin
+    wk = ops.pack_conv_weights_stacked(ws, ops.PACK_DGRAD)
+    gam = [torch.rand(cout, generator=g).to(dev) + 0.5 for _ in range(E)]
+    bet = [torch.randn(cout, generator=g).to(dev) * 0.3 for _ in range(E)]
+    rows = n * hw * hw
+    assert (rows // GT) % 128 == 0
+    zt = z.float().view(-1, 128, cout)
+    mean, rstd = ops.bn_finalize_sets(zt.sum(1).contiguous(), (zt * zt).sum(1).contiguous(), rows // GT, 1e-5, 0.1,
+                                      [torch.zeros(cout, device=dev) for _ in range(E)],
+                                      [torch.ones(cout, device=dev) for _ in range(E)], 1, G, E)
+    d_a = ops.conv_gemm_grouped(dy, wk, ksize, wgroups=E)
+    dz1, dg1, db1, gm1 = ops.bn_backward_sets(d_a, None, None, z, mean, rstd, gam, bet, want_g_out=True, groups=GT)
+    gm2, part = ops.conv_gemm_bnbwd_grouped(dy, wk, ksize, z, mean, rstd, gam, bet, GT)
+    dz2, dg2, db2 = ops.bn_backward_finish_sets(gm2, z, mean, rstd, gam, part, groups=GT)
+    torch.cuda.synchronize()
+    assert part.shape == (rows // 128, 2, cout)
+    assert torch.equal(gm2, gm1)
+    # per-tile partials against torch on the masked gradient
+    xhat = (z.float().view(GT, -1, cout) - mean.view(GT, 1, cout)) * rstd.view(GT, 1, cout)
+    gf = gm1.float().view(-1, 128, cout)
+    assert O.rel_l2(part[:, 0], gf.sum(1)) < 1e-5
+    assert O.rel_l2(part[:, 1], (gf * xhat.view(-1, 128, cout)).sum(1)) < 1e-5
+    for e in range(E):
+        assert O.rel_l2(dg2[e], dg1[e]) < 1e-5 and O.rel_l2(db2[e], db1[e]) < 1e-5, e
+    assert O.rel_l2(dz2.float(), dz1.float()) < 1e-4   # identical up to bf16 rounding flips from the fp32 sum order
+
+
 class _FakeBN:
     def __init__(self, rm, rv, w, b):
         self.running_mean, self.running_var, self.weight, self.bias, self.eps = rm, rv, w, b, 1e-5
@@ -208,7 +250,9 @@ def test_encoder_group_train_equals_three_passes(cuda_device):
             assert p2.grad is not None, n1
             worst = max(worst, O.rel_l2(p2.grad, p1.grad))
     print(f"[parity] lockstep vs separate encoder passes: worst param-grad rel-L2 {worst:.3e}")
-    assert worst < 1e-5
+    # the lockstep pass sums the BatchNorm backward statistics of bn1/bn2 per 128-pixel tile inside the dgrad epilogue,
+    # the per-encoder pass per row block: same terms, different fp32 order, hence rare bf16 rounding flips downstream
+    assert worst < 2e-4
     # in-place targets: same values, nothing returned to autograd
     targets = {p: torch.full_like(p, float("nan")) for e in grouped for p in e.parameters()}
     ref_grads = {p: p.grad.clone() for e in grouped for p in e.parameters()}
