@@ -180,6 +180,11 @@ int irfd_conv_gemm_bnbwd_grouped(const void* x, int n, int h, int w, int cin, co
                                  void* out, const void* bn_z, const float* bn_mean, const float* bn_rstd,
                                  const float* const* bn_gamma, const float* const* bn_beta, float* partial,
                                  int stat_groups, int wgroups, int force_block_n, irfd_stream_t stream);
+/* the BatchNorm that closes a Bottleneck: out = (dgrad + g2) * mask(mask_bits); see irfd_bn_apply_sets */
+int irfd_conv_gemm_bnbwd_res_grouped(const void* x, int n, int h, int w, int cin, const void* wk, int cout, int ksize,
+                                     void* out, const void* bn_z, const float* bn_mean, const float* bn_rstd,
+                                     const void* g2, const void* mask_bits, float* partial, int stat_groups,
+                                     int wgroups, int force_block_n, irfd_stream_t stream);
 int irfd_bn_backward_finish_sets(const void* g, const void* z, const float* mean, const float* rstd,
                                  const float* const* gamma, void* dz, float* const* dgamma, float* const* dbeta,
                                  float grad_beta, int batch_stats, long long rows, int c, int groups, int nsets,

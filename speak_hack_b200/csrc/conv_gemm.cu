@@ -30,7 +30,7 @@
 
 namespace irfd {
 
-enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_STYLE = 2, EPI_AFFINE = 3, EPI_BNBWD = 4 };
+enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_STYLE = 2, EPI_AFFINE = 3, EPI_BNBWD = 4, EPI_BNBWD_RES = 5 };
 
 struct ConvGemmArgs {
   int M_total, N_total;
@@ -57,7 +57,12 @@ struct ConvGemmArgs {
   // epilogue applies the ReLU mask (recomputed from z) to the activation gradient it produces and sums, per channel
   // and 128-pixel tile, g and g * xhat — the reduce pass of that BatchNorm's backward, which then needs no launch and
   // no second read of the gradient.  stat_sum receives the partials as [m tile][2][N_total].
+  // BNBWD_RES: the same for the BatchNorm that closes a Bottleneck (out = relu(bn3(z) + identity), resnet.py:154-161),
+  // whose output gradient is this GEMM's result (the next block's conv1 data gradient) PLUS that block's shortcut
+  // gradient bn_g2; the ReLU mask comes from the bit plane irfd_bn_apply_sets wrote (bn_bits, [M_total][N_total/8]).
   const __nv_bfloat16* bn_z;  // [M_total][N_total]
+  const __nv_bfloat16* bn_g2;
+  const uint8_t* bn_bits;
   const float* bn_mean;       // [statistic groups][N_total]
   const float* bn_rstd;
   const float* bn_gamma[4];   // per weight group
@@ -145,11 +150,18 @@ __device__ __forceinline__ void epilogue_acc(const ConvGemmArgs& p, const CUtens
   for (int chunk = 0; chunk < BLOCK_N / 64; ++chunk, ++chunk_counter) {
     uint32_t v[32];
     uint32_t zw[16];  // BNBWD: this thread's 16 rows x 2 channels of z for the column phase, in flight during the drain
-    if constexpr (MODE == EPI_BNBWD) {
-      const __nv_bfloat16* zp =
-          p.bn_z + (size_t)(m0 + (etid >> 5) * 16) * p.N_total + ng0 + chunk * 64 + 2 * (etid & 31);
+    uint32_t gw[16];  // BNBWD_RES: the shortcut gradient, same cells
+    uint8_t bw[16];   // BNBWD_RES: the mask byte of the 8 channels around this thread's pair
+    if constexpr (MODE == EPI_BNBWD || MODE == EPI_BNBWD_RES) {
+      const size_t cell0 = (size_t)(m0 + (etid >> 5) * 16) * p.N_total + ng0 + chunk * 64 + 2 * (etid & 31);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) zw[i] = __ldg(reinterpret_cast<const uint32_t*>(zp + (size_t)i * p.N_total));
+      for (int i = 0; i < 16; ++i) {
+        zw[i] = __ldg(reinterpret_cast<const uint32_t*>(p.bn_z + cell0 + (size_t)i * p.N_total));
+        if constexpr (MODE == EPI_BNBWD_RES) {
+          gw[i] = __ldg(reinterpret_cast<const uint32_t*>(p.bn_g2 + cell0 + (size_t)i * p.N_total));
+          bw[i] = __ldg(p.bn_bits + ((cell0 + (size_t)i * p.N_total) >> 3));
+        }
+      }
     }
     const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc_col + chunk * 64 + half * 32;
     tmem_ld32(taddr, v);
@@ -235,20 +247,25 @@ __device__ __forceinline__ void epilogue_acc(const ConvGemmArgs& p, const CUtens
     }
     fence_proxy_async_smem();
     named_bar_sync(1, kEpiThreads);
-    if constexpr (MODE == EPI_BNBWD) {
+    if constexpr (MODE == EPI_BNBWD || MODE == EPI_BNBWD_RES) {
       // column phase on the staged chunk: thread = (channel pair, 16-row group); mask the gradient in place, sum
-      // g and g * xhat over the rows (same expressions as bn_bwd_reduce_kernel<., 2>)
+      // g and g * xhat over the rows (same expressions as bn_bwd_reduce_kernel)
       const int pr = etid & 31;
       const int g = etid >> 5;
       const int cc = ng0 + chunk * 64 + 2 * pr;
-      const int grp = m_tile / p.wg_tiles;
-      const float* gam = grp == 0 ? p.bn_gamma[0] : (grp == 1 ? p.bn_gamma[1] : (grp == 2 ? p.bn_gamma[2] : p.bn_gamma[3]));
-      const float* bet = grp == 0 ? p.bn_beta[0] : (grp == 1 ? p.bn_beta[1] : (grp == 2 ? p.bn_beta[2] : p.bn_beta[3]));
       const size_t so = (size_t)(m_tile / p.sg_tiles) * p.N_total + cc;
       const float2 mm = __ldg(reinterpret_cast<const float2*>(p.bn_mean + so));
       const float2 rs = __ldg(reinterpret_cast<const float2*>(p.bn_rstd + so));
-      const float2 ga = __ldg(reinterpret_cast<const float2*>(gam + cc));
-      const float2 be = __ldg(reinterpret_cast<const float2*>(bet + cc));
+      float2 ga = make_float2(0.f, 0.f), be = make_float2(0.f, 0.f);
+      if constexpr (MODE == EPI_BNBWD) {
+        const int grp = m_tile / p.wg_tiles;
+        const float* gam =
+            grp == 0 ? p.bn_gamma[0] : (grp == 1 ? p.bn_gamma[1] : (grp == 2 ? p.bn_gamma[2] : p.bn_gamma[3]));
+        const float* bet = grp == 0 ? p.bn_beta[0] : (grp == 1 ? p.bn_beta[1] : (grp == 2 ? p.bn_beta[2] : p.bn_beta[3]));
+        ga = __ldg(reinterpret_cast<const float2*>(gam + cc));
+        be = __ldg(reinterpret_cast<const float2*>(bet + cc));
+      }
+      const int bit0 = (2 * pr) & 7;
       float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -258,8 +275,14 @@ __device__ __forceinline__ void epilogue_acc(const ConvGemmArgs& p, const CUtens
         float2 f = unpack_bf16x2(*cell);
         const float2 z = unpack_bf16x2(zw[i]);
         const float x0 = (z.x - mm.x) * rs.x, x1 = (z.y - mm.y) * rs.y;
-        f.x = (ga.x * x0 + be.x) > 0.f ? f.x : 0.f;
-        f.y = (ga.y * x1 + be.y) > 0.f ? f.y : 0.f;
+        if constexpr (MODE == EPI_BNBWD) {
+          f.x = (ga.x * x0 + be.x) > 0.f ? f.x : 0.f;
+          f.y = (ga.y * x1 + be.y) > 0.f ? f.y : 0.f;
+        } else {
+          const float2 h = unpack_bf16x2(gw[i]);
+          f.x = ((bw[i] >> bit0) & 1) ? f.x + h.x : 0.f;
+          f.y = ((bw[i] >> (bit0 + 1)) & 1) ? f.y + h.y : 0.f;
+        }
         *cell = pack_bf16x2(f.x, f.y);
         s0 += f.x;
         q0 += f.x * x0;
@@ -779,11 +802,13 @@ extern "C" int irfd_conv_gemm_m_tiles(int n, int h, int w) {
   return (int)((m + 127) / 128);
 }
 
-struct BnBwdFold {  // EPI_BNBWD operands (see ConvGemmArgs)
+struct BnBwdFold {  // EPI_BNBWD / EPI_BNBWD_RES operands (see ConvGemmArgs)
   const void* z;
   const float *mean, *rstd;
-  const float* const* gamma;
+  const float* const* gamma;  // BNBWD
   const float* const* beta;
+  const void* g2;             // BNBWD_RES
+  const void* bits;
   int stat_groups;
 };
 
@@ -796,7 +821,7 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
   IRFD_CHECK_ARG(ksize == 1 || ksize == 3, "conv_gemm: ksize must be 1 or 3 (got %d)", ksize);
   IRFD_CHECK_ARG(cin % 64 == 0 && cin > 0, "conv_gemm: Cin must be a multiple of 64 (got %d)", cin);
   IRFD_CHECK_ARG(cout % 64 == 0 && cout > 0, "conv_gemm: Cout must be a multiple of 64 (got %d)", cout);
-  IRFD_CHECK_ARG(mode >= 0 && mode <= 4, "conv_gemm: bad mode %d", mode);
+  IRFD_CHECK_ARG(mode >= 0 && mode <= 5, "conv_gemm: bad mode %d", mode);
   const long long m_total_ll = (long long)n * h * w;
   IRFD_CHECK_ARG(m_total_ll > 0 && m_total_ll < (1ll << 31) - 256, "conv_gemm: bad pixel count");
   const int m_total = (int)m_total_ll;
@@ -856,9 +881,14 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
   a.bn_mean = a.bn_rstd = nullptr;
   for (int i = 0; i < 4; ++i) a.bn_gamma[i] = a.bn_beta[i] = nullptr;
   a.sg_tiles = 0x7fffffff;
-  if (mode == EPI_BNBWD) {
-    IRFD_CHECK_ARG(fold && fold->z && fold->mean && fold->rstd && fold->gamma && fold->beta && stat_sum,
-                   "conv_gemm: BNBWD mode needs z, mean, rstd, gamma, beta and the partial buffer");
+  a.bn_g2 = nullptr;
+  a.bn_bits = nullptr;
+  if (mode == EPI_BNBWD || mode == EPI_BNBWD_RES) {
+    IRFD_CHECK_ARG(fold && fold->z && fold->mean && fold->rstd && stat_sum,
+                   "conv_gemm: BNBWD modes need z, mean, rstd and the partial buffer");
+    if (mode == EPI_BNBWD) IRFD_CHECK_ARG(fold->gamma && fold->beta, "conv_gemm: BNBWD mode needs gamma and beta");
+    if (mode == EPI_BNBWD_RES)
+      IRFD_CHECK_ARG(fold->g2 && fold->bits && cout % 8 == 0, "conv_gemm: BNBWD_RES mode needs g2 and the mask plane");
     IRFD_CHECK_ARG(wgroups <= 4 && m_total % 128 == 0 && fold->stat_groups >= wgroups &&
                        fold->stat_groups % wgroups == 0 && a.num_m_tiles % fold->stat_groups == 0,
                    "conv_gemm: BNBWD needs whole 128-pixel tiles per statistic group (%d tiles, %d groups, %d sets)",
@@ -866,11 +896,13 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
     a.bn_z = reinterpret_cast<const __nv_bfloat16*>(fold->z);
     a.bn_mean = fold->mean;
     a.bn_rstd = fold->rstd;
-    for (int i = 0; i < wgroups; ++i) {
+    for (int i = 0; i < wgroups && mode == EPI_BNBWD; ++i) {
       IRFD_CHECK_ARG(fold->gamma[i] && fold->beta[i], "conv_gemm: BNBWD gamma/beta pointer %d is null", i);
       a.bn_gamma[i] = fold->gamma[i];
       a.bn_beta[i] = fold->beta[i];
     }
+    a.bn_g2 = reinterpret_cast<const __nv_bfloat16*>(fold->g2);
+    a.bn_bits = reinterpret_cast<const uint8_t*>(fold->bits);
     a.sg_tiles = a.num_m_tiles / fold->stat_groups;
   }
 
@@ -892,7 +924,7 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
                  "conv_gemm: BLOCK_N %d incompatible with Cout %d", block_n, cout);
   // halo-reuse kernel: 3x3, rows of >= 128 pixels, Cout of one 64/128-wide tile (the fabric-bound generator layers)
   const int hmode = halo_mode();
-  const bool use_halo = hmode != 0 && mode != EPI_BNBWD && wgroups == 1 && ksize == 3 && W % 128 == 0 && H % 2 == 0 &&
+  const bool use_halo = hmode != 0 && mode != EPI_BNBWD && mode != EPI_BNBWD_RES && wgroups == 1 && ksize == 3 && W % 128 == 0 && H % 2 == 0 &&
                         (cout == 64 || cout == 128) &&
                         (force_block_n == 0 || force_block_n == cout);
   if (use_halo) block_n = cout;
@@ -947,6 +979,7 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
     case EPI_STYLE: return dispatch_block_n<EPI_STYLE>(block_n, ma, mb, mo, mo2, a, stream);
     case EPI_AFFINE: return dispatch_block_n<EPI_AFFINE>(block_n, ma, mb, mo, mo2, a, stream);
     case EPI_BNBWD: return dispatch_block_n<EPI_BNBWD>(block_n, ma, mb, mo, mo2, a, stream);
+    case EPI_BNBWD_RES: return dispatch_block_n<EPI_BNBWD_RES>(block_n, ma, mb, mo, mo2, a, stream);
   }
   return IRFD_ERR_INVALID_ARGUMENT;
 }
@@ -988,9 +1021,23 @@ extern "C" int irfd_conv_gemm_bnbwd_grouped(const void* x, int n, int h, int w, 
                                             const float* const* bn_beta, float* partial, int stat_groups, int wgroups,
                                             int force_block_n, cudaStream_t stream) {
   IRFD_CHECK_ARG(wgroups >= 1 && wgroups <= 4, "conv_gemm_bnbwd: 1..4 weight groups");
-  const BnBwdFold fold{bn_z, bn_mean, bn_rstd, bn_gamma, bn_beta, stat_groups};
+  const BnBwdFold fold{bn_z, bn_mean, bn_rstd, bn_gamma, bn_beta, nullptr, nullptr, stat_groups};
   return conv_gemm_impl(x, n, h, w, cin, wk, cout, ksize, out, nullptr, nullptr, EPI_BNBWD, nullptr, nullptr, nullptr,
                         nullptr, nullptr, partial, nullptr, nullptr, 0, force_block_n, stream, wgroups, 0, &fold);
+}
+
+// The same for the BatchNorm that closes a Bottleneck: out = (dgrad + g2) * mask, mask from the bit plane of
+// irfd_bn_apply_sets ([pixels][cout/8]); out is the masked gradient both bn3's backward and the shortcut consume.
+extern "C" int irfd_conv_gemm_bnbwd_res_grouped(const void* x, int n, int h, int w, int cin, const void* wk, int cout,
+                                                int ksize, void* out, const void* bn_z, const float* bn_mean,
+                                                const float* bn_rstd, const void* g2, const void* mask_bits,
+                                                float* partial, int stat_groups, int wgroups, int force_block_n,
+                                                cudaStream_t stream) {
+  IRFD_CHECK_ARG(wgroups >= 1 && wgroups <= 4, "conv_gemm_bnbwd_res: 1..4 weight groups");
+  const BnBwdFold fold{bn_z, bn_mean, bn_rstd, nullptr, nullptr, g2, mask_bits, stat_groups};
+  return conv_gemm_impl(x, n, h, w, cin, wk, cout, ksize, out, nullptr, nullptr, EPI_BNBWD_RES, nullptr, nullptr,
+                        nullptr, nullptr, nullptr, partial, nullptr, nullptr, 0, force_block_n, stream, wgroups, 0,
+                        &fold);
 }
 
 extern "C" int irfd_conv_gemm_affine_grouped(const void* x, int n, int h, int w, int cin, const void* wk, int cout,

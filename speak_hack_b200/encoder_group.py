@@ -33,7 +33,11 @@ from .encoder import BN_EPS, BN_MOMENTUM, ResNet50Encoder
 
 # IRFD_BN_FOLD (default 1): the reduce pass of bn1 / bn2's backward runs in the epilogue of the dgrad GEMM that produces
 # their activation gradient (irfd_conv_gemm_bnbwd_grouped); 0 = separate reduce launch (experiments, A/B timing).
+# IRFD_BN3_FOLD (default 1): the same for bn3 of every Bottleneck that is followed by an identity-shortcut block: the
+# next block's conv1 data gradient adds the shortcut gradient, applies the ReLU mask and sums in its epilogue
+# (irfd_conv_gemm_bnbwd_res_grouped).
 fold_bn_reduce = os.environ.get("IRFD_BN_FOLD", "1") != "0"
+fold_bn3_reduce = os.environ.get("IRFD_BN3_FOLD", "1") != "0"
 
 
 def _stack_pack(convs, mode, kpad=0):
@@ -237,14 +241,24 @@ class _EncoderGroupFn(torch.autograd.Function):
             side.launch(lambda: ops.conv_wgrad_grouped(xx, dy, ksize, dws, **kw), xx, dy, *dws)
 
         cur_li = None
-        for rec in reversed(S["blocks"]):
-            li, blks, xin, z1, st1, a1, col2, z2, st2, a2, z3, st3, xs, zd, std, obits = rec
+        pre = None   # (masked output gradient, partial sums) of this block's bn3 when the previous iteration formed them
+        blocks = S["blocks"]
+        for bidx in range(len(blocks) - 1, -1, -1):
+            li, blks, xin, z1, st1, a1, col2, z2, st2, a2, z3, st3, xs, zd, std, obits = blocks[bidx]
             if cur_li is not None and li != cur_li and cb is not None:
                 cb("stage", cur_li)  # every gradient of ResNet stage `cur_li` (all encoders) has been written
             cur_li = li
             nb, hh, ww, _cin = xin.shape
             planes = a1.shape[-1]
-            dz3, gmask = bn_bwd([b.bn3 for b in blks], st3, g, g2, None, z3, want_g_out=True, act_bits=obits)
+            if pre is not None:
+                gmask, part3 = pre
+                bn3 = [b.bn3 for b in blks]
+                dz3 = ops.bn_backward_finish_sets(gmask, z3, st3.mean, st3.rstd, [b.weight for b in bn3], part3,
+                                                  dgammas=[tgt(b.weight) for b in bn3],
+                                                  dbetas=[tgt(b.bias) for b in bn3], groups=GT)[0]
+                pre = None
+            else:
+                dz3, gmask = bn_bwd([b.bn3 for b in blks], st3, g, g2, None, z3, want_g_out=True, act_bits=obits)
             # dgrad first, wgrad second: the persistent dgrad takes the SMs, the wgrad (side stream) follows it and
             # runs beside the BatchNorm backward that consumes the dgrad's output
             finish = dgrad_bn(dz3, [b.conv3 for b in blks], 1, [b.bn2 for b in blks], st2, z2)
@@ -261,7 +275,16 @@ class _EncoderGroupFn(torch.autograd.Function):
                 wgrad([b.conv2 for b in blks], col2, dz2.view(m2, planes), 1, reduce_cin=planes, reduce_taps=9)
                 d_a1 = ops.col2im_3x3s2(dcol.view(m2, 9 * planes), nb, hh, ww, planes)
                 dz1 = bn_bwd([b.bn1 for b in blks], st1, d_a1, None, a1, z1, mask_from_z=True)
-            d_in = ops.conv_gemm_grouped(dz1, _stack_pack([b.conv1 for b in blks], ops.PACK_DGRAD), 1, wgroups=E)
+            wk1 = _stack_pack([b.conv1 for b in blks], ops.PACK_DGRAD)
+            if blks[0].downsample is None and fold_bn3_reduce:
+                # identity shortcut: this block's input gradient is conv1's data gradient + the masked output gradient,
+                # and the input is the previous block's relu(bn3(z3) + shortcut): that BatchNorm's reduce pass runs here
+                prev = blocks[bidx - 1]
+                pre = ops.conv_gemm_bnbwd_res_grouped(dz1, wk1, 1, prev[10], prev[11].mean, prev[11].rstd, gmask,
+                                                      prev[15], GT, wgroups=E)
+                wgrad([b.conv1 for b in blks], xin, dz1, 1)
+                continue
+            d_in = ops.conv_gemm_grouped(dz1, wk1, 1, wgroups=E)
             wgrad([b.conv1 for b in blks], xin, dz1, 1)
             if blks[0].downsample is not None:
                 dzd = bn_bwd([b.downsample[1] for b in blks], std, gmask, None, None, zd)

@@ -284,6 +284,31 @@ def conv_gemm_bnbwd_grouped(dy, wk, ksize, z, mean, rstd, gammas, betas, stat_gr
     return out, partial
 
 
+def conv_gemm_bnbwd_res_grouped(dy, wk, ksize, z, mean, rstd, g2, bits, stat_groups, wgroups=3, force_block_n=0):
+    """conv_gemm_bnbwd_grouped for the BatchNorm that closes a Bottleneck: g = (dgrad + g2) * mask with the mask from
+    the bit plane `bits` (bn_apply_sets(want_mask=True)).  Returns (g, partial)."""
+    lib = _lib.load()
+    _chk(dy, BF16, "dy")
+    _chk(wk, BF16, "wk")
+    _chk(z, BF16, "z")
+    _chk(g2, BF16, "g2")
+    n, h, w, cin = dy.shape
+    cout = wk.shape[0] // wgroups
+    m = n * h * w
+    if (wk.shape[0] % wgroups or wk.shape[1] != ksize * ksize * cin or z.shape != (n, h, w, cout) or g2.shape != z.shape
+            or bits.dtype != torch.uint8 or bits.numel() != m * cout // 8):
+        raise _lib.IrfdError(f"conv_gemm_bnbwd_res_grouped: wk {tuple(wk.shape)} / z {tuple(z.shape)} / g2 "
+                             f"{tuple(g2.shape)} / bits {tuple(bits.shape)} do not match dy {tuple(dy.shape)}")
+    out = torch.empty((n, h, w, cout), dtype=BF16, device=dy.device)
+    partial = torch.empty((lib.irfd_conv_gemm_m_tiles(n, h, w), 2, cout), dtype=F32, device=dy.device)
+    nbytes = 2.0 * m * cin + (3 + 1.0 / 16) * 2.0 * m * cout + 2.0 * wgroups * cin * cout * ksize * ksize
+    with _timed("conv_gemm_kernel (tcgen05 fprop/dgrad)", 2.0 * m * cout * cin * ksize * ksize, nbytes):
+        _call("irfd_conv_gemm_bnbwd_res_grouped", dy.data_ptr(), n, h, w, cin, wk.data_ptr(), cout, ksize, out.data_ptr(),
+              z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), g2.data_ptr(), bits.data_ptr(), partial.data_ptr(),
+              stat_groups, wgroups, force_block_n, _stream())
+    return out, partial
+
+
 def conv_gemm_affine_grouped(x, wk, ksize, scale, shift, res=None, relu=True, wgroups=3, a_shared=False,
                              force_block_n=0):
     """Grouped conv with y = act(acc*scale[g] + shift[g] [+ res]) in the epilogue; scale/shift are [wgroups, Cout]."""

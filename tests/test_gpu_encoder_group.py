@@ -203,6 +203,45 @@ def test_dgrad_with_folded_bn_reduce_equals_separate_passes(cuda_device, ksize, 
     assert O.rel_l2(dz2.float(), dz1.float()) < 1e-4   # identical up to bf16 rounding flips from the fp32 sum order
 
 
+@pytest.mark.parametrize("cin,cout,hw,n", [(64, 256, 16, 12), (128, 512, 8, 12), (512, 2048, 8, 12), (64, 256, 64, 12),
+                                           (256, 1024, 16, 24)])
+def test_dgrad_with_folded_bn3_reduce_equals_separate_passes(cuda_device, cin, cout, hw, n):
+    """irfd_conv_gemm_bnbwd_res_grouped (conv1's data gradient + shortcut gradient, ReLU mask from the bit plane, BN
+    backward sums in the epilogue) + finish against dgrad GEMM -> bn_backward_sets(g1, g2, act_bits, want_g_out)."""
+    import irfd_oracle as O
+    from speak_hack_b200 import ops
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(cin + cout + hw)
+    E, G = 3, 2
+    GT = E * G
+    dy = _bf(torch.randn(n, hw, hw, cin, generator=g).to(dev))
+    z = _bf(torch.randn(n, hw, hw, cout, generator=g).to(dev) * 1.5 + 0.2)
+    res = _bf(torch.randn(n, hw, hw, cout, generator=g).to(dev))
+    g2 = _bf(torch.randn(n, hw, hw, cout, generator=g).to(dev))
+    ws = [torch.randn(cin, cout, 1, 1, generator=g).to(dev) * 0.05 for _ in range(E)]   # forward conv1: cout -> cin
+    wk = ops.pack_conv_weights_stacked(ws, ops.PACK_DGRAD)
+    gam = [torch.rand(cout, generator=g).to(dev) + 0.5 for _ in range(E)]
+    bet = [torch.randn(cout, generator=g).to(dev) * 0.3 for _ in range(E)]
+    rows = n * hw * hw
+    zt = z.float().view(-1, 128, cout)
+    mean, rstd = ops.bn_finalize_sets(zt.sum(1).contiguous(), (zt * zt).sum(1).contiguous(), rows // GT, 1e-5, 0.1,
+                                      [torch.zeros(cout, device=dev) for _ in range(E)],
+                                      [torch.ones(cout, device=dev) for _ in range(E)], 1, G, E)
+    out, bits = ops.bn_apply_sets(z, mean, rstd, gam, bet, res=res, relu=True, groups=GT, want_mask=True)
+    d_in = ops.conv_gemm_grouped(dy, wk, 1, wgroups=E)
+    dz1, dg1, db1, gm1 = ops.bn_backward_sets(d_in, g2, None, z, mean, rstd, gam, None, want_g_out=True, groups=GT,
+                                              act_bits=bits)
+    gm2, part = ops.conv_gemm_bnbwd_res_grouped(dy, wk, 1, z, mean, rstd, g2, bits, GT, wgroups=E)
+    dz2, dg2, db2 = ops.bn_backward_finish_sets(gm2, z, mean, rstd, gam, part, groups=GT)
+    torch.cuda.synchronize()
+    assert torch.equal(gm2, gm1)
+    assert torch.equal(gm1.float(), ((d_in.float() + g2.float()) * (out.float() > 0)).to(torch.bfloat16).float())
+    for e in range(E):
+        assert O.rel_l2(dg2[e], dg1[e]) < 1e-5 and O.rel_l2(db2[e], db1[e]) < 1e-5, e
+    assert O.rel_l2(dz2.float(), dz1.float()) < 1e-4
+
+
 class _FakeBN:
     def __init__(self, rm, rv, w, b):
         self.running_mean, self.running_var, self.weight, self.bias, self.eps = rm, rv, w, b, 1e-5
@@ -236,6 +275,7 @@ def test_encoder_group_train_equals_three_passes(cuda_device, monkeypatch, fold)
     from speak_hack_b200.encoder_group import EncoderGroup
 
     monkeypatch.setattr(EG, "fold_bn_reduce", fold)
+    monkeypatch.setattr(EG, "fold_bn3_reduce", fold)
 
     dev = cuda_device
     sep, grouped = _three_encoders(dev)
