@@ -196,6 +196,8 @@ class _EncoderGroupFn(torch.autograd.Function):
         E = len(encs)
         GT = E * G
         cb = grp._bwd_cb
+        # parameter gradients of the generator's dense layers may still be in flight on the side stream (_FCFn.backward)
+        ops.side_stream(dfeat.device).join()
         if cb is not None:
             cb("pre", None)
         targets: Optional[Dict[nn.Parameter, torch.Tensor]] = grp.grad_targets

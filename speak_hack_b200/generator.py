@@ -38,6 +38,16 @@ class _FCFn(torch.autograd.Function):
         dz = ops.lrelu_bwd(dy, y) if lrelu else dy
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         tw, tb = _target(weight), (_target(ctx.bias) if has_bias else None)
+        if need_dx and need_dw and tw is not None and (tb is not None or not has_bias):
+            # only dx is on the critical path of the backward pass (the mapping network is a chain of eight of these
+            # between the synthesis backward and the encoders'): the parameter gradient goes straight into the trainer's
+            # flat buffer, so it can run on the side stream.  Joined by whoever reads that buffer next: the encoder
+            # group's backward (before its first data-parallel event) and the trainer after loss.backward().
+            dx, _, _ = ops.linear_bwd(dz, x, weight, wmul, bmul, need_dx=True, need_dw=False, has_bias=has_bias)
+            ops.side_stream(dz.device).launch(
+                lambda: ops.linear_bwd(dz, x, weight, wmul, bmul, need_dx=False, need_dw=True, has_bias=has_bias,
+                                       dw_out=tw, db_out=tb), dz, x, tw)
+            return dx, None, None, None, None, None
         dx, dw, db = ops.linear_bwd(dz, x, weight, wmul, bmul, need_dx=need_dx, need_dw=need_dw, has_bias=has_bias,
                                     dw_out=tw, db_out=tb)
         return dx, (None if tw is not None else dw), (None if tb is not None else db), None, None, None

@@ -178,6 +178,7 @@ class IRFDTrainer:
             loss.backward()
         finally:
             grp._bwd_cb = None
+        ops.side_stream(self.gflat.device).join()   # side-stream gradient launches (no-op when the encoders joined)
         if self.world > 1:
             self.schedule.final()
         self.step_count += 1
