@@ -2,12 +2,8 @@
 // Reference semantics: torch.nn.BatchNorm2d inside torchvision Bottleneck (torchvision/models/resnet.py:143-164):
 // batch statistics in train mode (biased variance for normalisation, unbiased for the running buffer, momentum 0.1,
 // eps 1e-5), running statistics in eval mode; ReLU and the residual add are fused into the apply pass.
-#include <cooperative_groups.h>
-
 #include "host_util.h"
 #include "rowvec.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace irfd {
 
@@ -79,31 +75,14 @@ __device__ __forceinline__ void fin_block_sums(double& a, double& b, double (*sa
   }
 }
 
-// Partial-row splits: the kernels below run as thread-block clusters of `gridDim.z` CTAs along z.  CTA z sums its
-// contiguous share of the partial rows, leaves the result in its own shared memory, and the cluster's first CTA adds the
-// shares in rank order through distributed shared memory (deterministic; no global scratch, no counters).  With the BN
-// backward sums coming from the dgrad epilogue there are up to 1024 partial rows per group and, for C = 64, only 8 x 3
-// channel blocks: one CTA per channel block took 35 us per launch.
-struct FinSplit {
-  int lo, n;  // this CTA's rows [lo, lo + n)
-  __device__ FinSplit(int rows) {
-    const int per = (rows + gridDim.z - 1) / gridDim.z;
-    lo = blockIdx.z * per;
-    n = rows - lo < per ? rows - lo : per;
-    if (n < 0) n = 0;
-  }
-};
-
 __global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int tiles, int C, double count,
                    float eps, float momentum, float* __restrict__ mean, float* __restrict__ rstd, FSetM running_mean_s,
                    FSetM running_var_s, int running_updates, int groups) {
   // statistic groups (e.g. the source and the target half of a paired encoder pass) are processed one after the
   // other so the running buffers can be updated in call order by the same thread.
-  cg::cluster_group cluster = cg::this_cluster();
   __shared__ double s_sum[32][kFinCh];
   __shared__ double s_sq[32][kFinCh];
-  __shared__ double xch[kMaxGroups][2][kFinCh];  // this CTA's share, read by the cluster's first CTA
   const int cl = threadIdx.x & (kFinCh - 1);
   const int lane = threadIdx.x / kFinCh;
   const int c = blockIdx.x * kFinCh + cl;  // C % 8 == 0 on this path
@@ -114,32 +93,14 @@ bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq
   rstd += (size_t)blockIdx.y * groups * C;
   float* running_mean = running_mean_s.p[blockIdx.y];
   float* running_var = running_var_s.p[blockIdx.y];
-  const FinSplit sp(tiles);
+  double gm[kMaxGroups], gv[kMaxGroups];
 #pragma unroll
   for (int g = 0; g < kMaxGroups; ++g) {
     if (g < groups) {
       double a, b;
-      const size_t off = ((size_t)g * tiles + sp.lo) * C + c;
-      fin_partial_sums(psum + off, psq + off, C, C, sp.n, lane, a, b);
+      fin_partial_sums(psum + (size_t)g * tiles * C + c, psq + (size_t)g * tiles * C + c, C, C, tiles, lane, a, b);
       fin_block_sums(a, b, s_sum, s_sq);
       if (threadIdx.x < kFinCh) {
-        xch[g][0][cl] = a;
-        xch[g][1][cl] = b;
-      }
-    }
-  }
-  cluster.sync();
-  if (blockIdx.z == 0 && threadIdx.x < kFinCh) {
-    double gm[kMaxGroups], gv[kMaxGroups];
-#pragma unroll
-    for (int g = 0; g < kMaxGroups; ++g) {
-      if (g < groups) {
-        double a = 0.0, b = 0.0;
-        for (unsigned r = 0; r < gridDim.z; ++r) {
-          const double* rem = cluster.map_shared_rank(&xch[0][0][0], r);
-          a += rem[(g * 2 + 0) * kFinCh + cl];
-          b += rem[(g * 2 + 1) * kFinCh + cl];
-        }
         const double m = a / count;
         double var = b / count - m * m;
         if (var < 0.0) var = 0.0;
@@ -149,32 +110,31 @@ bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq
         gv[g] = count > 1.0 ? var * count / (count - 1.0) : var;  // unbiased, for the running buffer
       }
     }
-    if (running_mean != nullptr) {
-      // update 1: the forward calls in order (group 0 first).  update 2 (optional): what the reference's reentrant
-      // checkpoint adds when it re-runs each forward during backward, i.e. the same statistics in reverse call order
-      // (model.py:84-90).
-      float rm = running_mean[c], rv = running_var[c];
-      for (int u = 0; u < running_updates; ++u)
-#pragma unroll
-        for (int i = 0; i < kMaxGroups; ++i) {
-          if (i < groups) {
-            const int g = (u & 1) ? groups - 1 - i : i;
-            double mg = gm[0], vg = gv[0];
-#pragma unroll
-            for (int k = 1; k < kMaxGroups; ++k)
-              if (k == g) {
-                mg = gm[k];
-                vg = gv[k];
-              }
-            rm = (1.f - momentum) * rm + momentum * (float)mg;
-            rv = (1.f - momentum) * rv + momentum * (float)vg;
-          }
-        }
-      running_mean[c] = rm;
-      running_var[c] = rv;
-    }
   }
-  cluster.sync();  // the other CTAs' shared memory must outlive the first CTA's reads
+  if (threadIdx.x < kFinCh && running_mean != nullptr) {
+    // update 1: the forward calls in order (group 0 first).  update 2 (optional): what the reference's reentrant
+    // checkpoint adds when it re-runs each forward during backward, i.e. the same statistics in reverse call order
+    // (model.py:84-90).
+    float rm = running_mean[c], rv = running_var[c];
+    for (int u = 0; u < running_updates; ++u)
+#pragma unroll
+      for (int i = 0; i < kMaxGroups; ++i) {
+        if (i < groups) {
+          const int g = (u & 1) ? groups - 1 - i : i;
+          double mg = gm[0], vg = gv[0];
+#pragma unroll
+          for (int k = 1; k < kMaxGroups; ++k)
+            if (k == g) {
+              mg = gm[k];
+              vg = gv[k];
+            }
+          rm = (1.f - momentum) * rm + momentum * (float)mg;
+          rv = (1.f - momentum) * rv + momentum * (float)vg;
+        }
+      }
+    running_mean[c] = rm;
+    running_var[c] = rv;
+  }
 }
 
 // Re-apply the momentum update from saved batch statistics (second update of the reference's checkpoint recompute).
@@ -447,10 +407,8 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
 __global__ void __launch_bounds__(1024)
 bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, double count, FSetM dgamma_s, FSetM dbeta_s,
                        float beta_acc, float* __restrict__ c1, float* __restrict__ c2, int batch_stats, int groups) {
-  cg::cluster_group cluster = cg::this_cluster();  // gridDim.z CTAs split the partial rows (see FinSplit)
   __shared__ double s0s[32][kFinCh];
   __shared__ double s1s[32][kFinCh];
-  __shared__ double xch[kMaxGroups][2][kFinCh];
   const int cl = threadIdx.x & (kFinCh - 1);
   const int lane = threadIdx.x / kFinCh;
   const int c = blockIdx.x * kFinCh + cl;
@@ -460,62 +418,24 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, doubl
   c2 += (size_t)blockIdx.y * groups * C;
   float* __restrict__ dgamma = dgamma_s.p[blockIdx.y];
   float* __restrict__ dbeta = dbeta_s.p[blockIdx.y];
-  const FinSplit sp(nblk);
+  double tot0 = 0.0, tot1 = 0.0;
   for (int g = 0; g < groups; ++g) {
-    const float* pg = partial + ((size_t)g * nblk + sp.lo) * 2 * C + c;
+    const float* pg = partial + (size_t)g * nblk * 2 * C + c;
     double s0, s1;
-    fin_partial_sums(pg, pg + C, (size_t)2 * C, (size_t)2 * C, sp.n, lane, s0, s1);
+    fin_partial_sums(pg, pg + C, (size_t)2 * C, (size_t)2 * C, nblk, lane, s0, s1);
     fin_block_sums(s0, s1, s0s, s1s);
     if (threadIdx.x < kFinCh) {
-      xch[g][0][cl] = s0;
-      xch[g][1][cl] = s1;
-    }
-  }
-  cluster.sync();
-  if (blockIdx.z == 0 && threadIdx.x < kFinCh) {
-    double tot0 = 0.0, tot1 = 0.0;
-    for (int g = 0; g < groups; ++g) {
-      double s0 = 0.0, s1 = 0.0;
-      for (unsigned r = 0; r < gridDim.z; ++r) {
-        const double* rem = cluster.map_shared_rank(&xch[0][0][0], r);
-        s0 += rem[(g * 2 + 0) * kFinCh + cl];
-        s1 += rem[(g * 2 + 1) * kFinCh + cl];
-      }
       // each group normalised with its own statistics; eval mode (constants) has no batch-statistic terms in dz
       c1[(size_t)g * C + c] = batch_stats ? (float)(s0 / count) : 0.f;
       c2[(size_t)g * C + c] = batch_stats ? (float)(s1 / count) : 0.f;
       tot0 += s0;
       tot1 += s1;
     }
+  }
+  if (threadIdx.x < kFinCh) {
     dbeta[c] = (beta_acc != 0.f ? beta_acc * dbeta[c] : 0.f) + (float)tot0;
     dgamma[c] = (beta_acc != 0.f ? beta_acc * dgamma[c] : 0.f) + (float)tot1;
   }
-  cluster.sync();
-}
-
-// Launch a finalize kernel as clusters of `splits` CTAs along z.
-static int fin_splits(int rows, int c, int nsets) {
-  // as many splits (<= 8, the portable cluster size) as keep >= 128 partial rows per CTA and the grid within ~4 waves
-  int s = 1;
-  while (s < 8 && rows / (2 * s) >= 128 && (long long)(c / kFinCh) * nsets * (2 * s) <= 4ll * num_sms()) s *= 2;
-  return s;
-}
-
-template <typename... KArgs, typename... Args>
-static void launch_fin(void (*kern)(KArgs...), int c, int nsets, int splits, cudaStream_t stream, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(c / kFinCh, nsets, splits);
-  cfg.blockDim = dim3(1024);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = splits;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 template <bool HAS_G2, int MASK, bool G_OUT>
@@ -630,8 +550,9 @@ static void launch_bn_bwd(const BnBwdLaunch& L) {
     bn_bwd_reduce_kernel<HAS_G2, MASK, false><<<L.grid, kRvThreads, L.smem, L.stream>>>(
         L.g1, L.g2, L.act, L.z, L.mean, L.rstd, L.gamma, L.beta, L.partial, nullptr, L.grows, L.c, L.rpb, L.gps,
         zigzag());
-  launch_fin(bn_bwd_finalize_kernel, L.c, L.nsets, fin_splits(L.nblk, L.c, L.nsets), L.stream, L.partial, L.nblk, L.c,
-             (double)L.grows, L.dgamma, L.dbeta, L.grad_beta, L.c1, L.c2, L.batch_stats, L.gps);
+  bn_bwd_finalize_kernel<<<dim3(L.c / kFinCh, L.nsets), 1024, 0, L.stream>>>(L.partial, L.nblk, L.c, (double)L.grows,
+                                                                             L.dgamma, L.dbeta, L.grad_beta, L.c1, L.c2,
+                                                                             L.batch_stats, L.gps);
   if (L.g_out != nullptr)  // the masked gradient is already in g_out (bf16, the value its other consumers see)
     bn_bwd_apply_kernel<false, 0, false><<<L.grid, kRvThreads, 0, L.stream>>>(
         L.g_out, nullptr, nullptr, L.z, L.mean, L.rstd, L.gamma, L.beta, L.c1, L.c2, L.dz, nullptr, L.grows, L.c, L.rpb,
@@ -670,9 +591,10 @@ extern "C" int irfd_bn_finalize_sets(const float* psum, const float* psq, int ti
   IRFD_CHECK_ARG(nsets >= 1 && nsets <= kMaxSets, "bn_finalize: 1..4 parameter sets");
   IRFD_CHECK_ARG(c % kFinCh == 0, "bn_finalize: C must be a multiple of 8 (got %d)", c);
   IRFD_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running buffers come in pairs");
-  launch_fin(bn_finalize_kernel, c, nsets, fin_splits(tiles, c, nsets), stream, psum, psq, tiles, c, (double)count, eps,
-             momentum, mean, rstd, make_fsetm(running_mean, nsets), make_fsetm(running_var, nsets), running_updates,
-             groups);
+  bn_finalize_kernel<<<dim3(c / kFinCh, nsets), 1024, 0, stream>>>(psum, psq, tiles, c, (double)count, eps, momentum,
+                                                                     mean, rstd, make_fsetm(running_mean, nsets),
+                                                                     make_fsetm(running_var, nsets), running_updates,
+                                                                     groups);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }
@@ -861,8 +783,10 @@ extern "C" int irfd_bn_backward_finish_sets(const void* g, const void* z, const 
   const int gps = groups / nsets;
   prefer_max_shared_carveout(reinterpret_cast<const void*>(&bn_bwd_apply_kernel<false, 0, false>));
   prefer_max_shared_carveout(reinterpret_cast<const void*>(&bn_bwd_finalize_kernel));
-  launch_fin(bn_bwd_finalize_kernel, c, nsets, fin_splits(tiles, c, nsets), stream, partial, tiles, c, (double)grows,
-             make_fsetm(dgamma, nsets), make_fsetm(dbeta, nsets), grad_beta, c1, c2, batch_stats, gps);
+  bn_bwd_finalize_kernel<<<dim3(c / kFinCh, nsets), 1024, 0, stream>>>(partial, tiles, c, (double)grows,
+                                                                        make_fsetm(dgamma, nsets),
+                                                                        make_fsetm(dbeta, nsets), grad_beta, c1, c2,
+                                                                        batch_stats, gps);
   bn_bwd_apply_kernel<false, 0, false><<<dim3(nblk, groups), kRvThreads, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(g), nullptr, nullptr, reinterpret_cast<const __nv_bfloat16*>(z), mean, rstd,
       ga, be, c1, c2, reinterpret_cast<__nv_bfloat16*>(dz), nullptr, grows, c, rpb, gps);
