@@ -39,7 +39,11 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
 // ---------------------------------------------------------------------------------------------------------------
 // One block per (image, output row): the 3 x 7 input rows it needs are staged once in shared memory (zero padded by
 // 3 columns on both sides and for out-of-range rows), then every thread assembles 8-element column vectors from
-// shared memory.  (The first version gathered each element straight from global memory: 0.45 ms, L1-wavefront-bound.)
+// shared memory.  (The first version gathered each element straight from global memory: 0.45 ms, L1-wavefront-bound;
+// the second decoded k = (c*7 + kh)*7 + kw with two integer divisions per ELEMENT: 0.25 ms, issue-bound.)  A thread
+// now owns one 8-element vector position v of the kpad-wide row for every eighth output pixel: its eight shared-memory
+// offsets are computed once, the loop over pixels is eight loads and one 16-byte store.
+constexpr int kStemPixPar = 8;  // output pixels in flight per block pass
 __global__ void __launch_bounds__(256)
 im2col_stem_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int H, int W, int kpad) {
   extern __shared__ float srow[];  // [3][7][W + 6]
@@ -54,21 +58,19 @@ im2col_stem_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col,
     srow[i] = v;
   }
   __syncthreads();
-  const int vec_per_row = kpad / 8;
+  const int vec_per_row = kpad / 8;            // blockDim.x == kStemPixPar * vec_per_row (host)
+  const int v = threadIdx.x % vec_per_row;
+  int off[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int k = v * 8 + t;                   // k = (c * 7 + kh) * 7 + kw
+    off[t] = k < 147 ? (k / 7) * P + (k % 7) : -1;
+  }
   const size_t pix0 = ((size_t)n * Ho + oh) * Wo;
-  for (int i = threadIdx.x; i < Wo * vec_per_row; i += blockDim.x) {
-    const int ow = i / vec_per_row, v = i - ow * vec_per_row;
+  for (int ow = threadIdx.x / vec_per_row; ow < Wo; ow += kStemPixPar) {
     float f[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int k = v * 8 + t;
-      float val = 0.f;
-      if (k < 147) {
-        const int cr = k / 7, kw = k - cr * 7;  // k = (c * 7 + kh) * 7 + kw
-        val = srow[cr * P + 2 * ow + kw];
-      }
-      f[t] = val;
-    }
+    for (int t = 0; t < 8; ++t) f[t] = off[t] >= 0 ? srow[off[t] + 2 * ow] : 0.f;
     store8(col + (pix0 + ow) * kpad + v * 8, f);
   }
 }
@@ -198,59 +200,70 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfl
   *reinterpret_cast<uint2*>(arg + (size_t)pix * C + v * 8) = packed;
 }
 
-// grid = (N*H input rows, segments of W*C/8 vectors): the row decode is per block, the column decode 32-bit.  An input
-// pixel lies in at most 2 x 2 pooling windows (stride 2, kernel 3, pad 1): row h belongs to output row h/2 through tap
-// kh = 1 when h is even, to rows (h+1)/2 (kh = 0) and (h-1)/2 (kh = 2) when it is odd; the candidates are listed once per
-// thread instead of walking 3 x 3 taps with parity tests (ncu, round 2: that version was issue-bound, 1.3 TB/s).
+// A thread owns a 2 x 2 quad of input pixels (rows 2i, 2i+1; columns 2j, 2j+1) for 8 channels.  With stride 2,
+// kernel 3, pad 1 the quad only lies in the pooling windows (i..i+1) x (j..j+1): an even row 2i belongs to window row i
+// through tap kh = 1, the odd row 2i+1 to window rows i+1 (kh = 0) and i (kh = 2).  The four windows' gradient and
+// argmax vectors are loaded ONCE and serve the nine (pixel, window) pairs; per pixel the candidates are added in
+// ascending tap order, the order of a 3 x 3 walk.  (Round-2 history: the 3 x 3 walk with parity tests was issue-bound
+// at 1.3 TB/s; one pixel per thread with its <= 2 x 2 candidate windows re-read every window 2.25 times: 1.8 TB/s.)
+// grid = (N * H/2 row pairs, segments of (W/2) * C/8 quads).
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ dout2,
                    const uint8_t* __restrict__ arg, __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C) {
   const unsigned Ho = H / 2, Wo = W / 2, vc = C >> 3;
-  const unsigned i = blockIdx.y * blockDim.x + threadIdx.x;
-  if (i >= (unsigned)W * vc) return;
-  const int w = i / vc, v = i - w * vc;
-  const int n = blockIdx.x / H, h = blockIdx.x - n * H;
-  int oh[2], kh[2], nh = 0, ow[2], kw[2], nw = 0;
-  if (h & 1) {  // ascending tap order, like the 3 x 3 walk it replaces (same summation order)
-    if ((unsigned)((h + 1) >> 1) < Ho) { oh[nh] = (h + 1) >> 1; kh[nh++] = 0; }
-    oh[nh] = (h - 1) >> 1; kh[nh++] = 2;
-  } else {
-    oh[nh] = h >> 1; kh[nh++] = 1;
-  }
-  if (w & 1) {
-    if ((unsigned)((w + 1) >> 1) < Wo) { ow[nw] = (w + 1) >> 1; kw[nw++] = 0; }
-    ow[nw] = (w - 1) >> 1; kw[nw++] = 2;
-  } else {
-    ow[nw] = w >> 1; kw[nw++] = 1;
-  }
-  float acc[8];
+  const unsigned q = blockIdx.y * blockDim.x + threadIdx.x;
+  if (q >= Wo * vc) return;
+  const int j = q / vc, v = q - j * vc;
+  const int n = blockIdx.x / Ho, i = blockIdx.x - n * Ho;
+  float g[2][2][8];
+  uint2 am[2][2];
 #pragma unroll
-  for (int t = 0; t < 8; ++t) acc[t] = 0.f;
-#pragma unroll
-  for (int a = 0; a < 2; ++a) {
-    if (a >= nh) break;
+  for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
-      if (b >= nw) break;
-      const size_t op = (((size_t)n * Ho + oh[a]) * Wo + ow[b]) * C + v * 8;
-      const uint2 packed = __ldg(reinterpret_cast<const uint2*>(arg + op));
-      float g[8];
-      unpack8(ldg16(dout + op), g);
-      if (dout2 != nullptr) {
-        float g2[8];
-        unpack8(ldg16(dout2 + op), g2);
+      am[a][b] = make_uint2(0xffffffffu, 0xffffffffu);  // no tap matches 0xff: windows outside the image contribute 0
 #pragma unroll
-        for (int t = 0; t < 8; ++t) g[t] += g2[t];
-      }
-      const unsigned tap = kh[a] * 3 + kw[b];
+      for (int t = 0; t < 8; ++t) g[a][b][t] = 0.f;
+      if ((unsigned)(i + a) < Ho && (unsigned)(j + b) < Wo) {
+        const size_t op = (((size_t)n * Ho + i + a) * Wo + j + b) * C + v * 8;
+        am[a][b] = __ldg(reinterpret_cast<const uint2*>(arg + op));
+        unpack8(ldg16(dout + op), g[a][b]);
+        if (dout2 != nullptr) {
+          float g2[8];
+          unpack8(ldg16(dout2 + op), g2);
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const unsigned am = ((t < 4 ? packed.x : packed.y) >> ((t & 3) * 8)) & 0xffu;
-        if (am == tap) acc[t] += g[t];
+          for (int t = 0; t < 8; ++t) g[a][b][t] += g2[t];
+        }
       }
     }
-  }
-  store8(dx + (((size_t)n * H + h) * W + w) * C + v * 8, acc);
+#pragma unroll
+  for (int pa = 0; pa < 2; ++pa)
+#pragma unroll
+    for (int pb = 0; pb < 2; ++pb) {
+      float acc[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+      // row candidates of input row 2i + pa in ascending tap order: (window a, tap kh)
+#pragma unroll
+      for (int ra = 0; ra < 2; ++ra) {
+        const int a = pa ? 1 - ra : 0;          // odd row: window i+1 (kh 0) first, then window i (kh 2)
+        const int kh = pa ? (ra ? 2 : 0) : 1;
+        if (!pa && ra) continue;                // an even row has one candidate
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb) {
+          const int b = pb ? 1 - rb : 0;
+          const int kw = pb ? (rb ? 2 : 0) : 1;
+          if (!pb && rb) continue;
+          const unsigned tap = kh * 3 + kw;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const unsigned m = ((t < 4 ? am[a][b].x : am[a][b].y) >> ((t & 3) * 8)) & 0xffu;
+            if (m == tap) acc[t] += g[a][b][t];
+          }
+        }
+      }
+      store8(dx + (((size_t)n * H + 2 * i + pa) * W + 2 * j + pb) * C + v * 8, acc);
+    }
 }
 
 // AdaptiveAvgPool2d(1): [N, HW, C] bf16 -> [N, C] fp32 ; backward broadcasts dfeat/HW
@@ -349,7 +362,8 @@ extern "C" int irfd_im2col_stem(const float* x, void* col, int n, int h, int w, 
   IRFD_CHECK_ARG(x && col && kpad >= 152 && kpad % 8 == 0 && h % 2 == 0 && w % 2 == 0, "im2col_stem: bad argument");
   const size_t smem = (size_t)21 * (w + 6) * sizeof(float);
   IRFD_CHECK_ARG(n > 0 && smem <= 48 * 1024, "im2col_stem: image too wide for the row stage (W <= 579)");
-  im2col_stem_kernel<<<(unsigned)(n * (h / 2)), 256, smem, stream>>>(x, BF(col), n, h, w, kpad);
+  IRFD_CHECK_ARG(kStemPixPar * (kpad / 8) <= 256, "im2col_stem: kpad <= 256");
+  im2col_stem_kernel<<<(unsigned)(n * (h / 2)), kStemPixPar * (kpad / 8), smem, stream>>>(x, BF(col), n, h, w, kpad);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }
@@ -405,7 +419,7 @@ extern "C" int irfd_maxpool_bwd(const void* dout, const void* dout2, const void*
                                 int c, cudaStream_t stream) {
   IRFD_CHECK_ARG(dout && dx && argmax && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "maxpool_bwd: bad argument");
   IRFD_CHECK_ARG((long long)w * c < (1ll << 24) && (long long)n * h < (1ll << 31), "maxpool_bwd: bad shape");
-  maxpool_bwd_kernel<<<dim3((unsigned)(n * h), (unsigned)((w * (c / 8) + 255) / 256)), 256, 0, stream>>>(
+  maxpool_bwd_kernel<<<dim3((unsigned)(n * (h / 2)), (unsigned)(((w / 2) * (c / 8) + 255) / 256)), 256, 0, stream>>>(
       CBF(dout), CBF(dout2), reinterpret_cast<const uint8_t*>(argmax), BF(dx), n, h, w, c);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;

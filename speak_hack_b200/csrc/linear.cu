@@ -56,7 +56,9 @@ linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, cons
 
 // Long-K variant (the 6144 -> 512 first mapping layer): COLS output columns per block, so the [B, K] activations go
 // through L2 N / COLS times instead of N times (168 us -> the x traffic of 805 MB drops 4x).  Per output the k partition
-// per thread and the reduction order are those of linear_fwd_kernel: bit-identical results.
+// per thread and the reduction order are those of linear_fwd_kernel: bit-identical results.  The ROWS-row passes over
+// the batch are blockIdx.y (the first version looped over them inside 128 four-warp blocks: less than one block per SM,
+// twelve dependent L2 round trips per pass, 190 us on the critical path between the encoders and the synthesis).
 template <int ROWS, int COLS>
 __global__ void __launch_bounds__(32 * kFcWarps)
 linear_fwd_cols_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
@@ -64,7 +66,8 @@ linear_fwd_cols_kernel(const float* __restrict__ x, const float* __restrict__ W,
   __shared__ float part[kFcWarps][ROWS][COLS];
   const int n0 = blockIdx.x * COLS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int b0 = 0; b0 < B; b0 += ROWS) {
+  {
+    const int b0 = blockIdx.y * ROWS;
     float acc[ROWS][COLS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
@@ -103,7 +106,6 @@ linear_fwd_cols_kernel(const float* __restrict__ x, const float* __restrict__ W,
         y[(size_t)(b0 + r) * N + n0 + c] = v;
       }
     }
-    __syncthreads();
   }
 }
 
@@ -241,7 +243,8 @@ extern "C" int irfd_linear_fwd(const float* x, const float* w, const float* bias
   IRFD_CHECK_ARG(x && w && y && b > 0 && n > 0 && k > 0 && k % 4 == 0, "linear_fwd: bad argument (K %% 4 == 0)");
   const dim3 grid(n), block(32 * kFcWarps);
   if (k >= 2048 && b > 8) {  // long K: four columns per block (x traffic through L2 / 4)
-    linear_fwd_cols_kernel<16, 4><<<dim3((n + 3) / 4), block, 0, stream>>>(x, w, bias, y, b, n, k, wmul, bmul, lrelu);
+    linear_fwd_cols_kernel<16, 4><<<dim3((n + 3) / 4, (b + 15) / 16), block, 0, stream>>>(x, w, bias, y, b, n, k, wmul, bmul,
+                                                                                   lrelu);
     IRFD_CHECK_LAUNCH();
     return IRFD_OK;
   }

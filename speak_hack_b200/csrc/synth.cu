@@ -434,7 +434,8 @@ to_rgb_bwd_kernel(const float* __restrict__ drgb, const __nv_bfloat16* __restric
       for (int u = 0; u < RB; ++u) {
         const long long rr = r + (long long)u * rv.rows_par;
         if (rr < r1) {
-          const unsigned b = (unsigned)(rr / HW), p = (unsigned)(rr - (long long)b * HW);
+          // 32-bit decode (rows < 2^31, host-checked): the 64-bit division here made the kernel issue-bound
+          const unsigned b = (unsigned)rr / (unsigned)HW, p = (unsigned)rr - b * (unsigned)HW;
           const float* g = drgb + (size_t)b * 3 * HW + p;
           g0[u] = __ldg(g);
           g1[u] = __ldg(g + HW);
@@ -630,6 +631,7 @@ extern "C" long long irfd_to_rgb_bwd_workspace_bytes(int b, int hw, int c) {
 extern "C" int irfd_to_rgb_bwd(const float* drgb, const void* y, const float* w, void* dy, float* dw, float* dbias,
                                int b, int hw, int c, void* workspace, long long workspace_bytes, cudaStream_t stream) {
   IRFD_CHECK_ARG(drgb && y && w && dy && dw && dbias && workspace && c % 8 == 0 && c <= 2048, "to_rgb_bwd: bad arg");
+  IRFD_CHECK_ARG((long long)b * hw < (1ll << 31), "to_rgb_bwd: too many pixels");
   int nblk, rpb;
   plan_row_blocks((long long)b * hw, c, num_sms(), &nblk, &rpb);
   IRFD_CHECK_ARG(workspace_bytes >= (long long)nblk * 4 * c * 4, "to_rgb_bwd: workspace too small");
