@@ -49,13 +49,29 @@ im2col_stem_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col,
   extern __shared__ float srow[];  // [3][7][W + 6]
   const int Ho = H / 2, Wo = W / 2, P = W + 6;
   const int n = blockIdx.x / Ho, oh = blockIdx.x - n * Ho;
-  for (int i = threadIdx.x; i < 21 * P; i += blockDim.x) {
-    const int cr = i / P, j = i - cr * P;  // cr = c * 7 + kh
+  // stage: one warp per (channel, kernel row) input row, 16-byte loads (W % 4 == 0, host-checked), all of a warp's loads
+  // independent (the per-element version walked 29 dependent iterations with two divisions each)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int cr = warp; cr < 21; cr += nwarps) {  // cr = c * 7 + kh
     const int c = cr / 7, kh = cr - c * 7;
-    const int ih = oh * 2 + kh - 3, iw = j - 3;
-    float v = 0.f;
-    if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(x + (((size_t)n * 3 + c) * H + ih) * W + iw);
-    srow[i] = v;
+    const int ih = oh * 2 + kh - 3;
+    float* dst = srow + cr * P;
+    if (lane < 3) {
+      dst[lane] = 0.f;
+      dst[P - 3 + lane] = 0.f;
+    }
+    if (ih >= 0 && ih < H) {
+      const float4* src = reinterpret_cast<const float4*>(x + (((size_t)n * 3 + c) * H + ih) * W);
+      for (int j = lane; j < W / 4; j += 32) {
+        const float4 q = __ldg(src + j);
+        dst[3 + 4 * j] = q.x;
+        dst[4 + 4 * j] = q.y;
+        dst[5 + 4 * j] = q.z;
+        dst[6 + 4 * j] = q.w;
+      }
+    } else {
+      for (int j = lane; j < W; j += 32) dst[3 + j] = 0.f;
+    }
   }
   __syncthreads();
   const int vec_per_row = kpad / 8;            // blockDim.x == kStemPixPar * vec_per_row (host)
@@ -362,7 +378,8 @@ extern "C" int irfd_im2col_stem(const float* x, void* col, int n, int h, int w, 
   IRFD_CHECK_ARG(x && col && kpad >= 152 && kpad % 8 == 0 && h % 2 == 0 && w % 2 == 0, "im2col_stem: bad argument");
   const size_t smem = (size_t)21 * (w + 6) * sizeof(float);
   IRFD_CHECK_ARG(n > 0 && smem <= 48 * 1024, "im2col_stem: image too wide for the row stage (W <= 579)");
-  IRFD_CHECK_ARG(kStemPixPar * (kpad / 8) <= 256, "im2col_stem: kpad <= 256");
+  IRFD_CHECK_ARG(kStemPixPar * (kpad / 8) <= 256 && (kpad / 8) % 4 == 0 && w % 4 == 0,
+                 "im2col_stem: kpad a multiple of 32 and <= 256, W a multiple of 4");
   im2col_stem_kernel<<<(unsigned)(n * (h / 2)), kStemPixPar * (kpad / 8), smem, stream>>>(x, BF(col), n, h, w, kpad);
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
