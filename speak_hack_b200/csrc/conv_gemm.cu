@@ -68,6 +68,7 @@ struct ConvGemmArgs {
   const float* bn_gamma[4];   // per weight group
   const float* bn_beta[4];
   int sg_tiles;               // m tiles per statistic group
+  int warp_epi;               // non-STYLE modes of conv_gemm_kernel: per-warp epilogue (epilogue_tile_warp)
 };
 
 constexpr int kNumThreads = 320;      // 10 warps
@@ -82,7 +83,7 @@ struct GemmCfg {
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int NUM_OUT = (MODE == EPI_STYLE) ? 2 : 1;
-  static constexpr int STG_TOTAL = NUM_OUT * 2 * kStgBytes;
+  static constexpr int STG_TOTAL = 4 * kStgBytes;  // STYLE: 2 outputs x 2 tiles; other modes: 8 warps x 2 slabs of 4 KB
   static constexpr int RAW_STAGES = (kSmemLimit - 1024 - STG_TOTAL - kMiscBytes) / STAGE_BYTES;
   static constexpr int STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STG_TOTAL + kMiscBytes;
@@ -354,6 +355,201 @@ __device__ __forceinline__ void epilogue_acc(const ConvGemmArgs& p, const CUtens
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Per-warp epilogue (conv_gemm_kernel, every mode but STYLE).  The pointwise layers of the encoders have one to eight
+// k-blocks per tile: their time is the epilogue, and in epilogue_acc all eight warps walk the 64-column chunks in
+// lockstep through two 256-thread barriers per chunk (drain -> barrier -> stage -> barrier -> one 16 KB TMA store).
+// Here the warps are decoupled: warp (q, h) owns rows 32q..32q+31 of every chunk whose running index has parity h,
+// drains all 64 columns of it, stages them in its OWN 4 KB slab (two per warp) and issues its own [32 x 64] TMA store:
+// only __syncwarp on the plain path.  The statistics modes add one 128-thread barrier per chunk (the four quarter
+// warps of a chunk combine their column sums in rank order: deterministic).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSlabBytes = 4096;
+
+template <int BLOCK_N, int MODE>
+__device__ __forceinline__ void epilogue_tile_warp(const ConvGemmArgs& p, const CUtensorMap* map_slab, uint32_t tmem_base,
+                                                   uint32_t acc_col, int m0, int n_tile, uint64_t* release_bar,
+                                                   uint8_t* stg_base, float* vec, uint32_t& chunk_counter,
+                                                   uint32_t& my_slabs) {
+  static_assert(MODE != EPI_STYLE, "STYLE keeps the two-output epilogue");
+  constexpr int CHUNKS = BLOCK_N / 64;
+  constexpr bool kSums = MODE == EPI_STATS || MODE == EPI_BNBWD || MODE == EPI_BNBWD_RES;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int e = warp - 2;
+  const int q = warp & 3;   // TMEM lane quarter this warp may touch
+  const int h = e >> 2;     // chunk parity this warp serves
+  const int m_tile = m0 >> 7;
+  const int ng0 = n_tile * BLOCK_N;
+  const int pg0 = (m_tile / p.wg_tiles) * p.N_total + ng0;
+  const int row = m0 + q * 32 + lane;  // this thread's output row
+  uint8_t* slabs = stg_base + e * 2 * kSlabBytes;
+  float* wvec = vec + e * 128;         // per-warp [2][64]: AFFINE scale | shift, PLAIN bias (statistics modes: `vec` = red)
+  // the chunks of this tile this warp serves: first, first + 2, ...
+  const int first = (h - (int)chunk_counter) & 1;
+  const int last_mine = first < CHUNKS ? first + 2 * ((CHUNKS - 1 - first) / 2) : -1;
+  if (last_mine < 0) {  // nothing to drain from this accumulator
+    __syncwarp();
+    if (lane == 0) mbar_arrive(release_bar);
+  }
+#pragma unroll 1
+  for (int chunk = first; chunk < CHUNKS; chunk += 2) {
+    const int cg0 = ng0 + chunk * 64;  // first channel of the chunk
+    uint32_t zw[32], gw[32];
+    uint8_t bw[32];
+    if constexpr (MODE == EPI_BNBWD || MODE == EPI_BNBWD_RES) {
+      // column phase operands (lane = channel pair, 32 rows of this warp), in flight during the drain
+      const size_t cell0 = (size_t)(m0 + q * 32) * p.N_total + cg0 + 2 * lane;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        zw[i] = __ldg(reinterpret_cast<const uint32_t*>(p.bn_z + cell0 + (size_t)i * p.N_total));
+        if constexpr (MODE == EPI_BNBWD_RES) {
+          gw[i] = __ldg(reinterpret_cast<const uint32_t*>(p.bn_g2 + cell0 + (size_t)i * p.N_total));
+          bw[i] = __ldg(p.bn_bits + ((cell0 + (size_t)i * p.N_total) >> 3));
+        }
+      }
+    }
+    if constexpr (MODE == EPI_AFFINE || MODE == EPI_PLAIN) {
+      if (MODE == EPI_AFFINE || p.bias != nullptr) {
+        __syncwarp();  // previous chunk's reads of wvec
+        wvec[lane] = MODE == EPI_AFFINE ? p.nw[pg0 + chunk * 64 + lane] : 0.f;            // scale
+        wvec[lane + 32] = MODE == EPI_AFFINE ? p.nw[pg0 + chunk * 64 + 32 + lane] : 0.f;
+        wvec[64 + lane] = p.bias[pg0 + chunk * 64 + lane];                                 // shift / bias
+        wvec[96 + lane] = p.bias[pg0 + chunk * 64 + 32 + lane];
+        __syncwarp();
+      }
+    }
+    uint32_t va[32], vb[32];
+    const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc_col + chunk * 64;
+    tmem_ld32(taddr, va);
+    tmem_ld32(taddr + 32, vb);
+    tmem_ld_wait();
+    if (chunk == last_mine) {  // this warp is done with the accumulator
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(release_bar);
+    }
+    uint8_t* slab = slabs + (my_slabs & 1) * kSlabBytes;
+    if (lane == 0) tma_store_wait_read<1>();  // the store issued from this slab two chunks ago has read it
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // 16-byte pieces of this thread's 128-byte staging row
+      float o[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int c = j * 8 + t;
+        const float acc = __uint_as_float(c < 32 ? va[c & 31] : vb[c & 31]);
+        if constexpr (MODE == EPI_AFFINE) o[t] = acc * wvec[c] + wvec[64 + c];
+        else if constexpr (MODE == EPI_PLAIN) o[t] = p.bias != nullptr ? acc + wvec[64 + c] : acc;
+        else o[t] = acc;
+      }
+      if constexpr (MODE == EPI_AFFINE) {
+        if (p.res != nullptr && row < p.M_total) {
+          const uint4 u = *reinterpret_cast<const uint4*>(p.res + (size_t)row * p.N_total + cg0 + j * 8);
+          const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+          o[0] += a0.x; o[1] += a0.y; o[2] += a1.x; o[3] += a1.y;
+          o[4] += a2.x; o[5] += a2.y; o[6] += a3.x; o[7] += a3.y;
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          o[t] = p.relu == 1 ? fmaxf(o[t], 0.f) : (p.relu == 2 ? (o[t] > 0.f ? o[t] : 0.2f * o[t]) : o[t]);
+      }
+      uint4 pk;
+      pk.x = pack_bf16x2(o[0], o[1]);
+      pk.y = pack_bf16x2(o[2], o[3]);
+      pk.z = pack_bf16x2(o[4], o[5]);
+      pk.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(slab + lane * 128 + ((j ^ (lane & 7)) << 4)) = pk;
+    }
+    if constexpr (kSums) {
+      __syncwarp();
+      // column phase: lane = channel pair (2 * lane, 2 * lane + 1) over the warp's 32 rows, straight from the slab
+      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+      if constexpr (MODE == EPI_STATS) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(slab + i * 128 + (((lane >> 2) ^ (i & 7)) << 4) + (lane & 3) * 4);
+          const float2 f = unpack_bf16x2(w);
+          s0 += f.x;
+          q0 += f.x * f.x;
+          s1 += f.y;
+          q1 += f.y * f.y;
+        }
+      } else {
+        const int cc = cg0 + 2 * lane;
+        const size_t so = (size_t)(m_tile / p.sg_tiles) * p.N_total + cc;
+        const float2 mm = __ldg(reinterpret_cast<const float2*>(p.bn_mean + so));
+        const float2 rs = __ldg(reinterpret_cast<const float2*>(p.bn_rstd + so));
+        float2 ga = make_float2(0.f, 0.f), be = make_float2(0.f, 0.f);
+        if constexpr (MODE == EPI_BNBWD) {
+          const int grp = m_tile / p.wg_tiles;
+          const float* gam =
+              grp == 0 ? p.bn_gamma[0] : (grp == 1 ? p.bn_gamma[1] : (grp == 2 ? p.bn_gamma[2] : p.bn_gamma[3]));
+          const float* bet = grp == 0 ? p.bn_beta[0] : (grp == 1 ? p.bn_beta[1] : (grp == 2 ? p.bn_beta[2] : p.bn_beta[3]));
+          ga = __ldg(reinterpret_cast<const float2*>(gam + cc));
+          be = __ldg(reinterpret_cast<const float2*>(bet + cc));
+        }
+        const int bit0 = (2 * lane) & 7;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          uint32_t* cell = reinterpret_cast<uint32_t*>(slab + i * 128 + (((lane >> 2) ^ (i & 7)) << 4) + (lane & 3) * 4);
+          float2 f = unpack_bf16x2(*cell);
+          const float2 z = unpack_bf16x2(zw[i]);
+          const float x0 = (z.x - mm.x) * rs.x, x1 = (z.y - mm.y) * rs.y;
+          if constexpr (MODE == EPI_BNBWD) {
+            f.x = (ga.x * x0 + be.x) > 0.f ? f.x : 0.f;
+            f.y = (ga.y * x1 + be.y) > 0.f ? f.y : 0.f;
+          } else {
+            const float2 g2 = unpack_bf16x2(gw[i]);
+            f.x = ((bw[i] >> bit0) & 1) ? f.x + g2.x : 0.f;
+            f.y = ((bw[i] >> (bit0 + 1)) & 1) ? f.y + g2.y : 0.f;
+          }
+          *cell = pack_bf16x2(f.x, f.y);
+          s0 += f.x;
+          q0 += f.x * x0;
+          s1 += f.y;
+          q1 += f.y * x1;
+        }
+      }
+      // red[slab parity][h][q][64 channels][2]: the four quarter warps of this chunk, combined by quarter 0
+      float* red = vec + ((((my_slabs & 1) * 2 + h) * 4 + q) * 64) * 2;
+      *reinterpret_cast<float4*>(red + 4 * lane) = make_float4(s0, q0, s1, q1);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(map_slab, slab, cg0, m0 + q * 32);
+      tma_store_commit();
+    }
+    if constexpr (kSums) {
+      named_bar_sync(1 + h, 128);
+      if (q == 0) {
+        const float* r0 = vec + ((((my_slabs & 1) * 2 + h) * 4) * 64) * 2 + 4 * lane;
+        float4 t = *reinterpret_cast<const float4*>(r0);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+          const float4 u = *reinterpret_cast<const float4*>(r0 + k * 128);
+          t.x += u.x;
+          t.y += u.y;
+          t.z += u.z;
+          t.w += u.w;
+        }
+        if constexpr (MODE == EPI_STATS) {
+          const size_t d = (size_t)m_tile * p.N_total + cg0 + 2 * lane;
+          *reinterpret_cast<float2*>(p.stat_sum + d) = make_float2(t.x, t.z);
+          *reinterpret_cast<float2*>(p.stat_sq + d) = make_float2(t.y, t.w);
+        } else {
+          const size_t d = (size_t)m_tile * 2 * p.N_total + cg0 + 2 * lane;
+          *reinterpret_cast<float2*>(p.stat_sum + d) = make_float2(t.x, t.z);
+          *reinterpret_cast<float2*>(p.stat_sum + d + p.N_total) = make_float2(t.y, t.w);
+        }
+      }
+    }
+    ++my_slabs;
+  }
+  chunk_counter += CHUNKS;
+}
+
 template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -473,7 +669,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
     int iter = 0;
-    uint32_t chunk_counter = 0;
+    uint32_t chunk_counter = 0, my_slabs = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
@@ -481,11 +677,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int n_tile = tile - m_tile * p.num_n_tiles;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
+      if constexpr (MODE != EPI_STYLE) {
+        if (p.warp_epi) {
+          epilogue_tile_warp<BLOCK_N, MODE>(p, &map_out2, tmem_base, as * BLOCK_N, m_tile * 128, n_tile, &tmem_empty[as],
+                                            stg_base, vec, chunk_counter, my_slabs);
+          continue;
+        }
+      }
       epilogue_acc<BLOCK_N, MODE, 2>(p, &map_out, &map_out2, tmem_base, as * BLOCK_N, m_tile * 128, n_tile,
                                      &tmem_empty[as], stg_base, vec, chunk_counter);
     }
     // the staging buffers only have to outlive the TMA engine's READS; global visibility comes with grid completion
-    if (warp == 2) {
+    if (MODE != EPI_STYLE && p.warp_epi) {
+      if (lane == 0) tma_store_wait_read<0>();
+    } else if (warp == 2) {
       __syncwarp();
       if (elect_one_sync()) tma_store_wait_read<0>();
     }
@@ -787,6 +992,12 @@ static int dispatch_halo(int block_n, const CUtensorMap& ma, const CUtensorMap& 
   return launch_conv_halo<128, MODE>(ma, mb, mo, mo2, a, h, stream);
 }
 
+// IRFD_WARP_EPI: 1 (default) = per-warp epilogue in conv_gemm_kernel (all modes but STYLE), 0 = the lockstep one.
+static int warp_epi_mode() {
+  const char* e = getenv("IRFD_WARP_EPI");
+  return e ? atoi(e) : 1;
+}
+
 // IRFD_CONV_HALO: 0 = never, 1 (default) = wide 3x3 layers with Cout 64/128, read at every call (tests flip it).
 static int halo_mode() {
   const char* e = getenv("IRFD_CONV_HALO");
@@ -877,6 +1088,7 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
     IRFD_CHECK_ARG(h * w >= 64, "conv_gemm: STYLE mode needs >= 64 pixels per image");
   }
   if (mode == EPI_STATS) IRFD_CHECK_ARG(stat_sum && stat_sq, "conv_gemm: STATS mode needs stat buffers");
+  a.warp_epi = (mode != EPI_STYLE && m_total % 128 == 0 && warp_epi_mode() != 0) ? 1 : 0;
   a.bn_z = nullptr;
   a.bn_mean = a.bn_rstd = nullptr;
   for (int i = 0; i < 4; ++i) a.bn_gamma[i] = a.bn_beta[i] = nullptr;
@@ -957,7 +1169,12 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
     const uint32_t box[2] = {64, 128};
     int rc = make_tmap_bf16(&mo, out, 2, dims, str, box, true);
     if (rc) return rc;
-    rc = make_tmap_bf16(&mo2, out2 ? out2 : out, 2, dims, str, box, true);
+    if (mode == EPI_STYLE) {
+      rc = make_tmap_bf16(&mo2, out2 ? out2 : out, 2, dims, str, box, true);
+    } else {  // the per-warp epilogue stores [32 pixels x 64 channels] slabs
+      const uint32_t slab_box[2] = {64, 32};
+      rc = make_tmap_bf16(&mo2, out, 2, dims, str, slab_box, true);
+    }
     if (rc) return rc;
   }
   if (use_halo) {
