@@ -550,7 +550,13 @@ __device__ __forceinline__ void epilogue_tile_warp(const ConvGemmArgs& p, const 
   chunk_counter += CHUNKS;
 }
 
-template <int BLOCK_N, int MODE>
+// CL = CTAs per cluster (1 or 2).  With CL = 2 the pair works on two vertically adjacent pixel tiles of the same n tile
+// and weight group: the [BLOCK_N x 64] weight tile of every k-block is the same for both, so each CTA fetches HALF of it
+// and multicasts that half into both CTAs' stages.  For BLOCK_N = 256 the weight tile is two thirds of what an SM pulls
+// from L2 per k-block (32 KB against 16 KB of pixels), and the large-K layers are bound by exactly that L2 -> SM stream
+// (ncu: 17.6 TB/s L2 -> SM at 56 % tensor activity); the pair cuts it by a third.  A stage may be refilled only when BOTH
+// CTAs' MMAs have read it: the MMA warp commits to the empty barrier of both CTAs (count CL).
+template <int BLOCK_N, int MODE, int CL = 1>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out2,
@@ -572,13 +578,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  // work unit = CL consecutive m tiles x one n tile; unit u -> (u / num_n_tiles, u % num_n_tiles); this CTA takes m tile
+  // CL * (u / num_n_tiles) + its rank in the cluster
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
+  const int total_units = (p.num_m_tiles / CL) * p.num_n_tiles;
   const int num_kb = p.taps * p.cin_chunks;
+  constexpr uint16_t kClusterMask = (1u << CL) - 1;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CL);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -590,6 +601,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -603,9 +615,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles;
-        const int n_tile = tile - m_tile * p.num_n_tiles;
+      for (int unit = unit0; unit < total_units; unit += unit_step) {
+        const int m_tile = (unit / p.num_n_tiles) * CL + crank;
+        const int n_tile = unit % p.num_n_tiles;
         const int m0 = (p.a_mod_tiles > 0 ? m_tile % p.a_mod_tiles : m_tile) * 128;
         const int w0 = m0 % p.W;
         const int h0 = (m0 / p.W) % p.H;
@@ -620,7 +632,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             if (elect_one_sync()) {
               mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
               tma_load_4d(sa, &map_a, &full_bar[stage], ch * 64, w0 + dw, h0 + dh, n0);
-              tma_load_2d(sa + Cfg::A_BYTES, &map_b, &full_bar[stage], (tap * p.cin_chunks + ch) * 64, b_row);
+              if (CL == 1)
+                tma_load_2d(sa + Cfg::A_BYTES, &map_b, &full_bar[stage], (tap * p.cin_chunks + ch) * 64, b_row);
+              else  // this CTA's share of the weight tile, into both CTAs' stage
+                tma_load_2d_mc(sa + Cfg::A_BYTES + crank * (Cfg::B_BYTES / CL), &map_b, &full_bar[stage],
+                               (tap * p.cin_chunks + ch) * 64, b_row + crank * (BLOCK_N / CL), kClusterMask);
             }
             __syncwarp();
             if (++stage == STAGES) {
@@ -638,7 +654,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      for (int unit = unit0; unit < total_units; unit += unit_step, ++iter) {
         const int as = iter & 1;
         const uint32_t aphase = (iter >> 1) & 1;
         mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -654,7 +670,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int k = 0; k < 4; ++k)  // +32 bytes per K=16 step: +2 in the descriptor's 16-byte address field
               umma_bf16(d_tmem, adesc0 + 2 * k, bdesc0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_commit(&empty_bar[stage]);
+            if (CL == 1) umma_commit(&empty_bar[stage]);
+            else umma_commit_mc(&empty_bar[stage], kClusterMask);
           }
           __syncwarp();
           if (++stage == STAGES) {
@@ -670,11 +687,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ------------------------------------------------------------------ epilogue (8 warps)
     int iter = 0;
     uint32_t chunk_counter = 0, my_slabs = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+    for (int unit = unit0; unit < total_units; unit += unit_step, ++iter) {
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
-      const int m_tile = tile / p.num_n_tiles;
-      const int n_tile = tile - m_tile * p.num_n_tiles;
+      const int m_tile = (unit / p.num_n_tiles) * CL + crank;
+      const int n_tile = unit % p.num_n_tiles;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       if constexpr (MODE != EPI_STYLE) {
@@ -698,6 +715,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer may still multicast into this CTA's stages / commit to its barriers
   if (warp == 0) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
@@ -931,12 +949,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, int CL = 1>
 static int launch_conv_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mo2,
                             const ConvGemmArgs& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, MODE>;
   static bool configured = false;
-  auto kern = conv_gemm_kernel<BLOCK_N, MODE>;
+  auto kern = conv_gemm_kernel<BLOCK_N, MODE, CL>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -945,16 +963,37 @@ static int launch_conv_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const 
     }
     configured = true;
   }
-  const int total = a.num_m_tiles * a.num_n_tiles;
-  const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, kNumThreads, Cfg::SMEM_BYTES, stream>>>(ma, mb, mo, mo2, a);
+  const int units = (a.num_m_tiles / CL) * a.num_n_tiles;
+  const int slots = num_sms() / CL;
+  const int grid = (units < slots ? units : slots) * CL;
+  if (CL == 1) {
+    kern<<<grid, kNumThreads, Cfg::SMEM_BYTES, stream>>>(ma, mb, mo, mo2, a);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, mo2, a);
+  }
   IRFD_CHECK_LAUNCH();
   return IRFD_OK;
 }
 
 template <int MODE>
 static int dispatch_block_n(int block_n, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo,
-                            const CUtensorMap& mo2, const ConvGemmArgs& a, cudaStream_t stream) {
+                            const CUtensorMap& mo2, const ConvGemmArgs& a, cudaStream_t stream, int cluster = 1) {
+  if (cluster == 2) {
+    if (block_n == 128) return launch_conv_gemm<128, MODE, 2>(ma, mb, mo, mo2, a, stream);
+    if (block_n == 256) return launch_conv_gemm<256, MODE, 2>(ma, mb, mo, mo2, a, stream);
+  }
   switch (block_n) {
     case 64: return launch_conv_gemm<64, MODE>(ma, mb, mo, mo2, a, stream);
     case 128: return launch_conv_gemm<128, MODE>(ma, mb, mo, mo2, a, stream);
@@ -990,6 +1029,15 @@ static int dispatch_halo(int block_n, const CUtensorMap& ma, const CUtensorMap& 
                          const CUtensorMap& mo2, const ConvGemmArgs& a, const HaloArgs& h, cudaStream_t stream) {
   if (block_n == 64) return launch_conv_halo<64, MODE>(ma, mb, mo, mo2, a, h, stream);
   return launch_conv_halo<128, MODE>(ma, mb, mo, mo2, a, h, stream);
+}
+
+// IRFD_GEMM_CLUSTER: 1 = CTA pairs with multicast weight tiles where the layer allows it, 0 (default) = never.
+// Measured (round 2, every GEMM shape of the train step, L2 flushed): 12.76 ms/step without, 12.83 ms with — each SM
+// still INGESTS the whole weight tile, and that per-SM ingest (not the L2's output) is what the large-K layers are bound
+// by.  Kept as a tested option; halving the ingest needs the 2-SM MMA (cta_group::2, half a weight tile per SM).
+static int cluster_mode() {
+  const char* e = getenv("IRFD_GEMM_CLUSTER");
+  return e ? atoi(e) : 0;
 }
 
 // IRFD_WARP_EPI: 1 (default) = per-warp epilogue in conv_gemm_kernel (all modes but STYLE), 0 = the lockstep one.
@@ -1141,6 +1189,11 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
                         (force_block_n == 0 || force_block_n == cout);
   if (use_halo) block_n = cout;
   a.num_n_tiles = cout / block_n;
+  // CTA pairs (multicast weight tiles): two consecutive m tiles must belong to the same weight group / A matrix
+  int cluster = 1;
+  if (!use_halo && cluster_mode() != 0 && block_n >= 128 && a.num_m_tiles % 2 == 0 &&
+      (wgroups == 1 || a.wg_tiles % 2 == 0) && (a.a_mod_tiles == 0 || a.a_mod_tiles % 2 == 0))
+    cluster = 2;
 
   CUtensorMap ma, mb, mo, mo2;
   {
@@ -1159,7 +1212,7 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
     const uint64_t ktot = (uint64_t)a.taps * cin;
     const uint64_t dims[2] = {ktot, (uint64_t)cout * wgroups};
     const uint64_t str[1] = {ktot * 2};
-    const uint32_t box[2] = {64, (uint32_t)block_n};
+    const uint32_t box[2] = {64, (uint32_t)(block_n / cluster)};  // a CTA pair loads half a weight tile each
     int rc = make_tmap_bf16(&mb, wk, 2, dims, str, box, true);
     if (rc) return rc;
   }
@@ -1191,12 +1244,12 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
     return IRFD_ERR_INVALID_ARGUMENT;
   }
   switch (mode) {
-    case EPI_PLAIN: return dispatch_block_n<EPI_PLAIN>(block_n, ma, mb, mo, mo2, a, stream);
-    case EPI_STATS: return dispatch_block_n<EPI_STATS>(block_n, ma, mb, mo, mo2, a, stream);
-    case EPI_STYLE: return dispatch_block_n<EPI_STYLE>(block_n, ma, mb, mo, mo2, a, stream);
-    case EPI_AFFINE: return dispatch_block_n<EPI_AFFINE>(block_n, ma, mb, mo, mo2, a, stream);
-    case EPI_BNBWD: return dispatch_block_n<EPI_BNBWD>(block_n, ma, mb, mo, mo2, a, stream);
-    case EPI_BNBWD_RES: return dispatch_block_n<EPI_BNBWD_RES>(block_n, ma, mb, mo, mo2, a, stream);
+    case EPI_PLAIN: return dispatch_block_n<EPI_PLAIN>(block_n, ma, mb, mo, mo2, a, stream, cluster);
+    case EPI_STATS: return dispatch_block_n<EPI_STATS>(block_n, ma, mb, mo, mo2, a, stream, cluster);
+    case EPI_STYLE: return dispatch_block_n<EPI_STYLE>(block_n, ma, mb, mo, mo2, a, stream, cluster);
+    case EPI_AFFINE: return dispatch_block_n<EPI_AFFINE>(block_n, ma, mb, mo, mo2, a, stream, cluster);
+    case EPI_BNBWD: return dispatch_block_n<EPI_BNBWD>(block_n, ma, mb, mo, mo2, a, stream, cluster);
+    case EPI_BNBWD_RES: return dispatch_block_n<EPI_BNBWD_RES>(block_n, ma, mb, mo, mo2, a, stream, cluster);
   }
   return IRFD_ERR_INVALID_ARGUMENT;
 }

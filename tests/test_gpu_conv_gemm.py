@@ -55,6 +55,41 @@ def test_plain(cuda_device, n, h, w, cin, cout, k, block_n):
     assert rel_l2(y.float(), ref) < 4e-3  # bf16 output rounding: 2^-9 per element
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,k", [(2, 16, 16, 256, 256, 1), (2, 32, 32, 512, 512, 3), (8, 32, 32, 128, 256, 3),
+                                              (12, 64, 64, 64, 256, 1), (6, 16, 16, 1024, 256, 1)])
+def test_kernel_variants_bit_identical(cuda_device, monkeypatch, n, h, w, cin, cout, k):
+    """The optional instances of conv_gemm_kernel compute the same tiles with the same MMA sequence:
+    IRFD_GEMM_CLUSTER=1 (CTA pairs, each CTA multicasts half of every weight tile into both) must give bit-identical
+    outputs and statistics; IRFD_WARP_EPI=0 (the lockstep epilogue) bit-identical outputs and statistics equal up to the
+    fp32 order of the per-tile row sums (16-row groups instead of 32-row warps)."""
+    from speak_hack_b200 import ops
+
+    x, wt, wk = _mk(n, h, w, cin, cout, k, cuda_device, seed=5)
+    base = ops.conv_gemm(x, wk, k, ops.EPI_STATS)
+    plain = ops.conv_gemm(x, wk, k, ops.EPI_PLAIN)
+    torch.cuda.synchronize()
+    assert torch.equal(plain, base[0])
+    monkeypatch.setenv("IRFD_GEMM_CLUSTER", "1")
+    got = ops.conv_gemm(x, wk, k, ops.EPI_STATS)
+    got_plain = ops.conv_gemm(x, wk, k, ops.EPI_PLAIN)
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(got, base)) and torch.equal(got_plain, plain)
+    if n % 3 == 0:   # grouped weights: pairs never straddle two weight groups
+        wk3 = torch.cat([wk, wk.flip(0), wk.roll(1, 0)]).contiguous()
+        monkeypatch.setenv("IRFD_GEMM_CLUSTER", "0")
+        g0 = ops.conv_gemm_grouped(x, wk3, k, ops.EPI_STATS, wgroups=3)
+        monkeypatch.setenv("IRFD_GEMM_CLUSTER", "1")
+        g1 = ops.conv_gemm_grouped(x, wk3, k, ops.EPI_STATS, wgroups=3)
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(g0, g1))
+    monkeypatch.setenv("IRFD_GEMM_CLUSTER", "0")
+    monkeypatch.setenv("IRFD_WARP_EPI", "0")
+    old = ops.conv_gemm(x, wk, k, ops.EPI_STATS)
+    torch.cuda.synchronize()
+    assert torch.equal(old[0], base[0])
+    assert torch.allclose(old[1], base[1], rtol=1e-5, atol=1e-3) and torch.allclose(old[2], base[2], rtol=1e-5, atol=1e-2)
+
+
 @pytest.mark.parametrize("n,h,w,cin,cout,k", [(2, 16, 16, 64, 64, 3), (4, 32, 32, 128, 256, 3), (2, 64, 64, 256, 64, 1)])
 def test_stats(cuda_device, n, h, w, cin, cout, k):
     from speak_hack_b200 import ops
