@@ -392,7 +392,7 @@ def build_roofline(fam, rsteps):
                                          "achieved_gbs": v["flops"] / (v["ms"] * 1e-3) / 1e9,
                                          "frac_of_measured_hbm": v["flops"] / (v["ms"] * 1e-3) / 1e9 / peak_bw}
                                      for k, v in hbm.items()},
-                    "ncu": "profiles/r2_launches_summary.md (launch list with DRAM bytes), profiles/r2_ncu_full_summary.md "
+                    "ncu": "profiles/r2_final_launches_summary.md (launch list with DRAM bytes), profiles/r2b_ncu_full_summary.md + r2_ncu_full_summary.md "
                            "(--set full of the top kernels), profiles/r2_conv_shapes.md (per-shape roofline), "
                            "profiles/r2_graph_timeline.md"}
 
