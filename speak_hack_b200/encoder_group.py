@@ -16,8 +16,15 @@ of the tensor peak, 18-55 us launches against 6-26 us bounds).  `EncoderGroup` r
   share the single wave, a third of the fp32 partials), written straight into the caller's gradient buffers when
   `grad_targets` is set.
 
-Numerically the grouped pass is the per-encoder pass: same kernels, same tiles, same summation order per tile
-(tests/test_gpu_encoder_group.py: features and BN buffers bit-identical, parameter gradients equal).
+* the backward of every BatchNorm that feeds a conv (bn1, bn2) has its reduce pass inside the epilogue of that conv's
+  data-gradient GEMM (`irfd_conv_gemm_bnbwd_grouped`: ReLU mask recomputed from z, per-tile sums of g and g*xhat), so the
+  activation gradient is written once, already masked, and read once; the block outputs keep their ReLU mask as a bit
+  plane (`irfd_bn_apply_sets(mask_bits)`) that bn3's backward reads instead of the activation.
+
+Numerically the forward of the grouped pass is the per-encoder pass: same kernels, same tiles, same summation order
+per tile (tests/test_gpu_encoder_group.py: features and BN buffers bit-identical).  The backward sums the BatchNorm
+statistics of bn1 / bn2 per 128-pixel tile instead of per row block: same terms in a different fp32 order
+(IRFD_BN_FOLD=0 restores the per-encoder launches and gradients equal to 3e-6).
 """
 from __future__ import annotations
 
