@@ -25,7 +25,9 @@ struct FSetM {
   float* p[kMaxSets];
 };
 constexpr int kFinCh = 8;       // channels per block
-constexpr int kFinLanes = 128;  // partial-row lanes per block (1024 threads)
+constexpr int kFinLanes = 64;   // partial-row lanes per block
+constexpr int kFinThreads = kFinCh * kFinLanes;  // 512
+constexpr int kFinWarps = kFinThreads / 32;
 constexpr int kFinBatch = 8;    // loads in flight per thread per stream
 
 // Sum `n` partial rows of two [n][C] fp32 arrays for channel c, this thread taking rows lane, lane+128, ...
@@ -49,7 +51,7 @@ __device__ __forceinline__ void fin_partial_sums(const float* __restrict__ p0, c
   }
 }
 
-// Block-wide sum over the 128 lanes of one channel: lanes of a warp by shuffle, the 32 warps through shared memory.
+// Block-wide sum over the lanes of one channel: lanes of a warp by shuffle, the warps through shared memory.
 // Valid in the threads with lane == 0 (threadIdx.x < kFinCh).
 __device__ __forceinline__ void fin_block_sums(double& a, double& b, double (*sa)[kFinCh], double (*sb)[kFinCh]) {
 #pragma unroll
@@ -68,21 +70,25 @@ __device__ __forceinline__ void fin_block_sums(double& a, double& b, double (*sa
     a = 0.0;
     b = 0.0;
 #pragma unroll 8
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < kFinWarps; ++i) {
       a += sa[i][threadIdx.x];
       b += sb[i][threadIdx.x];
     }
   }
 }
 
-__global__ void __launch_bounds__(1024)
+// 512-thread blocks, two per SM by the launch bound (<= 64 registers): the first version's 1024-thread block at 63
+// registers needed the whole register file of an SM, so inside the step's graph it had to wait for a persistent
+// weight-gradient CTA of the side stream to retire before it could start (CUPTI: 35 us per backward finalize against
+// 19 us alone).
+__global__ void __launch_bounds__(kFinThreads, 2)
 bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int tiles, int C, double count,
                    float eps, float momentum, float* __restrict__ mean, float* __restrict__ rstd, FSetM running_mean_s,
                    FSetM running_var_s, int running_updates, int groups) {
   // statistic groups (e.g. the source and the target half of a paired encoder pass) are processed one after the
   // other so the running buffers can be updated in call order by the same thread.
-  __shared__ double s_sum[32][kFinCh];
-  __shared__ double s_sq[32][kFinCh];
+  __shared__ double s_sum[kFinWarps][kFinCh];
+  __shared__ double s_sq[kFinWarps][kFinCh];
   const int cl = threadIdx.x & (kFinCh - 1);
   const int lane = threadIdx.x / kFinCh;
   const int c = blockIdx.x * kFinCh + cl;  // C % 8 == 0 on this path
@@ -404,11 +410,11 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
   block_reduce_rows<2>(rv, C, acc, red_smem, partial + (size_t)bx * 2 * C, (size_t)C);
 }
 
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(kFinThreads, 2)
 bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, double count, FSetM dgamma_s, FSetM dbeta_s,
                        float beta_acc, float* __restrict__ c1, float* __restrict__ c2, int batch_stats, int groups) {
-  __shared__ double s0s[32][kFinCh];
-  __shared__ double s1s[32][kFinCh];
+  __shared__ double s0s[kFinWarps][kFinCh];
+  __shared__ double s1s[kFinWarps][kFinCh];
   const int cl = threadIdx.x & (kFinCh - 1);
   const int lane = threadIdx.x / kFinCh;
   const int c = blockIdx.x * kFinCh + cl;
@@ -550,7 +556,7 @@ static void launch_bn_bwd(const BnBwdLaunch& L) {
     bn_bwd_reduce_kernel<HAS_G2, MASK, false><<<L.grid, kRvThreads, L.smem, L.stream>>>(
         L.g1, L.g2, L.act, L.z, L.mean, L.rstd, L.gamma, L.beta, L.partial, nullptr, L.grows, L.c, L.rpb, L.gps,
         zigzag());
-  bn_bwd_finalize_kernel<<<dim3(L.c / kFinCh, L.nsets), 1024, 0, L.stream>>>(L.partial, L.nblk, L.c, (double)L.grows,
+  bn_bwd_finalize_kernel<<<dim3(L.c / kFinCh, L.nsets), kFinThreads, 0, L.stream>>>(L.partial, L.nblk, L.c, (double)L.grows,
                                                                              L.dgamma, L.dbeta, L.grad_beta, L.c1, L.c2,
                                                                              L.batch_stats, L.gps);
   if (L.g_out != nullptr)  // the masked gradient is already in g_out (bf16, the value its other consumers see)
@@ -591,7 +597,7 @@ extern "C" int irfd_bn_finalize_sets(const float* psum, const float* psq, int ti
   IRFD_CHECK_ARG(nsets >= 1 && nsets <= kMaxSets, "bn_finalize: 1..4 parameter sets");
   IRFD_CHECK_ARG(c % kFinCh == 0, "bn_finalize: C must be a multiple of 8 (got %d)", c);
   IRFD_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running buffers come in pairs");
-  bn_finalize_kernel<<<dim3(c / kFinCh, nsets), 1024, 0, stream>>>(psum, psq, tiles, c, (double)count, eps, momentum,
+  bn_finalize_kernel<<<dim3(c / kFinCh, nsets), kFinThreads, 0, stream>>>(psum, psq, tiles, c, (double)count, eps, momentum,
                                                                      mean, rstd, make_fsetm(running_mean, nsets),
                                                                      make_fsetm(running_var, nsets), running_updates,
                                                                      groups);
@@ -783,7 +789,7 @@ extern "C" int irfd_bn_backward_finish_sets(const void* g, const void* z, const 
   const int gps = groups / nsets;
   prefer_max_shared_carveout(reinterpret_cast<const void*>(&bn_bwd_apply_kernel<false, 0, false>));
   prefer_max_shared_carveout(reinterpret_cast<const void*>(&bn_bwd_finalize_kernel));
-  bn_bwd_finalize_kernel<<<dim3(c / kFinCh, nsets), 1024, 0, stream>>>(partial, tiles, c, (double)grows,
+  bn_bwd_finalize_kernel<<<dim3(c / kFinCh, nsets), kFinThreads, 0, stream>>>(partial, tiles, c, (double)grows,
                                                                         make_fsetm(dgamma, nsets),
                                                                         make_fsetm(dbeta, nsets), grad_beta, c1, c2,
                                                                         batch_stats, gps);

@@ -44,7 +44,9 @@ struct WgCfg {
   static constexpr int A_BYTES = 2 * 8192;
   static constexpr int B_BYTES = (BLOCK_N / 64) * 8192;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int RAW_STAGES = (232448 - 1024 - 1024) / STAGE_BYTES;
+  // at most 196 KB per CTA: the weight gradients run on the side stream beside the row-streaming BatchNorm / style
+  // kernels and their finalize launches, which need the rest of the SM's shared memory to become co-resident
+  static constexpr int RAW_STAGES = (200704 - 1024 - 1024) / STAGE_BYTES;
   static constexpr int STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 1024;
   static constexpr uint32_t TMEM_COLS = BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256);
