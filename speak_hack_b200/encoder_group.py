@@ -42,9 +42,9 @@ from .encoder import BN_EPS, BN_MOMENTUM, ResNet50Encoder
 # their activation gradient (irfd_conv_gemm_bnbwd_grouped); 0 = separate reduce launch (experiments, A/B timing).
 # IRFD_BN3_FOLD (default 0): the same for bn3 of every Bottleneck that is followed by an identity-shortcut block: the
 # next block's conv1 data gradient adds the shortcut gradient, applies the ReLU mask and sums in its epilogue
-# (irfd_conv_gemm_bnbwd_res_grouped).  Measured (B=32 pairs): the BatchNorm family drops 7.4 -> 5.7 ms/step but the GEMM
-# family grows 13.5 -> 15.1 ms (its epilogue streams two more wide tensors at ~2.7 TB/s) and the step time is unchanged
-# (36.68 vs 36.69 ms), so it stays off.
+# (irfd_conv_gemm_bnbwd_res_grouped).  Measured (B=32 pairs, same box): the BatchNorm family drops 7.3 -> 5.7 ms/step but
+# the GEMM family grows 13.3 -> 15.7 ms (its epilogue streams two more wide tensors at < 3 TB/s) and the step gets
+# slower (35.8 -> 36.3 ms), so it stays off.
 fold_bn_reduce = os.environ.get("IRFD_BN_FOLD", "1") != "0"
 fold_bn3_reduce = os.environ.get("IRFD_BN3_FOLD", "0") != "0"
 
