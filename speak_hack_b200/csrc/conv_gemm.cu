@@ -370,8 +370,13 @@ template <int BLOCK_N, int MODE>
 __device__ __forceinline__ void epilogue_tile_warp(const ConvGemmArgs& p, const CUtensorMap* map_slab, uint32_t tmem_base,
                                                    uint32_t acc_col, int m0, int n_tile, uint64_t* release_bar,
                                                    uint8_t* stg_base, float* vec, uint32_t& chunk_counter,
-                                                   uint32_t& my_slabs) {
+                                                   uint32_t& my_slabs, bool release_at_leader = false) {
   static_assert(MODE != EPI_STYLE, "STYLE keeps the two-output epilogue");
+  // 2-SM MMA: the accumulators of both CTAs are written by the leader's MMA warp, which waits on ITS barrier
+  auto release = [&]() {
+    if (release_at_leader) mbar_arrive_cluster(release_bar, 0);
+    else mbar_arrive(release_bar);
+  };
   constexpr int CHUNKS = BLOCK_N / 64;
   constexpr bool kSums = MODE == EPI_STATS || MODE == EPI_BNBWD || MODE == EPI_BNBWD_RES;
   const int warp = threadIdx.x >> 5;
@@ -390,7 +395,7 @@ __device__ __forceinline__ void epilogue_tile_warp(const ConvGemmArgs& p, const 
   const int last_mine = first < CHUNKS ? first + 2 * ((CHUNKS - 1 - first) / 2) : -1;
   if (last_mine < 0) {  // nothing to drain from this accumulator
     __syncwarp();
-    if (lane == 0) mbar_arrive(release_bar);
+    if (lane == 0) release();
   }
 #pragma unroll 1
   for (int chunk = first; chunk < CHUNKS; chunk += 2) {
@@ -427,7 +432,7 @@ __device__ __forceinline__ void epilogue_tile_warp(const ConvGemmArgs& p, const 
     if (chunk == last_mine) {  // this warp is done with the accumulator
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(release_bar);
+      if (lane == 0) release();
     }
     uint8_t* slab = slabs + (my_slabs & 1) * kSlabBytes;
     if (lane == 0) tma_store_wait_read<1>();  // the store issued from this slab two chunks ago has read it
@@ -556,7 +561,11 @@ __device__ __forceinline__ void epilogue_tile_warp(const ConvGemmArgs& p, const 
 // from L2 per k-block (32 KB against 16 KB of pixels), and the large-K layers are bound by exactly that L2 -> SM stream
 // (ncu: 17.6 TB/s L2 -> SM at 56 % tensor activity); the pair cuts it by a third.  A stage may be refilled only when BOTH
 // CTAs' MMAs have read it: the MMA warp commits to the empty barrier of both CTAs (count CL).
-template <int BLOCK_N, int MODE, int CL = 1>
+//
+// MMA2 (with CL = 2): the pair executes 2-SM MMAs (tcgen05 cta_group::2, M = 256): each CTA loads ONLY its half of the
+// weight tile (its SM ingests A 16 KB + B 16 KB per k-block instead of 16 + 32), the leader's MMA warp issues for both,
+// commits go to both CTAs' barriers, both CTAs' epilogue warps release the accumulator at the leader.
+template <int BLOCK_N, int MODE, int CL = 1, bool MMA2 = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out2,
@@ -564,6 +573,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   using Cfg = GemmCfg<BLOCK_N, MODE>;
   constexpr int STAGES = Cfg::STAGES;
   static_assert(STAGES >= 2, "pipeline too shallow");
+  static_assert(!MMA2 || (CL == 2 && MODE != EPI_STYLE), "the 2-SM MMA needs a CTA pair and the per-warp epilogue");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -589,16 +599,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], CL);
+      mbar_init(&empty_bar[i], MMA2 ? 1 : CL);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
+      mbar_init(&tmem_empty[i], MMA2 ? 16 : 8);
     }
     fence_mbar_init();
   }
   __syncwarp();
-  if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  if (warp == 0) {
+    if (MMA2) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_ptr);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  }
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast at them
@@ -629,7 +642,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int ch = 0; ch < p.cin_chunks; ++ch) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-            if (elect_one_sync()) {
+            if (MMA2) {
+              if (elect_one_sync()) {  // both CTAs' bytes are counted on the leader's barrier
+                if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES / 2));
+                tma_load_4d_2sm(sa, &map_a, &full_bar[stage], ch * 64, w0 + dw, h0 + dh, n0);
+                tma_load_2d_2sm(sa + Cfg::A_BYTES, &map_b, &full_bar[stage], (tap * p.cin_chunks + ch) * 64,
+                                b_row + crank * (BLOCK_N / 2));
+              }
+            } else if (elect_one_sync()) {
               mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
               tma_load_4d(sa, &map_a, &full_bar[stage], ch * 64, w0 + dw, h0 + dh, n0);
               if (CL == 1)
@@ -649,8 +669,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (whole warp converged, one lane issues)
-    {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+    if (!MMA2 || crank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(MMA2 ? 256 : 128, BLOCK_N, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
@@ -669,8 +689,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (elect_one_sync()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)  // +32 bytes per K=16 step: +2 in the descriptor's 16-byte address field
-              umma_bf16(d_tmem, adesc0 + 2 * k, bdesc0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            if (CL == 1) umma_commit(&empty_bar[stage]);
+              if (MMA2) umma_bf16_2sm(d_tmem, adesc0 + 2 * k, bdesc0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16(d_tmem, adesc0 + 2 * k, bdesc0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (MMA2) umma_commit_2sm_mc(&empty_bar[stage], kClusterMask);
+            else if (CL == 1) umma_commit(&empty_bar[stage]);
             else umma_commit_mc(&empty_bar[stage], kClusterMask);
           }
           __syncwarp();
@@ -679,7 +701,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             phase ^= 1;
           }
         }
-        if (elect_one_sync()) umma_commit(&tmem_full[as]);
+        if (elect_one_sync()) {
+          if (MMA2) umma_commit_2sm_mc(&tmem_full[as], kClusterMask);
+          else umma_commit(&tmem_full[as]);
+        }
         __syncwarp();
       }
     }
@@ -697,7 +722,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if constexpr (MODE != EPI_STYLE) {
         if (p.warp_epi) {
           epilogue_tile_warp<BLOCK_N, MODE>(p, &map_out2, tmem_base, as * BLOCK_N, m_tile * 128, n_tile, &tmem_empty[as],
-                                            stg_base, vec, chunk_counter, my_slabs);
+                                            stg_base, vec, chunk_counter, my_slabs, MMA2);
           continue;
         }
       }
@@ -716,7 +741,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();  // the peer may still multicast into this CTA's stages / commit to its barriers
-  if (warp == 0) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  if (warp == 0) {
+    if (MMA2) tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
 }
 
 
@@ -949,12 +977,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
-template <int BLOCK_N, int MODE, int CL = 1>
+template <int BLOCK_N, int MODE, int CL = 1, bool MMA2 = false>
 static int launch_conv_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mo2,
                             const ConvGemmArgs& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, MODE>;
   static bool configured = false;
-  auto kern = conv_gemm_kernel<BLOCK_N, MODE, CL>;
+  auto kern = conv_gemm_kernel<BLOCK_N, MODE, CL, MMA2>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -990,7 +1018,13 @@ static int launch_conv_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const 
 template <int MODE>
 static int dispatch_block_n(int block_n, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo,
                             const CUtensorMap& mo2, const ConvGemmArgs& a, cudaStream_t stream, int cluster = 1) {
-  if (cluster == 2) {
+  if constexpr (MODE == EPI_PLAIN || MODE == EPI_STATS || MODE == EPI_BNBWD) {
+    if (cluster == 3) {  // CTA pairs with 2-SM MMAs
+      if (block_n == 128) return launch_conv_gemm<128, MODE, 2, true>(ma, mb, mo, mo2, a, stream);
+      if (block_n == 256) return launch_conv_gemm<256, MODE, 2, true>(ma, mb, mo, mo2, a, stream);
+    }
+  }
+  if (cluster >= 2) {
     if (block_n == 128) return launch_conv_gemm<128, MODE, 2>(ma, mb, mo, mo2, a, stream);
     if (block_n == 256) return launch_conv_gemm<256, MODE, 2>(ma, mb, mo, mo2, a, stream);
   }
@@ -1037,6 +1071,13 @@ static int dispatch_halo(int block_n, const CUtensorMap& ma, const CUtensorMap& 
 // by.  Kept as a tested option; halving the ingest needs the 2-SM MMA (cta_group::2, half a weight tile per SM).
 static int cluster_mode() {
   const char* e = getenv("IRFD_GEMM_CLUSTER");
+  return e ? atoi(e) : 0;
+}
+// IRFD_GEMM_2SM: 1 = CTA pairs with 2-SM MMAs (cta_group::2) for the plain / statistics / BN-backward epilogues; 0
+// (default).  Measured (every GEMM shape of the train step): 12.65 ms/step without, 13.49 ms with — bit-identical results,
+// no shape more than 4 % faster, the HBM-bound pointwise layers 20-45 % slower (the pair runs in lockstep).
+static int mma2_mode() {
+  const char* e = getenv("IRFD_GEMM_2SM");
   return e ? atoi(e) : 0;
 }
 
@@ -1191,9 +1232,9 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
   a.num_n_tiles = cout / block_n;
   // CTA pairs (multicast weight tiles): two consecutive m tiles must belong to the same weight group / A matrix
   int cluster = 1;
-  if (!use_halo && cluster_mode() != 0 && block_n >= 128 && a.num_m_tiles % 2 == 0 &&
+  if (!use_halo && (cluster_mode() != 0 || mma2_mode() != 0) && block_n >= 128 && a.num_m_tiles % 2 == 0 &&
       (wgroups == 1 || a.wg_tiles % 2 == 0) && (a.a_mod_tiles == 0 || a.a_mod_tiles % 2 == 0))
-    cluster = 2;
+    cluster = (mma2_mode() != 0 && a.warp_epi && (mode == EPI_PLAIN || mode == EPI_STATS || mode == EPI_BNBWD)) ? 3 : 2;
 
   CUtensorMap ma, mb, mo, mo2;
   {
@@ -1212,7 +1253,7 @@ static int conv_gemm_impl(const void* x, int n, int h, int w, int cin, const voi
     const uint64_t ktot = (uint64_t)a.taps * cin;
     const uint64_t dims[2] = {ktot, (uint64_t)cout * wgroups};
     const uint64_t str[1] = {ktot * 2};
-    const uint32_t box[2] = {64, (uint32_t)(block_n / cluster)};  // a CTA pair loads half a weight tile each
+    const uint32_t box[2] = {64, (uint32_t)(block_n / (cluster > 1 ? 2 : 1))};  // a CTA pair loads half a weight tile each
     int rc = make_tmap_bf16(&mb, wk, 2, dims, str, box, true);
     if (rc) return rc;
   }

@@ -83,6 +83,12 @@ def test_kernel_variants_bit_identical(cuda_device, monkeypatch, n, h, w, cin, c
         torch.cuda.synchronize()
         assert all(torch.equal(a, b) for a, b in zip(g0, g1))
     monkeypatch.setenv("IRFD_GEMM_CLUSTER", "0")
+    monkeypatch.setenv("IRFD_GEMM_2SM", "1")   # CTA pairs issuing 2-SM MMAs (cta_group::2), half a weight tile per SM
+    two = ops.conv_gemm(x, wk, k, ops.EPI_STATS)
+    two_plain = ops.conv_gemm(x, wk, k, ops.EPI_PLAIN)
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(two, base)) and torch.equal(two_plain, plain)
+    monkeypatch.setenv("IRFD_GEMM_2SM", "0")
     monkeypatch.setenv("IRFD_WARP_EPI", "0")
     old = ops.conv_gemm(x, wk, k, ops.EPI_STATS)
     torch.cuda.synchronize()
