@@ -558,9 +558,9 @@ __device__ __forceinline__ void epilogue_tile_warp(const ConvGemmArgs& p, const 
 // CL = CTAs per cluster (1 or 2).  With CL = 2 the pair works on two vertically adjacent pixel tiles of the same n tile
 // and weight group: the [BLOCK_N x 64] weight tile of every k-block is the same for both, so each CTA fetches HALF of it
 // and multicasts that half into both CTAs' stages.  For BLOCK_N = 256 the weight tile is two thirds of what an SM pulls
-// from L2 per k-block (32 KB against 16 KB of pixels), and the large-K layers are bound by exactly that L2 -> SM stream
-// (ncu: 17.6 TB/s L2 -> SM at 56 % tensor activity); the pair cuts it by a third.  A stage may be refilled only when BOTH
-// CTAs' MMAs have read it: the MMA warp commits to the empty barrier of both CTAs (count CL).
+// from L2 per k-block (32 KB against 16 KB of pixels); the pair cuts the L2's output by a third (optional: measured
+// neutral, see cluster_mode()).  A stage may be refilled only when BOTH CTAs' MMAs have read it: the MMA warp commits to
+// the empty barrier of both CTAs (count CL).
 //
 // MMA2 (with CL = 2): the pair executes 2-SM MMAs (tcgen05 cta_group::2, M = 256): each CTA loads ONLY its half of the
 // weight tile (its SM ingests A 16 KB + B 16 KB per k-block instead of 16 + 32), the leader's MMA warp issues for both,
@@ -1066,9 +1066,9 @@ static int dispatch_halo(int block_n, const CUtensorMap& ma, const CUtensorMap& 
 }
 
 // IRFD_GEMM_CLUSTER: 1 = CTA pairs with multicast weight tiles where the layer allows it, 0 (default) = never.
-// Measured (round 2, every GEMM shape of the train step, L2 flushed): 12.76 ms/step without, 12.83 ms with — each SM
-// still INGESTS the whole weight tile, and that per-SM ingest (not the L2's output) is what the large-K layers are bound
-// by.  Kept as a tested option; halving the ingest needs the 2-SM MMA (cta_group::2, half a weight tile per SM).
+// Measured (round 2, every GEMM shape of the train step, L2 flushed): 12.76 ms/step without, 12.83 ms with — on the
+// large-K layers the L2 -> SM stream is at 62 % of its peak and the tensor pipe busy 83 % of the cycles (ncu), so the
+// weight-tile traffic is not what bounds them.  Kept as a tested option.
 static int cluster_mode() {
   const char* e = getenv("IRFD_GEMM_CLUSTER");
   return e ? atoi(e) : 0;
