@@ -55,6 +55,22 @@ def test_plain(cuda_device, n, h, w, cin, cout, k, block_n):
     assert rel_l2(y.float(), ref) < 4e-3  # bf16 output rounding: 2^-9 per element
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,k", [(2, 16, 16, 64, 128, 1), (8, 32, 32, 128, 256, 3), (1, 1, 1000, 128, 64, 1)])
+def test_plain_with_bias(cuda_device, monkeypatch, n, h, w, cin, cout, k):
+    """PLAIN epilogue with a per-channel bias (C ABI: irfd_conv_gemm mode 0 + bias), per-warp and lockstep epilogues
+    (ragged M falls back to the lockstep one)."""
+    from speak_hack_b200 import ops
+
+    x, wt, wk = _mk(n, h, w, cin, cout, k, cuda_device, seed=7)
+    bias = torch.randn(cout, generator=torch.Generator().manual_seed(70)).to(cuda_device)
+    ref = _ref(x, wt, k) + bias.view(1, 1, 1, -1)
+    for epi in ("1", "0"):
+        monkeypatch.setenv("IRFD_WARP_EPI", epi)
+        y = ops.conv_gemm(x, wk, k, ops.EPI_PLAIN, bias=bias)
+        torch.cuda.synchronize()
+        assert rel_l2(y.float(), ref) < 4e-3, epi
+
+
 @pytest.mark.parametrize("n,h,w,cin,cout,k", [(2, 16, 16, 256, 256, 1), (2, 32, 32, 512, 512, 3), (8, 32, 32, 128, 256, 3),
                                               (12, 64, 64, 64, 256, 1), (6, 16, 16, 1024, 256, 1)])
 def test_kernel_variants_bit_identical(cuda_device, monkeypatch, n, h, w, cin, cout, k):
