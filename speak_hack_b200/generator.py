@@ -196,6 +196,17 @@ def _packed(conv_param: torch.Tensor, w: torch.Tensor, mode: int, co_p: int, ci_
     return ops._pack_conv_weight(_pad_to(_pad_to(w, 0, co_p), 1, ci_p).contiguous(), mode)
 
 
+def synthesis_pack_items(net) -> list:
+    """(weight, mode) pairs of every cached conv repack one synthesis forward + backward uses (ops.prepack_conv_weights)."""
+    items = []
+    for blk in net.layers:
+        for conv in (blk.conv1, blk.conv2):
+            w = conv.weight
+            if w.shape[0] % 64 == 0 and w.shape[1] % 64 == 0:   # padded shapes are packed into temporaries instead
+                items += [(w, ops.PACK_FPROP), (w, ops.PACK_DGRAD)]
+    return items
+
+
 class _SynthesisFn(torch.autograd.Function):
     """forward(w_rows [L,B,512] fp32, noises, *params) -> image [B,3,R,R] fp32.
 

@@ -435,6 +435,29 @@ def pack_conv_weight(w: torch.Tensor, mode: int, kpad: int = 0) -> torch.Tensor:
     return packed
 
 
+def prepack_conv_weights(items, side) -> int:
+    """Refresh the cached bf16 operands of `items` = [(fp32 OIHW weight, mode), ...] whose parameter changed, with the
+    pack kernels on the side stream (`side`: ops.SideStream): the generator's 3x3 weights change at every optimizer step,
+    and packed lazily each repack sits on the main stream right before the GEMM that needs it (24 launches per step).
+    Issued at the start of a step they hide behind the encoders' forward.  The destinations are allocated here, on the
+    calling stream; consumers must be ordered after the side stream's work (the synthesis forward waits, per layer, for a
+    style event recorded later on the same side stream).  Returns the number of repacks launched."""
+    todo = []
+    for w, mode in items:
+        key = (w.data_ptr(), mode, 0, tuple(w.shape))
+        hit = _pack_cache.get(key)
+        if hit is not None and hit[0] == w._version and hit[2]() is w:
+            continue
+        o, i, kh, kw = w.shape
+        shape = (o, kh * kw * i) if mode == PACK_FPROP else (i, kh * kw * o)
+        dst = torch.empty(shape, dtype=BF16, device=w.device)
+        todo.append((w, mode, dst))
+        _pack_cache[key] = (w._version, dst, weakref.ref(w))
+    if todo:
+        side.launch(lambda: [_pack_conv_weight(w, m, out=d) for w, m, d in todo], *[d for _, _, d in todo])
+    return len(todo)
+
+
 def pack_conv_weights_stacked(ws, mode: int, kpad: int = 0) -> torch.Tensor:
     """Packed bf16 operands of several same-shape conv weights stacked along the rows ([len(ws)*rows, K]) for the
     grouped launches; cached until any of the weights changes (same validity rule as pack_conv_weight)."""

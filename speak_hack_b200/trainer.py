@@ -25,6 +25,7 @@ the reference, train.py:346).
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -33,6 +34,7 @@ from . import ops
 from .dp import BucketSchedule, GradBuckets, broadcast_buffers
 from .model import IRFD, mse_loss
 
+_PREPACK = os.environ.get("IRFD_PREPACK", "1") != "0"   # 0: conv weights are repacked lazily on the main stream
 REAL_LABEL, FAKE_LABEL = 0.9, 0.1   # train.py:145-146 (one-sided label smoothing on both sides)
 STAGES = (7, 6, 5, 4, 3)  # ResNet50Encoder child indices 7..4 = layer4..layer1; 3 stands for the stem (children 0, 1)
 
@@ -262,6 +264,9 @@ class IRFDTrainer:
         grp.grad_targets = self._enc_targets
         generator.GRAD_TARGETS = self._gd_targets   # ONE generator call per step: its backward writes gflat in place
         try:
+            if _PREPACK:   # the generator's conv repacks (its weights changed in the last Adam step) behind the encoders
+                ops.prepack_conv_weights(generator.synthesis_pack_items(self.model.Gd.synthesis),
+                                         ops.side_stream(self.device))
             x = self._prep(x_all)
             img, f, _ = self.model.forward_static_stacked(x, self.ctrl)
             l_identity = mse_loss(f[0, :b], f[0, b:])
